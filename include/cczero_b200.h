@@ -1,0 +1,208 @@
+/* cczero_b200.h — C-ABI of libcczero_b200.so, the B200-native Xiangqi self-play hot path.
+ *
+ * The reference (NeymarL/ChineseChess-AlphaZero) is pure Python and has no FFI; the hot path
+ * sits behind three Python surfaces.  This header is what a ctypes binding of
+ * those surfaces calls instead.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative cz_status; nothing throws across the ABI;
+ *     cz_last_error() gives the message of the last failure on the calling thread.
+ *   - "dev" pointers are device memory owned by the caller (torch CUDA tensors: .data_ptr());
+ *     "host" pointers are ordinary host memory.  The library never frees caller memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     stream-ordered; only the functions documented as synchronising wait for the device.
+ *   - boards: BOARD_STRIDE (96) bytes each, first 90 = squares sq = y*9+x with y = 0 the
+ *     side-to-move's back rank; 0 empty, 1..7 = side-to-move P C R N E A K, 9..15 = opponent.
+ *   - moves: uint16 (from << 8) | to.
+ *   - one engine per GPU per process, driven by one host thread.
+ */
+#ifndef CCZERO_B200_H
+#define CCZERO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CZ_BOARD_STRIDE 96
+#define CZ_MAX_MOVES 128
+#define CZ_N_LABELS 2086
+#define CZ_MAX_NO_ACT 16
+
+typedef enum cz_status {
+  CZ_OK = 0,
+  CZ_ERR_ARG = -1,        /* bad argument */
+  CZ_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed */
+  CZ_ERR_STATE = -3,      /* call not valid in the engine's current state */
+  CZ_ERR_CAPACITY = -4,   /* a fixed-capacity device pool overflowed */
+  CZ_ERR_UNSUPPORTED = -5 /* e.g. tensor-core path requested in a build without it */
+} cz_status;
+
+const char* cz_last_error(void);
+/* 1 when this build runs kernels on a CUDA device, 0 for the CPU SIMT-emulation test build
+ * (tests/simt_emul; never shipped). */
+int cz_build_is_cuda(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Lookup tables — environment/lookup_tables.py:62-134 (create_action_labels / ActionLabelsRed)
+ * labels_host: 2086*4 chars "x0y0x1y1" (no terminators); lut_host: 90*90 int16, label index of
+ * (from,to) or -1.  Host-only, no device work.
+ * ---------------------------------------------------------------------------------------- */
+int cz_action_labels(char* labels_host, int16_t* lut_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched rules kernels (one warp per board) — environment/static_env.py
+ * ---------------------------------------------------------------------------------------- */
+/* get_legal_moves :256-321.  moves_dev [n][CZ_MAX_MOVES] in reference order, counts_dev [n]. */
+int cz_env_movegen(const uint8_t* boards_dev, int n, uint16_t* moves_dev, int32_t* counts_dev, void* stream);
+/* done :14-77.  out_dev [n][4] int8 = {over, v, check, 0}; final_move_dev [n] (0xFFFF = None). */
+int cz_env_done(const uint8_t* boards_dev, int n, int need_check, int8_t* out_dev, uint16_t* final_move_dev,
+                void* stream);
+/* step / new_step :79-98 (move, then rotate + swap colours).  no_eat_dev may be NULL. */
+int cz_env_step(const uint8_t* boards_dev, const uint16_t* moves_dev, int n, uint8_t* boards_out_dev,
+                uint8_t* no_eat_dev, void* stream);
+/* state_to_planes :137-156.  planes_dev [n][14][10][9] float32. */
+int cz_env_encode_planes(const uint8_t* boards_dev, int n, float* planes_dev, void* stream);
+/* will_check_or_catch :390-421, be_catched :456-469, has_attack_chessman :471-479.
+ * Any of the three outputs may be NULL. */
+int cz_env_check_catch(const uint8_t* boards_dev, const uint16_t* moves_dev, int n, uint8_t* will_cc_dev,
+                       uint8_t* be_catched_dev, uint8_t* has_attack_dev, void* stream);
+/* 128-bit canonical position keys (replaces the state-string dict key, agent/player.py:49). */
+int cz_env_keys(const uint8_t* boards_dev, int n, uint64_t* keys_dev /* [n][2] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Search engine — agent/player.py (CChessPlayer) for many concurrent games
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cz_engine cz_engine;
+
+typedef struct cz_config {
+  int32_t struct_bytes;        /* sizeof(cz_config), for ABI checking */
+  int32_t device;              /* CUDA device ordinal */
+  int32_t n_games;             /* concurrent games held by this engine */
+  int32_t sims_per_move;       /* play_config.simulation_num_per_move */
+  int32_t leaves_per_round;    /* config.play.search_threads (K): sims launched per round */
+  int32_t virtual_loss;        /* config.play.virtual_loss */
+  int32_t max_nodes_per_game;  /* node pool capacity per game */
+  int32_t max_edges_per_game;  /* edge pool capacity per game */
+  int32_t max_path;            /* longest root->leaf path stored per simulation */
+  int32_t noise_mode;          /* 0 = host table (parity), 1 = on-device Philox gamma sampler */
+  int32_t max_plies;           /* 2*max_game_length, capacity of the per-game record */
+  int32_t nn_filters;          /* cnn_filter_num (0 = no network, external evaluator only) */
+  int32_t nn_blocks;           /* res_layer_num */
+  int32_t nn_value_fc;         /* value_fc_size */
+  double c_puct;               /* play_config.c_puct */
+  double noise_eps;            /* play_config.noise_eps */
+  double dirichlet_alpha;      /* play_config.dirichlet_alpha */
+  double tau_decay_rate;       /* play_config.tau_decay_rate */
+  double resign_threshold;     /* play_config.resign_threshold */
+  int32_t min_resign_turn;     /* play_config.min_resign_turn */
+  int32_t max_game_length;     /* play_config.max_game_length */
+  uint64_t seed;               /* Philox key (seed, rank) for the on-device streams */
+  int32_t rank;                /* data-parallel rank, selects the RNG sub-stream */
+  int32_t reserved;
+} cz_config;
+
+/* Device workspace the caller must provide (a torch.uint8 CUDA tensor). */
+int cz_workspace_bytes(const cz_config* cfg, uint64_t* bytes);
+int cz_create(const cz_config* cfg, void* workspace_dev, uint64_t workspace_bytes, void* stream, cz_engine** out);
+void cz_destroy(cz_engine* e);
+
+/* Start games: boards_host [n_games][CZ_BOARD_STRIDE] or NULL for INIT_STATE (static_env.py:9).
+ * Clears every tree (a new CChessPlayer with search_tree=None, player.py:48-51). */
+int cz_reset_games(cz_engine* e, const uint8_t* boards_host);
+/* Replace the root position of one game, keeping its tree (the per-move path of
+ * worker/self_play.py:122-147: the same player object searches the next state). */
+int cz_set_root(cz_engine* e, int game, const uint8_t* board_host);
+
+typedef struct cz_root_opts {
+  /* per game, may be NULL for "none" */
+  const uint16_t* no_act_host;     /* [n_games][CZ_MAX_NO_ACT] moves banned at the root, 0xFFFF-terminated */
+  const uint8_t* increase_temp_host; /* [n_games] */
+  const uint8_t* active_host;      /* [n_games] 0 = skip this game */
+  const double* noise_dev;         /* noise_mode 0: [n_games][noise_stride] Dirichlet[0] draws in call order */
+  int64_t noise_stride;
+  int32_t sims_override;           /* >0: depth argument of action() (player.py:160-161) */
+  int32_t reserved;
+} cz_root_opts;
+
+/* CChessPlayer.action up to the search (player.py:145-186), split so that an external
+ * evaluator can stand in for CChessModelAPI:
+ *   cz_search_begin            tree reuse + task count (player.py:147-171)
+ *   loop: cz_search_wave       descents until every queued simulation is at a leaf / terminal /
+ *                              repetition / parked (MCTS_search, player.py:198-260), immediate
+ *                              results backed up (update_tree, :340-373); returns #leaves to
+ *                              evaluate and whether any game still has work (synchronises)
+ *         cz_leaf_planes       state_to_planes of those leaves (expand_and_evaluate, :322-338)
+ *         cz_search_apply      attach (policy, value) to the leaves, back up, resume parked sims
+ * The schedule is the canonical one of SURVEY.md Appendix C. */
+int cz_search_begin(cz_engine* e, const cz_root_opts* opts);
+int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active);
+int cz_leaf_planes(cz_engine* e, float* planes_dev /* [n_leaves][14][10][9] */);
+int cz_leaf_boards(cz_engine* e, uint8_t* boards_dev /* [n_leaves][CZ_BOARD_STRIDE] */);
+int cz_search_apply(cz_engine* e, const float* policy_dev /* [n_leaves][2086] */, const float* value_dev /* [n_leaves] */);
+/* Whole search with the built-in network as evaluator (needs cz_nn_set_weights). Synchronises. */
+int cz_search(cz_engine* e, const cz_root_opts* opts);
+
+typedef struct cz_root_info {
+  int32_t n_moves;                 /* legal moves of the root (0 if the root was never expanded) */
+  int32_t sum_n;
+  int32_t noise_used;              /* Dirichlet draws consumed during the last search */
+  int32_t sims_run;                /* simulations completed during the last search */
+  uint16_t moves[CZ_MAX_MOVES];
+  int32_t n[CZ_MAX_MOVES];         /* N(s,a) */
+  double w[CZ_MAX_MOVES];          /* W(s,a) */
+  float p[CZ_MAX_MOVES];           /* P(s,a) after legal-move renormalisation */
+} cz_root_info;
+/* node.a of the root (read by calc_policy, player.py:375-406).  Synchronises. */
+int cz_get_root(cz_engine* e, int game, cz_root_info* out_host);
+
+/* Counters since cz_create: [0] simulations completed, [1] NN positions evaluated,
+ * [2] wave iterations, [3] nodes created, [4] tree resets forced by pool overflow. */
+int cz_get_counters(cz_engine* e, uint64_t* out_host /* [8] */);
+
+/* ------------------------------------------------------------------------------------------
+ * On-device self-play — worker/self_play.py:95-212 (start_game loop) for all games at once
+ * ---------------------------------------------------------------------------------------- */
+/* One ply for every live game: calc_policy + apply_temperature + sampling (player.py:375-406,
+ * 453-470,195), new_step, draw / repetition / resign adjudication (self_play.py:126-175), final
+ * move and value signs (:177-191).  Finished games are recorded and restarted from INIT_STATE.
+ * n_finished counts games that ended in this call.  Synchronises. */
+int cz_play_move(cz_engine* e, int32_t* n_finished);
+/* Search + play until `target_games` games finished or `max_moves` plies were played. */
+int cz_selfplay(cz_engine* e, int32_t target_games, int32_t max_moves, int32_t* games_done, int64_t* sims_done);
+
+typedef struct cz_record_hdr {
+  int32_t n_plies;      /* moves stored (including a final king capture) */
+  int32_t value_red;    /* result from red's view: 1, -1, 0 (self_play.py:190-191) */
+  int32_t game_index;   /* running index of the game on this engine */
+  int32_t flags;        /* bit0 resign, bit1 draw by rule */
+} cz_record_hdr;
+/* Drain finished-game records into host memory: hdr_host [cap], moves_host [cap][max_plies+1]
+ * (moves as seen by the side that played them, i.e. the strings self_play.py:132 appends).
+ * Returns the number drained in *n.  Synchronises. */
+int cz_drain_records(cz_engine* e, cz_record_hdr* hdr_host, uint16_t* moves_host, int32_t cap, int32_t* n);
+/* Device-side view of the same ring (for the NCCL gather of play records). */
+int cz_record_buffer(cz_engine* e, void** dev_ptr, uint64_t* bytes, int32_t* n_ready);
+
+/* ------------------------------------------------------------------------------------------
+ * Policy + value network — agent/model.py:32-83 behind agent/api.py:37-74
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cz_tensor_desc {
+  const char* name;     /* Keras layer weight name, e.g. "res3_conv1-3-256/kernel" */
+  const void* dev;      /* float32, Keras layout (conv HWIO, dense (in,out), vectors (C)) */
+  int64_t numel;
+} cz_tensor_desc;
+/* Fold BatchNorm (eps 1e-3) into fp16 GEMM operands and upload; weights stay caller-owned. */
+int cz_nn_set_weights(cz_engine* e, const cz_tensor_desc* descs, int32_t n);
+/* predict_on_batch (api.py:62-64): planes_dev [B][14][10][9] f32 -> policy_dev [B][2086] f32
+ * (softmax), value_dev [B] f32 (tanh). */
+int cz_nn_forward(cz_engine* e, const float* planes_dev, int32_t batch, float* policy_dev, float* value_dev);
+/* Same from packed boards (plane encoding fused into the first convolution). */
+int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch, float* policy_dev, float* value_dev);
+/* Kernel launches issued by this engine since creation (bench.py "gpu_launches"). */
+int cz_launch_count(cz_engine* e, uint64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCZERO_B200_H */
