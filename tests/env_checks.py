@@ -83,7 +83,7 @@ def check_single_api(env):
                   '7275 7276 7279 0304 2324 4344 6364 8384').split()
     s1 = env.step(init, '0001')
     assert s1 == 'rkemsmek1/8r/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RKEMSMEKR'
-    assert env.step(s1, '1229') == 'rkemsmekr/9/1c7/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/R8/1KEMSMEcR'
+    assert env.step(s1, '1219') == 'rkemsmekr/9/1c7/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/R8/1KEMSMEcR'
     pl = env.state_to_planes(init)
     assert pl.shape == (14, 10, 9) and pl.sum() == 32
     assert pl.sum(axis=(1, 2)).tolist() == [5, 2, 2, 2, 2, 2, 1, 5, 2, 2, 2, 2, 2, 1]
