@@ -1,0 +1,231 @@
+// cz_igemm.cuh — the one dense contraction of the hot path: implicit-GEMM 3x3 convolution (and the
+// plain GEMM of the policy head) on tcgen05 tensor cores, TMEM accumulators, TMA-fed operands.
+//
+// Replaces the Conv2D/BatchNormalization/Add/Activation stack of agent/model.py:68-83 (residual
+// block) and the Dense of :54 (policy_out) that the reference runs through Keras/TF/cuDNN.
+//
+// Activation layout in HBM ("strip" layout): fp16 [n_boards*11][9][C].  Board b occupies strip rows
+//   b*11 .. b*11+9 (network row r = 9 - y), strip row b*11+10 is an all-zero separator shared as the
+//   vertical halo of board b (below) and b+1 (above).  Horizontal halo and the rows above board 0 /
+//   below the last board come from TMA out-of-bounds zero fill.  A 3x3 tap (dy,dx) is therefore ONE
+//   TMA box load at coordinates (c0, dx, r0+dy): no im2col, no masking in the MMA.
+// Tile: 14 strip rows x 9 columns = 126 pixels -> UMMA M = 128 (rows 126,127 are don't-care: an A row
+//   only feeds the same D row), N = N_TILE output channels (<= 256), K walks taps x C_in in 64-channel
+//   blocks (128-byte swizzled rows).  Useful fraction of the MMA work: (90/99)*(126/128) = 89.5 %.
+// Pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue (TMEM -> registers -> +bias (+residual) -> ReLU -> fp16 -> HBM).  kStages-deep
+//   smem ring (full/empty mbarriers) and two TMEM accumulators (tfull/tempty) so the epilogue of tile i
+//   overlaps the MMAs of tile i+1.  Persistent: grid = #SMs, tiles strided over CTAs.
+#pragma once
+#include <cuda_fp16.h>
+#include "cz_umma.cuh"
+
+namespace igemm {
+
+constexpr int kStages = 4;
+constexpr int kBlockK = 64;                 // fp16 per k-block row = 128 B = swizzle span
+constexpr int kTileM = 128;
+constexpr int kAStageBytes = kTileM * 128;  // 16 KB
+constexpr int kThreads = 256;
+
+struct Args {
+  int n_taps;        // 9 (3x3 conv) or 1 (plain GEMM)
+  int k_chunks;      // C_in / 64
+  int m_tiles;       // ceil(rows / box_r)
+  int n_tiles;       // ceil(N / N_TILE)
+  int box_w;         // 9 (conv) or 1 (GEMM)
+  int box_r;         // 14 (conv) or 128 (GEMM): A-box extent along the outer row dimension
+  int rows;          // conv: strip rows (n_boards*11); GEMM: M
+  int n_total;       // B-operand rows per tap (C_out padded to N_TILE multiple)
+  int n_valid;       // real number of output columns
+  int ldo;           // output leading dimension in elements
+  int conv;          // 1: strip layout, separator rows forced to zero
+  int relu;
+  int out_f32;       // 1: float output (GEMM logits), 0: fp16
+  const float* bias; // [n_total] or null
+  const __half* residual;  // same layout as out (fp16) or null
+  void* out;
+  uint32_t a_bytes;  // TMA bytes per A box
+};
+
+template <int N_TILE>
+struct Cfg {
+  static constexpr int kBStageBytes = N_TILE * 128;
+  static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+  static constexpr int kTmemCols = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128
+                                   : (2 * N_TILE <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;  // + barriers + alignment slack
+  static_assert(2 * N_TILE <= 512, "two accumulators must fit TMEM");
+  static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128");
+};
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kThreads, 1)
+k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  using C = Cfg<N_TILE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes);
+  uint64_t* full = bars;                 // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + kStages;      // [kStages]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * kStages;  // [2]        MMA -> epilogue
+  uint64_t* tempty = tfull + 2;          // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmA);
+    umma::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 128); }
+    umma::fence_barrier_init();
+    umma::fence_proxy_async();
+  }
+  if (warp == 2) umma::tmem_alloc<C::kTmemCols>(tmem_slot);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_kb = a.n_taps * a.k_chunks;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
+        for (int tap = 0; tap < a.n_taps; ++tap) {
+          const int dy = a.n_taps == 9 ? tap / 3 - 1 : 0;
+          const int dx = a.n_taps == 9 ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            umma::mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sA = smem + s * C::kStageBytes;
+            uint8_t* sB = sA + kAStageBytes;
+            umma::mbar_expect_tx(&full[s], a.a_bytes + (uint32_t)C::kBStageBytes);
+            umma::tma_load_3d(sA, &tmA, &full[s], kc * kBlockK, dx, m_tile * a.box_r + dy);
+            umma::tma_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + n_tile * N_TILE);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma::idesc_f16(kTileM, N_TILE);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        umma::mbar_wait(&tempty[acc], aph ^ 1);
+        umma::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          umma::mbar_wait(&full[s], ph);
+          umma::tc_fence_after();
+          const uint32_t sA = umma::smem_u32(smem + s * C::kStageBytes);
+          const uint64_t da = umma::smem_desc_sw128(sA);
+          const uint64_t db = umma::smem_desc_sw128(sA + kAStageBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per UMMA_K step inside the swizzle atom
+            umma::mma_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma::mma_commit(&empty[s]);
+        }
+        umma::mma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp - 4;                 // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;            // accumulator row == pixel inside the tile
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      umma::mbar_wait(&tfull[acc], aph);
+      umma::tc_fence_after();
+      long long grow;       // global output row
+      bool valid, zero = false;
+      if (a.conv) {
+        const int srow = m_tile * a.box_r + m / 9;          // strip row
+        valid = m < a.box_r * 9 && srow < a.rows;
+        zero = (srow % 11) == 10;                           // separator row stays zero
+        grow = (long long)m_tile * a.box_r * 9 + m;
+      } else {
+        grow = (long long)m_tile * kTileM + m;
+        valid = grow < a.rows;
+      }
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t v[32];
+        umma::tmem_ld_32x32(t_row + c0, v);
+        const int n0 = n_tile * N_TILE + c0;
+        if (valid && n0 < a.n_valid) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (a.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(a.bias + n0 + j);
+          }
+          if (a.out_f32) {
+            float* o = reinterpret_cast<float*>(a.out) + grow * a.ldo + n0;
+            if (n0 + 32 <= a.n_valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = a.relu ? fmaxf(f[j], 0.f) : f[j];
+            } else {
+              for (int j = 0; j < 32 && n0 + j < a.n_valid; ++j) o[j] = a.relu ? fmaxf(f[j], 0.f) : f[j];
+            }
+          } else {
+            __half* o = reinterpret_cast<__half*>(a.out) + grow * a.ldo + n0;
+            if (a.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldo + n0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 rv = __ldg(rp + g);
+                const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 x = __half22float2(h[j]);
+                  f[g * 8 + 2 * j] += x.x;
+                  f[g * 8 + 2 * j + 1] += x.y;
+                }
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 ov;
+              __half2* h = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float x0 = f[g * 8 + 2 * j], x1 = f[g * 8 + 2 * j + 1];
+                if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                if (zero) { x0 = 0.f; x1 = 0.f; }
+                h[j] = __floats2half2_rn(x0, x1);
+              }
+              op[g] = ov;
+            }
+          }
+        }
+      }
+      umma::tc_fence_before();
+      umma::mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace igemm

@@ -1,0 +1,608 @@
+// cz_nn.cu — policy + value network forward (agent/model.py:32-83) on B200.
+//
+//   packed boards --k_conv_first--> strip activations (5x5 input conv over one-hot planes is a gather-sum
+//                                   of <= 25 weight rows per pixel; plane encoding never materialises)
+//   2 x blocks of  igemm::k_igemm   3x3 conv as implicit GEMM on tcgen05 (BN folded, +skip, ReLU fused)
+//   k_heads                         1x1 policy/value convs + BN + ReLU, value MLP + tanh
+//   igemm::k_igemm (GEMM mode)      policy_out Dense 360 -> 2086 on tcgen05
+//   k_softmax                       2086-way softmax
+//
+// BatchNormalization is inference-mode (moving statistics, eps = 1e-3, data/model/model_best_config.json)
+// and folded into fp16 weights + fp32 shift.  Weights arrive in Keras layout, caller-owned.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "cz_err.h"
+#include "cz_igemm.cuh"
+#include "cz_nn.cuh"
+
+namespace cznn {
+
+#define CZ_CUDA(x)                                                                           \
+  do {                                                                                       \
+    cudaError_t e__ = (x);                                                                   \
+    if (e__ != cudaSuccess) return cz_fail(CZ_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int kLabels = CZ_N_LABELS;
+constexpr int kPolK = 384;      // 360 policy features padded to 6 k-blocks
+constexpr int kPolN = 2304;     // 2086 labels padded to 9 N tiles of 256
+constexpr float kBnEps = 1e-3f;
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) return cz_fail(CZ_ERR_CUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+
+// fp16 tensor [rows][w][c] (c contiguous), box {64, box_w, box_r}, 128B swizzle, zero OOB fill
+static int make_map_3d(CUtensorMap* m, const void* base, int c, int w, long long rows, int box_w, int box_r) {
+  if (load_encode()) return CZ_ERR_CUDA;
+  cuuint64_t dims[3] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * w};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_w, (cuuint32_t)box_r};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cz_fail(CZ_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return 0;
+}
+// fp16 matrix [rows][k] (k contiguous), box {64, box_rows}
+static int make_map_2d(CUtensorMap* m, const void* base, int k, long long rows, int box_rows) {
+  if (load_encode()) return CZ_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cz_fail(CZ_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int N_TILE>
+static int launch_igemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const igemm::Args& a, cudaStream_t st) {
+  using C = igemm::Cfg<N_TILE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CZ_CUDA(cudaFuncSetAttribute(igemm::k_igemm<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = a.m_tiles * a.n_tiles;
+  if (tiles <= 0) return 0;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  igemm::k_igemm<N_TILE><<<grid, igemm::kThreads, C::kSmemBytes, st>>>(tmA, tmB, a);
+  CZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_igemm(int n_tile, const CUtensorMap& tmA, const CUtensorMap& tmB, const igemm::Args& a, cudaStream_t st) {
+  switch (n_tile) {
+    case 64: return launch_igemm_t<64>(tmA, tmB, a, st);
+    case 128: return launch_igemm_t<128>(tmA, tmB, a, st);
+    case 192: return launch_igemm_t<192>(tmA, tmB, a, st);
+    case 256: return launch_igemm_t<256>(tmA, tmB, a, st);
+  }
+  return cz_fail(CZ_ERR_UNSUPPORTED, "igemm: unsupported N tile %d (filters must be 64/128/192/256)", n_tile);
+}
+
+static igemm::Args conv_args(int n_boards, int c, const float* bias, const __half* residual, __half* out, int relu) {
+  igemm::Args a;
+  memset(&a, 0, sizeof(a));
+  a.n_taps = 9; a.k_chunks = c / 64; a.box_w = 9; a.box_r = 14;
+  a.rows = n_boards * 11; a.m_tiles = (a.rows + 13) / 14; a.n_tiles = 1;
+  a.n_total = c; a.n_valid = c; a.ldo = c; a.conv = 1; a.relu = relu; a.out_f32 = 0;
+  a.bias = bias; a.residual = residual; a.out = out; a.a_bytes = 64 * 9 * 14 * 2;
+  return a;
+}
+
+static igemm::Args dense_args(int m, int n_valid, int n_pad, int k_pad, int n_tile, const float* bias, float* out, int ldo) {
+  igemm::Args a;
+  memset(&a, 0, sizeof(a));
+  a.n_taps = 1; a.k_chunks = k_pad / 64; a.box_w = 1; a.box_r = 128;
+  a.rows = m; a.m_tiles = (m + 127) / 128; a.n_tiles = n_pad / n_tile;
+  a.n_total = n_pad; a.n_valid = n_valid; a.ldo = ldo; a.conv = 0; a.relu = 0; a.out_f32 = 1;
+  a.bias = bias; a.residual = nullptr; a.out = out; a.a_bytes = 64 * 128 * 2;
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// packed board -> plane index per network pixel (pix = r*9 + col, r = 9 - y), -1 = empty
+__device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 8) ? c - 2 : c - 1); }
+
+// 5x5 "same" input convolution + BN + ReLU from packed boards (model.py:34-41, static_env.py:137-156 fused).
+// grid = batch, block = C threads (one output channel each).  w: HWIO [5][5][14][C] fp16 (BN scale folded).
+__global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
+                             const float* __restrict__ shift, __half* __restrict__ out, int c_out) {
+  __shared__ int8_t pl[90];
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c < 90) {
+    const int r = c / 9, col = c % 9;
+    pl[c] = (int8_t)plane_of(boards[(size_t)b * CZ_BOARD_STRIDE + (9 - r) * 9 + col]);
+  }
+  __syncthreads();
+  if (c >= c_out) return;
+  const float sh = shift[c];
+  __half* o = out + (size_t)b * 11 * 9 * c_out;
+  for (int pix = 0; pix < 90; ++pix) {
+    const int r = pix / 9, col = pix % 9;
+    float acc = sh;
+#pragma unroll
+    for (int kh = 0; kh < 5; ++kh) {
+      const int rr = r + kh - 2;
+      if (rr < 0 || rr > 9) continue;
+#pragma unroll
+      for (int kw = 0; kw < 5; ++kw) {
+        const int cc = col + kw - 2;
+        if (cc < 0 || cc > 8) continue;
+        const int p = pl[rr * 9 + cc];
+        if (p >= 0) acc += __half2float(__ldg(w + ((size_t)((kh * 5 + kw) * 14 + p)) * c_out + c));
+      }
+    }
+    o[(size_t)pix * c_out + c] = __float2half_rn(fmaxf(acc, 0.f));
+  }
+  for (int col = 0; col < 9; ++col) o[(size_t)(90 + col) * c_out + c] = __float2half_rn(0.f);   // separator row
+}
+
+// one-hot planes [B][14][10][9] f32 -> packed boards (inverse of state_to_planes)
+__global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __restrict__ boards, int n) {
+  const int b = blockIdx.x;
+  if (b >= n) return;
+  const int t = threadIdx.x;
+  if (t < 96) {
+    uint8_t code = 0;
+    if (t < 90) {
+      const int y = t / 9, x = t % 9, r = 9 - y;
+      for (int p = 0; p < 14; ++p)
+        if (planes[((size_t)b * 14 + p) * 90 + r * 9 + x] > 0.5f) code = (uint8_t)(p < 7 ? p + 1 : p + 2);
+    }
+    boards[(size_t)b * CZ_BOARD_STRIDE + t] = code;
+  }
+}
+
+// Heads (model.py:47-63): 1x1 conv to 4 policy + 2 value channels, BN, ReLU; policy features to the GEMM
+// operand [B][384] (index c*90 + pix, Keras Flatten of channels_first); value: Dense(H)+ReLU, Dense(1)+tanh.
+// grid = batch, block = 256.
+__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, int c_in,
+                                                const float* __restrict__ w6,      // [6][c_in], BN scale folded
+                                                const float* __restrict__ shift6,  // [6]
+                                                const float* __restrict__ wv1,     // [180][H]
+                                                const float* __restrict__ bv1,     // [H]
+                                                const float* __restrict__ wv2,     // [H]
+                                                const float* __restrict__ bv2,     // [1]
+                                                int hidden, __half* __restrict__ pol_feat, float* __restrict__ value) {
+  __shared__ float feat[6][90];
+  __shared__ float hid[256];
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __half* a = act + (size_t)b * 11 * 9 * c_in;
+  for (int pix = warp; pix < 90; pix += 8) {
+    float s[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = lane * 8; c < c_in; c += 256) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + (size_t)pix * c_in + c));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+#pragma unroll
+      for (int o = 0; o < 6; ++o) {
+        const float* wr = w6 + (size_t)o * c_in + c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[o] += x[j] * __ldg(wr + j);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 6; ++o) {
+      float v = s[o];
+      for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (lane == 0) feat[o][pix] = fmaxf(v + shift6[o], 0.f);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kPolK; i += 256)
+    pol_feat[(size_t)b * kPolK + i] = __float2half_rn(i < 360 ? feat[i / 90][i % 90] : 0.f);
+  float h = 0.f;
+  if (tid < hidden) {
+    float acc = bv1[tid];
+    for (int i = 0; i < 180; ++i) acc += feat[4 + i / 90][i % 90] * __ldg(wv1 + (size_t)i * hidden + tid);
+    h = fmaxf(acc, 0.f) * wv2[tid];
+  }
+  hid[tid] = h;
+  __syncthreads();
+  float v = hid[tid];
+  for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (tid == 0) {
+    float s = bv2[0];
+    for (int i = 0; i < 8; ++i) s += red[i];
+    value[b] = tanhf(s);
+  }
+}
+
+// softmax over the 2086 labels; logits [B][ldl] f32 -> policy [B][2086] f32. grid = batch, block = 256.
+__global__ void __launch_bounds__(256) k_softmax(const float* __restrict__ logits, int ldl, float* __restrict__ policy) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* l = logits + (size_t)b * ldl;
+  float mx = -INFINITY;
+  for (int i = tid; i < kLabels; i += 256) mx = fmaxf(mx, l[i]);
+  for (int m = 16; m; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) { float v = red[0]; for (int i = 1; i < 8; ++i) v = fmaxf(v, red[i]); bc = v; }
+  __syncthreads();
+  mx = bc;
+  float e[(kLabels + 255) / 256];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < (kLabels + 255) / 256; ++j) {
+    const int i = tid + j * 256;
+    e[j] = i < kLabels ? expf(l[i] - mx) : 0.f;
+    s += e[j];
+  }
+  for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (tid == 0) { float v = 0.f; for (int i = 0; i < 8; ++i) v += red[i]; bc = 1.f / v; }
+  __syncthreads();
+  const float inv = bc;
+#pragma unroll
+  for (int j = 0; j < (kLabels + 255) / 256; ++j) {
+    const int i = tid + j * 256;
+    if (i < kLabels) policy[(size_t)b * kLabels + i] = e[j] * inv;
+  }
+}
+
+// ---- weight preparation (Keras layout f32 -> folded operands)
+__global__ void k_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float* scale,
+                          float* shift, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    const float s = gamma[i] / sqrtf(var[i] + kBnEps);
+    scale[i] = s;
+    shift[i] = beta[i] - mean[i] * s;
+  }
+}
+// HWIO [kh][kw][ci][co] -> same layout fp16 with scale[co] folded (first conv)
+__global__ void k_prep_hwio(const float* w, const float* scale, __half* out, long long n, int co) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(w[i] * scale[i % co]);
+}
+// HWIO [3][3][ci][co] -> [tap][co][ci] fp16, scale[co] folded (B operand, K-major)
+__global__ void k_prep_conv3(const float* w, const float* scale, __half* out, int c) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = 9LL * c * c;
+  if (i < n) {
+    const int ci = (int)(i % c), co = (int)((i / c) % c), tap = (int)(i / ((long long)c * c));
+    out[i] = __float2half_rn(w[((long long)tap * c + ci) * c + co] * scale[co]);
+  }
+}
+// 1x1 conv HWIO [1][1][ci][co] -> [co][ci] f32 rows at out_row0.., scale folded
+__global__ void k_prep_1x1(const float* w, const float* scale, float* out, int ci_n, int co_n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ci_n * co_n) {
+    const int ci = i % ci_n, co = i / ci_n;
+    out[(size_t)co * ci_n + ci] = w[(size_t)ci * co_n + co] * scale[co];
+  }
+}
+// Dense (in,out) [360][2086] -> [kPolN][kPolK] fp16 (zero padded), K-major
+__global__ void k_prep_policy(const float* w, __half* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)kPolN * kPolK) {
+    const int k = (int)(i % kPolK), n = (int)(i / kPolK);
+    out[i] = __float2half_rn((k < 360 && n < kLabels) ? w[(size_t)k * kLabels + n] : 0.f);
+  }
+}
+__global__ void k_copy_pad(const float* src, float* dst, int n_src, int n_dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_dst) dst[i] = i < n_src ? src[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Carver {
+  uint8_t* base; size_t off, cap;
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct NnRuntime {
+  int filters, blocks, value_fc, max_batch;
+  cudaStream_t stream;
+  bool ready;
+  uint64_t launches;
+  // activations
+  __half *x, *t, *y, *pol_feat;
+  float* logits;
+  uint8_t* boards_tmp;
+  // weights
+  __half* w_first; float* shift_first;
+  __half* w_conv;  float* shift_conv;      // [2*blocks][9*C*C], [2*blocks][C]
+  float *w6, *shift6, *wv1, *bv1, *wv2, *bv2;
+  __half* w_pol; float* b_pol;
+  float* scratch;                            // 2*C floats for BN folding
+  // tensor maps
+  CUtensorMap map_x, map_t, map_y, map_pf, map_wpol;
+  std::vector<CUtensorMap> map_w;
+};
+
+static void layout(NnRuntime* r, Carver& cv) {
+  const int c = r->filters;
+  const size_t act = (size_t)r->max_batch * 11 * 9 * c * sizeof(__half);
+  r->x = (__half*)cv.take(act);
+  r->t = (__half*)cv.take(act);
+  r->y = (__half*)cv.take(act);
+  r->pol_feat = (__half*)cv.take(((size_t)r->max_batch + 128) * kPolK * sizeof(__half));
+  r->logits = (float*)cv.take((size_t)r->max_batch * kPolN * sizeof(float));
+  r->boards_tmp = (uint8_t*)cv.take((size_t)r->max_batch * CZ_BOARD_STRIDE);
+  r->w_first = (__half*)cv.take((size_t)25 * 14 * c * sizeof(__half));
+  r->shift_first = (float*)cv.take(c * sizeof(float));
+  r->w_conv = (__half*)cv.take((size_t)2 * r->blocks * 9 * c * c * sizeof(__half));
+  r->shift_conv = (float*)cv.take((size_t)2 * r->blocks * c * sizeof(float));
+  r->w6 = (float*)cv.take((size_t)6 * c * sizeof(float));
+  r->shift6 = (float*)cv.take(8 * sizeof(float));
+  r->wv1 = (float*)cv.take((size_t)180 * r->value_fc * sizeof(float));
+  r->bv1 = (float*)cv.take(r->value_fc * sizeof(float));
+  r->wv2 = (float*)cv.take(r->value_fc * sizeof(float));
+  r->bv2 = (float*)cv.take(4 * sizeof(float));
+  r->w_pol = (__half*)cv.take((size_t)kPolN * kPolK * sizeof(__half));
+  r->b_pol = (float*)cv.take(kPolN * sizeof(float));
+  r->scratch = (float*)cv.take((size_t)2 * 256 * sizeof(float));
+}
+
+size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch) {
+  NnRuntime tmp;
+  tmp.filters = filters; tmp.blocks = blocks; tmp.value_fc = value_fc; tmp.max_batch = max_batch;
+  Carver cv{nullptr, 0, 0};
+  layout(&tmp, cv);
+  return cv.off + 4096;
+}
+
+NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_batch, void* workspace, size_t bytes,
+                     void* stream) {
+  (void)device;
+  if (filters % 64 != 0 || filters < 64 || filters > 256) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: filters must be 64..256 step 64"); return nullptr; }
+  if (value_fc > 256 || value_fc < 1) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: value_fc_size must be <= 256"); return nullptr; }
+  if (bytes < nn_workspace_bytes(filters, blocks, value_fc, max_batch)) { cz_fail(CZ_ERR_ARG, "nn: workspace too small"); return nullptr; }
+  NnRuntime* r = new NnRuntime();
+  r->filters = filters; r->blocks = blocks; r->value_fc = value_fc; r->max_batch = max_batch;
+  r->stream = (cudaStream_t)stream; r->ready = false; r->launches = 0;
+  Carver cv{(uint8_t*)workspace, 0, bytes};
+  layout(r, cv);
+  const int c = filters;
+  const long long rows = (long long)max_batch * 11;
+  int rc = 0;
+  rc |= make_map_3d(&r->map_x, r->x, c, 9, rows, 9, 14);
+  rc |= make_map_3d(&r->map_t, r->t, c, 9, rows, 9, 14);
+  rc |= make_map_3d(&r->map_y, r->y, c, 9, rows, 9, 14);
+  rc |= make_map_3d(&r->map_pf, r->pol_feat, kPolK, 1, (long long)max_batch + 128, 1, 128);
+  rc |= make_map_2d(&r->map_wpol, r->w_pol, kPolK, kPolN, 256);
+  r->map_w.resize(2 * blocks);
+  for (int i = 0; i < 2 * blocks; ++i)
+    rc |= make_map_2d(&r->map_w[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c);
+  if (rc) { delete r; return nullptr; }
+  // separator rows and padding must start as zeros
+  cudaMemsetAsync(r->x, 0, (size_t)max_batch * 11 * 9 * c * 2, r->stream);
+  cudaMemsetAsync(r->t, 0, (size_t)max_batch * 11 * 9 * c * 2, r->stream);
+  cudaMemsetAsync(r->y, 0, (size_t)max_batch * 11 * 9 * c * 2, r->stream);
+  cudaMemsetAsync(r->pol_feat, 0, ((size_t)max_batch + 128) * kPolK * 2, r->stream);
+  return r;
+}
+
+void nn_destroy(NnRuntime* r) { delete r; }
+bool nn_ready(const NnRuntime* r) { return r && r->ready; }
+uint64_t nn_launches(const NnRuntime* r) { return r ? r->launches : 0; }
+
+// ---- weights -----------------------------------------------------------------------------------
+struct WeightSet {
+  const cz_tensor_desc* d; int n;
+  // find "<layer prefix>...<'/'><weight>" ; Keras appends "-<k>-<f>" to conv layer names and ":0" to weights
+  const cz_tensor_desc* find(const std::string& layer, const std::string& weight) const {
+    for (int i = 0; i < n; ++i) {
+      std::string nm = d[i].name ? d[i].name : "";
+      const size_t slash = nm.find('/');
+      if (slash == std::string::npos) continue;
+      std::string l = nm.substr(0, slash), w = nm.substr(slash + 1);
+      const size_t colon = w.find(':');
+      if (colon != std::string::npos) w = w.substr(0, colon);
+      const size_t s2 = w.find('/');            // "layer/layer/kernel" style
+      if (s2 != std::string::npos) w = w.substr(s2 + 1);
+      if (w != weight) continue;
+      if (l == layer || (l.size() > layer.size() && l.compare(0, layer.size(), layer) == 0 && l[layer.size()] == '-')) return &d[i];
+    }
+    return nullptr;
+  }
+};
+
+#define NEED(var, layer, weight, count)                                                                      \
+  const cz_tensor_desc* var = ws.find(layer, weight);                                                        \
+  if (!var || var->numel != (long long)(count))                                                              \
+    return cz_fail(CZ_ERR_ARG, "cz_nn_set_weights: missing or mis-sized tensor %s/%s (want %lld)", std::string(layer).c_str(), weight, (long long)(count));
+
+static int fold_bn(NnRuntime* r, const WeightSet& ws, const std::string& layer, int c, float* scale, float* shift) {
+  NEED(g, layer, "gamma", c);
+  NEED(b, layer, "beta", c);
+  NEED(m, layer, "moving_mean", c);
+  NEED(v, layer, "moving_variance", c);
+  k_bn_fold<<<(c + 127) / 128, 128, 0, r->stream>>>((const float*)g->dev, (const float*)b->dev, (const float*)m->dev,
+                                                     (const float*)v->dev, scale, shift, c);
+  r->launches++;
+  return 0;
+}
+
+int nn_set_weights(NnRuntime* r, const cz_tensor_desc* descs, int n) {
+  if (!r) return cz_fail(CZ_ERR_STATE, "cz_nn_set_weights: engine was created without a network (nn_filters = 0)");
+  WeightSet ws{descs, n};
+  const int c = r->filters;
+  cudaStream_t st = r->stream;
+  float* scale = r->scratch;
+  {
+    NEED(k, "input_conv", "kernel", 25LL * 14 * c);
+    if (fold_bn(r, ws, "input_batchnorm", c, scale, r->shift_first)) return CZ_ERR_ARG;
+    const long long nn = 25LL * 14 * c;
+    k_prep_hwio<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>((const float*)k->dev, scale, r->w_first, nn, c);
+  }
+  for (int i = 0; i < r->blocks; ++i) {
+    for (int j = 0; j < 2; ++j) {
+      const std::string conv = "res" + std::to_string(i + 1) + "_conv" + std::to_string(j + 1);
+      const std::string bn = "res" + std::to_string(i + 1) + "_batchnorm" + std::to_string(j + 1);
+      NEED(k, conv, "kernel", 9LL * c * c);
+      const int li = 2 * i + j;
+      if (fold_bn(r, ws, bn, c, scale, r->shift_conv + (size_t)li * c)) return CZ_ERR_ARG;
+      const long long nn = 9LL * c * c;
+      k_prep_conv3<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>((const float*)k->dev, scale, r->w_conv + (size_t)li * nn, c);
+    }
+  }
+  {
+    NEED(kp, "policy_conv", "kernel", 4LL * c);
+    if (fold_bn(r, ws, "policy_batchnorm", 4, scale, r->shift6)) return CZ_ERR_ARG;
+    k_prep_1x1<<<(4 * c + 255) / 256, 256, 0, st>>>((const float*)kp->dev, scale, r->w6, c, 4);
+    NEED(kv, "value_conv", "kernel", 2LL * c);
+    if (fold_bn(r, ws, "value_batchnorm", 2, scale + 8, r->shift6 + 4)) return CZ_ERR_ARG;
+    k_prep_1x1<<<(2 * c + 255) / 256, 256, 0, st>>>((const float*)kv->dev, scale + 8, r->w6 + (size_t)4 * c, c, 2);
+  }
+  {
+    NEED(k, "policy_out", "kernel", 360LL * kLabels);
+    NEED(b, "policy_out", "bias", kLabels);
+    const long long nn = (long long)kPolN * kPolK;
+    k_prep_policy<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>((const float*)k->dev, r->w_pol);
+    k_copy_pad<<<(kPolN + 255) / 256, 256, 0, st>>>((const float*)b->dev, r->b_pol, kLabels, kPolN);
+  }
+  {
+    const int h = r->value_fc;
+    NEED(k1, "value_dense", "kernel", 180LL * h);
+    NEED(b1, "value_dense", "bias", h);
+    NEED(k2, "value_out", "kernel", h);
+    NEED(b2, "value_out", "bias", 1);
+    CZ_CUDA(cudaMemcpyAsync(r->wv1, k1->dev, (size_t)180 * h * 4, cudaMemcpyDeviceToDevice, st));
+    CZ_CUDA(cudaMemcpyAsync(r->bv1, b1->dev, (size_t)h * 4, cudaMemcpyDeviceToDevice, st));
+    CZ_CUDA(cudaMemcpyAsync(r->wv2, k2->dev, (size_t)h * 4, cudaMemcpyDeviceToDevice, st));
+    CZ_CUDA(cudaMemcpyAsync(r->bv2, b2->dev, 4, cudaMemcpyDeviceToDevice, st));
+  }
+  r->launches += 6 + 2 * r->blocks;
+  CZ_CUDA(cudaGetLastError());
+  CZ_CUDA(cudaStreamSynchronize(st));
+  r->ready = true;
+  return 0;
+}
+
+// ---- forward -----------------------------------------------------------------------------------
+static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* policy, float* value) {
+  const int c = r->filters;
+  cudaStream_t st = r->stream;
+  k_conv_first<<<n, c < 96 ? 96 : c, 0, st>>>(boards, r->w_first, r->shift_first, r->x, c);
+  r->launches++;
+  __half *x = r->x, *y = r->y;
+  CUtensorMap *mx = &r->map_x, *my = &r->map_y;
+  for (int i = 0; i < r->blocks; ++i) {
+    const size_t wsz = (size_t)c;
+    igemm::Args a1 = conv_args(n, c, r->shift_conv + (size_t)(2 * i) * wsz, nullptr, r->t, 1);
+    if (launch_igemm(c, *mx, r->map_w[2 * i], a1, st)) return CZ_ERR_CUDA;
+    igemm::Args a2 = conv_args(n, c, r->shift_conv + (size_t)(2 * i + 1) * wsz, x, y, 1);
+    if (launch_igemm(c, r->map_t, r->map_w[2 * i + 1], a2, st)) return CZ_ERR_CUDA;
+    r->launches += 2;
+    __half* tx = x; x = y; y = tx;
+    CUtensorMap* tm = mx; mx = my; my = tm;
+  }
+  k_heads<<<n, 256, 0, st>>>(x, c, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
+  igemm::Args ap = dense_args(n, kLabels, kPolN, kPolK, 256, r->b_pol, r->logits, kPolN);
+  if (launch_igemm(256, r->map_pf, r->map_wpol, ap, st)) return CZ_ERR_CUDA;
+  k_softmax<<<n, 256, 0, st>>>(r->logits, kPolN, policy);
+  r->launches += 3;
+  CZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int nn_forward_boards(NnRuntime* r, const uint8_t* boards, int batch, float* policy, float* value) {
+  if (!r || !r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
+  for (int off = 0; off < batch; off += r->max_batch) {
+    const int n = batch - off < r->max_batch ? batch - off : r->max_batch;
+    const int rc = forward_chunk(r, boards + (size_t)off * CZ_BOARD_STRIDE, n, policy + (size_t)off * kLabels, value + off);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int nn_forward_planes(NnRuntime* r, const float* planes, int batch, float* policy, float* value) {
+  if (!r || !r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
+  for (int off = 0; off < batch; off += r->max_batch) {
+    const int n = batch - off < r->max_batch ? batch - off : r->max_batch;
+    k_planes_to_boards<<<n, 96, 0, r->stream>>>(planes + (size_t)off * 14 * 90, r->boards_tmp, n);
+    r->launches++;
+    const int rc = forward_chunk(r, r->boards_tmp, n, policy + (size_t)off * kLabels, value + off);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace cznn
+
+// ------------------------------------------------------------------------------------------------
+// Building blocks exported for parity tests and profiling (not part of the reference-facing surface).
+extern "C" {
+
+// 3x3 "same" convolution on strip-layout activations: out = relu?(conv(in, w) + bias (+ residual)).
+//   act_in/out/residual: fp16 [n_boards*11][9][c] (separator rows of act_in must be zero)
+//   w: fp16 [9][c_out = c][c_in = c] ; bias f32 [c]
+int cz_igemm_conv3x3(const void* act_in, const void* w, const float* bias, const void* residual, void* act_out,
+                     int n_boards, int c, int relu, void* stream) {
+  using namespace cznn;
+  if (c % 64 || c < 64 || c > 256 || n_boards <= 0) return cz_fail(CZ_ERR_ARG, "cz_igemm_conv3x3: bad shape");
+  CUtensorMap ma, mb;
+  if (make_map_3d(&ma, act_in, c, 9, (long long)n_boards * 11, 9, 14)) return CZ_ERR_CUDA;
+  if (make_map_2d(&mb, w, c, 9LL * c, c)) return CZ_ERR_CUDA;
+  igemm::Args a = conv_args(n_boards, c, bias, (const __half*)residual, (__half*)act_out, relu);
+  return launch_igemm(c, ma, mb, a, (cudaStream_t)stream);
+}
+
+// out[m][n] = sum_k a[m][k] * w[n][k] + bias[n]; a fp16 [m_alloc >= ceil128(m)][k], w fp16 [n_pad][k], k % 64 == 0,
+// n_pad % n_tile == 0, out f32 [m][ldo].
+int cz_igemm_dense(const void* a_dev, const void* w_dev, const float* bias, float* out, int m, int n_valid, int n_pad,
+                   int k, int n_tile, int ldo, void* stream) {
+  using namespace cznn;
+  if (k % 64 || n_pad % n_tile || m <= 0) return cz_fail(CZ_ERR_ARG, "cz_igemm_dense: bad shape");
+  CUtensorMap ma, mb;
+  if (make_map_3d(&ma, a_dev, k, 1, (long long)m, 1, 128)) return CZ_ERR_CUDA;
+  if (make_map_2d(&mb, w_dev, k, n_pad, n_tile)) return CZ_ERR_CUDA;
+  igemm::Args a = dense_args(m, n_valid, n_pad, k, n_tile, bias, out, ldo);
+  return launch_igemm(n_tile, ma, mb, a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -90,7 +90,11 @@ _SIGS = {
     "cz_nn_forward": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "cz_nn_forward_boards": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "cz_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "cz_igemm_conv3x3": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "cz_igemm_dense": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
+# entry points that only exist in the CUDA build (tensor cores cannot be emulated on the CPU)
+CUDA_ONLY = {"cz_igemm_conv3x3", "cz_igemm_dense"}
 
 
 class CzLib:

@@ -202,6 +202,19 @@ int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch,
 /* Kernel launches issued by this engine since creation (bench.py "gpu_launches"). */
 int cz_launch_count(cz_engine* e, uint64_t* n);
 
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core building blocks, exported for parity tests and profiling of the dominant kernel
+ * (the residual-block convolutions of agent/model.py:68-83 and the policy Dense of :54).
+ * ---------------------------------------------------------------------------------------- */
+/* 3x3 "same" convolution + bias (+ residual) (+ ReLU) on fp16 strip-layout activations
+ * [n_boards*11][9][c] (row b*11+10 of every board is an all-zero separator); w fp16 [9][c][c]
+ * = [tap kh*3+kw][c_out][c_in]; bias f32 [c]. */
+int cz_igemm_conv3x3(const void* act_in_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
+                     void* act_out_dev, int n_boards, int c, int relu, void* stream);
+/* out[m][n] = sum_k a[m][k] * w[n][k] + bias[n]; a fp16 [m][k], w fp16 [n_pad][k], out f32 [m][ldo]. */
+int cz_igemm_dense(const void* a_dev, const void* w_dev, const float* bias_dev, float* out_dev, int m, int n_valid,
+                   int n_pad, int k, int n_tile, int ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
