@@ -20,6 +20,25 @@ enum { SIM_IDLE = 0, SIM_LEAF = 1, SIM_PARKED = 2 };
 enum { NODE_WAITING = 1u << 8 };
 enum { GAME_ERR_PATH = 1, GAME_ERR_POOL = 2, GAME_ERR_NOISE = 4, GAME_ERR_NOMOVE = 8 };
 
+struct RecordHdr { int32_t n_plies, value_red, game_index, flags; };
+
+// per-game state of the on-device game loop (cz_selfplay.cuh)
+struct SelfplayDev {
+  int32_t* turns;          // [G] plies played in the current game
+  int32_t* no_eat;         // [G] consecutive non-capturing plies
+  int32_t* enable_resign;  // [G]
+  int32_t* games_started;  // [G] games begun in this slot (RNG stream + game index)
+  uint64_t* hist_k0;       // [G][hist_stride] keys of the states s_0..s_turns
+  uint64_t* hist_k1;
+  uint16_t* hist_move;     // [G][hist_stride] actions a_0..a_{turns-1}
+  RecordHdr* rec_hdr;      // [rec_cap]
+  uint16_t* rec_moves;     // [rec_cap][hist_stride]
+  int32_t* rec_count;      // [1] records in the ring
+  int32_t* finished;       // [1] games finished by the last cz_play_move
+  int32_t rec_cap, hist_stride;
+  double enable_resign_rate;
+};
+
 struct EngineDev {
   // ---- configuration
   int n_games, sims, K, vl, ncap, ecap, hcap, max_path, noise_mode, max_plies;
@@ -72,6 +91,7 @@ struct EngineDev {
   int32_t* totals;               // [4]: total leaves, any active, -, -
   uint8_t* leaf_dense;           // [G*K][96] leaves of all games, dense
   unsigned long long* counters;  // [8]
+  SelfplayDev sp;
 };
 
 struct TreeSmem {                // per warp
@@ -168,6 +188,7 @@ CZ_D void tt_insert(const EngineDev& E, int g, uint64_t k0, int node) {
 // Returns the node index or -1 when a pool is exhausted.
 CZ_D int node_create(const EngineDev& E, int g, uint64_t k0, uint64_t k1, const move_t* list, int L) {
   const int nn = E.n_nodes[g], ne = E.n_edges[g];
+  czs::syncwarp();                                   // every lane has read the counters before lane 0 bumps them
   if (nn + 1 > E.ncap || ne + L > E.ecap) return -1;
   const size_t ni = (size_t)g * E.ncap + nn;
   const size_t eo = (size_t)g * E.ecap + ne;
@@ -516,8 +537,9 @@ CZ_D void game_begin(const EngineDev& E, int g, int sims_override, TreeSmem* sm)
   if (sims_override > 0) num_task = sims_override > done ? sims_override - done : 0;
   if (num_task < 0) num_task = 0;
   // pools must be able to hold this search; otherwise start from an empty table (counted)
-  const bool low = E.ncap - E.n_nodes[g] < num_task + 2 || E.ecap - E.n_edges[g] < (num_task + 2) * 64;
-  if (low && E.n_nodes[g] > 0) {
+  const bool low = (E.ncap - E.n_nodes[g] < num_task + 2 || E.ecap - E.n_edges[g] < (num_task + 2) * 64) && E.n_nodes[g] > 0;
+  czs::syncwarp();                                   // reads above complete before lane 0 rewrites the counters
+  if (low) {
     uint32_t* h = E.hash + (size_t)g * E.hcap;
     for (int i = czs::lane(); i < E.hcap; i += 32) h[i] = 0;
     if (czs::lane() == 0) {

@@ -1,0 +1,480 @@
+// cz_tree_api.cu — the search engine object behind the C-ABI: workspace carving, kernels (one warp per
+// game), and the cz_search_* / cz_get_root entry points.  Builds with nvcc (product) or g++ -DCZ_EMUL
+// (CPU test tier; the network is unavailable there and only the external-evaluator path works).
+#include "../../include/cczero_b200.h"
+#include "cz_tree.cuh"
+#include "cz_selfplay.cuh"
+#include "cz_rt.h"
+#include "cz_err.h"
+#if !defined(CZ_EMUL)
+#include "cz_nn.cuh"
+#endif
+#include <stdlib.h>
+#include <new>
+#include <vector>
+
+using namespace cz;
+
+namespace {
+
+constexpr int kWarps = 4;   // games per block
+
+CZ_D TreeSmem* tree_smem() { return reinterpret_cast<TreeSmem*>(czs::dyn_smem()) + czs::warp_in_block(); }
+CZ_D int my_game() { return czs::block_idx() * czs::warps_per_block() + czs::warp_in_block(); }
+
+CZ_KERNEL(k_begin)(EngineDev E, int sims_override) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  game_begin(E, g, sims_override, tree_smem());
+}
+CZ_KERNEL(k_wave)(EngineDev E) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  game_wave(E, g, tree_smem());
+}
+CZ_KERNEL(k_apply)(EngineDev E, const float* policy, const float* value) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  game_apply(E, g, policy, value, tree_smem());
+}
+// single warp: exclusive scan of the per-game leaf counts, totals[0] = leaves, totals[1] = any game busy
+CZ_KERNEL(k_scan)(EngineDev E) {
+  int base = 0, busy = 0;
+  for (int g0 = 0; g0 < E.n_games; g0 += 32) {
+    const int g = g0 + czs::lane();
+    const int n = g < E.n_games ? E.n_leaf[g] : 0;
+    int tot;
+    const int off = czs::warp_excl_scan(n, &tot);
+    if (g < E.n_games) {
+      E.leaf_off[g] = base + off;
+      if (E.active[g] && (E.round_pending[g] > 0 || E.tasks_left[g] > 0)) busy = 1;
+    }
+    base += tot;
+  }
+  busy = czs::any(busy != 0) ? 1 : 0;
+  if (czs::lane() == 0) { E.totals[0] = base; E.totals[1] = busy; }
+}
+CZ_KERNEL(k_gather)(EngineDev E) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  const int n = E.n_leaf[g], off = E.leaf_off[g];
+  for (int j = 0; j < n; ++j) {
+    const uint8_t* s = E.leaf_board + ((size_t)g * E.K + j) * BOARD_STRIDE;
+    uint8_t* d = E.leaf_dense + (size_t)(off + j) * BOARD_STRIDE;
+    if (czs::lane() < BOARD_STRIDE / 16) reinterpret_cast<uint4*>(d)[czs::lane()] = reinterpret_cast<const uint4*>(s)[czs::lane()];
+  }
+}
+CZ_KERNEL(k_planes_dense)(const uint8_t* boards, int n, float* planes) {
+  const int i = my_game();
+  if (i >= n) return;
+  TreeSmem* sm = tree_smem();
+  copy_board(boards + (size_t)i * BOARD_STRIDE, sm->board);
+  encode_planes_f32(sm->board, planes + (size_t)i * 14 * NSQ);
+}
+CZ_KERNEL(k_reset)(EngineDev E, const uint8_t* boards /* [G][96] or null */, const uint8_t* init_board, int clear_game /* -1 all */) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  if (clear_game >= 0 && g != clear_game) return;
+  const uint8_t* src = boards ? boards + (size_t)g * BOARD_STRIDE : init_board;
+  for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) E.root_board[(size_t)g * BOARD_STRIDE + k] = k < NSQ ? src[k] : (uint8_t)0;
+  uint32_t* h = E.hash + (size_t)g * E.hcap;
+  for (int i = czs::lane(); i < E.hcap; i += 32) h[i] = 0;
+  if (czs::lane() == 0) {
+    E.n_nodes[g] = 0; E.n_edges[g] = 0; E.root_node[g] = -1;
+    E.tasks_left[g] = 0; E.round_pending[g] = 0; E.n_leaf[g] = 0; E.n_park[g] = 0; E.n_resume[g] = 0;
+    E.sims_run[g] = 0; E.noise_used[g] = 0; E.game_err[g] = 0; E.n_no_act[g] = 0; E.increase_temp[g] = 0; E.active[g] = 1;
+  }
+  czs::syncwarp();
+  selfplay_reset_game(E, g);
+}
+CZ_KERNEL(k_set_root)(EngineDev E, int game, const uint8_t* board) {
+  for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) E.root_board[(size_t)game * BOARD_STRIDE + k] = k < NSQ ? board[k] : (uint8_t)0;
+}
+CZ_KERNEL(k_root_info)(EngineDev E, int g, cz_root_info* out) {
+  TreeSmem* sm = tree_smem();
+  copy_board(E.root_board + (size_t)g * BOARD_STRIDE, sm->board);
+  uint64_t k0, k1;
+  board_key(sm->board, &k0, &k1);
+  const int root = tt_lookup(E, g, k0, k1);
+  int L = 0;
+  if (root >= 0) {
+    const size_t ni = (size_t)g * E.ncap + root;
+    L = (int)(E.node_meta[ni] & 0xff);
+    const size_t eo = (size_t)g * E.ecap + E.node_edge_off[ni];
+    for (int i = czs::lane(); i < L; i += 32) {
+      out->moves[i] = E.edge_move[eo + i]; out->n[i] = E.edge_n[eo + i]; out->w[i] = E.edge_w[eo + i]; out->p[i] = E.edge_p[eo + i];
+    }
+    if (czs::lane() == 0) out->sum_n = E.node_sum_n[ni];
+  } else if (czs::lane() == 0) out->sum_n = 0;
+  if (czs::lane() == 0) { out->n_moves = L; out->noise_used = E.noise_used[g]; out->sims_run = E.sims_run[g]; }
+}
+CZ_KERNEL(k_set_opts)(EngineDev E, const uint16_t* no_act, const uint8_t* inc, const uint8_t* act) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  if (czs::lane() == 0) {
+    int n = 0;
+    if (no_act) {
+      for (; n < CZ_MAX_NO_ACT; ++n) {
+        const uint16_t m = no_act[(size_t)g * CZ_MAX_NO_ACT + n];
+        if (m == 0xFFFF) break;
+        E.no_act[(size_t)g * CZ_MAX_NO_ACT + n] = m;
+      }
+    }
+    E.n_no_act[g] = n;
+    E.increase_temp[g] = inc ? inc[g] : 0;
+    E.active[g] = act ? act[g] : 1;
+  }
+}
+
+struct Carver {
+  uint8_t* base; size_t off;
+  template <class T> T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+struct cz_engine {
+  cz_config cfg;
+  EngineDev d;
+  cz_stream_t stream;
+  uint8_t* ws; size_t ws_bytes;
+  uint8_t* init_board_dev;
+  uint8_t* opt_no_act; uint8_t* opt_inc; uint8_t* opt_act;   // device staging for cz_root_opts
+  cz_root_info* root_info_dev;
+  float* policy_buf; float* value_buf;                      // evaluator outputs for the built-in network
+  uint8_t* board_stage;                                     // [G][96] staging for reset / set_root
+  int last_leaves;
+  uint64_t launches;
+  uint64_t total_sims, total_positions, total_waves;
+#if !defined(CZ_EMUL)
+  cznn::NnRuntime* nn;
+  size_t nn_bytes;
+#endif
+};
+
+namespace {
+
+size_t carve(cz_engine* e, uint8_t* base) {
+  const cz_config& c = e->cfg;
+  EngineDev& d = e->d;
+  Carver cv{base, 0};
+  const size_t G = c.n_games, K = c.leaves_per_round, N = (size_t)c.max_nodes_per_game, Ecap = (size_t)c.max_edges_per_game;
+  const size_t H = (size_t)next_pow2(2 * c.max_nodes_per_game);
+  d.hcap = (int)H;
+  d.label_lut = cv.take<int16_t>(8100);
+  d.root_board = cv.take<uint8_t>(G * BOARD_STRIDE);
+  d.root_node = cv.take<int32_t>(G); d.active = cv.take<int32_t>(G); d.tasks_left = cv.take<int32_t>(G);
+  d.round_pending = cv.take<int32_t>(G); d.sims_run = cv.take<int32_t>(G); d.noise_used = cv.take<int32_t>(G);
+  d.game_err = cv.take<int32_t>(G); d.no_act = cv.take<uint16_t>(G * CZ_MAX_NO_ACT); d.n_no_act = cv.take<int32_t>(G);
+  d.increase_temp = cv.take<int32_t>(G);
+  d.n_nodes = cv.take<int32_t>(G); d.n_edges = cv.take<int32_t>(G);
+  d.node_key0 = cv.take<uint64_t>(G * N); d.node_key1 = cv.take<uint64_t>(G * N);
+  d.node_sum_n = cv.take<int32_t>(G * N); d.node_edge_off = cv.take<uint32_t>(G * N); d.node_meta = cv.take<uint32_t>(G * N);
+  d.hash = cv.take<uint32_t>(G * H);
+  d.edge_n = cv.take<int32_t>(G * Ecap); d.edge_w = cv.take<double>(G * Ecap); d.edge_p = cv.take<float>(G * Ecap);
+  d.edge_move = cv.take<uint16_t>(G * Ecap); d.edge_child = cv.take<int32_t>(G * Ecap);
+  d.sim_depth = cv.take<int32_t>(G * K); d.sim_leaf_node = cv.take<int32_t>(G * K);
+  d.sim_node = cv.take<int32_t>(G * K * c.max_path); d.sim_edge = cv.take<int32_t>(G * K * c.max_path);
+  d.leaf_sim = cv.take<int32_t>(G * K); d.n_leaf = cv.take<int32_t>(G);
+  d.leaf_board = cv.take<uint8_t>(G * K * BOARD_STRIDE);
+  d.resume_sim = cv.take<int32_t>(G * K); d.n_resume = cv.take<int32_t>(G);
+  d.park_sim = cv.take<int32_t>(G * K); d.park_node = cv.take<int32_t>(G * K); d.n_park = cv.take<int32_t>(G);
+  d.leaf_off = cv.take<int32_t>(G); d.totals = cv.take<int32_t>(4);
+  d.leaf_dense = cv.take<uint8_t>(G * K * BOARD_STRIDE);
+  d.counters = cv.take<unsigned long long>(8);
+  selfplay_carve(d.sp, cv, c);
+  e->init_board_dev = cv.take<uint8_t>(BOARD_STRIDE);
+  e->opt_no_act = cv.take<uint8_t>(G * CZ_MAX_NO_ACT * 2); e->opt_inc = cv.take<uint8_t>(G); e->opt_act = cv.take<uint8_t>(G);
+  e->root_info_dev = cv.take<cz_root_info>(1);
+  e->board_stage = cv.take<uint8_t>(G * BOARD_STRIDE);
+  if (c.nn_filters > 0) {
+    e->policy_buf = cv.take<float>(G * K * (size_t)CZ_N_LABELS);
+    e->value_buf = cv.take<float>(G * K);
+  } else {
+    e->policy_buf = nullptr; e->value_buf = nullptr;
+  }
+  return cv.off + 1024;
+}
+
+int check_cfg(const cz_config* c) {
+  if (!c || c->struct_bytes != (int)sizeof(cz_config)) return cz_fail(CZ_ERR_ARG, "cz_config: struct_bytes mismatch (%d vs %d)", c ? c->struct_bytes : -1, (int)sizeof(cz_config));
+  if (c->n_games < 1 || c->sims_per_move < 1 || c->leaves_per_round < 1 || c->leaves_per_round > 64)
+    return cz_fail(CZ_ERR_ARG, "cz_config: n_games >= 1, sims >= 1, 1 <= leaves_per_round <= 64 required");
+  if (c->max_nodes_per_game < 16 || c->max_edges_per_game < 256 || c->max_path < 8)
+    return cz_fail(CZ_ERR_ARG, "cz_config: pools too small");
+  if (c->virtual_loss < 0 || c->max_plies < 2) return cz_fail(CZ_ERR_ARG, "cz_config: bad virtual_loss / max_plies");
+  return 0;
+}
+
+const char kInit[] = "rkemsmekr/9/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RKEMSMEKR";   // static_env.py:9
+void init_board(uint8_t* b) {
+  memset(b, 0, BOARD_STRIDE);
+  int y = 9, x = 0;
+  for (const char* p = kInit; *p; ++p) {
+    const char ch = *p;
+    if (ch == '/') { --y; x = 0; continue; }
+    if (ch >= '1' && ch <= '9') { x += ch - '0'; continue; }
+    uint8_t code = 0;
+    switch (ch | 0x20) { case 'p': code = PC_P; break; case 'c': code = PC_C; break; case 'r': code = PC_R; break;
+      case 'k': code = PC_N; break; case 'e': code = PC_E; break; case 'm': code = PC_A; break; case 's': code = PC_K; break; }
+    if (ch >= 'a') code |= PC_OPP;
+    b[y * 9 + x++] = code;
+  }
+}
+
+int launch_ok(cz_engine* e, const char* what, int n = 1) {
+  e->launches += n;
+  const char* msg;
+  const int rc = czrt_last_error(&msg);
+  if (rc) return cz_fail(CZ_ERR_CUDA, "%s: %s", what, msg);
+  return 0;
+}
+
+#define GAME_LAUNCH(e, kern, ...) \
+  CZ_LAUNCH(kern, ((e)->cfg.n_games + kWarps - 1) / kWarps, kWarps, sizeof(TreeSmem) * kWarps, (e)->stream, __VA_ARGS__)
+
+}  // namespace
+
+extern "C" {
+
+int cz_workspace_bytes(const cz_config* cfg, uint64_t* bytes) {
+  if (check_cfg(cfg) || !bytes) return CZ_ERR_ARG;
+  cz_engine tmp;
+  tmp.cfg = *cfg;
+  size_t n = carve(&tmp, nullptr);
+#if !defined(CZ_EMUL)
+  if (cfg->nn_filters > 0)
+    n += cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, cfg->n_games * cfg->leaves_per_round) + 4096;
+#endif
+  *bytes = n;
+  return 0;
+}
+
+int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, void* stream, cz_engine** out) {
+  if (check_cfg(cfg) || !workspace || !out) return cz_fail(CZ_ERR_ARG, "cz_create: bad argument");
+  uint64_t need = 0;
+  cz_workspace_bytes(cfg, &need);
+  if (workspace_bytes < need) return cz_fail(CZ_ERR_ARG, "cz_create: workspace %llu < required %llu", (unsigned long long)workspace_bytes, (unsigned long long)need);
+  cz_engine* e = new (std::nothrow) cz_engine();
+  if (!e) return cz_fail(CZ_ERR_STATE, "cz_create: out of host memory");
+  e->cfg = *cfg;
+  e->stream = (cz_stream_t)stream;
+  e->ws = (uint8_t*)workspace; e->ws_bytes = workspace_bytes;
+  e->launches = 0; e->last_leaves = 0; e->total_sims = e->total_positions = e->total_waves = 0;
+  EngineDev& d = e->d;
+  memset(&d, 0, sizeof(d));
+  d.n_games = cfg->n_games; d.sims = cfg->sims_per_move; d.K = cfg->leaves_per_round; d.vl = cfg->virtual_loss;
+  d.ncap = cfg->max_nodes_per_game; d.ecap = cfg->max_edges_per_game; d.max_path = cfg->max_path;
+  d.noise_mode = cfg->noise_mode; d.max_plies = cfg->max_plies;
+  d.c_puct = cfg->c_puct; d.noise_eps = cfg->noise_eps; d.alpha = cfg->dirichlet_alpha; d.tau_decay = cfg->tau_decay_rate;
+  d.resign_threshold = cfg->resign_threshold; d.min_resign_turn = cfg->min_resign_turn; d.max_game_length = cfg->max_game_length;
+  d.seed = cfg->seed; d.rank = cfg->rank;
+  const size_t used = carve(e, e->ws);
+#if !defined(CZ_EMUL)
+  e->nn = nullptr; e->nn_bytes = 0;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { delete e; return cz_fail(CZ_ERR_CUDA, "cz_create: cudaSetDevice(%d) failed", cfg->device); }
+#endif
+  // tables + initial state
+  std::vector<int16_t> lut(8100);
+  cz_action_labels(nullptr, lut.data());
+  czrt_copy(const_cast<int16_t*>(d.label_lut), lut.data(), 8100 * sizeof(int16_t), e->stream);
+  uint8_t ib[BOARD_STRIDE];
+  init_board(ib);
+  czrt_copy(e->init_board_dev, ib, BOARD_STRIDE, e->stream);
+  czrt_memset(d.counters, 0, 8 * sizeof(unsigned long long), e->stream);
+  czrt_sync(e->stream);
+#if !defined(CZ_EMUL)
+  if (cfg->nn_filters > 0) {
+    const int maxb = cfg->n_games * cfg->leaves_per_round;
+    e->nn_bytes = cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb);
+    uint8_t* nnws = e->ws + ((used + 4095) & ~(size_t)4095);
+    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream);
+    if (!e->nn) { delete e; return CZ_ERR_CUDA; }
+  }
+#else
+  (void)used;
+#endif
+  *out = e;
+  return cz_reset_games(e, nullptr);
+}
+
+void cz_destroy(cz_engine* e) {
+  if (!e) return;
+#if !defined(CZ_EMUL)
+  cznn::nn_destroy(e->nn);
+#endif
+  delete e;
+}
+
+int cz_reset_games(cz_engine* e, const uint8_t* boards_host) {
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_reset_games: null engine");
+  const uint8_t* src = nullptr;
+  if (boards_host) {
+    czrt_copy(e->board_stage, boards_host, (size_t)e->cfg.n_games * BOARD_STRIDE, e->stream);
+    src = e->board_stage;
+  }
+  GAME_LAUNCH(e, k_reset, e->d, src, (const uint8_t*)e->init_board_dev, -1);
+  if (launch_ok(e, "cz_reset_games")) return CZ_ERR_CUDA;
+  return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_reset_games: sync failed") : 0;
+}
+
+int cz_set_root(cz_engine* e, int game, const uint8_t* board_host) {
+  if (!e || game < 0 || game >= e->cfg.n_games || !board_host) return cz_fail(CZ_ERR_ARG, "cz_set_root: bad argument");
+  czrt_copy(e->board_stage, board_host, BOARD_STRIDE, e->stream);
+  CZ_LAUNCH(k_set_root, 1, 1, 0, e->stream, e->d, game, (const uint8_t*)e->board_stage);
+  if (launch_ok(e, "cz_set_root")) return CZ_ERR_CUDA;
+  return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_set_root: sync failed") : 0;
+}
+
+int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_begin: null engine");
+  const size_t G = e->cfg.n_games;
+  const uint16_t* na = nullptr; const uint8_t* inc = nullptr; const uint8_t* act = nullptr;
+  int sims_override = 0;
+  e->d.noise_table = nullptr; e->d.noise_stride = 0;
+  if (opts) {
+    if (opts->no_act_host) { czrt_copy(e->opt_no_act, opts->no_act_host, G * CZ_MAX_NO_ACT * 2, e->stream); na = (const uint16_t*)e->opt_no_act; }
+    if (opts->increase_temp_host) { czrt_copy(e->opt_inc, opts->increase_temp_host, G, e->stream); inc = e->opt_inc; }
+    if (opts->active_host) { czrt_copy(e->opt_act, opts->active_host, G, e->stream); act = e->opt_act; }
+    e->d.noise_table = opts->noise_dev; e->d.noise_stride = opts->noise_stride;
+    sims_override = opts->sims_override;
+  }
+  if (opts) GAME_LAUNCH(e, k_set_opts, e->d, na, inc, act);   // NULL keeps the options the game loop maintains
+  GAME_LAUNCH(e, k_begin, e->d, sims_override);
+  e->last_leaves = 0;
+  return launch_ok(e, "cz_search_begin", 2);
+}
+
+int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active) {
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_wave: null engine");
+  if (e->last_leaves != 0) return cz_fail(CZ_ERR_STATE, "cz_search_wave: %d leaves of the previous wave were not applied", e->last_leaves);
+  GAME_LAUNCH(e, k_wave, e->d);
+  CZ_LAUNCH(k_scan, 1, 1, 0, e->stream, e->d);
+  GAME_LAUNCH(e, k_gather, e->d);
+  if (launch_ok(e, "cz_search_wave", 3)) return CZ_ERR_CUDA;
+  int32_t t[4];
+  czrt_copy(t, e->d.totals, sizeof(t), e->stream);
+  if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_search_wave: device failure");
+  e->last_leaves = t[0];
+  e->total_waves++;
+  if (n_leaves) *n_leaves = t[0];
+  if (any_active) *any_active = t[1] || t[0] > 0;
+  return 0;
+}
+
+int cz_leaf_planes(cz_engine* e, float* planes_dev) {
+  if (!e || !planes_dev) return cz_fail(CZ_ERR_ARG, "cz_leaf_planes: bad argument");
+  const int n = e->last_leaves;
+  if (n == 0) return 0;
+  CZ_LAUNCH(k_planes_dense, (n + kWarps - 1) / kWarps, kWarps, sizeof(TreeSmem) * kWarps, e->stream,
+            (const uint8_t*)e->d.leaf_dense, n, planes_dev);
+  return launch_ok(e, "cz_leaf_planes");
+}
+
+int cz_leaf_boards(cz_engine* e, uint8_t* boards_dev) {
+  if (!e || !boards_dev) return cz_fail(CZ_ERR_ARG, "cz_leaf_boards: bad argument");
+  if (e->last_leaves == 0) return 0;
+  return czrt_copy(boards_dev, e->d.leaf_dense, (size_t)e->last_leaves * BOARD_STRIDE, e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_leaf_boards: copy failed") : 0;
+}
+
+int cz_search_apply(cz_engine* e, const float* policy_dev, const float* value_dev) {
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_apply: null engine");
+  if (e->last_leaves == 0) return 0;
+  if (!policy_dev || !value_dev) return cz_fail(CZ_ERR_ARG, "cz_search_apply: null evaluation");
+  GAME_LAUNCH(e, k_apply, e->d, policy_dev, value_dev);
+  e->total_positions += (uint64_t)e->last_leaves;
+  e->last_leaves = 0;
+  return launch_ok(e, "cz_search_apply");
+}
+
+int cz_search(cz_engine* e, const cz_root_opts* opts) {
+#if defined(CZ_EMUL)
+  (void)e; (void)opts;
+  return cz_fail(CZ_ERR_UNSUPPORTED, "cz_search: the CPU emulation build has no network; use the wave/apply API");
+#else
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_search: null engine");
+  if (!e->nn || !cznn::nn_ready(e->nn)) return cz_fail(CZ_ERR_STATE, "cz_search: network weights not set");
+  int rc = cz_search_begin(e, opts);
+  if (rc) return rc;
+  for (;;) {
+    int32_t n = 0, busy = 0;
+    if ((rc = cz_search_wave(e, &n, &busy))) return rc;
+    if (n > 0) {
+      if ((rc = cznn::nn_forward_boards(e->nn, e->d.leaf_dense, n, e->policy_buf, e->value_buf))) return rc;
+      if ((rc = cz_search_apply(e, e->policy_buf, e->value_buf))) return rc;
+    }
+    if (!busy) break;
+  }
+  return 0;
+#endif
+}
+
+int cz_get_root(cz_engine* e, int game, cz_root_info* out) {
+  if (!e || !out || game < 0 || game >= e->cfg.n_games) return cz_fail(CZ_ERR_ARG, "cz_get_root: bad argument");
+  CZ_LAUNCH(k_root_info, 1, 1, sizeof(TreeSmem), e->stream, e->d, game, e->root_info_dev);
+  if (launch_ok(e, "cz_get_root")) return CZ_ERR_CUDA;
+  czrt_copy(out, e->root_info_dev, sizeof(cz_root_info), e->stream);
+  return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_get_root: device failure") : 0;
+}
+
+int cz_get_counters(cz_engine* e, uint64_t* out) {
+  if (!e || !out) return cz_fail(CZ_ERR_ARG, "cz_get_counters: bad argument");
+  unsigned long long dc[8];
+  czrt_copy(dc, e->d.counters, sizeof(dc), e->stream);
+  if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_get_counters: device failure");
+  std::vector<int32_t> sr(e->cfg.n_games);
+  out[0] = e->total_sims; out[1] = e->total_positions; out[2] = e->total_waves; out[3] = dc[3]; out[4] = dc[4];
+  out[5] = dc[5]; out[6] = dc[6]; out[7] = dc[7];
+  return 0;
+}
+
+int cz_launch_count(cz_engine* e, uint64_t* n) {
+  if (!e || !n) return cz_fail(CZ_ERR_ARG, "cz_launch_count: bad argument");
+  uint64_t v = e->launches;
+#if !defined(CZ_EMUL)
+  v += cznn::nn_launches(e->nn);
+#endif
+  *n = v;
+  return 0;
+}
+
+int cz_nn_set_weights(cz_engine* e, const cz_tensor_desc* descs, int32_t n) {
+#if defined(CZ_EMUL)
+  (void)e; (void)descs; (void)n;
+  return cz_fail(CZ_ERR_UNSUPPORTED, "cz_nn_set_weights: no tensor cores in the CPU emulation build");
+#else
+  if (!e || !descs) return cz_fail(CZ_ERR_ARG, "cz_nn_set_weights: bad argument");
+  return cznn::nn_set_weights(e->nn, descs, n);
+#endif
+}
+
+int cz_nn_forward(cz_engine* e, const float* planes_dev, int32_t batch, float* policy_dev, float* value_dev) {
+#if defined(CZ_EMUL)
+  (void)e; (void)planes_dev; (void)batch; (void)policy_dev; (void)value_dev;
+  return cz_fail(CZ_ERR_UNSUPPORTED, "cz_nn_forward: no tensor cores in the CPU emulation build");
+#else
+  if (!e || !planes_dev || !policy_dev || !value_dev || batch < 0) return cz_fail(CZ_ERR_ARG, "cz_nn_forward: bad argument");
+  return cznn::nn_forward_planes(e->nn, planes_dev, batch, policy_dev, value_dev);
+#endif
+}
+
+int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch, float* policy_dev, float* value_dev) {
+#if defined(CZ_EMUL)
+  (void)e; (void)boards_dev; (void)batch; (void)policy_dev; (void)value_dev;
+  return cz_fail(CZ_ERR_UNSUPPORTED, "cz_nn_forward_boards: no tensor cores in the CPU emulation build");
+#else
+  if (!e || !boards_dev || !policy_dev || !value_dev || batch < 0) return cz_fail(CZ_ERR_ARG, "cz_nn_forward_boards: bad argument");
+  return cznn::nn_forward_boards(e->nn, boards_dev, batch, policy_dev, value_dev);
+#endif
+}
+
+}  // extern "C"
+
+#include "cz_selfplay_api.inc"

@@ -1,0 +1,232 @@
+"""Python handle on a `cz_engine` (include/cczero_b200.h): many concurrent games, GPU-resident trees.
+
+PyTorch is only the allocator / stream provider here: the workspace is one uint8 CUDA tensor handed to
+the library, everything else happens in the kernels behind the C-ABI.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .env import board_to_state, move_to_u16, state_to_board, u16_to_move
+from .lib import (BOARD_STRIDE, MAX_MOVES, MAX_NO_ACT, N_LABELS, CzConfig, CzRecordHdr, CzRootInfo, CzRootOpts,
+                  get_lib)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, lib=None, device=None, n_games=1, sims_per_move=800, leaves_per_round=8, virtual_loss=3,
+                 max_nodes_per_game=None, max_edges_per_game=None, max_path=128, noise_mode=1, max_game_length=100,
+                 nn_filters=0, nn_blocks=0, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
+                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0):
+        self.lib = lib or get_lib()
+        if device is None:
+            device = 'cuda' if self.lib.is_cuda else 'cpu'
+        self.device = torch.device(device)
+        if self.lib.is_cuda and self.device.type != 'cuda':
+            raise ValueError("the CUDA library needs a CUDA device")
+        if max_nodes_per_game is None:
+            max_nodes_per_game = max(64, 4 * sims_per_move + 64)
+        if max_edges_per_game is None:
+            max_edges_per_game = max_nodes_per_game * 48
+        cfg = CzConfig()
+        cfg.struct_bytes = C.sizeof(CzConfig)
+        cfg.device = self.device.index or 0 if self.device.type == 'cuda' else 0
+        cfg.n_games, cfg.sims_per_move, cfg.leaves_per_round = n_games, sims_per_move, leaves_per_round
+        cfg.virtual_loss, cfg.max_nodes_per_game, cfg.max_edges_per_game = virtual_loss, max_nodes_per_game, max_edges_per_game
+        cfg.max_path, cfg.noise_mode, cfg.max_plies = max_path, noise_mode, 2 * max_game_length
+        cfg.nn_filters, cfg.nn_blocks, cfg.nn_value_fc = nn_filters, nn_blocks, nn_value_fc
+        cfg.c_puct, cfg.noise_eps, cfg.dirichlet_alpha = c_puct, noise_eps, dirichlet_alpha
+        cfg.tau_decay_rate, cfg.resign_threshold, cfg.enable_resign_rate = tau_decay_rate, resign_threshold, enable_resign_rate
+        cfg.min_resign_turn, cfg.max_game_length = min_resign_turn, max_game_length
+        cfg.seed, cfg.rank = seed, rank
+        self.cfg = cfg
+        nbytes = C.c_uint64(0)
+        self.lib.call("cz_workspace_bytes", C.byref(cfg), C.byref(nbytes))
+        self.workspace_bytes = nbytes.value
+        self.workspace = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        self._h = C.c_void_p(0)
+        self.lib.call("cz_create", C.byref(cfg), _ptr(self.workspace), nbytes, self._stream(), C.byref(self._h))
+        self.n_games = n_games
+        self.K = leaves_per_round
+        self._keep = []
+
+    def _stream(self):
+        if self.lib.is_cuda:
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
+
+    def close(self):
+        if self._h:
+            self.lib.raw("cz_destroy")(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- games
+    def reset(self, states=None):
+        if states is None:
+            self.lib.call("cz_reset_games", self._h, C.c_void_p(0))
+            return
+        assert len(states) == self.n_games
+        b = np.ascontiguousarray(np.stack([state_to_board(s) for s in states]))
+        self.lib.call("cz_reset_games", self._h, C.c_void_p(b.ctypes.data))
+
+    def set_root(self, game, state):
+        b = np.ascontiguousarray(state_to_board(state))
+        self.lib.call("cz_set_root", self._h, game, C.c_void_p(b.ctypes.data))
+
+    # ---- search
+    def make_opts(self, no_act=None, increase_temp=None, active=None, noise=None, sims_override=0):
+        o = CzRootOpts()
+        keep = []
+        if no_act is not None:
+            a = np.full((self.n_games, MAX_NO_ACT), 0xFFFF, dtype=np.uint16)
+            for g, lst in enumerate(no_act):
+                for k, m in enumerate(lst or []):
+                    a[g, k] = move_to_u16(m)
+            keep.append(a)
+            o.no_act_host = a.ctypes.data
+        if increase_temp is not None:
+            a = np.ascontiguousarray(np.asarray(increase_temp, dtype=np.uint8))
+            keep.append(a)
+            o.increase_temp_host = a.ctypes.data
+        if active is not None:
+            a = np.ascontiguousarray(np.asarray(active, dtype=np.uint8))
+            keep.append(a)
+            o.active_host = a.ctypes.data
+        if noise is not None:
+            t = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float64)).to(self.device)
+            assert t.dim() == 2 and t.shape[0] == self.n_games
+            keep.append(t)
+            o.noise_dev = t.data_ptr()
+            o.noise_stride = t.shape[1]
+        o.sims_override = sims_override
+        self._keep = keep
+        return o
+
+    def search_begin(self, opts=None):
+        self.lib.call("cz_search_begin", self._h, C.byref(opts) if opts is not None else None)
+
+    def search_wave(self):
+        n, busy = C.c_int32(0), C.c_int32(0)
+        self.lib.call("cz_search_wave", self._h, C.byref(n), C.byref(busy))
+        return n.value, bool(busy.value)
+
+    def leaf_planes(self, n):
+        planes = torch.empty((n, 14, 10, 9), dtype=torch.float32, device=self.device)
+        self.lib.call("cz_leaf_planes", self._h, _ptr(planes))
+        return planes
+
+    def leaf_boards(self, n):
+        b = torch.empty((n, BOARD_STRIDE), dtype=torch.uint8, device=self.device)
+        self.lib.call("cz_leaf_boards", self._h, _ptr(b))
+        return b
+
+    def search_apply(self, policy, value):
+        assert policy.dtype == torch.float32 and value.dtype == torch.float32
+        self._keep.append((policy, value))
+        self.lib.call("cz_search_apply", self._h, _ptr(policy), _ptr(value))
+
+    def search_external(self, evaluate_planes, opts=None):
+        """Whole search with `evaluate_planes(np.float32[n,14,10,9]) -> (policy[n,2086] f32, value[n] f32)`
+        standing in for the network (the role CChessModelAPI plays for the reference player)."""
+        self.search_begin(opts)
+        stats = {"waves": 0, "positions": 0}
+        while True:
+            n, busy = self.search_wave()
+            stats["waves"] += 1
+            if n > 0:
+                planes = self.leaf_planes(n).cpu().numpy()
+                pol, val = evaluate_planes(planes)
+                self.search_apply(torch.as_tensor(np.ascontiguousarray(pol, dtype=np.float32)).to(self.device),
+                                  torch.as_tensor(np.ascontiguousarray(val, dtype=np.float32)).to(self.device))
+                stats["positions"] += n
+            if not busy:
+                break
+        return stats
+
+    def search(self, opts=None):
+        """Whole search with the built-in tensor-core network."""
+        self.lib.call("cz_search", self._h, C.byref(opts) if opts is not None else None)
+
+    def root(self, game):
+        info = CzRootInfo()
+        self.lib.call("cz_get_root", self._h, game, C.byref(info))
+        L = info.n_moves
+        return {
+            "moves": [u16_to_move(info.moves[i]) for i in range(L)],
+            "n": [info.n[i] for i in range(L)], "w": [info.w[i] for i in range(L)], "p": [info.p[i] for i in range(L)],
+            "sum_n": info.sum_n, "noise_used": info.noise_used, "sims_run": info.sims_run,
+        }
+
+    def counters(self):
+        a = np.zeros(8, dtype=np.uint64)
+        self.lib.call("cz_get_counters", self._h, C.c_void_p(a.ctypes.data))
+        return a
+
+    def launch_count(self):
+        n = C.c_uint64(0)
+        self.lib.call("cz_launch_count", self._h, C.byref(n))
+        return n.value
+
+    # ---- on-device game loop
+    def play_move(self):
+        f = C.c_int32(0)
+        self.lib.call("cz_play_move", self._h, C.byref(f))
+        return f.value
+
+    def selfplay(self, target_games=0, max_moves=0):
+        g, s = C.c_int32(0), C.c_int64(0)
+        self.lib.call("cz_selfplay", self._h, target_games, max_moves, C.byref(g), C.byref(s))
+        return g.value, s.value
+
+    def drain_records(self, cap=None):
+        cap = cap or max(64, 2 * self.n_games)
+        row = self.cfg.max_plies + 1
+        hdr = (CzRecordHdr * cap)()
+        moves = np.zeros((cap, row), dtype=np.uint16)
+        n = C.c_int32(0)
+        self.lib.call("cz_drain_records", self._h, C.cast(hdr, C.c_void_p), C.c_void_p(moves.ctypes.data), cap, C.byref(n))
+        out = []
+        for i in range(n.value):
+            h = hdr[i]
+            out.append({"n_plies": h.n_plies, "value_red": h.value_red, "game_index": h.game_index, "flags": h.flags,
+                        "moves": [u16_to_move(v) for v in moves[i, :h.n_plies]]})
+        return out
+
+    # ---- network
+    def set_weights(self, named_tensors):
+        """named_tensors: dict Keras-style name -> float32 tensor on self.device (Keras layouts)."""
+        from .lib import CzTensorDesc
+        arr = (CzTensorDesc * len(named_tensors))()
+        keep = []
+        for i, (k, t) in enumerate(named_tensors.items()):
+            t = t.detach().to(self.device, torch.float32).contiguous()
+            keep.append(t)
+            arr[i].name = k.encode()
+            arr[i].dev = t.data_ptr()
+            arr[i].numel = t.numel()
+        self._weights_keep = keep
+        self.lib.call("cz_nn_set_weights", self._h, arr, len(named_tensors))
+
+    def nn_forward_planes(self, planes):
+        n = planes.shape[0]
+        pol = torch.empty((n, N_LABELS), dtype=torch.float32, device=self.device)
+        val = torch.empty((n,), dtype=torch.float32, device=self.device)
+        self.lib.call("cz_nn_forward", self._h, _ptr(planes), n, _ptr(pol), _ptr(val))
+        return pol, val
+
+    def nn_forward_boards(self, boards):
+        n = boards.shape[0]
+        pol = torch.empty((n, N_LABELS), dtype=torch.float32, device=self.device)
+        val = torch.empty((n,), dtype=torch.float32, device=self.device)
+        self.lib.call("cz_nn_forward_boards", self._h, _ptr(boards), n, _ptr(pol), _ptr(val))
+        return pol, val

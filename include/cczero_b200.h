@@ -95,6 +95,7 @@ typedef struct cz_config {
   double dirichlet_alpha;      /* play_config.dirichlet_alpha */
   double tau_decay_rate;       /* play_config.tau_decay_rate */
   double resign_threshold;     /* play_config.resign_threshold */
+  double enable_resign_rate;   /* play_config.enable_resign_rate (self_play.py:102-105) */
   int32_t min_resign_turn;     /* play_config.min_resign_turn */
   int32_t max_game_length;     /* play_config.max_game_length */
   uint64_t seed;               /* Philox key (seed, rank) for the on-device streams */
@@ -135,6 +136,7 @@ typedef struct cz_root_opts {
  *         cz_leaf_planes       state_to_planes of those leaves (expand_and_evaluate, :322-338)
  *         cz_search_apply      attach (policy, value) to the leaves, back up, resume parked sims
  * The schedule is the canonical one of SURVEY.md Appendix C. */
+/* opts == NULL keeps the per-game options the on-device game loop maintains (no_act / increase_temp). */
 int cz_search_begin(cz_engine* e, const cz_root_opts* opts);
 int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active);
 int cz_leaf_planes(cz_engine* e, float* planes_dev /* [n_leaves][14][10][9] */);

@@ -1,0 +1,84 @@
+"""K=1 seeded searches of the REAL reference CChessPlayer (fake deterministic network) -> tests/golden/mcts_k1.json.gz.
+Build-container only.  Each case is a sequence of action() calls on ONE player object (tree reuse across moves)."""
+import gzip
+import json
+import os
+import random
+
+from . import ref_import
+from .ref_player_harness import real_player_moves
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _midgame_states(n, seed):
+    r = ref_import.senv()
+    rng = random.Random(seed)
+    out = []
+    while len(out) < n:
+        s = r.INIT_STATE
+        plies = rng.randint(20, 70)
+        ok = True
+        for _ in range(plies):
+            if r.done(s)[0]:
+                ok = False
+                break
+            s = r.step(s, rng.choice(r.get_legal_moves(s)))
+        if ok and not r.done(s)[0]:
+            out.append(s)
+    return out
+
+
+def gen_mcts():
+    r = ref_import.senv()
+    cases = []
+    init = r.INIT_STATE
+    mids = _midgame_states(4, 7)
+    specs = [
+        dict(name="init_60", seed=0, sims=60, calls=[(init, 0, None, False)]),
+        dict(name="init_250", seed=3, sims=250, calls=[(init, 0, None, False)]),
+        dict(name="mid0_200", seed=5, sims=200, calls=[(mids[0], 31, None, False)]),
+        dict(name="mid1_400", seed=11, sims=400, calls=[(mids[1], 44, None, False)]),
+        dict(name="mid2_no_act", seed=13, sims=150, calls=[(mids[2], 40, "FIRST2", False)]),
+        dict(name="mid3_inc_temp", seed=17, sims=150, calls=[(mids[3], 12, None, True)]),
+    ]
+    for sp in specs:
+        calls = []
+        for (s, t, na, inc) in sp["calls"]:
+            if na == "FIRST2":
+                na = r.get_legal_moves(s)[:2]
+            calls.append((s, t, na, inc))
+        res = real_player_moves(calls, sp["sims"], sp["seed"])
+        cases.append({"name": sp["name"], "seed": sp["seed"], "sims": sp["sims"],
+                      "calls": [{"state": c[0], "turns": c[1], "no_act": c[2], "increase_temp": c[3],
+                                 "action": a, "sum_n": sn, "legal": r.get_legal_moves(c[0]),
+                                 "edges": {m: list(v) for m, v in e.items()}}
+                                for c, (a, e, sn) in zip(calls, res)]})
+    # one player, three consecutive plies of a game (tree reuse, player.py:153-158)
+    seed, sims = 23, 120
+    import numpy as np
+    calls, s, t = [], init, 0
+    pm = ref_import.player_module()
+    from .ref_player_harness import FakeNetServer, make_config
+    cfg = make_config(sims, 1)
+    srv = FakeNetServer()
+    np.random.seed(seed)
+    player = pm.CChessPlayer(cfg, pipes=srv.you, enable_resign=False)
+    seq = []
+    for ply in range(3):
+        a, _ = player.action(s, t)
+        node = player.tree[s]
+        seq.append({"state": s, "turns": t, "no_act": None, "increase_temp": False, "action": a, "sum_n": int(node.sum_n),
+                    "legal": r.get_legal_moves(s),
+                    "edges": {m: [int(x.n), float(x.w), float(x.q), float(x.p)] for m, x in node.a.items()}})
+        s = r.step(s, a)
+        t += 1
+    player.close(wait=False)
+    srv.close()
+    cases.append({"name": "three_plies_reuse", "seed": seed, "sims": sims, "calls": seq})
+    out = {"generator": "oracle/gen_golden_mcts.py", "reference": "NeymarL/ChineseChess-AlphaZero @7f45b0c agent/player.py",
+           "config": {"search_threads": 1, "c_puct": 1.5, "noise_eps": 0.25, "dirichlet_alpha": 0.2, "tau_decay_rate": 0.98,
+                      "virtual_loss": 3}, "cases": cases}
+    with gzip.open(os.path.join(GOLD, "mcts_k1.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("mcts cases:", [(c["name"], [x["action"] for x in c["calls"]]) for c in cases])

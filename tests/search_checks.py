@@ -1,0 +1,176 @@
+"""Shared search-parity checks (run against the CUDA library with -m gpu and against the CPU SIMT-emulation
+build of the same kernel source otherwise)."""
+import gzip
+import json
+import os
+import threading
+from multiprocessing import Pipe
+from types import SimpleNamespace
+
+import numpy as np
+
+from cczero_b200.engine import Engine
+from cczero_b200.player import CChessPlayer
+from oracle import player as op
+from oracle import senv as osenv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_mcts_golden():
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "mcts_k1.json.gz"), "rt") as f:
+        return json.load(f)
+
+
+class FakeNetServer:
+    """Stands in for CChessModelAPI.predict_batch_worker (api.py:37-74) with the deterministic pseudo-network."""
+
+    def __init__(self):
+        self.me, self.you = Pipe()
+        self.stop = False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while not self.stop:
+            if self.me.poll(0.001):
+                try:
+                    planes = self.me.recv()
+                except EOFError:
+                    return
+                self.me.send([op.fake_eval_from_planes(p) for p in planes])
+
+    def close(self):
+        self.stop = True
+
+
+def make_config(sims, k, **over):
+    play = SimpleNamespace(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.25, dirichlet_alpha=0.2,
+                           tau_decay_rate=0.98, virtual_loss=3, resign_threshold=-0.92, min_resign_turn=20, max_game_length=100)
+    for key, v in over.items():
+        setattr(play, key, v)
+    return SimpleNamespace(play=play, opts=SimpleNamespace(evaluate=False), model=None)
+
+
+def eval_planes(planes):
+    out = [op.fake_eval_from_planes(p) for p in planes]
+    return np.stack([o[0] for o in out]), np.array([o[1] for o in out], dtype=np.float32)
+
+
+def check_golden_k1(lib, device):
+    """The drop-in CChessPlayer must reproduce the REAL reference player (search_threads=1): chosen move,
+    N, W, P of every root edge, for every call of every golden case (tests/golden/mcts_k1.json.gz)."""
+    gold = load_mcts_golden()
+    for case in gold["cases"]:
+        srv = FakeNetServer()
+        np.random.seed(case["seed"])
+        player = CChessPlayer(make_config(case["sims"], 1), pipes=srv.you, lib=lib, device=device)
+        try:
+            for call in case["calls"]:
+                action, policy = player.action(call["state"], call["turns"], call["no_act"], increase_temp=call["increase_temp"])
+                root = player.engine.root(0)
+                assert root["moves"] == call["legal"], case["name"]
+                assert root["sum_n"] == call["sum_n"], (case["name"], root["sum_n"], call["sum_n"])
+                for m, n, w, p in zip(root["moves"], root["n"], root["w"], root["p"]):
+                    gn, gw, gq, gp = call["edges"].get(m, [0, 0.0, 0.0, 0.0])
+                    assert n == gn and w == gw and float(np.float32(p)) == gp, (case["name"], m, (n, w, p), (gn, gw, gp))
+                assert action == call["action"], (case["name"], action, call["action"])
+                assert abs(sum(policy) - 1.0) < 1e-9
+        finally:
+            player.close()
+            srv.close()
+
+
+def oracle_search(state, sims, k, seed, no_act=None, increase_temp=False, eps=0.25):
+    pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=eps, dirichlet_alpha=0.2,
+                       tau_decay_rate=0.98, virtual_loss=3)
+    np.random.seed(seed)
+    pl = op.OraclePlayer(pc, op.fake_evaluate_states)
+    pl.search(state, no_act, increase_temp)
+    return pl
+
+
+def engine_search(lib, device, states, sims, k, seed, no_act=None, increase_temp=False, eps=0.25):
+    """All games share the seed: game g searches states[g] with its own copy of the oracle's noise stream."""
+    g = len(states)
+    tables = []
+    for s in states:
+        L = len(osenv.get_legal_moves(s))
+        np.random.seed(seed)
+        tables.append([np.random.dirichlet(0.2 * np.ones(L))[0] for _ in range((sims + 40) * L)])
+    width = max(len(t) for t in tables)
+    noise = np.zeros((g, width))
+    for i, t in enumerate(tables):
+        noise[i, :len(t)] = t
+    eng = Engine(lib, device, n_games=g, sims_per_move=sims, leaves_per_round=k, noise_mode=0, c_puct=1.5, noise_eps=eps,
+                 dirichlet_alpha=0.2, tau_decay_rate=0.98)
+    eng.reset(states)
+    stats = eng.search_external(eval_planes, eng.make_opts(no_act=[no_act] * g if no_act else None,
+                                                           increase_temp=[1 if increase_temp else 0] * g, noise=noise))
+    return eng, stats
+
+
+def compare_root(eng, game, pl, state):
+    node = pl.tree[state]
+    r = eng.root(game)
+    assert r["moves"] == node.legal_moves
+    assert r["sum_n"] == node.sum_n
+    for m, n, w, p in zip(r["moves"], r["n"], r["w"], r["p"]):
+        e = node.a.get(m)
+        en, ew, ep = (e.n, float(e.w), float(e.p)) if e is not None else (0, 0.0, 0.0)
+        assert (n, w, float(np.float32(p))) == (en, ew, ep), (state, m, (n, w, p), (en, ew, ep))
+    assert r["noise_used"] == pl.stats["noise_draws"]
+    assert r["sims_run"] == pl.stats["sims"]
+
+
+def midgame_states(n, seed, lo=15, hi=80):
+    rng = np.random.RandomState(seed)
+    out = []
+    while len(out) < n:
+        s = osenv.INIT_STATE
+        ok = True
+        for _ in range(rng.randint(lo, hi)):
+            if osenv.done(s)[0]:
+                ok = False
+                break
+            lm = osenv.get_legal_moves(s)
+            s = osenv.step(s, lm[rng.randint(len(lm))])
+        if ok and not osenv.done(s)[0]:
+            out.append(s)
+    return out
+
+
+def check_vs_oracle(lib, device, cases):
+    """Canonical K-round schedule: engine == oracle restatement bit for bit (N, W, P, sum_n, noise draws)."""
+    for (sims, k, seed, n_states) in cases:
+        states = [osenv.INIT_STATE] + midgame_states(n_states - 1, seed)
+        eng, stats = engine_search(lib, device, states, sims, k, seed)
+        for g, s in enumerate(states):
+            pl = oracle_search(s, sims, k, seed)
+            compare_root(eng, g, pl, s)
+        eng.close()
+
+
+def check_no_act_and_temp(lib, device):
+    s = midgame_states(1, 99)[0]
+    ban = osenv.get_legal_moves(s)[:3]
+    eng, _ = engine_search(lib, device, [s], 120, 4, 5, no_act=ban)
+    compare_root(eng, 0, oracle_search(s, 120, 4, 5, no_act=ban), s)
+    eng.close()
+    eng, _ = engine_search(lib, device, [s], 90, 8, 6, increase_temp=True)
+    compare_root(eng, 0, oracle_search(s, 90, 8, 6, increase_temp=True), s)
+    eng.close()
+
+
+def check_terminal_and_repetition(lib, device):
+    """Positions one or two plies from a king capture, and long searches that revisit positions in-path."""
+    # a bare-kings-plus-rooks ending: lots of checks, captures and repetitions inside the search
+    endings = ['3s5/9/9/9/4r4/9/9/4R4/9/4S4', '4s4/4m4/9/9/9/9/2R6/9/4M4/3S1r3',
+               '2e1s4/4m4/4e4/9/9/9/9/4C4/4M4/3S5']
+    for i, s in enumerate(endings):
+        if osenv.done(s)[0]:
+            continue
+        for (sims, k) in ((300, 1), (400, 8)):
+            eng, _ = engine_search(lib, device, [s], sims, k, 40 + i, eps=0.25)
+            compare_root(eng, 0, oracle_search(s, sims, k, 40 + i), s)
+            eng.close()

@@ -1,0 +1,59 @@
+"""MCTS parity: CUDA tree kernels == real reference player (K=1 golden) == oracle restatement (any K)."""
+import pytest
+
+from tests import search_checks as sc
+
+
+def test_oracle_player_matches_golden_k1():
+    """oracle/player.py against the fixtures recorded from the REAL reference CChessPlayer."""
+    import numpy as np
+    from oracle import player as op
+    gold = sc.load_mcts_golden()
+    for case in gold["cases"]:
+        pc = op.PlayConfig(simulation_num_per_move=case["sims"], search_threads=1, c_puct=1.5, noise_eps=0.25,
+                           dirichlet_alpha=0.2, tau_decay_rate=0.98, virtual_loss=3, resign_threshold=-0.92, min_resign_turn=20)
+        np.random.seed(case["seed"])
+        pl = op.OraclePlayer(pc, op.fake_evaluate_states)
+        for call in case["calls"]:
+            a, _ = pl.action(call["state"], call["turns"], call["no_act"], increase_temp=call["increase_temp"])
+            node = pl.tree[call["state"]]
+            got = {m: [int(e.n), float(e.w), float(e.q), float(e.p)] for m, e in node.a.items()}
+            assert got == call["edges"], case["name"]
+            assert a == call["action"] and node.sum_n == call["sum_n"]
+
+
+def test_emul_golden_k1(emul_lib):
+    sc.check_golden_k1(emul_lib, "cpu")
+
+
+def test_emul_vs_oracle(emul_lib):
+    sc.check_vs_oracle(emul_lib, "cpu", [(100, 1, 1, 2), (150, 4, 2, 3), (240, 8, 3, 3), (300, 16, 4, 2), (130, 40, 5, 2)])
+
+
+def test_emul_no_act_and_temp(emul_lib):
+    sc.check_no_act_and_temp(emul_lib, "cpu")
+
+
+def test_emul_terminal_and_repetition(emul_lib):
+    sc.check_terminal_and_repetition(emul_lib, "cpu")
+
+
+@pytest.mark.gpu
+def test_cuda_golden_k1(cuda_lib):
+    sc.check_golden_k1(cuda_lib, "cuda")
+
+
+@pytest.mark.gpu
+def test_cuda_vs_oracle(cuda_lib):
+    sc.check_vs_oracle(cuda_lib, "cuda", [(100, 1, 1, 2), (150, 4, 2, 3), (240, 8, 3, 4), (300, 16, 4, 3), (130, 40, 5, 2),
+                                          (800, 8, 6, 2)])
+
+
+@pytest.mark.gpu
+def test_cuda_no_act_and_temp(cuda_lib):
+    sc.check_no_act_and_temp(cuda_lib, "cuda")
+
+
+@pytest.mark.gpu
+def test_cuda_terminal_and_repetition(cuda_lib):
+    sc.check_terminal_and_repetition(cuda_lib, "cuda")
