@@ -361,7 +361,23 @@ struct NnRuntime {
   // tensor maps
   CUtensorMap map_x, map_t, map_y, map_pf, map_wpol;
   std::vector<CUtensorMap> map_w;
+  // optional CUDA-event timing of the residual-tower launches (bench.py roofline)
+  bool profile;
+  std::vector<cudaEvent_t> ev;        // pairs, recycled
+  size_t ev_used;
+  std::vector<double> ev_flops;       // algorithmic flops bracketed by pair i
+  double prof_ms, prof_flops; uint64_t prof_launches;
 };
+
+static void prof_collect(NnRuntime* r) {
+  for (size_t i = 0; i + 1 < r->ev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r->ev[i], r->ev[i + 1]) == cudaSuccess) {
+      r->prof_ms += ms; r->prof_flops += r->ev_flops[i / 2]; r->prof_launches += (uint64_t)(2 * r->blocks);
+    }
+  }
+  r->ev_used = 0;
+}
 
 static void layout(NnRuntime* r, Carver& cv) {
   const int c = r->filters;
@@ -404,6 +420,7 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   NnRuntime* r = new NnRuntime();
   r->filters = filters; r->blocks = blocks; r->value_fc = value_fc; r->max_batch = max_batch;
   r->stream = (cudaStream_t)stream; r->ready = false; r->launches = 0;
+  r->profile = false; r->ev_used = 0; r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0;
   Carver cv{(uint8_t*)workspace, 0, bytes};
   layout(r, cv);
   const int c = filters;
@@ -426,7 +443,23 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   return r;
 }
 
-void nn_destroy(NnRuntime* r) { delete r; }
+void nn_destroy(NnRuntime* r) {
+  if (!r) return;
+  for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
+  delete r;
+}
+void nn_profile(NnRuntime* r, bool on) { if (r) { r->profile = on; } }
+// Synchronises the stream. ms = device time spent in the residual-tower igemm launches since the last read.
+int nn_profile_read(NnRuntime* r, double* ms, uint64_t* launches, double* flops) {
+  if (!r) return cz_fail(CZ_ERR_STATE, "no network");
+  CZ_CUDA(cudaStreamSynchronize(r->stream));
+  prof_collect(r);
+  if (ms) *ms = r->prof_ms;
+  if (launches) *launches = r->prof_launches;
+  if (flops) *flops = r->prof_flops;
+  r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0;
+  return 0;
+}
 bool nn_ready(const NnRuntime* r) { return r && r->ready; }
 uint64_t nn_launches(const NnRuntime* r) { return r ? r->launches : 0; }
 
@@ -531,6 +564,15 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
   r->launches++;
   __half *x = r->x, *y = r->y;
   CUtensorMap *mx = &r->map_x, *my = &r->map_y;
+  size_t pe = (size_t)-1;
+  if (r->profile) {
+    if (r->ev_used + 2 > 4096) { cudaStreamSynchronize(st); prof_collect(r); }
+    while (r->ev.size() < r->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); r->ev.push_back(e); }
+    pe = r->ev_used; r->ev_used += 2;
+    if (r->ev_flops.size() < r->ev_used / 2) r->ev_flops.resize(r->ev_used / 2);
+    r->ev_flops[pe / 2] = 2.0 * 90.0 * 9.0 * c * c * (double)n * 2.0 * r->blocks;
+    cudaEventRecord(r->ev[pe], st);
+  }
   for (int i = 0; i < r->blocks; ++i) {
     const size_t wsz = (size_t)c;
     igemm::Args a1 = conv_args(n, c, r->shift_conv + (size_t)(2 * i) * wsz, nullptr, r->t, 1);
@@ -541,6 +583,7 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     __half* tx = x; x = y; y = tx;
     CUtensorMap* tm = mx; mx = my; my = tm;
   }
+  if (pe != (size_t)-1) cudaEventRecord(r->ev[pe + 1], st);
   k_heads<<<n, 256, 0, st>>>(x, c, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
   igemm::Args ap = dense_args(n, kLabels, kPolN, kPolK, 256, r->b_pol, r->logits, kPolN);
   if (launch_igemm(256, r->map_pf, r->map_wpol, ap, st)) return CZ_ERR_CUDA;

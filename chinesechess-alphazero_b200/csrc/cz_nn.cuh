@@ -20,5 +20,7 @@ bool nn_ready(const NnRuntime*);
 int nn_forward_boards(NnRuntime*, const uint8_t* boards_dev, int batch, float* policy_dev, float* value_dev);
 int nn_forward_planes(NnRuntime*, const float* planes_dev, int batch, float* policy_dev, float* value_dev);
 uint64_t nn_launches(const NnRuntime*);
+void nn_profile(NnRuntime*, bool on);
+int nn_profile_read(NnRuntime*, double* ms, uint64_t* launches, double* flops);
 
 }  // namespace cznn

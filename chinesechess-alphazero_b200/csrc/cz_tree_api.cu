@@ -475,6 +475,17 @@ int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch,
 #endif
 }
 
+int cz_nn_profile(cz_engine* e, int enable, double* ms, uint64_t* launches, double* flops) {
+#if defined(CZ_EMUL)
+  (void)e; (void)enable; (void)ms; (void)launches; (void)flops;
+  return cz_fail(CZ_ERR_UNSUPPORTED, "cz_nn_profile: no network in the CPU emulation build");
+#else
+  if (!e || !e->nn) return cz_fail(CZ_ERR_STATE, "cz_nn_profile: engine has no network");
+  cznn::nn_profile(e->nn, enable != 0);
+  return cznn::nn_profile_read(e->nn, ms, launches, flops);
+#endif
+}
+
 }  // extern "C"
 
 #include "cz_selfplay_api.inc"

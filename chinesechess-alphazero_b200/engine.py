@@ -177,6 +177,12 @@ class Engine:
         self.lib.call("cz_launch_count", self._h, C.byref(n))
         return n.value
 
+    def nn_profile(self, enable=True):
+        """(ms, launches, flops) of the residual-tower igemm launches since the last call."""
+        ms, n, fl = C.c_double(0), C.c_uint64(0), C.c_double(0)
+        self.lib.call("cz_nn_profile", self._h, int(enable), C.byref(ms), C.byref(n), C.byref(fl))
+        return ms.value, n.value, fl.value
+
     # ---- on-device game loop
     def play_move(self):
         f = C.c_int32(0)

@@ -201,6 +201,10 @@ int cz_nn_set_weights(cz_engine* e, const cz_tensor_desc* descs, int32_t n);
 int cz_nn_forward(cz_engine* e, const float* planes_dev, int32_t batch, float* policy_dev, float* value_dev);
 /* Same from packed boards (plane encoding fused into the first convolution). */
 int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch, float* policy_dev, float* value_dev);
+/* CUDA-event timing of the residual-tower tensor-core launches (the dominant kernel): switches the
+ * bracketing on/off and returns + clears what accumulated since the last call: device milliseconds,
+ * launches and algorithmic FLOPs (2*90*9*C*C per position per launch).  Synchronises. */
+int cz_nn_profile(cz_engine* e, int enable, double* ms, uint64_t* launches, double* flops);
 /* Kernel launches issued by this engine since creation (bench.py "gpu_launches"). */
 int cz_launch_count(cz_engine* e, uint64_t* n);
 
