@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — MCTS simulations/s of the B200 self-play hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                      CPU arm: the reference's algorithm (oracle port) on host cores
+
+A "step" is one move of self-play for every concurrent game: a full PUCT search (sims/move simulations per game,
+tree walk + leaf evaluation by the residual network + backup, all on the device) followed by the on-device move
+selection / adjudication.  Workload = BASELINE.json configs[2] (the one the metric is quoted on: 1024 concurrent
+games per GPU, 800 sims/move, 20x256 resnet, random-init weights, games from INIT_STATE; weak scaling: every rank
+runs its own 1024 games).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (games per GPU, sims/move, filters, blocks)
+    "c3": (1024, 800, 256, 20),     # BASELINE.json configs[2]/[3] (per GPU)
+    "c2": (256, 200, 128, 7),       # BASELINE.json configs[1]
+    "tiny": (32, 40, 64, 2),        # plumbing check
+}
+
+
+def net_flops(filters, blocks):
+    return 2 * 90 * (350 * filters + blocks * 18 * filters * filters + 6 * filters) + 2 * (360 * 2086 + 180 * 256 + 256)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1428.0))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_sample(filters, blocks, sims, k, budget_s, threads):
+    """The reference's algorithm on host cores: oracle MCTS player (agent/player.py restated) + env restatement +
+    the fp32 PyTorch restatement of agent/model.py as predict_on_batch.  One game from INIT_STATE, `sims` simulations
+    in rounds of k, stopped after ~budget_s seconds.  Returns (sims_per_s, sims_done, seconds)."""
+    import numpy as np
+    import torch
+    from oracle import model as om
+    from oracle import player as op
+    from oracle import senv
+    torch.set_num_threads(threads)
+    w = om.init_weights(filters, blocks, 256, seed=0)
+    net = om.TorchNet(w, blocks)
+    t_end = [0.0]
+
+    class Stop(Exception):
+        pass
+
+    def evaluate(states):
+        if time.time() > t_end[0]:
+            raise Stop()
+        planes = np.stack([senv.state_to_planes(s) for s in states])
+        p, v = net.predict_on_batch(planes)
+        return [(p[i], float(v[i, 0])) for i in range(len(states))]
+
+    pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
+                       tau_decay_rate=0.9, virtual_loss=3)
+    np.random.seed(0)
+    pl = op.OraclePlayer(pc, evaluate)
+    t0 = time.time()
+    t_end[0] = t0 + budget_s
+    try:
+        pl.search(senv.INIT_STATE)
+    except Stop:
+        pass
+    dt = time.time() - t0
+    done = pl.stats["positions"]          # one simulation ~ one evaluated position
+    return done / dt, done, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    games, sims, filters, blocks = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    budget = max(5.0, min(40.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, n, dt = cpu_reference_sample(filters, blocks, sims, args.leaves, budget, cores)
+        if i >= args.warmup:
+            vals.append((v, n, dt))
+    tot_n = sum(x[1] for x in vals)
+    tot_t = sum(x[2] for x in vals)
+    value = tot_n / tot_t
+    sample = (f"1 game from INIT_STATE, search_threads={args.leaves}, {filters}x{blocks} fp32 torch-CPU network, "
+              f"{budget:.0f} s of search per step ({tot_n} simulations in {tot_t:.1f} s)")
+    line = {
+        "impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, INIT_STATE)",
+        "config": {"workload": f"{args.workload}: {games} games/GPU, {sims} sims/move, {filters}x{blocks} resnet",
+                   "leaves_per_round": args.leaves},
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from cczero_b200.engine import Engine
+    from cczero_b200.lib import get_lib
+    from cczero_b200 import records as rec
+    from oracle import model as om   # weight INITIALISER only (Keras-equivalent glorot init shared with the CPU arm)
+
+    lib = get_lib()
+    games, sims, filters, blocks = WORKLOADS[args.workload]
+    if args.games:
+        games = args.games
+    if args.sims:
+        sims = args.sims
+    K = args.leaves
+    eng = Engine(lib, f"cuda:{local}", n_games=games, sims_per_move=sims, leaves_per_round=K, noise_mode=1,
+                 nn_filters=filters, nn_blocks=blocks, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
+                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, max_game_length=100,
+                 max_nodes_per_game=args.nodes or max(4096, 24 * sims), seed=args.seed, rank=rank)
+    w = om.init_weights(filters, blocks, 256, seed=0)
+    eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    eng.reset()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        g, s = eng.selfplay(target_games=0, max_moves=1)
+        return s, g
+
+    # pinned host staging for the end-to-end arm
+    init_boards = rec.init_boards_pinned(games)
+    root_host = rec.RootStage(eng)
+
+    def step_e2e():
+        """Through the host-facing API: root positions come from pinned host memory, the search runs, the move is
+        played and the per-game result (root visit counts + chosen move + finished records) is read back."""
+        boards = eng.download_roots(root_host)            # D2H (previous result feeds the next request)
+        eng.upload_roots(boards)                           # H2D of this step's inputs
+        eng.search(None)
+        stats = eng.download_root_stats(root_host)         # D2H visit counts of every root
+        s = int(eng.sims_run().sum())
+        f = eng.play_move()
+        recs = eng.drain_records()
+        return s, f, stats, recs
+
+    for _ in range(args.warmup):
+        step_device()
+    # ---- device-resident timing
+    eng.nn_profile(True)
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sims_total, games_done = 0, 0
+    for _ in range(args.steps):
+        s, g = step_device()
+        sims_total += s
+        games_done += g
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    conv_ms, conv_launches, conv_flops = eng.nn_profile(False)
+    launches = eng.launch_count() - launches0
+    positions = int(eng.counters()[1])
+    # ---- NCCL gather of finished play records (the only inter-GPU traffic of the path), timed with the step region
+    gathered = 0
+    if world > 1:
+        gathered = rec.gather_records(eng, dist, world)
+    # ---- end-to-end timing through the host API
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    e2e_sims = 0
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        s, f, stats, recs = step_e2e()
+        e2e_sims += s
+        h2d = root_host.h2d_bytes
+        d2h = root_host.d2h_bytes
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e, conv_ms], device="cuda", dtype=torch.float64)
+    c = torch.tensor([sims_total, e2e_sims, launches, conv_launches, games_done], device="cuda", dtype=torch.float64)
+    fl = torch.tensor([conv_flops], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
+    ms, ms_e2e, conv_ms = [float(x) for x in t.tolist()]
+    sims_total, e2e_sims, launches, conv_launches, games_done = [float(x) for x in c.tolist()]
+    conv_flops = float(fl.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # per-rank achieved rate of the dominant kernel (conv_ms is the max over ranks, flops the sum)
+        achieved = (conv_flops / world) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        value = sims_total / (ms * 1e-3)
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, n, dt = cpu_reference_sample(filters, blocks, sims, K, args.cpu_seconds, cores)
+            cpu = {"value": v, "unit": "sims/s", "cores": cores, "kind": "port",
+                   "sample": f"oracle port (agent/player.py + static_env.py restated, fp32 torch-CPU {filters}x{blocks} net), 1 game from "
+                             f"INIT_STATE, search_threads={K}: {n} simulations in {dt:.1f} s"}
+        line = {
+            "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic (random-init Keras-equivalent weights, games from INIT_STATE)",
+            "config": {"workload": f"{args.workload} = BASELINE.json configs[2]: {games} concurrent games/GPU, {sims} sims/move, "
+                                   f"{filters}x{blocks} resnet", "games_per_gpu": games, "sims_per_move": sims,
+                       "leaves_per_round": K, "parallelism": f"dp{world} (games sharded, no data-path collective)",
+                       "l2": "inputs larger than L2 (activations ~1.2 GB/round, trees ~GBs)", "nn_positions": positions,
+                       "games_finished": games_done, "records_gathered": gathered},
+            "nn_positions_per_sec": None,
+            "e2e": {"value": e2e_sims / (ms_e2e * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "igemm::k_igemm<C> (3x3 residual conv, tcgen05)",
+                         "launches": int(conv_launches), "avg_launch_ms": conv_ms / max(1.0, conv_launches / world),
+                         "peak_source": peak_src, "share_of_step": conv_ms / ms},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        line["nn_positions_per_sec"] = (conv_flops / (2.0 * 90 * 9 * filters * filters * 2 * blocks)) / (ms * 1e-3)
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--leaves", type=int, default=8, help="simulations per game per round (reference search_threads)")
+    ap.add_argument("--games", type=int, default=0)
+    ap.add_argument("--sims", type=int, default=0)
+    ap.add_argument("--nodes", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -108,6 +108,29 @@ CZ_KERNEL(k_root_info)(EngineDev E, int g, cz_root_info* out) {
   } else if (czs::lane() == 0) out->sum_n = 0;
   if (czs::lane() == 0) { out->n_moves = L; out->noise_used = E.noise_used[g]; out->sims_run = E.sims_run[g]; }
 }
+// visit counts of every root (the policy target the trainer consumes, calc_policy player.py:384-385)
+CZ_KERNEL(k_root_stats)(EngineDev E, int32_t* n_out, uint16_t* mv_out, int32_t* cnt_out) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  const int root = E.root_node[g];
+  int L = 0;
+  if (root >= 0) {
+    const size_t ni = (size_t)g * E.ncap + root;
+    L = (int)(E.node_meta[ni] & 0xff);
+    const size_t eo = (size_t)g * E.ecap + E.node_edge_off[ni];
+    for (int i = czs::lane(); i < MAX_MOVES; i += 32) {
+      n_out[(size_t)g * MAX_MOVES + i] = i < L ? E.edge_n[eo + i] : 0;
+      mv_out[(size_t)g * MAX_MOVES + i] = i < L ? E.edge_move[eo + i] : (uint16_t)0xFFFF;
+    }
+  }
+  if (czs::lane() == 0) cnt_out[g] = L;
+}
+CZ_KERNEL(k_set_roots)(EngineDev E, const uint8_t* boards) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  for (int k = czs::lane(); k < BOARD_STRIDE; k += 32)
+    E.root_board[(size_t)g * BOARD_STRIDE + k] = k < NSQ ? boards[(size_t)g * BOARD_STRIDE + k] : (uint8_t)0;
+}
 CZ_KERNEL(k_set_opts)(EngineDev E, const uint16_t* no_act, const uint8_t* inc, const uint8_t* act) {
   const int g = my_game();
   if (g >= E.n_games) return;
@@ -150,6 +173,7 @@ struct cz_engine {
   cz_root_info* root_info_dev;
   float* policy_buf; float* value_buf;                      // evaluator outputs for the built-in network
   uint8_t* board_stage;                                     // [G][96] staging for reset / set_root
+  int32_t* stat_n; uint16_t* stat_mv; int32_t* stat_cnt;    // staging for cz_get_root_stats
   int last_leaves;
   uint64_t launches;
   uint64_t total_sims, total_positions, total_waves;
@@ -194,6 +218,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   e->opt_no_act = cv.take<uint8_t>(G * CZ_MAX_NO_ACT * 2); e->opt_inc = cv.take<uint8_t>(G); e->opt_act = cv.take<uint8_t>(G);
   e->root_info_dev = cv.take<cz_root_info>(1);
   e->board_stage = cv.take<uint8_t>(G * BOARD_STRIDE);
+  e->stat_n = cv.take<int32_t>(G * MAX_MOVES); e->stat_mv = cv.take<uint16_t>(G * MAX_MOVES); e->stat_cnt = cv.take<int32_t>(G);
   if (c.nn_filters > 0) {
     e->policy_buf = cv.take<float>(G * K * (size_t)CZ_N_LABELS);
     e->value_buf = cv.take<float>(G * K);
@@ -331,6 +356,31 @@ int cz_set_root(cz_engine* e, int game, const uint8_t* board_host) {
   CZ_LAUNCH(k_set_root, 1, 1, 0, e->stream, e->d, game, (const uint8_t*)e->board_stage);
   if (launch_ok(e, "cz_set_root")) return CZ_ERR_CUDA;
   return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_set_root: sync failed") : 0;
+}
+
+int cz_set_roots(cz_engine* e, const uint8_t* boards_host) {
+  if (!e || !boards_host) return cz_fail(CZ_ERR_ARG, "cz_set_roots: bad argument");
+  czrt_copy(e->board_stage, boards_host, (size_t)e->cfg.n_games * BOARD_STRIDE, e->stream);
+  GAME_LAUNCH(e, k_set_roots, e->d, (const uint8_t*)e->board_stage);
+  return launch_ok(e, "cz_set_roots");
+}
+
+int cz_get_roots(cz_engine* e, uint8_t* boards_host) {
+  if (!e || !boards_host) return cz_fail(CZ_ERR_ARG, "cz_get_roots: bad argument");
+  czrt_copy(boards_host, e->d.root_board, (size_t)e->cfg.n_games * BOARD_STRIDE, e->stream);
+  return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_get_roots: device failure") : 0;
+}
+
+int cz_get_root_stats(cz_engine* e, int32_t* n_host, uint16_t* moves_host, int32_t* counts_host, int32_t* sims_run_host) {
+  if (!e || !n_host || !moves_host || !counts_host) return cz_fail(CZ_ERR_ARG, "cz_get_root_stats: bad argument");
+  const size_t G = e->cfg.n_games;
+  GAME_LAUNCH(e, k_root_stats, e->d, e->stat_n, e->stat_mv, e->stat_cnt);
+  if (launch_ok(e, "cz_get_root_stats")) return CZ_ERR_CUDA;
+  czrt_copy(n_host, e->stat_n, G * MAX_MOVES * sizeof(int32_t), e->stream);
+  czrt_copy(moves_host, e->stat_mv, G * MAX_MOVES * sizeof(uint16_t), e->stream);
+  czrt_copy(counts_host, e->stat_cnt, G * sizeof(int32_t), e->stream);
+  if (sims_run_host) czrt_copy(sims_run_host, e->d.sims_run, G * sizeof(int32_t), e->stream);
+  return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_get_root_stats: device failure") : 0;
 }
 
 int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {

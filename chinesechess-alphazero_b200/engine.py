@@ -167,6 +167,28 @@ class Engine:
             "sum_n": info.sum_n, "noise_used": info.noise_used, "sims_run": info.sims_run,
         }
 
+    # ---- bulk host <-> device staging (pinned buffers owned by a records.RootStage)
+    def upload_roots(self, boards_pinned):
+        self.lib.call("cz_set_roots", self._h, C.c_void_p(boards_pinned.data_ptr()))
+
+    def download_roots(self, stage):
+        self.lib.call("cz_get_roots", self._h, C.c_void_p(stage.boards.data_ptr()))
+        stage.d2h_bytes_acc += stage.boards.numel()
+        return stage.boards
+
+    def download_root_stats(self, stage):
+        self.lib.call("cz_get_root_stats", self._h, C.c_void_p(stage.n.data_ptr()), C.c_void_p(stage.moves.data_ptr()),
+                      C.c_void_p(stage.counts.data_ptr()), C.c_void_p(stage.sims.data_ptr()))
+        return stage.n, stage.moves, stage.counts
+
+    def sims_run(self):
+        st = getattr(self, "_sims_stage", None)
+        if st is None:
+            from .records import RootStage
+            st = self._sims_stage = RootStage(self)
+        self.download_root_stats(st)
+        return st.sims.numpy()
+
     def counters(self):
         a = np.zeros(8, dtype=np.uint64)
         self.lib.call("cz_get_counters", self._h, C.c_void_p(a.ctypes.data))

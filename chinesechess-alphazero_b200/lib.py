@@ -74,6 +74,9 @@ _SIGS = {
     "cz_destroy": (None, [_P]),
     "cz_reset_games": (C.c_int, [_P, _P]),
     "cz_set_root": (C.c_int, [_P, C.c_int, _P]),
+    "cz_set_roots": (C.c_int, [_P, _P]),
+    "cz_get_roots": (C.c_int, [_P, _P]),
+    "cz_get_root_stats": (C.c_int, [_P, _P, _P, _P, _P]),
     "cz_search_begin": (C.c_int, [_P, C.POINTER(CzRootOpts)]),
     "cz_search_wave": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cz_leaf_planes": (C.c_int, [_P, _P]),

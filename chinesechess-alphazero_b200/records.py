@@ -1,0 +1,82 @@
+"""Play records and host staging.
+
+Record format of the reference (worker/self_play.py:202-208 -> lib/data_helper.py:17-19): one JSON list per game,
+`[init_state, [move, value], [move, -value], ...]` with `value` the result from red's view for the first entry and
+alternating sign after it; moves are the 4-digit strings in the mover's own frame.
+"""
+import json
+import os
+from datetime import datetime, timedelta, timezone
+
+import numpy as np
+import torch
+
+from .env import INIT_STATE, state_to_board
+from .lib import BOARD_STRIDE, MAX_MOVES
+
+
+def record_to_play_data(rec, init_state=INIT_STATE):
+    """cz_drain_records entry -> the list self_play.py:202-208 builds."""
+    data = [init_state]
+    value = rec["value_red"]
+    for m in rec["moves"]:
+        data.append([m, value])
+        value = -value
+    return data
+
+
+def write_play_data(play_data_dir, data, filename_tmpl="play_%s.json"):
+    """save_play_data (self_play.py:214-227): Beijing-time stamped file, json.dump of the buffer."""
+    os.makedirs(play_data_dir, exist_ok=True)
+    bj = datetime.now(timezone.utc).astimezone(timezone(timedelta(hours=8)))
+    path = os.path.join(play_data_dir, filename_tmpl % bj.strftime("%Y%m%d-%H%M%S.%f"))
+    with open(path, "wt") as f:
+        json.dump(data, f)
+    return path
+
+
+def init_boards_pinned(n_games):
+    b = torch.from_numpy(np.tile(state_to_board(INIT_STATE), (n_games, 1)))
+    return b.pin_memory() if torch.cuda.is_available() else b
+
+
+class RootStage:
+    """Pinned host buffers for the per-step host<->device traffic of the end-to-end path."""
+
+    def __init__(self, engine):
+        g = engine.n_games
+        pin = engine.lib.is_cuda and torch.cuda.is_available()
+
+        def mk(shape, dtype):
+            t = torch.zeros(shape, dtype=dtype)
+            return t.pin_memory() if pin else t
+        self.boards = mk((g, BOARD_STRIDE), torch.uint8)
+        self.n = mk((g, MAX_MOVES), torch.int32)
+        self.moves = mk((g, MAX_MOVES), torch.int16)
+        self.counts = mk((g,), torch.int32)
+        self.sims = mk((g,), torch.int32)
+        self.d2h_bytes_acc = 0
+
+    @property
+    def h2d_bytes(self):
+        return self.boards.numel()
+
+    @property
+    def d2h_bytes(self):
+        return self.boards.numel() + self.n.numel() * 4 + self.moves.numel() * 2 + self.counts.numel() * 4 + self.sims.numel() * 4
+
+
+def gather_records(engine, dist, world):
+    """NCCL all_gather of the finished-game record ring of every rank: the only inter-GPU traffic of the
+    path.  The ring lives inside the engine's workspace tensor, so the collective reads it in place."""
+    import ctypes as C
+    ptr, nbytes, ready = C.c_void_p(0), C.c_uint64(0), C.c_int32(0)
+    engine.lib.call("cz_record_buffer", engine._h, C.byref(ptr), C.byref(nbytes), C.byref(ready))
+    off = ptr.value - engine.workspace.data_ptr()
+    ring = engine.workspace[off:off + nbytes.value]
+    count = torch.tensor([ready.value], device=engine.device, dtype=torch.int32)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count)
+    rings = [torch.empty_like(ring) for _ in range(world)]
+    dist.all_gather(rings, ring)
+    return int(sum(int(c.item()) for c in counts))

@@ -115,6 +115,11 @@ int cz_reset_games(cz_engine* e, const uint8_t* boards_host);
  * worker/self_play.py:122-147: the same player object searches the next state). */
 int cz_set_root(cz_engine* e, int game, const uint8_t* board_host);
 
+/* Bulk variants for all games (host buffers [n_games][CZ_BOARD_STRIDE]; pinned memory makes them async):
+ * cz_set_roots is stream-ordered, cz_get_roots synchronises. */
+int cz_set_roots(cz_engine* e, const uint8_t* boards_host);
+int cz_get_roots(cz_engine* e, uint8_t* boards_host);
+
 typedef struct cz_root_opts {
   /* per game, may be NULL for "none" */
   const uint16_t* no_act_host;     /* [n_games][CZ_MAX_NO_ACT] moves banned at the root, 0xFFFF-terminated */
@@ -157,6 +162,10 @@ typedef struct cz_root_info {
 } cz_root_info;
 /* node.a of the root (read by calc_policy, player.py:375-406).  Synchronises. */
 int cz_get_root(cz_engine* e, int game, cz_root_info* out_host);
+
+/* Visit counts of every root after a search: n_host [n_games][CZ_MAX_MOVES], moves_host likewise
+ * (0xFFFF padded), counts_host [n_games] legal-move counts, sims_run_host [n_games] or NULL.  Synchronises. */
+int cz_get_root_stats(cz_engine* e, int32_t* n_host, uint16_t* moves_host, int32_t* counts_host, int32_t* sims_run_host);
 
 /* Counters since cz_create: [0] simulations completed, [1] NN positions evaluated,
  * [2] wave iterations, [3] nodes created, [4] tree resets forced by pool overflow. */
