@@ -95,43 +95,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_sample(filters, blocks, sims, k, budget_s, threads):
-    """The reference's algorithm on host cores: oracle MCTS player (agent/player.py restated) + env restatement +
-    the fp32 PyTorch restatement of agent/model.py as predict_on_batch.  One game from INIT_STATE, `sims` simulations
-    in rounds of k, stopped after ~budget_s seconds.  Returns (sims_per_s, sims_done, seconds)."""
-    import numpy as np
-    import torch
-    from oracle import model as om
-    from oracle import player as op
-    from oracle import senv
-    torch.set_num_threads(threads)
-    w = om.init_weights(filters, blocks, 256, seed=0)
-    net = om.TorchNet(w, blocks)
-    t_end = [0.0]
-
-    class Stop(Exception):
-        pass
-
-    def evaluate(states):
-        if time.time() > t_end[0]:
-            raise Stop()
-        planes = np.stack([senv.state_to_planes(s) for s in states])
-        p, v = net.predict_on_batch(planes)
-        return [(p[i], float(v[i, 0])) for i in range(len(states))]
-
-    pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
-                       tau_decay_rate=0.9, virtual_loss=3)
-    np.random.seed(0)
-    pl = op.OraclePlayer(pc, evaluate)
-    t0 = time.time()
-    t_end[0] = t0 + budget_s
-    try:
-        pl.search(senv.INIT_STATE)
-    except Stop:
-        pass
-    dt = time.time() - t0
-    done = pl.stats["positions"]          # one simulation ~ one evaluated position (SURVEY.md §8d)
-    return done / dt, done, dt
+def cpu_reference_sample(filters, blocks, sims, k, budget_s, procs):
+    """The reference's algorithm on the host cores: `procs` single-threaded workers (the reference's own scaling knob is
+    processes, worker/self_play.py:55-60), each the oracle port of agent/player.py + static_env.py with the fp32 PyTorch
+    restatement of agent/model.py as predict_on_batch, self-playing from INIT_STATE for ~budget_s seconds.
+    Returns (aggregate sims/s, simulations, mean window seconds)."""
+    from oracle import cpu_baseline
+    rate, n, dt, _ = cpu_baseline.run(filters, blocks, sims, k, budget_s, procs)
+    return rate, n, dt
 
 
 def run_reference_arm(args):
@@ -148,9 +119,9 @@ def run_reference_arm(args):
             vals.append((v, n, dt))
     tot_n = sum(x[1] for x in vals)
     tot_t = sum(x[2] for x in vals)
-    value = tot_n / tot_t
-    sample = (f"1 game from INIT_STATE, search_threads={args.leaves}, {filters}x{blocks} fp32 torch-CPU network, "
-              f"{budget:.0f} s of search per step ({tot_n} simulations in {tot_t:.1f} s)")
+    value = sum(x[0] for x in vals) / len(vals)
+    sample = (f"{cores} single-threaded worker processes, each 1 game of self-play from INIT_STATE, search_threads={args.leaves}, "
+              f"{filters}x{blocks} fp32 torch-CPU network, {budget:.0f} s window per step ({tot_n} simulations over {len(vals)} windows)")
     line = {
         "impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
@@ -182,7 +153,8 @@ def run_ours(args):
     from cczero_b200.engine import Engine
     from cczero_b200.lib import get_lib
     from cczero_b200 import records as rec
-    from oracle import model as om   # weight INITIALISER only (Keras-equivalent glorot init shared with the CPU arm)
+    from cczero_b200.model import CChessModel
+    from types import SimpleNamespace
 
     lib = get_lib()
     games, sims, filters, blocks = WORKLOADS[args.workload]
@@ -195,8 +167,10 @@ def run_ours(args):
                  nn_filters=filters, nn_blocks=blocks, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
                  tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, max_game_length=100,
                  max_nodes_per_game=args.nodes or max(4096, 24 * sims), seed=args.seed, rank=rank)
-    w = om.init_weights(filters, blocks, 256, seed=0)
-    eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    model = CChessModel(SimpleNamespace(model=SimpleNamespace(cnn_filter_num=filters, res_layer_num=blocks, value_fc_size=256,
+                                                              cnn_first_filter_size=5, cnn_filter_size=3, input_depth=14)))
+    model.build(seed=0)                      # random-init, Keras-equivalent (agent/model.py:32-66 defaults)
+    eng.set_weights(model.torch_weights())
     eng.reset()
 
     def barrier():
@@ -287,8 +261,9 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             v, n, dt = cpu_reference_sample(filters, blocks, sims, K, args.cpu_seconds, cores)
             cpu = {"value": v, "unit": "sims/s", "cores": cores, "kind": "port",
-                   "sample": f"oracle port (agent/player.py + static_env.py restated, fp32 torch-CPU {filters}x{blocks} net), 1 game from "
-                             f"INIT_STATE, search_threads={K}: {n} simulations in {dt:.1f} s"}
+                   "sample": f"oracle port (agent/player.py + static_env.py restated, fp32 torch-CPU {filters}x{blocks} net): {cores} "
+                             f"single-threaded worker processes x 1 self-play game from INIT_STATE, search_threads={K}, "
+                             f"{n} simulations in a {dt:.1f} s window"}
         line = {
             "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -1,0 +1,106 @@
+"""`CChessModelAPI` drop-in (reference: cchess_alphazero/agent/api.py:16-117): the batching prediction server.
+
+Same wire protocol as the reference, so UNMODIFIED reference players can be served by the B200 network:
+a client sends `list[np.float32[14,10,9]]` on its pipe end, the server answers `list[(np.float32[2086], float)]`
+in the same order (api.py:48-74 <-> player.py:118-120,131-140).  One daemon thread waits on every pipe, drains
+what is ready, runs ONE batched forward (`cz_nn_forward`: tensor-core pipeline) and scatters the results.
+
+Weight hot-reload: the reference re-reads the best-model file every 600 s when its digest changed
+(api.py:42-44,76-88); `try_reload_model()` does the same against the `.npz` path in config.resource.
+"""
+from multiprocessing import Pipe, connection
+from threading import Thread
+from time import time
+
+import numpy as np
+import torch
+
+from .engine import Engine
+from .lib import get_lib
+
+
+class CChessModelAPI:
+    def __init__(self, config, agent_model, lib=None, device=None, max_batch=2048):
+        self.agent_model = agent_model
+        self.pipes = []
+        self.config = config
+        self.need_reload = True
+        self.done = False
+        self.lib = lib or get_lib()
+        self.device = device or "cuda"
+        self.max_batch = max_batch
+        self.engine = None
+        self.positions = 0
+        self.batches = 0
+
+    def _ensure_engine(self):
+        if self.engine is None:
+            mc = self.config.model
+            self.engine = Engine(self.lib, self.device, n_games=self.max_batch, sims_per_move=1, leaves_per_round=1,
+                                 max_nodes_per_game=16, max_edges_per_game=256, max_path=8,
+                                 nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size)
+            self.engine.set_weights(self.agent_model.torch_weights())
+
+    def start(self, need_reload=True):
+        self.need_reload = need_reload
+        self._ensure_engine()
+        t = Thread(target=self.predict_batch_worker, name="prediction_worker", daemon=True)
+        t.start()
+        self.thread = t
+
+    def get_pipe(self, need_reload=True):
+        me, you = Pipe()
+        self.pipes.append(me)
+        self.need_reload = need_reload
+        return you
+
+    def predict_batch_worker(self):
+        if self.engine.lib.is_cuda:
+            torch.cuda.set_device(self.engine.device)
+        last_check = time()
+        while not self.done:
+            if last_check + 600 < time() and self.need_reload:
+                self.try_reload_model()
+                last_check = time()
+            ready = connection.wait(self.pipes, timeout=0.001)
+            if not ready:
+                continue
+            data, result_pipes, data_len = [], [], []
+            for pipe in ready:
+                while pipe.poll():
+                    try:
+                        tmp = pipe.recv()
+                    except EOFError:
+                        pipe.close()
+                        if pipe in self.pipes:
+                            self.pipes.remove(pipe)
+                        break
+                    data.extend(tmp)
+                    data_len.append(len(tmp))
+                    result_pipes.append(pipe)
+            if not data:
+                continue
+            planes = torch.from_numpy(np.asarray(data, dtype=np.float32)).to(self.engine.device)
+            pol, val = self.engine.nn_forward_planes(planes)
+            policy_ary, value_ary = pol.cpu().numpy(), val.cpu().numpy()
+            self.positions += len(data)
+            self.batches += 1
+            k = 0
+            for pipe, n in zip(result_pipes, data_len):
+                pipe.send([(policy_ary[k + i], float(value_ary[k + i])) for i in range(n)])
+                k += n
+
+    def try_reload_model(self, config_file=None):
+        rc = getattr(self.config, "resource", None)
+        if rc is None:
+            return
+        path = rc.model_best_weight_path
+        digest = self.agent_model.fetch_digest(path)
+        if digest and digest != self.agent_model.digest:
+            if self.agent_model.load(rc.model_best_config_path, path):
+                self.engine.set_weights(self.agent_model.torch_weights())
+
+    def close(self):
+        self.done = True
+        if self.engine is not None and getattr(self, "thread", None) is not None:
+            self.thread.join(timeout=2)

@@ -1,0 +1,145 @@
+"""`CChessModel` drop-in (reference: cchess_alphazero/agent/model.py:22-126).
+
+The reference object wraps a Keras model; here it is a plain container of the network weights in Keras names and
+layouts (conv kernels HWIO, dense (in,out), BatchNormalization gamma/beta/moving_mean/moving_variance) plus the
+geometry from `config.model`.  The forward pass itself is the tensor-core pipeline inside the engine
+(`cz_nn_set_weights` / `cz_nn_forward`), reached through `get_pipes()` exactly like the reference reaches Keras
+through CChessModelAPI.
+
+Weight files: `.npz` (one array per Keras weight name) next to a JSON config.  Reading Keras `.h5` files needs an
+HDF5 reader that this environment does not have; it is listed as a "next" row and `load()` says so.
+"""
+import hashlib
+import json
+import math
+import os
+
+import numpy as np
+
+N_LABELS = 2086
+BN_WEIGHTS = ("gamma", "beta", "moving_mean", "moving_variance")
+
+
+def layer_names(filters, blocks, first=5, k=3):
+    """Keras layer names the reference builds (model.py:37-62, 71-80)."""
+    conv = [f"input_conv-{first}-{filters}"]
+    bn = ["input_batchnorm"]
+    for i in range(1, blocks + 1):
+        conv += [f"res{i}_conv1-{k}-{filters}", f"res{i}_conv2-{k}-{filters}"]
+        bn += [f"res{i}_batchnorm1", f"res{i}_batchnorm2"]
+    conv += ["policy_conv-1-2", "value_conv-1-4"]
+    bn += ["policy_batchnorm", "value_batchnorm"]
+    return conv, bn, ["policy_out", "value_dense", "value_out"]
+
+
+class CChessModel:
+    def __init__(self, config):
+        self.config = config
+        self.weights = None          # dict: "<layer>/<weight>" -> np.float32 array (Keras layout)
+        self.model = None            # attribute kept for callers that test `model.model is not None`
+        self.digest = None
+        self.n_labels = N_LABELS
+        self.graph = None
+        self.api = None
+
+    # ---- model.py:32-66 — same topology, Keras default initialisers (glorot_uniform kernels, zero biases,
+    #      BN gamma = 1, beta = 0, moving_mean = 0, moving_variance = 1)
+    def build(self, seed=None):
+        mc = self.config.model
+        rng = np.random.RandomState(seed)
+        f, blocks, vfc = mc.cnn_filter_num, mc.res_layer_num, mc.value_fc_size
+        w = {}
+
+        def glorot(shape, fan_in, fan_out):
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+        def conv(name, k, cin, cout):
+            w[name + "/kernel"] = glorot((k, k, cin, cout), k * k * cin, k * k * cout)
+
+        def bn(name, c):
+            w[name + "/gamma"] = np.ones(c, np.float32)
+            w[name + "/beta"] = np.zeros(c, np.float32)
+            w[name + "/moving_mean"] = np.zeros(c, np.float32)
+            w[name + "/moving_variance"] = np.ones(c, np.float32)
+
+        def dense(name, cin, cout):
+            w[name + "/kernel"] = glorot((cin, cout), cin, cout)
+            w[name + "/bias"] = np.zeros(cout, np.float32)
+
+        first = getattr(mc, "cnn_first_filter_size", 5)
+        k = getattr(mc, "cnn_filter_size", 3)
+        if first != 5 or k != 3 or getattr(mc, "input_depth", 14) != 14:
+            raise NotImplementedError("the B200 path implements the 5x5 -> 3x3 residual tower on 14 input planes")
+        conv(f"input_conv-{first}-{f}", first, 14, f)
+        bn("input_batchnorm", f)
+        for i in range(1, blocks + 1):
+            for j in (1, 2):
+                conv(f"res{i}_conv{j}-{k}-{f}", k, f, f)
+                bn(f"res{i}_batchnorm{j}", f)
+        conv("policy_conv-1-2", 1, f, 4)
+        bn("policy_batchnorm", 4)
+        dense("policy_out", 360, N_LABELS)
+        conv("value_conv-1-4", 1, f, 2)
+        bn("value_batchnorm", 2)
+        dense("value_dense", 180, vfc)
+        dense("value_out", vfc, 1)
+        self.weights = w
+        self.model = self
+        return self
+
+    @staticmethod
+    def fetch_digest(weight_path):
+        """model.py:85-92."""
+        if os.path.exists(weight_path):
+            m = hashlib.sha256()
+            with open(weight_path, "rb") as f:
+                m.update(f.read())
+            return m.hexdigest()
+        return None
+
+    def load(self, config_path, weight_path):
+        """model.py:95-107.  `weight_path` must be an .npz written by `save()`."""
+        if not (os.path.exists(config_path) and os.path.exists(weight_path)):
+            return False
+        if weight_path.endswith(".h5"):
+            raise NotImplementedError("Keras .h5 weights need an HDF5 reader (not available here); convert to .npz "
+                                      "with Keras names first (SURVEY.md §8f row 3)")
+        with open(config_path, "rt") as f:
+            cfg = json.load(f)
+        mc = self.config.model
+        mc.cnn_filter_num, mc.res_layer_num = cfg["cnn_filter_num"], cfg["res_layer_num"]
+        mc.value_fc_size = cfg.get("value_fc_size", 256)
+        with np.load(weight_path) as z:
+            self.weights = {k.replace("__", "/"): z[k].astype(np.float32) for k in z.files}
+        self.digest = self.fetch_digest(weight_path)
+        self.model = self
+        return True
+
+    def save(self, config_path, weight_path):
+        """model.py:109-115."""
+        mc = self.config.model
+        os.makedirs(os.path.dirname(config_path) or ".", exist_ok=True)
+        with open(config_path, "wt") as f:
+            json.dump({"cnn_filter_num": mc.cnn_filter_num, "res_layer_num": mc.res_layer_num,
+                       "value_fc_size": mc.value_fc_size, "format": "cczero-b200 npz, Keras weight names"}, f)
+        with open(weight_path, "wb") as f:          # np.savez would append ".npz" to a bare path
+            np.savez(f, **{k.replace("/", "__"): v for k, v in self.weights.items()})
+        self.digest = self.fetch_digest(weight_path)
+
+    def torch_weights(self, device=None):
+        import torch
+        return {k: torch.as_tensor(v).to(device) if device else torch.as_tensor(v) for k, v in self.weights.items()}
+
+    # ---- model.py:117-126
+    def get_pipes(self, num=1, api=None, need_reload=True):
+        if self.api is None:
+            from .api import CChessModelAPI
+            self.api = CChessModelAPI(self.config, self)
+            self.api.start(need_reload)
+        return self.api.get_pipe(need_reload)
+
+    def close_pipes(self):
+        if self.api is not None:
+            self.api.close()
+            self.api = None

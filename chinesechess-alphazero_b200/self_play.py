@@ -1,0 +1,130 @@
+"""`worker.self_play` drop-in (reference: cchess_alphazero/worker/self_play.py:48-232).
+
+`start(config)` and `SelfPlayWorker(config, pipes, pid, use_history).start() / .start_game(idx, search_tree)` keep the
+reference names, arguments and return values.  Where the reference runs `max_processes` OS processes with one game
+each, all talking to one prediction thread, this worker holds `config.play.max_processes x games_per_process`
+concurrent games in ONE engine on the GPU: the whole per-ply loop of start_game (search, move choice, adjudication,
+record) runs in the kernels behind `cz_selfplay` and the host only writes the play-data files
+(`data/play_data/play_<Beijing time>.json`, self_play.py:214-227) with the reference's record layout.
+"""
+import os
+from logging import getLogger
+from time import time
+
+from .engine import Engine
+from .lib import get_lib
+from .model import CChessModel
+from .records import record_to_play_data, write_play_data
+from .env import INIT_STATE, StaticEnv
+
+logger = getLogger(__name__)
+
+
+def load_model(config):
+    """self_play.py:29-46: load the best model or build + save a fresh one."""
+    model = CChessModel(config)
+    rc = config.resource
+    cfg_path, w_path = rc.model_best_config_path, rc.model_best_weight_path
+    if not (os.path.exists(cfg_path) and os.path.exists(w_path) and model.load(cfg_path, w_path)):
+        model.build()
+        os.makedirs(os.path.dirname(w_path), exist_ok=True)
+        model.save(cfg_path, w_path)
+    return model, False
+
+
+def start(config, games_per_process=128, max_games=None):
+    """self_play.py:48-60."""
+    model, use_history = load_model(config)
+    worker = SelfPlayWorker(config, pipes=None, pid=0, use_history=use_history, model=model,
+                            concurrent_games=config.play.max_processes * games_per_process)
+    return worker.start(max_games=max_games)
+
+
+class SelfPlayWorker:
+    def __init__(self, config, pipes=None, pid=None, use_history=False, model=None, concurrent_games=None, lib=None,
+                 device=None, seed=0, rank=0):
+        if use_history:
+            raise NotImplementedError("28-plane history input is outside the built hot path (SURVEY.md §8f)")
+        self.config = config
+        self.cur_pipes = pipes          # unused: evaluation happens inside the engine
+        self.id = pid
+        self.pid = os.getpid()
+        self.buffer = []
+        self.use_history = use_history
+        self.lib = lib or get_lib()
+        pc, mc = config.play, config.model
+        self.model = model
+        if self.model is None:
+            self.model, _ = load_model(config)
+        g = concurrent_games or max(1, pc.max_processes)
+        self.engine = Engine(
+            self.lib, device, n_games=g, sims_per_move=pc.simulation_num_per_move, leaves_per_round=pc.search_threads,
+            virtual_loss=pc.virtual_loss, noise_mode=1, c_puct=pc.c_puct, noise_eps=pc.noise_eps,
+            dirichlet_alpha=pc.dirichlet_alpha, tau_decay_rate=pc.tau_decay_rate, resign_threshold=pc.resign_threshold,
+            enable_resign_rate=pc.enable_resign_rate, min_resign_turn=pc.min_resign_turn, max_game_length=pc.max_game_length,
+            max_nodes_per_game=max(4096, 24 * pc.simulation_num_per_move),
+            nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size, seed=seed, rank=rank)
+        self.engine.set_weights(self.model.torch_weights())
+        self.engine.reset()
+        self.pending = []               # finished games not yet handed out by start_game
+        self.games_written = 0
+        self.env = None
+
+    # ---- self_play.py:72-93
+    def start(self, max_games=None):
+        idx = 1
+        while max_games is None or idx <= max_games:
+            t0 = time()
+            value, turns, state, store = self.start_game(idx, None)
+            logger.debug(f"Process {self.pid}-{self.id} play game {idx} time={(time() - t0):.1f} sec, "
+                         f"turn={turns / 2}, winner = {value:.2f} (1 = red, -1 = black, 0 draw)")
+            if store:
+                idx += 1
+        return idx - 1
+
+    # ---- self_play.py:95-212: returns (v, turns, state, store) of the next finished game
+    def start_game(self, idx, search_tree):
+        while not self.pending:
+            self.engine.selfplay(target_games=1, max_moves=0)
+            self.pending.extend(self.engine.drain_records())
+        rec = self.pending.pop(0)
+        store = not (rec["flags"] & 4)
+        if store:
+            self.save_play_data(idx, record_to_play_data(rec))
+        state = self._final_state(rec["moves"])
+        return rec["value_red"], rec["n_plies"], state, store
+
+    def play_games(self, n):
+        """Batch entry point: run until n games finished, write their files, return the records."""
+        out = list(self.pending)
+        self.pending = []
+        while len(out) < n:
+            self.engine.selfplay(target_games=n - len(out), max_moves=0)
+            out.extend(self.engine.drain_records())
+        for i, rec in enumerate(out):
+            if not (rec["flags"] & 4):
+                self.save_play_data(self.games_written + 1, record_to_play_data(rec))
+        return out
+
+    # ---- self_play.py:214-227
+    def save_play_data(self, idx, data):
+        self.buffer += data
+        if not idx % self.config.play_data.nb_game_in_file == 0:
+            return
+        rc = self.config.resource
+        path = write_play_data(rc.play_data_dir, self.buffer, rc.play_data_filename_tmpl)
+        logger.info(f"Process {self.pid} save play data to {path}")
+        self.buffer = []
+        self.games_written += 1
+
+    def _final_state(self, moves):
+        if self.env is None:
+            self.env = StaticEnv(self.lib, self.engine.device)
+        boards = self.env.boards_from_states([INIT_STATE])
+        for m in moves:
+            boards, _ = self.env.step_batch(boards, self.env.moves_tensor([m]))
+        from .env import board_to_state
+        return board_to_state(boards[0].cpu().numpy())
+
+    def close(self):
+        self.engine.close()

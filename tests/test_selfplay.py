@@ -1,0 +1,60 @@
+"""On-device game loop (cz_play_move) vs the restated reference loop (worker/self_play.py:95-212), move for move."""
+import numpy as np
+import pytest
+
+from cczero_b200.engine import Engine
+from oracle import player as op
+from oracle import selfplay as osp
+from oracle import senv as osenv
+from tests.search_checks import eval_planes
+
+
+def run_device_games(lib, device, n_games, sims, k, seed, want, max_game_length, tau_decay):
+    eng = Engine(lib, device, n_games=n_games, sims_per_move=sims, leaves_per_round=k, noise_mode=1, noise_eps=0.0,
+                 c_puct=1.5, tau_decay_rate=tau_decay, max_game_length=max_game_length, resign_threshold=-0.6,
+                 enable_resign_rate=0.5, min_resign_turn=4, seed=seed, max_nodes_per_game=sims * 2 * max_game_length + 64)
+    eng.reset()
+    recs = []
+    for _ in range(4 * max_game_length * (want // n_games + 2)):
+        eng.search_external(eval_planes, None)
+        if eng.play_move():
+            recs += eng.drain_records()
+        if len(recs) >= want:
+            break
+    assert int(eng.counters()[4]) == 0          # no tree reset happened (pools were large enough)
+    eng.close()
+    return recs
+
+
+def check_selfplay(lib, device, n_games=3, sims=20, k=4, seed=11, want=6, max_game_length=25, tau_decay=0.9):
+    recs = run_device_games(lib, device, n_games, sims, k, seed, want, max_game_length, tau_decay)
+    assert len(recs) >= want
+    label_of = {m: i for i, m in enumerate(osenv.ActionLabelsRed)}
+    pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.0, dirichlet_alpha=0.2,
+                       tau_decay_rate=tau_decay, virtual_loss=3, resign_threshold=-0.6, min_resign_turn=4)
+    kinds = set()
+    for r in recs:
+        slot, started = r["game_index"] % n_games, r["game_index"] // n_games
+        ref = osp.play_game(pc, op.fake_evaluate_states, osp.DeviceDraws(seed, 0, slot, started, label_of),
+                            max_game_length=max_game_length, enable_resign_rate=0.5)
+        assert r["moves"] == ref["moves"], (r["game_index"], r["moves"], ref["moves"])
+        assert r["value_red"] == ref["value_red"] and r["n_plies"] == ref["turns"]
+        assert (r["flags"] & 3) == ref["flags"] and bool(r["flags"] & 4) == (not ref["store"])
+        kinds.add((r["flags"] & 3, r["value_red"]))
+    return kinds
+
+
+def test_emul_selfplay_matches_restated_game_loop(emul_lib):
+    kinds = check_selfplay(emul_lib, "cpu")
+    assert len(kinds) >= 1
+
+
+def test_play_data_format():
+    from cczero_b200.records import record_to_play_data
+    d = record_to_play_data({"moves": ["7747", "7062", "1219"], "value_red": -1})
+    assert d == [osenv.INIT_STATE, ["7747", -1], ["7062", 1], ["1219", -1]]
+
+
+@pytest.mark.gpu
+def test_cuda_selfplay_matches_restated_game_loop(cuda_lib):
+    check_selfplay(cuda_lib, "cuda", n_games=4, want=8)
