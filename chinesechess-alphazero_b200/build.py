@@ -84,7 +84,7 @@ def build_cuda(force=False, verbose=False):
             raise RuntimeError("nvcc failed")
         if verbose and out.strip():
             print(out)
-    _run([nvcc, "-shared", "-o", CUDA_LIB] + objs + ["-lcudart", "-ldl"])
+    _run([nvcc, "-shared", "-Xlinker", "-Bsymbolic", "-o", CUDA_LIB] + objs + ["-lcudart", "-ldl"])
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return CUDA_LIB
@@ -106,7 +106,7 @@ def build_emul(force=False):
         cmd += ["-x", "c++", s]
     for s in host + [emul]:
         cmd += ["-x", "c++", s]
-    cmd += ["-o", EMUL_LIB, "-lpthread"]
+    cmd += ["-Wl,-Bsymbolic", "-o", EMUL_LIB, "-lpthread"]
     _run(cmd)
     with open(stamp_file, "w") as f:
         f.write(stamp)

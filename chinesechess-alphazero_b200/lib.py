@@ -1,8 +1,8 @@
 """ctypes binding of libcczero_b200.so (include/cczero_b200.h).
 
 `get_lib()` loads the nvcc-built library and raises if it is missing — there is no CPU fallback in
-the product.  `CzLib(path)` is also used by the CPU test tier to bind tests/simt_emul/libcz_emul.so,
-which executes the same integer-kernel source under a SIMT emulator.
+the product.  `CzLib(path)` is also used by the CPU test tier to bind the emulator build of the same kernels,
+which executes the same integer-kernel source under a SIMT emulator (test tier only).
 """
 import ctypes as C
 import os
@@ -110,7 +110,7 @@ class CzLib:
                 f"native library missing: {path} — build it with "
                 "`python chinesechess-alphazero_b200/build.py cuda` (there is no CPU fallback)")
         self.path = path
-        self._dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self._dll = C.CDLL(path, mode=C.RTLD_LOCAL)
         self.missing = []
         for name, (res, args) in _SIGS.items():
             try:
