@@ -228,4 +228,178 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
   }
 }
 
+// =====================================================================================================
+// CTA-pair variant of the 3x3 convolution (cta_group::2).  ncu on the single-CTA kernel (profiles/r01_*):
+// tensor pipe 56-60 %, L2 40 %, DRAM 6 % -> bound by the 128 B/cycle shared-memory port: per k-block the
+// MMAs read 48 KB of operands while TMA writes another 48 KB.  Here two CTAs of a cluster compute two
+// adjacent M-tiles with ONE tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own A tile and only
+// HALF of the weight tile (N/2 rows), so TMA writes drop to 32 KB and MMA operand reads to 32 KB per
+// k-block per SM, and the smaller stage allows a 6-deep ring.
+// Leader = cluster rank 0: owns the full[] barriers (both CTAs' TMA loads complete_tx there), issues the
+// MMAs, and its tempty[] barriers collect the epilogue arrivals of both CTAs.  tcgen05.commit multicasts
+// to the empty[] / tfull[] barriers of both CTAs.
+constexpr int kStages2 = 6;
+
+template <int N_TILE>
+struct Cfg2 {
+  static constexpr int kBHalfBytes = (N_TILE / 2) * 128;
+  static constexpr int kStageBytes = kAStageBytes + kBHalfBytes;
+  static constexpr int kTmemCols = Cfg<N_TILE>::kTmemCols;
+  static constexpr int kSmemBytes = kStages2 * kStageBytes + 256 + 1024;
+  static_assert(N_TILE % 32 == 0 && N_TILE <= 256, "UMMA N constraint for M=256 and an even split of B");
+};
+
+template <int N_TILE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  using C = Cfg2<N_TILE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * C::kStageBytes);
+  uint64_t* full = bars;                  // [kStages2]  (used in the leader only)
+  uint64_t* empty = bars + kStages2;      // [kStages2]  per CTA, signalled by multicast commit
+  uint64_t* tfull = bars + 2 * kStages2;  // [2]         per CTA, signalled by multicast commit
+  uint64_t* tempty = tfull + 2;           // [2]         leader: 256 arrivals (both epilogues)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = umma::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmA);
+    umma::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages2; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 256); }
+    umma::fence_barrier_init();
+    umma::fence_proxy_async();
+  }
+  if (warp == 2) umma::tmem_alloc2<C::kTmemCols>(tmem_slot);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync_all();               // barriers of both CTAs are initialised before any remote arrive / TMA
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_kb = a.n_taps * a.k_chunks;
+  const int pairs = (a.m_tiles + 1) / 2;
+  const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one per CTA)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pair = cluster_id; pair < pairs; pair += n_clusters) {
+        const int m_tile = 2 * pair + (int)rank;
+        for (int tap = 0; tap < a.n_taps; ++tap) {
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
+            const uint32_t s = it % kStages2, ph = (it / kStages2) & 1;
+            umma::mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sA = smem + s * C::kStageBytes;
+            uint8_t* sB = sA + kAStageBytes;
+            if (leader) umma::mbar_expect_tx(&full[s], 2u * (a.a_bytes + (uint32_t)C::kBHalfBytes));
+            umma::tma2_load_3d(sA, &tmA, &full[s], kc * kBlockK, dx, m_tile * a.box_r + dy);
+            umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + (int)rank * (N_TILE / 2));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma::idesc_f16(256, N_TILE);
+      uint32_t it = 0, tcount = 0;
+      for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        umma::mbar_wait_cluster(&tempty[acc], aph ^ 1);
+        umma::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const uint32_t s = it % kStages2, ph = (it / kStages2) & 1;
+          umma::mbar_wait_cluster(&full[s], ph);
+          umma::tc_fence_after();
+          const uint32_t sA = umma::smem_u32(smem + s * C::kStageBytes);
+          const uint64_t da = umma::smem_desc_sw128(sA);
+          const uint64_t db = umma::smem_desc_sw128(sA + kAStageBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma::mma2_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma::mma2_commit_multicast(&empty[s]);
+        }
+        umma::mma2_commit_multicast(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (each CTA drains its own 128 rows)
+    const int q = warp - 4;
+    const int m = q * 32 + lane;
+    uint32_t tempty_remote[2];
+    tempty_remote[0] = umma::mapa_shared(&tempty[0], 0);
+    tempty_remote[1] = umma::mapa_shared(&tempty[1], 0);
+    uint32_t tcount = 0;
+    for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
+      const int m_tile = 2 * pair + (int)rank;
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      umma::mbar_wait(&tfull[acc], aph);
+      umma::tc_fence_after();
+      const int srow = m_tile * a.box_r + m / 9;
+      const bool valid = m < a.box_r * 9 && srow < a.rows;
+      const bool zero = (srow % 11) == 10;
+      const long long grow = (long long)m_tile * a.box_r * 9 + m;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t v[32];
+        umma::tmem_ld_32x32(t_row + c0, v);
+        if (valid) {
+          __half* o = reinterpret_cast<__half*>(a.out) + grow * a.ldo + c0;
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
+          uint4 rv[4];
+          if (a.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldo + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
+            float x[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
+                          __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
+                          __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
+                          __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
+            if (a.residual) {
+              const __half2* h = reinterpret_cast<const __half2*>(&rv[g]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 r2 = __half22float2(h[j]); x[2 * j] += r2.x; x[2 * j + 1] += r2.y; }
+            }
+            uint4 ov;
+            __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x0 = x[2 * j], x1 = x[2 * j + 1];
+              if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              if (zero) { x0 = 0.f; x1 = 0.f; }
+              oh[j] = __floats2half2_rn(x0, x1);
+            }
+            reinterpret_cast<uint4*>(o)[g] = ov;
+          }
+        }
+      }
+      umma::tc_fence_before();
+      umma::mbar_arrive_cluster(tempty_remote[acc]);
+    }
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync_all();               // nobody frees TMEM / exits while the peer may still touch this CTA
+  if (warp == 2) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc2<C::kTmemCols>(tmem_base);
+  }
+}
+
 }  // namespace igemm

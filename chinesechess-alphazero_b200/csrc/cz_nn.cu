@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -104,6 +105,37 @@ static int launch_igemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   igemm::k_igemm<N_TILE><<<grid, igemm::kThreads, C::kSmemBytes, st>>>(tmA, tmB, a);
   CZ_CUDA(cudaGetLastError());
   return 0;
+}
+
+// CTA-pair conv: B tensor map must have box rows = N_TILE / 2
+template <int N_TILE>
+static int launch_igemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const igemm::Args& a, cudaStream_t st) {
+  using C = igemm::Cfg2<N_TILE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CZ_CUDA(cudaFuncSetAttribute(igemm::k_igemm2<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int pairs = (a.m_tiles + 1) / 2;
+  if (pairs <= 0) return 0;
+  const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
+  igemm::k_igemm2<N_TILE><<<2 * clusters, igemm::kThreads, C::kSmemBytes, st>>>(tmA, tmB_half, a);
+  CZ_CUDA(cudaGetLastError());
+  return 0;
+}
+static int launch_igemm2(int n_tile, const CUtensorMap& tmA, const CUtensorMap& tmB_half, const igemm::Args& a, cudaStream_t st) {
+  switch (n_tile) {
+    case 64: return launch_igemm2_t<64>(tmA, tmB_half, a, st);
+    case 128: return launch_igemm2_t<128>(tmA, tmB_half, a, st);
+    case 192: return launch_igemm2_t<192>(tmA, tmB_half, a, st);
+    case 256: return launch_igemm2_t<256>(tmA, tmB_half, a, st);
+  }
+  return cz_fail(CZ_ERR_UNSUPPORTED, "igemm2: unsupported N tile %d", n_tile);
+}
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CZ_IGEMM_1CTA"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
 }
 
 static int launch_igemm(int n_tile, const CUtensorMap& tmA, const CUtensorMap& tmB, const igemm::Args& a, cudaStream_t st) {
@@ -361,6 +393,7 @@ struct NnRuntime {
   // tensor maps
   CUtensorMap map_x, map_t, map_y, map_pf, map_wpol;
   std::vector<CUtensorMap> map_w;
+  std::vector<CUtensorMap> map_w_half;   // box rows = C/2 for the CTA-pair kernel
   // optional CUDA-event timing of the residual-tower launches (bench.py roofline)
   bool profile;
   std::vector<cudaEvent_t> ev;        // pairs, recycled
@@ -432,8 +465,11 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   rc |= make_map_3d(&r->map_pf, r->pol_feat, kPolK, 1, (long long)max_batch + 128, 1, 128);
   rc |= make_map_2d(&r->map_wpol, r->w_pol, kPolK, kPolN, 256);
   r->map_w.resize(2 * blocks);
-  for (int i = 0; i < 2 * blocks; ++i)
+  r->map_w_half.resize(2 * blocks);
+  for (int i = 0; i < 2 * blocks; ++i) {
     rc |= make_map_2d(&r->map_w[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c);
+    rc |= make_map_2d(&r->map_w_half[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c / 2);
+  }
   if (rc) { delete r; return nullptr; }
   // separator rows and padding must start as zeros
   cudaMemsetAsync(r->x, 0, (size_t)max_batch * 11 * 9 * c * 2, r->stream);
@@ -576,9 +612,14 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
   for (int i = 0; i < r->blocks; ++i) {
     const size_t wsz = (size_t)c;
     igemm::Args a1 = conv_args(n, c, r->shift_conv + (size_t)(2 * i) * wsz, nullptr, r->t, 1);
-    if (launch_igemm(c, *mx, r->map_w[2 * i], a1, st)) return CZ_ERR_CUDA;
     igemm::Args a2 = conv_args(n, c, r->shift_conv + (size_t)(2 * i + 1) * wsz, x, y, 1);
-    if (launch_igemm(c, r->map_t, r->map_w[2 * i + 1], a2, st)) return CZ_ERR_CUDA;
+    if (use_pair_kernel()) {
+      if (launch_igemm2(c, *mx, r->map_w_half[2 * i], a1, st)) return CZ_ERR_CUDA;
+      if (launch_igemm2(c, r->map_t, r->map_w_half[2 * i + 1], a2, st)) return CZ_ERR_CUDA;
+    } else {
+      if (launch_igemm(c, *mx, r->map_w[2 * i], a1, st)) return CZ_ERR_CUDA;
+      if (launch_igemm(c, r->map_t, r->map_w[2 * i + 1], a2, st)) return CZ_ERR_CUDA;
+    }
     r->launches += 2;
     __half* tx = x; x = y; y = tx;
     CUtensorMap* tm = mx; mx = my; my = tm;
@@ -630,8 +671,12 @@ int cz_igemm_conv3x3(const void* act_in, const void* w, const float* bias, const
   if (c % 64 || c < 64 || c > 256 || n_boards <= 0) return cz_fail(CZ_ERR_ARG, "cz_igemm_conv3x3: bad shape");
   CUtensorMap ma, mb;
   if (make_map_3d(&ma, act_in, c, 9, (long long)n_boards * 11, 9, 14)) return CZ_ERR_CUDA;
-  if (make_map_2d(&mb, w, c, 9LL * c, c)) return CZ_ERR_CUDA;
   igemm::Args a = conv_args(n_boards, c, bias, (const __half*)residual, (__half*)act_out, relu);
+  if (use_pair_kernel()) {
+    if (make_map_2d(&mb, w, c, 9LL * c, c / 2)) return CZ_ERR_CUDA;
+    return launch_igemm2(c, ma, mb, a, (cudaStream_t)stream);
+  }
+  if (make_map_2d(&mb, w, c, 9LL * c, c)) return CZ_ERR_CUDA;
   return launch_igemm(c, ma, mb, a, (cudaStream_t)stream);
 }
 
