@@ -31,6 +31,10 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes per launch of the dominant kernel measured once with ncu (None where no capture exists)
+NCU_TRAFFIC = {("c3", 1024, 8): 7.83e8}
+
+
 def net_flops(filters, blocks):
     return 2 * 90 * (350 * filters + blocks * 18 * filters * filters + 6 * filters) + 2 * (360 * 2086 + 180 * 256 + 256)
 
@@ -278,7 +282,11 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "igemm::k_igemm<C> (3x3 residual conv, tcgen05)",
+                         "traffic": NCU_TRAFFIC.get((args.workload, games, K)),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of a full-batch "
+                                           "launch (profiles/r01b_igemm2_cta_pair_ncu_raw.csv); algorithmic bytes/launch = activations in + out "
+                                           "(+ skip) = 2 x 415 MB at 8192 boards x 256 ch",
+                         "kernel": "igemm::k_igemm2<C> (3x3 residual conv, tcgen05 cta_group::2)",
                          "launches": int(conv_launches), "avg_launch_ms": conv_ms / max(1.0, conv_launches / world),
                          "peak_source": peak_src, "share_of_step": conv_ms / ms},
             "cpu_baseline": cpu,

@@ -174,37 +174,54 @@ static igemm::Args dense_args(int m, int n_valid, int n_pad, int k_pad, int n_ti
 __device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 8) ? c - 2 : c - 1); }
 
 // 5x5 "same" input convolution + BN + ReLU from packed boards (model.py:34-41, static_env.py:137-156 fused).
-// grid = batch, block = C threads (one output channel each).  w: HWIO [5][5][14][C] fp16 (BN scale folded).
+// The 14 input planes are one-hot, so an output pixel is the sum of <= 25 weight rows w[tap][plane(piece on the
+// tapped square)][:].  Phase 1: 90 threads list the occupied taps of their pixel (row index = tap*14 + plane);
+// phase 2: every thread owns two adjacent output channels and walks the lists (half2 loads, fp32 accumulate).
+// grid = batch, block = max(96, C/2) threads.  w: HWIO [5][5][14][C] fp16 (BN scale folded).
 __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
                              const float* __restrict__ shift, __half* __restrict__ out, int c_out) {
   __shared__ int8_t pl[90];
-  const int b = blockIdx.x, c = threadIdx.x;
-  if (c < 90) {
-    const int r = c / 9, col = c % 9;
-    pl[c] = (int8_t)plane_of(boards[(size_t)b * CZ_BOARD_STRIDE + (9 - r) * 9 + col]);
+  __shared__ uint16_t rows[90][26];
+  __shared__ uint8_t cnt[90];
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (t < 90) {
+    const int r = t / 9, col = t % 9;
+    pl[t] = (int8_t)plane_of(boards[(size_t)b * CZ_BOARD_STRIDE + (9 - r) * 9 + col]);
   }
   __syncthreads();
-  if (c >= c_out) return;
-  const float sh = shift[c];
-  __half* o = out + (size_t)b * 11 * 9 * c_out;
-  for (int pix = 0; pix < 90; ++pix) {
-    const int r = pix / 9, col = pix % 9;
-    float acc = sh;
-#pragma unroll
+  if (t < 90) {
+    const int r = t / 9, col = t % 9;
+    int n = 0;
     for (int kh = 0; kh < 5; ++kh) {
       const int rr = r + kh - 2;
       if (rr < 0 || rr > 9) continue;
-#pragma unroll
       for (int kw = 0; kw < 5; ++kw) {
         const int cc = col + kw - 2;
         if (cc < 0 || cc > 8) continue;
         const int p = pl[rr * 9 + cc];
-        if (p >= 0) acc += __half2float(__ldg(w + ((size_t)((kh * 5 + kw) * 14 + p)) * c_out + c));
+        if (p >= 0) rows[t][n++] = (uint16_t)((kh * 5 + kw) * 14 + p);
       }
     }
-    o[(size_t)pix * c_out + c] = __float2half_rn(fmaxf(acc, 0.f));
+    cnt[t] = (uint8_t)n;
   }
-  for (int col = 0; col < 9; ++col) o[(size_t)(90 + col) * c_out + c] = __float2half_rn(0.f);   // separator row
+  __syncthreads();
+  const int c = 2 * t;
+  if (c >= c_out) return;
+  const float2 sh = *reinterpret_cast<const float2*>(shift + c);
+  __half* o = out + (size_t)b * 11 * 9 * c_out;
+  const __half2* w2 = reinterpret_cast<const __half2*>(w + c);
+  const int stride2 = c_out / 2;
+  for (int pix = 0; pix < 90; ++pix) {
+    float a0 = sh.x, a1 = sh.y;
+    const int n = cnt[pix];
+    for (int k = 0; k < n; ++k) {
+      const float2 v = __half22float2(__ldg(w2 + (size_t)rows[pix][k] * stride2));
+      a0 += v.x; a1 += v.y;
+    }
+    *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+  }
+  for (int col = 0; col < 9; ++col)
+    *reinterpret_cast<__half2*>(o + (size_t)(90 + col) * c_out + c) = __floats2half2_rn(0.f, 0.f);   // separator row
 }
 
 // one-hot planes [B][14][10][9] f32 -> packed boards (inverse of state_to_planes)
@@ -225,8 +242,10 @@ __global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __
 
 // Heads (model.py:47-63): 1x1 conv to 4 policy + 2 value channels, BN, ReLU; policy features to the GEMM
 // operand [B][384] (index c*90 + pix, Keras Flatten of channels_first); value: Dense(H)+ReLU, Dense(1)+tanh.
-// grid = batch, block = 256.
-__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, int c_in,
+// A block handles kHeadPos positions so the 180 x H value weights are read once per group.
+// Phase 1: warp per pixel, lane owns 8 channels whose 6 x 8 folded weights sit in registers.
+constexpr int kHeadPos = 4;
+__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, int c_in, int n_pos,
                                                 const float* __restrict__ w6,      // [6][c_in], BN scale folded
                                                 const float* __restrict__ shift6,  // [6]
                                                 const float* __restrict__ wv1,     // [180][H]
@@ -234,52 +253,76 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, i
                                                 const float* __restrict__ wv2,     // [H]
                                                 const float* __restrict__ bv2,     // [1]
                                                 int hidden, __half* __restrict__ pol_feat, float* __restrict__ value) {
-  __shared__ float feat[6][90];
-  __shared__ float hid[256];
-  __shared__ float red[8];
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __half* a = act + (size_t)b * 11 * 9 * c_in;
-  for (int pix = warp; pix < 90; pix += 8) {
+  __shared__ float feat[kHeadPos][6][90];
+  __shared__ float red[kHeadPos][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * kHeadPos;
+  const int npos = n_pos - b0 < kHeadPos ? n_pos - b0 : kHeadPos;
+  const int cbase = lane * 8;
+  const bool lane_on = cbase < c_in;
+  float wr[6][8];
+#pragma unroll
+  for (int o = 0; o < 6; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[o][j] = lane_on ? __ldg(w6 + (size_t)o * c_in + cbase + j) : 0.f;
+  float sh6[6];
+#pragma unroll
+  for (int o = 0; o < 6; ++o) sh6[o] = shift6[o];
+  for (int item = warp; item < npos * 90; item += 8) {
+    const int p = item / 90, pix = item % 90;
+    const __half* a = act + ((size_t)(b0 + p) * 11 * 9 + pix) * c_in;
     float s[6] = {0, 0, 0, 0, 0, 0};
-    for (int c = lane * 8; c < c_in; c += 256) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + (size_t)pix * c_in + c));
+    if (lane_on) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + cbase));
       const __half2* h = reinterpret_cast<const __half2*>(&v);
       float x[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
 #pragma unroll
-      for (int o = 0; o < 6; ++o) {
-        const float* wr = w6 + (size_t)o * c_in + c;
+      for (int o = 0; o < 6; ++o)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[o] += x[j] * __ldg(wr + j);
-      }
+        for (int j = 0; j < 8; ++j) s[o] += x[j] * wr[o][j];
     }
 #pragma unroll
     for (int o = 0; o < 6; ++o) {
       float v = s[o];
       for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-      if (lane == 0) feat[o][pix] = fmaxf(v + shift6[o], 0.f);
+      if (lane == 0) feat[p][o][pix] = fmaxf(v + sh6[o], 0.f);
     }
   }
   __syncthreads();
-  for (int i = tid; i < kPolK; i += 256)
-    pol_feat[(size_t)b * kPolK + i] = __float2half_rn(i < 360 ? feat[i / 90][i % 90] : 0.f);
-  float h = 0.f;
-  if (tid < hidden) {
-    float acc = bv1[tid];
-    for (int i = 0; i < 180; ++i) acc += feat[4 + i / 90][i % 90] * __ldg(wv1 + (size_t)i * hidden + tid);
-    h = fmaxf(acc, 0.f) * wv2[tid];
+  for (int i = tid; i < npos * kPolK; i += 256) {
+    const int p = i / kPolK, k = i % kPolK;
+    pol_feat[(size_t)(b0 + p) * kPolK + k] = __float2half_rn(k < 360 ? feat[p][k / 90][k % 90] : 0.f);
   }
-  hid[tid] = h;
+  float h[kHeadPos];
+#pragma unroll
+  for (int p = 0; p < kHeadPos; ++p) h[p] = 0.f;
+  if (tid < hidden) {
+    float acc[kHeadPos];
+    const float bb = bv1[tid];
+#pragma unroll
+    for (int p = 0; p < kHeadPos; ++p) acc[p] = bb;
+    for (int i = 0; i < 180; ++i) {
+      const float wv = __ldg(wv1 + (size_t)i * hidden + tid);
+#pragma unroll
+      for (int p = 0; p < kHeadPos; ++p) acc[p] += feat[p][4 + i / 90][i % 90] * wv;
+    }
+    const float w2 = wv2[tid];
+#pragma unroll
+    for (int p = 0; p < kHeadPos; ++p) h[p] = fmaxf(acc[p], 0.f) * w2;
+  }
+#pragma unroll
+  for (int p = 0; p < kHeadPos; ++p) {
+    float v = h[p];
+    for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) red[p][warp] = v;
+  }
   __syncthreads();
-  float v = hid[tid];
-  for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  if (tid == 0) {
-    float s = bv2[0];
-    for (int i = 0; i < 8; ++i) s += red[i];
-    value[b] = tanhf(s);
+  if (tid < npos) {
+    float sum = bv2[0];
+    for (int i = 0; i < 8; ++i) sum += red[tid][i];
+    value[b0 + tid] = tanhf(sum);
   }
 }
 
@@ -596,7 +639,7 @@ int nn_set_weights(NnRuntime* r, const cz_tensor_desc* descs, int n) {
 static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* policy, float* value) {
   const int c = r->filters;
   cudaStream_t st = r->stream;
-  k_conv_first<<<n, c < 96 ? 96 : c, 0, st>>>(boards, r->w_first, r->shift_first, r->x, c);
+  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, c);
   r->launches++;
   __half *x = r->x, *y = r->y;
   CUtensorMap *mx = &r->map_x, *my = &r->map_y;
@@ -625,7 +668,7 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     CUtensorMap* tm = mx; mx = my; my = tm;
   }
   if (pe != (size_t)-1) cudaEventRecord(r->ev[pe + 1], st);
-  k_heads<<<n, 256, 0, st>>>(x, c, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
+  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, st>>>(x, c, n, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
   igemm::Args ap = dense_args(n, kLabels, kPolN, kPolK, 256, r->b_pol, r->logits, kPolN);
   if (launch_igemm(256, r->map_pf, r->map_wpol, ap, st)) return CZ_ERR_CUDA;
   k_softmax<<<n, 256, 0, st>>>(r->logits, kPolN, policy);

@@ -131,6 +131,10 @@ CZ_KERNEL(k_set_roots)(EngineDev E, const uint8_t* boards) {
   for (int k = czs::lane(); k < BOARD_STRIDE; k += 32)
     E.root_board[(size_t)g * BOARD_STRIDE + k] = k < NSQ ? boards[(size_t)g * BOARD_STRIDE + k] : (uint8_t)0;
 }
+// test hook: draws of the on-device root-noise sampler (noise_mode 1)
+CZ_KERNEL(k_noise_sample)(EngineDev E, int game, int n_moves, int count, double* out) {
+  for (int i = czs::block_idx() * 32 + czs::lane(); i < count; i += 32 * 64) out[i] = dirichlet_first(E, game, (uint32_t)i, n_moves);
+}
 CZ_KERNEL(k_set_opts)(EngineDev E, const uint16_t* no_act, const uint8_t* inc, const uint8_t* act) {
   const int g = my_game();
   if (g >= E.n_games) return;
@@ -523,6 +527,12 @@ int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch,
   if (!e || !boards_dev || !policy_dev || !value_dev || batch < 0) return cz_fail(CZ_ERR_ARG, "cz_nn_forward_boards: bad argument");
   return cznn::nn_forward_boards(e->nn, boards_dev, batch, policy_dev, value_dev);
 #endif
+}
+
+int cz_noise_sample(cz_engine* e, int game, int n_moves, int count, double* out_dev) {
+  if (!e || !out_dev || count < 0 || n_moves < 1) return cz_fail(CZ_ERR_ARG, "cz_noise_sample: bad argument");
+  CZ_LAUNCH(k_noise_sample, 64, 1, 0, e->stream, e->d, game, n_moves, count, out_dev);
+  return launch_ok(e, "cz_noise_sample");
 }
 
 int cz_nn_profile(cz_engine* e, int enable, double* ms, uint64_t* launches, double* flops) {

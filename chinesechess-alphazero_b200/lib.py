@@ -94,6 +94,7 @@ _SIGS = {
     "cz_nn_forward_boards": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "cz_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "cz_nn_profile": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "cz_noise_sample": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "cz_igemm_conv3x3": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "cz_igemm_dense": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }

@@ -226,6 +226,9 @@ int cz_launch_count(cz_engine* e, uint64_t* n);
  * = [tap kh*3+kw][c_out][c_in]; bias f32 [c]. */
 int cz_igemm_conv3x3(const void* act_in_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
                      void* act_out_dev, int n_boards, int c, int relu, void* stream);
+/* `count` draws of the on-device root-noise sampler (noise_mode 1): the first component of
+ * Dirichlet(alpha * 1_n_moves), i.e. what np.random.dirichlet(alpha*ones(n))[0] (player.py:304) is distributed as. */
+int cz_noise_sample(cz_engine* e, int game, int n_moves, int count, double* out_dev);
 /* out[m][n] = sum_k a[m][k] * w[n][k] + bias[n]; a fp16 [m][k], w fp16 [n_pad][k], out f32 [m][ldo]. */
 int cz_igemm_dense(const void* a_dev, const void* w_dev, const float* bias_dev, float* out_dev, int m, int n_valid,
                    int n_pad, int k, int n_tile, int ldo, void* stream);

@@ -1,0 +1,98 @@
+"""Reference-facing drop-ins on the GPU: CChessModel / CChessModelAPI wire protocol, CChessPlayer with the built-in
+network, SelfPlayWorker play-data files."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as om
+from oracle import player as op
+from oracle import senv as osenv
+
+pytestmark = pytest.mark.gpu
+
+
+def _config(tmp, filters=64, blocks=2, sims=32, k=4):
+    play = SimpleNamespace(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.25, dirichlet_alpha=0.2,
+                           tau_decay_rate=0.98, virtual_loss=3, resign_threshold=-0.92, min_resign_turn=20, max_game_length=12,
+                           enable_resign_rate=0.5, max_processes=2)
+    model = SimpleNamespace(cnn_filter_num=filters, res_layer_num=blocks, value_fc_size=256, cnn_first_filter_size=5,
+                            cnn_filter_size=3, input_depth=14, l2_reg=1e-4)
+    res = SimpleNamespace(play_data_dir=os.path.join(tmp, "play_data"), play_data_filename_tmpl="play_%s.json",
+                          model_best_config_path=os.path.join(tmp, "model", "model_best_config.json"),
+                          model_best_weight_path=os.path.join(tmp, "model", "model_best_weight.npz"))
+    return SimpleNamespace(play=play, model=model, resource=res, opts=SimpleNamespace(evaluate=False),
+                           play_data=SimpleNamespace(nb_game_in_file=1))
+
+
+def test_model_api_serves_reference_wire_protocol(cuda_lib, tmp_path):
+    """An oracle (reference-algorithm) player talks to CChessModelAPI over a Pipe exactly like player.py:108-143."""
+    from cczero_b200.model import CChessModel
+    cfg = _config(str(tmp_path))
+    model = CChessModel(cfg).build(seed=4)
+    model.save(cfg.resource.model_best_config_path, cfg.resource.model_best_weight_path)
+    m2 = CChessModel(cfg)
+    assert m2.load(cfg.resource.model_best_config_path, cfg.resource.model_best_weight_path)
+    assert m2.digest == model.digest and set(m2.weights) == set(model.weights)
+    pipe = m2.get_pipes()
+    states = [osenv.INIT_STATE, osenv.step(osenv.INIT_STATE, "1219")]
+    pipe.send([osenv.state_to_planes(s) for s in states])
+    rets = pipe.recv()
+    assert len(rets) == 2 and rets[0][0].shape == (2086,) and isinstance(rets[0][1], float)
+    ref_p, ref_v = om.forward(model.weights, np.stack([osenv.state_to_planes(s) for s in states]), 2)
+    for (p, v), rp, rv in zip(rets, ref_p, ref_v):
+        assert np.abs(p - rp).max() < 1e-3 and abs(v - rv) < 1e-3
+
+    # a reference-algorithm player searching through that pipe
+    def evaluate(ss):
+        pipe.send([osenv.state_to_planes(s) for s in ss])
+        return pipe.recv()
+    pl = op.OraclePlayer(op.PlayConfig(simulation_num_per_move=40, search_threads=4), evaluate)
+    np.random.seed(0)
+    a, pol = pl.action(osenv.INIT_STATE, 0)
+    assert a in osenv.get_legal_moves(osenv.INIT_STATE) and abs(sum(pol) - 1) < 1e-9
+    m2.close_pipes()
+
+
+def test_player_with_builtin_network(cuda_lib, tmp_path):
+    from cczero_b200.model import CChessModel
+    from cczero_b200.player import CChessPlayer
+    cfg = _config(str(tmp_path), sims=48, k=4)
+    model = CChessModel(cfg).build(seed=2)
+    np.random.seed(1)
+    player = CChessPlayer(cfg, pipes=None, weights=model.torch_weights())
+    state, turns = osenv.INIT_STATE, 0
+    for _ in range(3):
+        a, pol = player.action(state, turns)
+        assert a in osenv.get_legal_moves(state)
+        root = player.engine.root(0)
+        assert root["sum_n"] >= 48 and sum(root["n"]) >= 40
+        state = osenv.step(state, a)
+        turns += 1
+    player.close()
+
+
+def test_selfplay_worker_writes_reference_records(cuda_lib, tmp_path):
+    from cczero_b200.self_play import SelfPlayWorker
+    cfg = _config(str(tmp_path), sims=16, k=4)
+    w = SelfPlayWorker(cfg, concurrent_games=8, seed=3)
+    v, turns, state, store = w.start_game(1, None)
+    assert v in (-1, 0, 1) and turns > 0
+    recs = w.play_games(4)
+    assert len(recs) >= 4
+    files = sorted(os.listdir(cfg.resource.play_data_dir)) if os.path.isdir(cfg.resource.play_data_dir) else []
+    stored = [r for r in recs if not (r["flags"] & 4)]
+    assert len(files) >= min(1, len(stored))
+    for fn in files:
+        data = json.load(open(os.path.join(cfg.resource.play_data_dir, fn)))
+        assert data[0] == osenv.INIT_STATE
+        s = data[0]
+        val = data[1][1]
+        for i, (m, vv) in enumerate(data[1:]):
+            assert m in osenv.get_legal_moves(s), (fn, i, m)
+            assert vv == val * (-1) ** i
+            s = osenv.step(s, m)
+    w.close()
