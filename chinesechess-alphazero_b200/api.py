@@ -8,6 +8,7 @@ what is ready, runs ONE batched forward (`cz_nn_forward`: tensor-core pipeline) 
 Weight hot-reload: the reference re-reads the best-model file every 600 s when its digest changed
 (api.py:42-44,76-88); `try_reload_model()` does the same against the `.npz` path in config.resource.
 """
+from logging import getLogger
 from multiprocessing import Pipe, connection
 from threading import Thread
 from time import time
@@ -17,6 +18,8 @@ import torch
 
 from .engine import Engine
 from .lib import get_lib
+
+logger = getLogger(__name__)
 
 
 class CChessModelAPI:
@@ -32,6 +35,8 @@ class CChessModelAPI:
         self.engine = None
         self.positions = 0
         self.batches = 0
+        self.last_error = None
+        self._last_check = time()
 
     def _ensure_engine(self):
         if self.engine is None:
@@ -55,40 +60,46 @@ class CChessModelAPI:
         return you
 
     def predict_batch_worker(self):
-        if self.engine.lib.is_cuda:
+        if self.engine.lib.is_cuda and self.engine.device.index is not None:
             torch.cuda.set_device(self.engine.device)
-        last_check = time()
         while not self.done:
-            if last_check + 600 < time() and self.need_reload:
-                self.try_reload_model()
-                last_check = time()
-            ready = connection.wait(self.pipes, timeout=0.001)
-            if not ready:
-                continue
-            data, result_pipes, data_len = [], [], []
-            for pipe in ready:
-                while pipe.poll():
-                    try:
-                        tmp = pipe.recv()
-                    except EOFError:
-                        pipe.close()
-                        if pipe in self.pipes:
-                            self.pipes.remove(pipe)
-                        break
-                    data.extend(tmp)
-                    data_len.append(len(tmp))
-                    result_pipes.append(pipe)
-            if not data:
-                continue
-            planes = torch.from_numpy(np.asarray(data, dtype=np.float32)).to(self.engine.device)
-            pol, val = self.engine.nn_forward_planes(planes)
-            policy_ary, value_ary = pol.cpu().numpy(), val.cpu().numpy()
-            self.positions += len(data)
-            self.batches += 1
-            k = 0
-            for pipe, n in zip(result_pipes, data_len):
-                pipe.send([(policy_ary[k + i], float(value_ary[k + i])) for i in range(n)])
-                k += n
+            try:
+                self._serve_once()
+            except Exception as e:           # keep serving: a dead prediction thread would block every player
+                self.last_error = e
+                logger.error(f"prediction worker: {e!r}")
+
+    def _serve_once(self):
+        if self._last_check + 600 < time() and self.need_reload:
+            self.try_reload_model()
+            self._last_check = time()
+        ready = connection.wait(self.pipes, timeout=0.001)
+        if not ready:
+            return
+        data, result_pipes, data_len = [], [], []
+        for pipe in ready:
+            while pipe.poll():
+                try:
+                    tmp = pipe.recv()
+                except EOFError:
+                    pipe.close()
+                    if pipe in self.pipes:
+                        self.pipes.remove(pipe)
+                    break
+                data.extend(tmp)
+                data_len.append(len(tmp))
+                result_pipes.append(pipe)
+        if not data:
+            return
+        planes = torch.from_numpy(np.asarray(data, dtype=np.float32)).to(self.engine.device)
+        pol, val = self.engine.nn_forward_planes(planes)
+        policy_ary, value_ary = pol.cpu().numpy(), val.cpu().numpy()
+        self.positions += len(data)
+        self.batches += 1
+        k = 0
+        for pipe, n in zip(result_pipes, data_len):
+            pipe.send([(policy_ary[k + i], float(value_ary[k + i])) for i in range(n)])
+            k += n
 
     def try_reload_model(self, config_file=None):
         rc = getattr(self.config, "resource", None)

@@ -40,6 +40,7 @@ def test_model_api_serves_reference_wire_protocol(cuda_lib, tmp_path):
     pipe = m2.get_pipes()
     states = [osenv.INIT_STATE, osenv.step(osenv.INIT_STATE, "1219")]
     pipe.send([osenv.state_to_planes(s) for s in states])
+    assert pipe.poll(60), f"prediction worker did not answer: {m2.api.last_error!r}"
     rets = pipe.recv()
     assert len(rets) == 2 and rets[0][0].shape == (2086,) and isinstance(rets[0][1], float)
     ref_p, ref_v = om.forward(model.weights, np.stack([osenv.state_to_planes(s) for s in states]), 2)
@@ -49,6 +50,7 @@ def test_model_api_serves_reference_wire_protocol(cuda_lib, tmp_path):
     # a reference-algorithm player searching through that pipe
     def evaluate(ss):
         pipe.send([osenv.state_to_planes(s) for s in ss])
+        assert pipe.poll(60), f"prediction worker did not answer: {m2.api.last_error!r}"
         return pipe.recv()
     pl = op.OraclePlayer(op.PlayConfig(simulation_num_per_move=40, search_threads=4), evaluate)
     np.random.seed(0)
