@@ -39,7 +39,7 @@ struct Args {
   int n_total;       // B-operand rows per tap (C_out padded to N_TILE multiple)
   int n_valid;       // real number of output columns
   int ldo;           // output leading dimension in elements
-  int conv;          // 1: strip layout, separator rows forced to zero
+  int conv;          // 1: strip layout, separator rows forced to zero; 2: dense [B*90][C] pixels fed by im2col TMA
   int relu;
   int out_f32;       // 1: float output (GEMM logits), 0: fp16
   const float* bias; // [n_total] or null
@@ -293,6 +293,8 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       uint32_t it = 0;
       for (int pair = cluster_id; pair < pairs; pair += n_clusters) {
         const int m_tile = 2 * pair + (int)rank;
+        // dense mode: first output pixel of this tile as (image, row, column); im2col walks on from there
+        const int pix0 = m_tile * kTileM, img0 = pix0 / 90, row0 = (pix0 % 90) / 9, col0 = pix0 % 9;
         for (int tap = 0; tap < a.n_taps; ++tap) {
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
           for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
@@ -301,7 +303,10 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             uint8_t* sA = smem + s * C::kStageBytes;
             uint8_t* sB = sA + kAStageBytes;
             if (leader) umma::mbar_expect_tx(&full[s], 2u * (a.a_bytes + (uint32_t)C::kBHalfBytes));
-            umma::tma2_load_3d(sA, &tmA, &full[s], kc * kBlockK, dx, m_tile * a.box_r + dy);
+            if (a.conv == 2)
+              umma::tma2_load_im2col_4d(sA, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1));
+            else
+              umma::tma2_load_3d(sA, &tmA, &full[s], kc * kBlockK, dx, m_tile * a.box_r + dy);
             umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + (int)rank * (N_TILE / 2));
           }
         }
@@ -345,10 +350,18 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       umma::mbar_wait(&tfull[acc], aph);
       umma::tc_fence_after();
-      const int srow = m_tile * a.box_r + m / 9;
-      const bool valid = m < a.box_r * 9 && srow < a.rows;
-      const bool zero = (srow % 11) == 10;
-      const long long grow = (long long)m_tile * a.box_r * 9 + m;
+      bool valid, zero;
+      long long grow;
+      if (a.conv == 2) {                                     // dense pixels, 128 per tile
+        grow = (long long)m_tile * kTileM + m;
+        valid = grow < a.rows;
+        zero = false;
+      } else {
+        const int srow = m_tile * a.box_r + m / 9;
+        valid = m < a.box_r * 9 && srow < a.rows;
+        zero = (srow % 11) == 10;
+        grow = (long long)m_tile * a.box_r * 9 + m;
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE;
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {

@@ -41,7 +41,11 @@ constexpr float kBnEps = 1e-3f;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
 
 static int load_encode() {
   if (g_encode) return 0;
@@ -50,6 +54,26 @@ static int load_encode() {
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || !fn) return cz_fail(CZ_ERR_CUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
   g_encode = (EncodeTiledFn)fn;
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+  if (e == cudaSuccess && fn) g_encode_im2col = (EncodeIm2colFn)fn;
+  return 0;
+}
+
+// fp16 NHWC activations [n][10][9][c] read in im2col mode for a 3x3 "same" convolution: the bounding box of base pixels is
+// [-1, dim-2] in w and h (lower corner = -pad, upper corner = pad - (filter-1)), 64 channels x 128 output pixels per load;
+// taps outside the image are zero-filled by the TMA unit, and the 128-pixel column walks across rows and images.
+static int make_map_im2col(CUtensorMap* m, const void* base, int c, long long n_images) {
+  if (load_encode()) return CZ_ERR_CUDA;
+  if (!g_encode_im2col) return cz_fail(CZ_ERR_UNSUPPORTED, "cuTensorMapEncodeIm2col not available");
+  cuuint64_t dims[4] = {(cuuint64_t)c, 9, 10, (cuuint64_t)n_images};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * 9, (cuuint64_t)c * 2 * 90};
+  int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper, 64, 128,
+                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cz_fail(CZ_ERR_CUDA, "cuTensorMapEncodeIm2col failed: %d", (int)r);
   return 0;
 }
 
@@ -132,6 +156,11 @@ static int launch_igemm2(int n_tile, const CUtensorMap& tmA, const CUtensorMap& 
   }
   return cz_fail(CZ_ERR_UNSUPPORTED, "igemm2: unsupported N tile %d", n_tile);
 }
+static bool use_im2col() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CZ_CONV_STRIP"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
 static bool use_pair_kernel() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CZ_IGEMM_1CTA"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -158,6 +187,13 @@ static igemm::Args conv_args(int n_boards, int c, const float* bias, const __hal
   return a;
 }
 
+// dense pixel layout [n_boards*90][c] + im2col TMA (CTA-pair kernel only)
+static igemm::Args conv_args_dense(int n_boards, int c, const float* bias, const __half* residual, __half* out, int relu) {
+  igemm::Args a = conv_args(n_boards, c, bias, residual, out, relu);
+  a.conv = 2; a.rows = n_boards * 90; a.m_tiles = (a.rows + 127) / 128; a.a_bytes = 128 * 128;
+  return a;
+}
+
 static igemm::Args dense_args(int m, int n_valid, int n_pad, int k_pad, int n_tile, const float* bias, float* out, int ldo) {
   igemm::Args a;
   memset(&a, 0, sizeof(a));
@@ -179,7 +215,7 @@ __device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 
 // phase 2: every thread owns two adjacent output channels and walks the lists (half2 loads, fp32 accumulate).
 // grid = batch, block = max(96, C/2) threads.  w: HWIO [5][5][14][C] fp16 (BN scale folded).
 __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
-                             const float* __restrict__ shift, __half* __restrict__ out, int c_out) {
+                             const float* __restrict__ shift, __half* __restrict__ out, int c_out, int board_pixels) {
   __shared__ int8_t pl[90];
   __shared__ uint16_t rows[90][26];
   __shared__ uint8_t cnt[90];
@@ -208,7 +244,7 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
   const int c = 2 * t;
   if (c >= c_out) return;
   const float2 sh = *reinterpret_cast<const float2*>(shift + c);
-  __half* o = out + (size_t)b * 11 * 9 * c_out;
+  __half* o = out + (size_t)b * board_pixels * c_out;
   const __half2* w2 = reinterpret_cast<const __half2*>(w + c);
   const int stride2 = c_out / 2;
   for (int pix = 0; pix < 90; ++pix) {
@@ -220,8 +256,8 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
     }
     *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
   }
-  for (int col = 0; col < 9; ++col)
-    *reinterpret_cast<__half2*>(o + (size_t)(90 + col) * c_out + c) = __floats2half2_rn(0.f, 0.f);   // separator row
+  for (int col = 90; col < board_pixels; ++col)
+    *reinterpret_cast<__half2*>(o + (size_t)col * c_out + c) = __floats2half2_rn(0.f, 0.f);          // separator row (strip layout)
 }
 
 // one-hot planes [B][14][10][9] f32 -> packed boards (inverse of state_to_planes)
@@ -245,7 +281,7 @@ __global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __
 // A block handles kHeadPos positions so the 180 x H value weights are read once per group.
 // Phase 1: warp per pixel, lane owns 8 channels whose 6 x 8 folded weights sit in registers.
 constexpr int kHeadPos = 4;
-__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, int c_in, int n_pos,
+__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, int c_in, int n_pos, int board_pixels,
                                                 const float* __restrict__ w6,      // [6][c_in], BN scale folded
                                                 const float* __restrict__ shift6,  // [6]
                                                 const float* __restrict__ wv1,     // [180][H]
@@ -270,7 +306,7 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, i
   for (int o = 0; o < 6; ++o) sh6[o] = shift6[o];
   for (int item = warp; item < npos * 90; item += 8) {
     const int p = item / 90, pix = item % 90;
-    const __half* a = act + ((size_t)(b0 + p) * 11 * 9 + pix) * c_in;
+    const __half* a = act + ((size_t)(b0 + p) * board_pixels + pix) * c_in;
     float s[6] = {0, 0, 0, 0, 0, 0};
     if (lane_on) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + cbase));
@@ -437,6 +473,8 @@ struct NnRuntime {
   CUtensorMap map_x, map_t, map_y, map_pf, map_wpol;
   std::vector<CUtensorMap> map_w;
   std::vector<CUtensorMap> map_w_half;   // box rows = C/2 for the CTA-pair kernel
+  int board_pixels;                      // 99 = strip layout (separator row per board), 90 = dense + im2col TMA
+  CUtensorMap imap_x, imap_t, imap_y;    // im2col maps of the three activation buffers (dense layout)
   // optional CUDA-event timing of the residual-tower launches (bench.py roofline)
   bool profile;
   std::vector<cudaEvent_t> ev;        // pairs, recycled
@@ -502,6 +540,12 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   const int c = filters;
   const long long rows = (long long)max_batch * 11;
   int rc = 0;
+  r->board_pixels = (use_im2col() && use_pair_kernel()) ? 90 : 99;
+  if (r->board_pixels == 90) {
+    rc |= make_map_im2col(&r->imap_x, r->x, c, max_batch);
+    rc |= make_map_im2col(&r->imap_t, r->t, c, max_batch);
+    rc |= make_map_im2col(&r->imap_y, r->y, c, max_batch);
+  }
   rc |= make_map_3d(&r->map_x, r->x, c, 9, rows, 9, 14);
   rc |= make_map_3d(&r->map_t, r->t, c, 9, rows, 9, 14);
   rc |= make_map_3d(&r->map_y, r->y, c, 9, rows, 9, 14);
@@ -639,7 +683,9 @@ int nn_set_weights(NnRuntime* r, const cz_tensor_desc* descs, int n) {
 static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* policy, float* value) {
   const int c = r->filters;
   cudaStream_t st = r->stream;
-  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, c);
+  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, c, r->board_pixels);
+  const bool dense = r->board_pixels == 90;
+  CUtensorMap *ix = &r->imap_x, *iy = &r->imap_y;
   r->launches++;
   __half *x = r->x, *y = r->y;
   CUtensorMap *mx = &r->map_x, *my = &r->map_y;
@@ -656,7 +702,13 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     const size_t wsz = (size_t)c;
     igemm::Args a1 = conv_args(n, c, r->shift_conv + (size_t)(2 * i) * wsz, nullptr, r->t, 1);
     igemm::Args a2 = conv_args(n, c, r->shift_conv + (size_t)(2 * i + 1) * wsz, x, y, 1);
-    if (use_pair_kernel()) {
+    if (dense) {
+      igemm::Args d1 = conv_args_dense(n, c, a1.bias, nullptr, r->t, 1);
+      igemm::Args d2 = conv_args_dense(n, c, a2.bias, x, y, 1);
+      if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
+      if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
+      CUtensorMap* ti = ix; ix = iy; iy = ti;
+    } else if (use_pair_kernel()) {
       if (launch_igemm2(c, *mx, r->map_w_half[2 * i], a1, st)) return CZ_ERR_CUDA;
       if (launch_igemm2(c, r->map_t, r->map_w_half[2 * i + 1], a2, st)) return CZ_ERR_CUDA;
     } else {
@@ -668,7 +720,7 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     CUtensorMap* tm = mx; mx = my; my = tm;
   }
   if (pe != (size_t)-1) cudaEventRecord(r->ev[pe + 1], st);
-  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, st>>>(x, c, n, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
+  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, st>>>(x, c, n, r->board_pixels, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
   igemm::Args ap = dense_args(n, kLabels, kPolN, kPolK, 256, r->b_pol, r->logits, kPolN);
   if (launch_igemm(256, r->map_pf, r->map_wpol, ap, st)) return CZ_ERR_CUDA;
   k_softmax<<<n, 256, 0, st>>>(r->logits, kPolN, policy);
@@ -721,6 +773,18 @@ int cz_igemm_conv3x3(const void* act_in, const void* w, const float* bias, const
   }
   if (make_map_2d(&mb, w, c, 9LL * c, c)) return CZ_ERR_CUDA;
   return launch_igemm(c, ma, mb, a, (cudaStream_t)stream);
+}
+
+// Same convolution on DENSE activations fp16 [n_boards][10][9][c] through the im2col TMA path (CTA-pair kernel).
+int cz_igemm_conv3x3_dense(const void* act_in, const void* w, const float* bias, const void* residual, void* act_out,
+                           int n_boards, int c, int relu, void* stream) {
+  using namespace cznn;
+  if (c % 64 || c < 64 || c > 256 || n_boards <= 0) return cz_fail(CZ_ERR_ARG, "cz_igemm_conv3x3_dense: bad shape");
+  CUtensorMap ma, mb;
+  if (make_map_im2col(&ma, act_in, c, n_boards)) return CZ_ERR_CUDA;
+  if (make_map_2d(&mb, w, c, 9LL * c, c / 2)) return CZ_ERR_CUDA;
+  igemm::Args a = conv_args_dense(n_boards, c, bias, (const __half*)residual, (__half*)act_out, relu);
+  return launch_igemm2(c, ma, mb, a, (cudaStream_t)stream);
 }
 
 // out[m][n] = sum_k a[m][k] * w[n][k] + bias[n]; a fp16 [m_alloc >= ceil128(m)][k], w fp16 [n_pad][k], k % 64 == 0,

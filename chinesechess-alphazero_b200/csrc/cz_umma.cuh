@@ -163,6 +163,14 @@ __device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* t, ui
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(t)), "r"(mapa_shared(bar, 0)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// im2col-mode load for a CTA pair: {c, w, h, n} is the base pixel (output pixel minus padding), {ow, oh} the filter tap.
+__device__ __forceinline__ void tma2_load_im2col_4d(void* dst, const CUtensorMap* t, uint64_t* bar, int c, int w, int h, int n,
+                                                    uint16_t ow, uint16_t oh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(t)), "r"(mapa_shared(bar, 0)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+      : "memory");
+}
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc2(uint32_t* slot_in_smem) {   // one full warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(kCols)

@@ -96,10 +96,11 @@ _SIGS = {
     "cz_nn_profile": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "cz_noise_sample": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "cz_igemm_conv3x3": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "cz_igemm_conv3x3_dense": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "cz_igemm_dense": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 # entry points that only exist in the CUDA build (tensor cores cannot be emulated on the CPU)
-CUDA_ONLY = {"cz_igemm_conv3x3", "cz_igemm_dense"}
+CUDA_ONLY = {"cz_igemm_conv3x3", "cz_igemm_conv3x3_dense", "cz_igemm_dense"}
 
 
 class CzLib:

@@ -226,6 +226,9 @@ int cz_launch_count(cz_engine* e, uint64_t* n);
  * = [tap kh*3+kw][c_out][c_in]; bias f32 [c]. */
 int cz_igemm_conv3x3(const void* act_in_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
                      void* act_out_dev, int n_boards, int c, int relu, void* stream);
+/* Same convolution on dense activations fp16 [n_boards][10][9][c] (no separator rows), fed by im2col-mode TMA. */
+int cz_igemm_conv3x3_dense(const void* act_in_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
+                           void* act_out_dev, int n_boards, int c, int relu, void* stream);
 /* `count` draws of the on-device root-noise sampler (noise_mode 1): the first component of
  * Dirichlet(alpha * 1_n_moves), i.e. what np.random.dirichlet(alpha*ones(n))[0] (player.py:304) is distributed as. */
 int cz_noise_sample(cz_engine* e, int game, int n_moves, int count, double* out_dev);

@@ -73,3 +73,30 @@ def test_conv3x3_matches_torch(cuda_lib, n_boards, c, residual, relu):
     assert err < 2e-2, err                                    # fp16 output rounding of O(1..10) values
     rel = ((got - ref).abs() / (ref.abs() + 1.0)).max().item()
     assert rel < 2e-3, rel
+
+
+@pytest.mark.parametrize("n_boards,c,residual,relu", [(1, 128, False, True), (5, 256, True, True), (29, 128, True, False),
+                                                       (64, 256, False, False), (200, 192, True, True), (3, 64, True, True),
+                                                       (1000, 256, True, True)])
+def test_conv3x3_dense_im2col_matches_torch(cuda_lib, n_boards, c, residual, relu):
+    """Dense NHWC activations through im2col-mode TMA (no separator rows, 128 useful pixels per tile)."""
+    g = torch.Generator(device="cuda").manual_seed(n_boards * 1000 + c + 1)
+    x = torch.randn(n_boards, c, 10, 9, device="cuda", generator=g).half().float()
+    w = (torch.randn(c, c, 3, 3, device="cuda", generator=g) * (1.0 / (3 * c ** 0.5))).half().float()
+    bias = torch.randn(c, device="cuda", generator=g)
+    res = torch.randn(n_boards, c, 10, 9, device="cuda", generator=g).half().float() if residual else None
+    xs = x.permute(0, 2, 3, 1).contiguous().half()                       # [B,10,9,C]
+    ws = w.permute(2, 3, 0, 1).reshape(9, c, c).contiguous().half()
+    rs = res.permute(0, 2, 3, 1).contiguous().half() if residual else None
+    out = torch.full((n_boards, 10, 9, c), float("nan"), device="cuda", dtype=torch.half)
+    cuda_lib.call("cz_igemm_conv3x3_dense", _p(xs), _p(ws), _p(bias), _p(rs), _p(out), n_boards, c, int(relu), _stream())
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x, w, bias, padding=1)
+    if residual:
+        ref = ref + res
+    if relu:
+        ref = ref.relu()
+    got = out.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 2e-2
+    assert ((got - ref).abs() / (ref.abs() + 1.0)).max().item() < 2e-3
