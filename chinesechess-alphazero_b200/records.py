@@ -80,3 +80,41 @@ def gather_records(engine, dist, world):
     rings = [torch.empty_like(ring) for _ in range(world)]
     dist.all_gather(rings, ring)
     return int(sum(int(c.item()) for c in counts))
+
+
+# ---- trainer-side view of the records (worker/optimize.py:223-292, lib/data_helper.py:11-24) -------------------
+def get_game_data_filenames(rc):
+    from glob import glob
+    return sorted(glob(os.path.join(rc.play_data_dir, rc.play_data_filename_tmpl % "*")))
+
+
+def read_game_data_from_file(path):
+    with open(path, "rt") as f:
+        return json.load(f)
+
+
+def expanding_data(data, env):
+    """expanding_data + convert_to_trainging_data (optimize.py:234-281, 14-plane path): one play record
+    `[init_state, [move, value], ...]` -> (planes f32 [T,14,10,9], one-hot policy f32 [T,2086], value f32 [T]).
+    The positions are replayed and encoded by the rules kernels (`env` is a StaticEnv)."""
+    from .env import move_to_u16
+    moves = [item[0] for item in data[1:]]
+    values = np.asarray([item[1] for item in data[1:]], dtype=np.float32)
+    t = len(moves)
+    boards = env.boards_from_states([data[0]])
+    seq = [boards]
+    for m in moves[:-1]:
+        boards, _ = env.step_batch(boards, env.moves_tensor([m]))
+        seq.append(boards)
+    if t == 0:
+        return (np.zeros((0, 14, 10, 9), np.float32), np.zeros((0, len(env.labels)), np.float32), values)
+    planes = env.planes_batch(torch.cat(seq, dim=0)).cpu().numpy()
+    policy = np.zeros((t, len(env.labels)), dtype=np.float32)
+    lut = env.label_lut
+    for i, m in enumerate(moves):
+        v = move_to_u16(m)
+        lab = int(lut[(v >> 8) * 90 + (v & 0xFF)])
+        if lab < 0:
+            raise ValueError(f"move {m} is not an action label")
+        policy[i, lab] = 1
+    return planes, policy, values

@@ -58,3 +58,24 @@ def test_play_data_format():
 @pytest.mark.gpu
 def test_cuda_selfplay_matches_restated_game_loop(cuda_lib):
     check_selfplay(cuda_lib, "cuda", n_games=4, want=8)
+
+
+def test_emul_expanding_data_matches_reference_layout(emul_env):
+    """records.expanding_data == optimize.py:234-281 on a replayed game (planes, one-hot policy, alternating value)."""
+    from cczero_b200.records import expanding_data, record_to_play_data
+    rng = np.random.RandomState(5)
+    s, moves = osenv.INIT_STATE, []
+    for _ in range(30):
+        lm = osenv.get_legal_moves(s)
+        m = lm[rng.randint(len(lm))]
+        moves.append(m)
+        s = osenv.step(s, m)
+    data = record_to_play_data({"moves": moves, "value_red": 1})
+    planes, policy, value = expanding_data(data, emul_env)
+    assert planes.shape == (30, 14, 10, 9) and policy.shape == (30, 2086) and value.shape == (30,)
+    s = osenv.INIT_STATE
+    for i, m in enumerate(moves):
+        assert (planes[i] == osenv.state_to_planes(s)).all()
+        assert policy[i].sum() == 1 and policy[i, osenv.ActionLabelsRed.index(m)] == 1
+        assert value[i] == (1 if i % 2 == 0 else -1)
+        s = osenv.step(s, m)
