@@ -44,6 +44,8 @@ struct Args {
   int out_f32;       // 1: float output (GEMM logits), 0: fp16
   const float* bias; // [n_total] or null
   const __half* residual;  // same layout as out (fp16) or null
+  const float* residual32; // fp32 skip stream (takes precedence over `residual`) or null
+  float* out32;            // optional fp32 copy of the output (the skip stream of the next block) or null
   void* out;
   uint32_t a_bytes;  // TMA bytes per A box
 };
@@ -371,7 +373,9 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           __half* o = reinterpret_cast<__half*>(a.out) + grow * a.ldo + c0;
           const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
           uint4 rv[4];
-          if (a.residual) {
+          const float4* r32 = a.residual32 ? reinterpret_cast<const float4*>(a.residual32 + grow * a.ldo + c0) : nullptr;
+          float4* o32 = a.out32 ? reinterpret_cast<float4*>(a.out32 + grow * a.ldo + c0) : nullptr;
+          if (!r32 && a.residual) {
             const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldo + c0);
 #pragma unroll
             for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
@@ -383,21 +387,25 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                           __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
                           __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
                           __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
-            if (a.residual) {
+            if (r32) {
+              const float4 ra = __ldg(r32 + 2 * g), rb = __ldg(r32 + 2 * g + 1);
+              x[0] += ra.x; x[1] += ra.y; x[2] += ra.z; x[3] += ra.w; x[4] += rb.x; x[5] += rb.y; x[6] += rb.z; x[7] += rb.w;
+            } else if (a.residual) {
               const __half2* h = reinterpret_cast<const __half2*>(&rv[g]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) { const float2 r2 = __half22float2(h[j]); x[2 * j] += r2.x; x[2 * j + 1] += r2.y; }
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (a.relu) x[j] = fmaxf(x[j], 0.f);
+              if (zero) x[j] = 0.f;
+            }
             uint4 ov;
             __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x0 = x[2 * j], x1 = x[2 * j + 1];
-              if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              if (zero) { x0 = 0.f; x1 = 0.f; }
-              oh[j] = __floats2half2_rn(x0, x1);
-            }
+            for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
             reinterpret_cast<uint4*>(o)[g] = ov;
+            if (o32) { o32[2 * g] = make_float4(x[0], x[1], x[2], x[3]); o32[2 * g + 1] = make_float4(x[4], x[5], x[6], x[7]); }
           }
         }
       }

@@ -215,7 +215,8 @@ __device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 
 // phase 2: every thread owns two adjacent output channels and walks the lists (half2 loads, fp32 accumulate).
 // grid = batch, block = max(96, C/2) threads.  w: HWIO [5][5][14][C] fp16 (BN scale folded).
 __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
-                             const float* __restrict__ shift, __half* __restrict__ out, int c_out, int board_pixels) {
+                             const float* __restrict__ shift, __half* __restrict__ out, float* __restrict__ out32, int c_out,
+                             int board_pixels) {
   __shared__ int8_t pl[90];
   __shared__ uint16_t rows[90][26];
   __shared__ uint8_t cnt[90];
@@ -254,7 +255,9 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
       const float2 v = __half22float2(__ldg(w2 + (size_t)rows[pix][k] * stride2));
       a0 += v.x; a1 += v.y;
     }
-    *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+    a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
+    *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = __floats2half2_rn(a0, a1);
+    if (out32) *reinterpret_cast<float2*>(out32 + ((size_t)b * board_pixels + pix) * c_out + c) = make_float2(a0, a1);
   }
   for (int col = 90; col < board_pixels; ++col)
     *reinterpret_cast<__half2*>(o + (size_t)col * c_out + c) = __floats2half2_rn(0.f, 0.f);          // separator row (strip layout)
@@ -281,7 +284,8 @@ __global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __
 // A block handles kHeadPos positions so the 180 x H value weights are read once per group.
 // Phase 1: warp per pixel, lane owns 8 channels whose 6 x 8 folded weights sit in registers.
 constexpr int kHeadPos = 4;
-__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, int c_in, int n_pos, int board_pixels,
+__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, const float* __restrict__ act32, int c_in, int n_pos,
+                                                int board_pixels,
                                                 const float* __restrict__ w6,      // [6][c_in], BN scale folded
                                                 const float* __restrict__ shift6,  // [6]
                                                 const float* __restrict__ wv1,     // [180][H]
@@ -309,11 +313,17 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, i
     const __half* a = act + ((size_t)(b0 + p) * board_pixels + pix) * c_in;
     float s[6] = {0, 0, 0, 0, 0, 0};
     if (lane_on) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + cbase));
-      const __half2* h = reinterpret_cast<const __half2*>(&v);
       float x[8];
+      if (act32) {
+        const float4* a4 = reinterpret_cast<const float4*>(act32 + ((size_t)(b0 + p) * board_pixels + pix) * c_in + cbase);
+        const float4 u = __ldg(a4), w4 = __ldg(a4 + 1);
+        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w4.x; x[5] = w4.y; x[6] = w4.z; x[7] = w4.w;
+      } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + cbase));
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+      }
 #pragma unroll
       for (int o = 0; o < 6; ++o)
 #pragma unroll
@@ -461,6 +471,7 @@ struct NnRuntime {
   uint64_t launches;
   // activations
   __half *x, *t, *y, *pol_feat;
+  float *x32, *y32;                      // fp32 skip stream (dense layout only)
   float* logits;
   uint8_t* boards_tmp;
   // weights
@@ -499,6 +510,8 @@ static void layout(NnRuntime* r, Carver& cv) {
   r->x = (__half*)cv.take(act);
   r->t = (__half*)cv.take(act);
   r->y = (__half*)cv.take(act);
+  r->x32 = (float*)cv.take(act * 2);
+  r->y32 = (float*)cv.take(act * 2);
   r->pol_feat = (__half*)cv.take(((size_t)r->max_batch + 128) * kPolK * sizeof(__half));
   r->logits = (float*)cv.take((size_t)r->max_batch * kPolN * sizeof(float));
   r->boards_tmp = (uint8_t*)cv.take((size_t)r->max_batch * CZ_BOARD_STRIDE);
@@ -683,8 +696,12 @@ int nn_set_weights(NnRuntime* r, const cz_tensor_desc* descs, int n) {
 static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* policy, float* value) {
   const int c = r->filters;
   cudaStream_t st = r->stream;
-  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, c, r->board_pixels);
   const bool dense = r->board_pixels == 90;
+  static int fp32_skip = -1;
+  if (fp32_skip < 0) { const char* e = getenv("CZ_FP16_SKIP"); fp32_skip = (e && e[0] == '1') ? 0 : 1; }
+  const bool s32 = dense && fp32_skip;
+  float *x32 = s32 ? r->x32 : nullptr, *y32 = s32 ? r->y32 : nullptr;
+  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, x32, c, r->board_pixels);
   CUtensorMap *ix = &r->imap_x, *iy = &r->imap_y;
   r->launches++;
   __half *x = r->x, *y = r->y;
@@ -705,6 +722,8 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     if (dense) {
       igemm::Args d1 = conv_args_dense(n, c, a1.bias, nullptr, r->t, 1);
       igemm::Args d2 = conv_args_dense(n, c, a2.bias, x, y, 1);
+      d2.residual32 = x32; d2.out32 = y32;
+      { float* t32 = x32; x32 = y32; y32 = t32; }
       if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
       if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
       CUtensorMap* ti = ix; ix = iy; iy = ti;
@@ -720,7 +739,7 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     CUtensorMap* tm = mx; mx = my; my = tm;
   }
   if (pe != (size_t)-1) cudaEventRecord(r->ev[pe + 1], st);
-  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, st>>>(x, c, n, r->board_pixels, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
+  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, st>>>(x, x32, c, n, r->board_pixels, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
   igemm::Args ap = dense_args(n, kLabels, kPolN, kPolK, 256, r->b_pol, r->logits, kPolN);
   if (launch_igemm(256, r->map_pf, r->map_wpol, ap, st)) return CZ_ERR_CUDA;
   k_softmax<<<n, 256, 0, st>>>(r->logits, kPolN, policy);
