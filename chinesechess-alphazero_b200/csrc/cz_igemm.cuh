@@ -251,8 +251,10 @@ struct Cfg2 {
   static_assert(N_TILE % 32 == 0 && N_TILE <= 256, "UMMA N constraint for M=256 and an even split of B");
 };
 
+constexpr int kThreads2 = 384;             // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
+
 template <int N_TILE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
   using C = Cfg2<N_TILE>;
   extern __shared__ uint8_t smem_raw[];
@@ -261,7 +263,7 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   uint64_t* full = bars;                  // [kStages2]  (used in the leader only)
   uint64_t* empty = bars + kStages2;      // [kStages2]  per CTA, signalled by multicast commit
   uint64_t* tfull = bars + 2 * kStages2;  // [2]         per CTA, signalled by multicast commit
-  uint64_t* tempty = tfull + 2;           // [2]         leader: 256 arrivals (both epilogues)
+  uint64_t* tempty = tfull + 2;           // [2]         leader: 512 arrivals (8 epilogue warps of both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -274,7 +276,7 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 256); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 512); }
     umma::fence_barrier_init();
     umma::fence_proxy_async();
   }
@@ -340,18 +342,18 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (each CTA drains its own 128 rows)
-    const int q = warp - 4;
+    // ------------------------------------------------------------ epilogue: 8 warps per CTA; warps w and w+4 share a TMEM
+    // lane quarter (w % 4) and split the columns in halves.  The skip-stream chunk of step i+1 is fetched before chunk i is
+    // converted and stored, so the global-load latency overlaps the stores.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;                        // 0: columns [0, N/2), 1: [N/2, N)
     const int m = q * 32 + lane;
-    uint32_t tempty_remote[2];
-    tempty_remote[0] = umma::mapa_shared(&tempty[0], 0);
-    tempty_remote[1] = umma::mapa_shared(&tempty[1], 0);
+    const uint32_t tempty_remote[2] = {umma::mapa_shared(&tempty[0], 0), umma::mapa_shared(&tempty[1], 0)};
+    constexpr int kChunks = N_TILE / 64;                     // 32-column chunks per half
     uint32_t tcount = 0;
     for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
       const int m_tile = 2 * pair + (int)rank;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      umma::mbar_wait(&tfull[acc], aph);
-      umma::tc_fence_after();
       bool valid, zero;
       long long grow;
       if (a.conv == 2) {                                     // dense pixels, 128 per tile
@@ -364,22 +366,46 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         zero = (srow % 11) == 10;
         grow = (long long)m_tile * a.box_r * 9 + m;
       }
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE;
+      const int cbeg = half * (N_TILE / 2);
+      const float* r32 = (a.residual32 && valid) ? a.residual32 + grow * a.ldo + cbeg : nullptr;
+      const __half* r16 = (!a.residual32 && a.residual && valid) ? a.residual + grow * a.ldo + cbeg : nullptr;
+      float4 nf[8];                                          // next chunk of the fp32 skip stream
+      uint4 nh[4];                                           // next chunk of the fp16 skip stream
+      if (r32) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) nf[g] = __ldg(reinterpret_cast<const float4*>(r32) + g);
+      } else if (r16) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) nh[g] = __ldg(reinterpret_cast<const uint4*>(r16) + g);
+      }
+      umma::mbar_wait(&tfull[acc], aph);
+      umma::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + cbeg;
 #pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      for (int ch = 0; ch < kChunks; ++ch) {
+        const int c0 = cbeg + ch * 32;
         uint32_t v[32];
-        umma::tmem_ld_32x32(t_row + c0, v);
+        umma::tmem_ld_32x32(t_row + ch * 32, v);
+        float4 cf[8]; uint4 chh[4];
+        if (r32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) cf[g] = nf[g];
+          if (ch + 1 < kChunks) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) nf[g] = __ldg(reinterpret_cast<const float4*>(r32 + (ch + 1) * 32) + g);
+          }
+        } else if (r16) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) chh[g] = nh[g];
+          if (ch + 1 < kChunks) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) nh[g] = __ldg(reinterpret_cast<const uint4*>(r16 + (ch + 1) * 32) + g);
+          }
+        }
         if (valid) {
           __half* o = reinterpret_cast<__half*>(a.out) + grow * a.ldo + c0;
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
-          uint4 rv[4];
-          const float4* r32 = a.residual32 ? reinterpret_cast<const float4*>(a.residual32 + grow * a.ldo + c0) : nullptr;
           float4* o32 = a.out32 ? reinterpret_cast<float4*>(a.out32 + grow * a.ldo + c0) : nullptr;
-          if (!r32 && a.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldo + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
-          }
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
@@ -388,10 +414,10 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                           __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
                           __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
             if (r32) {
-              const float4 ra = __ldg(r32 + 2 * g), rb = __ldg(r32 + 2 * g + 1);
+              const float4 ra = cf[2 * g], rb = cf[2 * g + 1];
               x[0] += ra.x; x[1] += ra.y; x[2] += ra.z; x[3] += ra.w; x[4] += rb.x; x[5] += rb.y; x[6] += rb.z; x[7] += rb.w;
-            } else if (a.residual) {
-              const __half2* h = reinterpret_cast<const __half2*>(&rv[g]);
+            } else if (r16) {
+              const __half2* h = reinterpret_cast<const __half2*>(&chh[g]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) { const float2 r2 = __half22float2(h[j]); x[2 * j] += r2.x; x[2 * j + 1] += r2.y; }
             }

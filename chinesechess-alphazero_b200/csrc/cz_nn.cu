@@ -143,7 +143,7 @@ static int launch_igemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   const int pairs = (a.m_tiles + 1) / 2;
   if (pairs <= 0) return 0;
   const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
-  igemm::k_igemm2<N_TILE><<<2 * clusters, igemm::kThreads, C::kSmemBytes, st>>>(tmA, tmB_half, a);
+  igemm::k_igemm2<N_TILE><<<2 * clusters, igemm::kThreads2, C::kSmemBytes, st>>>(tmA, tmB_half, a);
   CZ_CUDA(cudaGetLastError());
   return 0;
 }
