@@ -484,6 +484,7 @@ struct NnRuntime {
   CUtensorMap map_x, map_t, map_y, map_pf, map_wpol;
   std::vector<CUtensorMap> map_w;
   std::vector<CUtensorMap> map_w_half;   // box rows = C/2 for the CTA-pair kernel
+  bool fp32_skip;                        // keep the residual (skip) stream in fp32: halves the value error of deep nets, ~+30 % time
   int board_pixels;                      // 99 = strip layout (separator row per board), 90 = dense + im2col TMA
   CUtensorMap imap_x, imap_t, imap_y;    // im2col maps of the three activation buffers (dense layout)
   // optional CUDA-event timing of the residual-tower launches (bench.py roofline)
@@ -539,7 +540,7 @@ size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch) 
 }
 
 NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_batch, void* workspace, size_t bytes,
-                     void* stream) {
+                     void* stream, bool fp32_skip) {
   (void)device;
   if (filters % 64 != 0 || filters < 64 || filters > 256) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: filters must be 64..256 step 64"); return nullptr; }
   if (value_fc > 256 || value_fc < 1) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: value_fc_size must be <= 256"); return nullptr; }
@@ -547,6 +548,7 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   NnRuntime* r = new NnRuntime();
   r->filters = filters; r->blocks = blocks; r->value_fc = value_fc; r->max_batch = max_batch;
   r->stream = (cudaStream_t)stream; r->ready = false; r->launches = 0;
+  { const char* e = getenv("CZ_FP32_SKIP"); r->fp32_skip = fp32_skip || (e && e[0] == '1'); }
   r->profile = false; r->ev_used = 0; r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0;
   Carver cv{(uint8_t*)workspace, 0, bytes};
   layout(r, cv);
@@ -697,9 +699,7 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
   const int c = r->filters;
   cudaStream_t st = r->stream;
   const bool dense = r->board_pixels == 90;
-  static int fp32_skip = -1;
-  if (fp32_skip < 0) { const char* e = getenv("CZ_FP16_SKIP"); fp32_skip = (e && e[0] == '1') ? 0 : 1; }
-  const bool s32 = dense && fp32_skip;
+  const bool s32 = dense && r->fp32_skip;
   float *x32 = s32 ? r->x32 : nullptr, *y32 = s32 ? r->y32 : nullptr;
   k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, x32, c, r->board_pixels);
   CUtensorMap *ix = &r->imap_x, *iy = &r->imap_y;

@@ -100,7 +100,7 @@ typedef struct cz_config {
   int32_t max_game_length;     /* play_config.max_game_length */
   uint64_t seed;               /* Philox key (seed, rank) for the on-device streams */
   int32_t rank;                /* data-parallel rank, selects the RNG sub-stream */
-  int32_t reserved;
+  int32_t nn_fp32_skip;        /* 1: keep the residual (skip) stream in fp32 (value error of 20x256 6e-4 instead of 1.1e-3, ~+30 % time) */
 } cz_config;
 
 /* Device workspace the caller must provide (a torch.uint8 CUDA tensor). */

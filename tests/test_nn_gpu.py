@@ -11,19 +11,23 @@ from tests.search_checks import midgame_states
 pytestmark = pytest.mark.gpu
 
 
-def _engine(cuda_lib, filters, blocks, batch):
+def _engine(cuda_lib, filters, blocks, batch, fp32_skip=False):
     from cczero_b200.engine import Engine
     return Engine(cuda_lib, "cuda", n_games=batch, sims_per_move=8, leaves_per_round=1, nn_filters=filters,
-                  nn_blocks=blocks, nn_value_fc=256)
+                  nn_blocks=blocks, nn_value_fc=256, nn_fp32_skip=fp32_skip)
 
 
-@pytest.mark.parametrize("filters,blocks,trained", [(128, 7, True), (256, 3, True), (192, 2, False), (256, 20, False)])
-def test_forward_matches_fp32_restatement(cuda_lib, cuda_env, filters, blocks, trained):
+# Tolerance 1e-3 on policy probabilities and value (north_star).  Measured (tools/nn_error_report.py, profiles/):
+# policy <= 1.4e-4 everywhere; value <= 7e-4 except the UNTRAINED 256x20 net (BN statistics = identity, activations
+# grow ~1.5x per block) where the default fp16 skip stream gives 1.1e-3; `nn_fp32_skip` brings it to 6e-4.
+@pytest.mark.parametrize("filters,blocks,trained,fp32_skip", [(128, 7, True, False), (256, 3, True, False), (192, 2, False, False),
+                                                              (256, 20, True, False), (256, 20, False, True)])
+def test_forward_matches_fp32_restatement(cuda_lib, cuda_env, filters, blocks, trained, fp32_skip):
     w = om.init_weights(filters, blocks, 256, seed=filters + blocks, trained_like=trained)
     states = [osenv.INIT_STATE] + midgame_states(40, 3, lo=1, hi=120)
     planes = np.stack([osenv.state_to_planes(s) for s in states])
     ref_p, ref_v = om.forward(w, planes, blocks)
-    eng = _engine(cuda_lib, filters, blocks, 64)
+    eng = _engine(cuda_lib, filters, blocks, 64, fp32_skip)
     eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
     pol, val = eng.nn_forward_planes(torch.as_tensor(planes).cuda())
     pol2, val2 = eng.nn_forward_boards(cuda_env.boards_from_states(states))
@@ -33,7 +37,7 @@ def test_forward_matches_fp32_restatement(cuda_lib, cuda_env, filters, blocks, t
     assert np.isfinite(pol).all() and np.isfinite(val).all()
     assert np.abs(pol.sum(1) - 1).max() < 1e-4
     assert np.abs(pol - ref_p).max() < 1e-3, np.abs(pol - ref_p).max()
-    assert np.abs(val - ref_v).max() < 1e-3 * (2 if blocks >= 20 else 1) + (4e-3 if blocks >= 20 else 0), np.abs(val - ref_v).max()
+    assert np.abs(val - ref_v).max() < 1e-3, np.abs(val - ref_v).max()
     # the ordering of the top moves is what the search consumes
     assert (pol.argmax(1) == ref_p.argmax(1)).mean() > 0.9
     eng.close()
@@ -51,4 +55,17 @@ def test_forward_chunks_and_batch_of_one(cuda_lib, cuda_env):
     assert torch.allclose(pol[4], p1[0], atol=1e-6) and torch.allclose(val[4], v1[0], atol=1e-6)
     ref_p, ref_v = om.forward(w, np.stack([osenv.state_to_planes(s) for s in states]), 2)
     assert np.abs(pol.cpu().numpy() - ref_p).max() < 1e-3 and np.abs(val.cpu().numpy() - ref_v).max() < 1e-3
+    eng.close()
+
+
+def test_untrained_deep_net_default_precision(cuda_lib, cuda_env):
+    """The one case above 1e-3 with the default fp16 skip stream: random-init 256x20 (the bench workload). Bound it at 2e-3."""
+    w = om.init_weights(256, 20, 256, seed=276, trained_like=False)
+    states = [osenv.INIT_STATE] + midgame_states(40, 3, lo=1, hi=120)
+    ref_p, ref_v = om.forward(w, np.stack([osenv.state_to_planes(s) for s in states]), 20)
+    eng = _engine(cuda_lib, 256, 20, 64)
+    eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    pol, val = eng.nn_forward_boards(cuda_env.boards_from_states(states))
+    assert np.abs(pol.cpu().numpy() - ref_p).max() < 1e-3
+    assert np.abs(val.cpu().numpy() - ref_v).max() < 2e-3
     eng.close()
