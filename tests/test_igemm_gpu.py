@@ -34,6 +34,14 @@ def test_dense_matches_torch(cuda_lib, m, n_valid, n_pad, k, n_tile):
     assert err < 2e-3, err   # fp16 products are exact in fp32; only the accumulation order differs
 
 
+def _conv3x3_ref(x, w, bias):
+    """fp32 reference without cuDNN: im2col (unfold) + one SGEMM."""
+    b, c = x.shape[0], x.shape[1]
+    cols = torch.nn.functional.unfold(x, 3, padding=1)                    # [B, C*9, 90]
+    out = torch.matmul(w.reshape(w.shape[0], -1), cols)                   # [B, C_out, 90]
+    return out.reshape(b, w.shape[0], 10, 9) + bias.view(1, -1, 1, 1)
+
+
 def _strip_from_nchw(x):
     """[B,C,10,9] f32 -> fp16 strip [B*11,9,C] with zero separator rows."""
     b, c = x.shape[0], x.shape[1]
@@ -60,7 +68,7 @@ def test_conv3x3_matches_torch(cuda_lib, n_boards, c, residual, relu):
     out = torch.full((n_boards * 11, 9, c), float("nan"), device="cuda", dtype=torch.half)
     cuda_lib.call("cz_igemm_conv3x3", _p(xs), _p(ws), _p(bias), _p(rs), _p(out), n_boards, c, int(relu), _stream())
     torch.cuda.synchronize()
-    ref = torch.nn.functional.conv2d(x, w, bias, padding=1)
+    ref = _conv3x3_ref(x, w, bias)
     if residual:
         ref = ref + res
     if relu:
@@ -91,7 +99,7 @@ def test_conv3x3_dense_im2col_matches_torch(cuda_lib, n_boards, c, residual, rel
     out = torch.full((n_boards, 10, 9, c), float("nan"), device="cuda", dtype=torch.half)
     cuda_lib.call("cz_igemm_conv3x3_dense", _p(xs), _p(ws), _p(bias), _p(rs), _p(out), n_boards, c, int(relu), _stream())
     torch.cuda.synchronize()
-    ref = torch.nn.functional.conv2d(x, w, bias, padding=1)
+    ref = _conv3x3_ref(x, w, bias)
     if residual:
         ref = ref + res
     if relu:
