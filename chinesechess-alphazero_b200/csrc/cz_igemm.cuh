@@ -240,14 +240,17 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 // Leader = cluster rank 0: owns the full[] barriers (both CTAs' TMA loads complete_tx there), issues the
 // MMAs, and its tempty[] barriers collect the epilogue arrivals of both CTAs.  tcgen05.commit multicasts
 // to the empty[] / tfull[] barriers of both CTAs.
-constexpr int kStages2 = 6;
+constexpr int kStages2 = 5;
+constexpr int kEpiWarps2 = 8;
+constexpr int kStageRow = 36;                                  // floats per staged row (32 + 4 pad: conflict-free both ways)
+constexpr int kEpiStageBytes = kEpiWarps2 * 32 * kStageRow * 4; // 36 KB: one 32x32 fp32 block per epilogue warp
 
 template <int N_TILE>
 struct Cfg2 {
   static constexpr int kBHalfBytes = (N_TILE / 2) * 128;
   static constexpr int kStageBytes = kAStageBytes + kBHalfBytes;
   static constexpr int kTmemCols = Cfg<N_TILE>::kTmemCols;
-  static constexpr int kSmemBytes = kStages2 * kStageBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kStages2 * kStageBytes + kEpiStageBytes + 256 + 1024;
   static_assert(N_TILE % 32 == 0 && N_TILE <= 256, "UMMA N constraint for M=256 and an even split of B");
 };
 
@@ -259,7 +262,8 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   using C = Cfg2<N_TILE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * C::kStageBytes);
+  float* epi_stage = reinterpret_cast<float*>(smem + kStages2 * C::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * C::kStageBytes + kEpiStageBytes);
   uint64_t* full = bars;                  // [kStages2]  (used in the leader only)
   uint64_t* empty = bars + kStages2;      // [kStages2]  per CTA, signalled by multicast commit
   uint64_t* tfull = bars + 2 * kStages2;  // [2]         per CTA, signalled by multicast commit
@@ -343,97 +347,101 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: 8 warps per CTA; warps w and w+4 share a TMEM
-    // lane quarter (w % 4) and split the columns in halves.  The skip-stream chunk of step i+1 is fetched before chunk i is
-    // converted and stored, so the global-load latency overlaps the stores.
+    // lane quarter (w % 4) and split the columns in halves.  TMEM hands every thread one accumulator ROW, but a warp that
+    // loads / stores "one row per lane" touches 32 different 128-byte lines per instruction and saturates L1 (ncu: l1tex
+    // 50-60 % with the fp16 skip stream alone).  Each warp therefore transposes its 32x32 block through a padded
+    // shared-memory tile, so global accesses cover whole lines: 8 lanes per row for fp32, 4 lanes per row for fp16.
+    // Dense pixel layout only (a.conv == 2); the strip layout is served by the single-CTA kernel.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;                        // 0: columns [0, N/2), 1: [N/2, N)
-    const int m = q * 32 + lane;
+    float* S = epi_stage + (warp - 4) * 32 * kStageRow;
     const uint32_t tempty_remote[2] = {umma::mapa_shared(&tempty[0], 0), umma::mapa_shared(&tempty[1], 0)};
     constexpr int kChunks = N_TILE / 64;                     // 32-column chunks per half
+    const int r4 = lane >> 3, c4 = (lane & 7) * 4;           // fp32 view: rows r4 + 4k, 4 floats at column c4
+    const int r8 = lane >> 2, c8 = (lane & 3) * 8;           // fp16 view: rows r8 + 8k, 8 halves at column c8
+    const int cbeg = half * (N_TILE / 2);
     uint32_t tcount = 0;
     for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
       const int m_tile = 2 * pair + (int)rank;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      bool valid, zero;
-      long long grow;
-      if (a.conv == 2) {                                     // dense pixels, 128 per tile
-        grow = (long long)m_tile * kTileM + m;
-        valid = grow < a.rows;
-        zero = false;
-      } else {
-        const int srow = m_tile * a.box_r + m / 9;
-        valid = m < a.box_r * 9 && srow < a.rows;
-        zero = (srow % 11) == 10;
-        grow = (long long)m_tile * a.box_r * 9 + m;
-      }
-      const int cbeg = half * (N_TILE / 2);
-      const float* r32 = (a.residual32 && valid) ? a.residual32 + grow * a.ldo + cbeg : nullptr;
-      const __half* r16 = (!a.residual32 && a.residual && valid) ? a.residual + grow * a.ldo + cbeg : nullptr;
-      float4 nf[8];                                          // next chunk of the fp32 skip stream
-      uint4 nh[4];                                           // next chunk of the fp16 skip stream
-      if (r32) {
+      const long long rbase = (long long)m_tile * kTileM + q * 32;     // first global pixel row of this warp
+      const float* r32 = a.residual32 ? a.residual32 + rbase * a.ldo + cbeg : nullptr;
+      const __half* r16 = (!a.residual32 && a.residual) ? a.residual + rbase * a.ldo + cbeg : nullptr;
+      float4 nf[8];                                          // skip stream of the next chunk, line-coalesced
+      uint4 nh[4];
+      auto fetch = [&](int ch) {
+        if (r32) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) nf[g] = __ldg(reinterpret_cast<const float4*>(r32) + g);
-      } else if (r16) {
+          for (int k = 0; k < 8; ++k)
+            nf[k] = (rbase + r4 + 4 * k < a.rows) ? __ldg(reinterpret_cast<const float4*>(r32 + (size_t)(r4 + 4 * k) * a.ldo + ch * 32 + c4))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (r16) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) nh[g] = __ldg(reinterpret_cast<const uint4*>(r16) + g);
-      }
+          for (int k = 0; k < 4; ++k)
+            nh[k] = (rbase + r8 + 8 * k < a.rows) ? __ldg(reinterpret_cast<const uint4*>(r16 + (size_t)(r8 + 8 * k) * a.ldo + ch * 32 + c8))
+                                                  : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      fetch(0);
       umma::mbar_wait(&tfull[acc], aph);
       umma::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + cbeg;
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch) {
         const int c0 = cbeg + ch * 32;
-        uint32_t v[32];
-        umma::tmem_ld_32x32(t_row + ch * 32, v);
-        float4 cf[8]; uint4 chh[4];
+        // 1. skip stream of this chunk: coalesced registers -> staged tile
         if (r32) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) cf[g] = nf[g];
-          if (ch + 1 < kChunks) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) nf[g] = __ldg(reinterpret_cast<const float4*>(r32 + (ch + 1) * 32) + g);
-          }
+          for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(S + (r4 + 4 * k) * kStageRow + c4) = nf[k];
         } else if (r16) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) chh[g] = nh[g];
-          if (ch + 1 < kChunks) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) nh[g] = __ldg(reinterpret_cast<const uint4*>(r16 + (ch + 1) * 32) + g);
+          for (int k = 0; k < 4; ++k) {
+            const __half2* h = reinterpret_cast<const __half2*>(&nh[k]);
+            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+            float* d = S + (r8 + 8 * k) * kStageRow + c8;
+            *reinterpret_cast<float4*>(d) = make_float4(f0.x, f0.y, f1.x, f1.y);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
           }
         }
-        if (valid) {
-          __half* o = reinterpret_cast<__half*>(a.out) + grow * a.ldo + c0;
-          float4* o32 = a.out32 ? reinterpret_cast<float4*>(a.out32 + grow * a.ldo + c0) : nullptr;
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
+        if (ch + 1 < kChunks) fetch(ch + 1);
+        uint32_t v[32];
+        umma::tmem_ld_32x32(t_row + ch * 32, v);
+        __syncwarp();
+        // 2. own row: accumulator + shift (+ skip), ReLU
+        const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
+        float* own = S + lane * kStageRow;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
-            float x[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
-                          __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
-                          __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
-                          __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
-            if (r32) {
-              const float4 ra = cf[2 * g], rb = cf[2 * g + 1];
-              x[0] += ra.x; x[1] += ra.y; x[2] += ra.z; x[3] += ra.w; x[4] += rb.x; x[5] += rb.y; x[6] += rb.z; x[7] += rb.w;
-            } else if (r16) {
-              const __half2* h = reinterpret_cast<const __half2*>(&chh[g]);
+        for (int g = 0; g < 8; ++g) {
+          const float4 b = __ldg(bp + g);
+          float4 x = make_float4(__uint_as_float(v[4 * g]) + b.x, __uint_as_float(v[4 * g + 1]) + b.y,
+                                 __uint_as_float(v[4 * g + 2]) + b.z, __uint_as_float(v[4 * g + 3]) + b.w);
+          if (r32 || r16) { const float4 rr = *reinterpret_cast<const float4*>(own + 4 * g); x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w; }
+          if (a.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+          *reinterpret_cast<float4*>(own + 4 * g) = x;
+        }
+        __syncwarp();
+        // 3. line-coalesced stores: fp32 copy (next block's skip stream) and fp16 activations (next conv's operand)
+        if (a.out32) {
+          float* o32 = a.out32 + rbase * a.ldo + c0;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { const float2 r2 = __half22float2(h[j]); x[2 * j] += r2.x; x[2 * j + 1] += r2.y; }
-            }
+          for (int k = 0; k < 8; ++k)
+            if (rbase + r4 + 4 * k < a.rows)
+              *reinterpret_cast<float4*>(o32 + (size_t)(r4 + 4 * k) * a.ldo + c4) = *reinterpret_cast<const float4*>(S + (r4 + 4 * k) * kStageRow + c4);
+        }
+        {
+          __half* o16 = reinterpret_cast<__half*>(a.out) + rbase * a.ldo + c0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (a.relu) x[j] = fmaxf(x[j], 0.f);
-              if (zero) x[j] = 0.f;
-            }
+          for (int k = 0; k < 4; ++k) {
+            const float* sp = S + (r8 + 8 * k) * kStageRow + c8;
+            const float4 x0 = *reinterpret_cast<const float4*>(sp), x1 = *reinterpret_cast<const float4*>(sp + 4);
             uint4 ov;
             __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-            reinterpret_cast<uint4*>(o)[g] = ov;
-            if (o32) { o32[2 * g] = make_float4(x[0], x[1], x[2], x[3]); o32[2 * g + 1] = make_float4(x[4], x[5], x[6], x[7]); }
+            oh[0] = __floats2half2_rn(x0.x, x0.y); oh[1] = __floats2half2_rn(x0.z, x0.w);
+            oh[2] = __floats2half2_rn(x1.x, x1.y); oh[3] = __floats2half2_rn(x1.z, x1.w);
+            if (rbase + r8 + 8 * k < a.rows) *reinterpret_cast<uint4*>(o16 + (size_t)(r8 + 8 * k) * a.ldo + c8) = ov;
           }
         }
+        __syncwarp();
       }
       umma::tc_fence_before();
       umma::mbar_arrive_cluster(tempty_remote[acc]);

@@ -727,9 +727,6 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
       if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
       if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
       CUtensorMap* ti = ix; ix = iy; iy = ti;
-    } else if (use_pair_kernel()) {
-      if (launch_igemm2(c, *mx, r->map_w_half[2 * i], a1, st)) return CZ_ERR_CUDA;
-      if (launch_igemm2(c, r->map_t, r->map_w_half[2 * i + 1], a2, st)) return CZ_ERR_CUDA;
     } else {
       if (launch_igemm(c, *mx, r->map_w[2 * i], a1, st)) return CZ_ERR_CUDA;
       if (launch_igemm(c, r->map_t, r->map_w[2 * i + 1], a2, st)) return CZ_ERR_CUDA;
@@ -786,10 +783,6 @@ int cz_igemm_conv3x3(const void* act_in, const void* w, const float* bias, const
   CUtensorMap ma, mb;
   if (make_map_3d(&ma, act_in, c, 9, (long long)n_boards * 11, 9, 14)) return CZ_ERR_CUDA;
   igemm::Args a = conv_args(n_boards, c, bias, (const __half*)residual, (__half*)act_out, relu);
-  if (use_pair_kernel()) {
-    if (make_map_2d(&mb, w, c, 9LL * c, c / 2)) return CZ_ERR_CUDA;
-    return launch_igemm2(c, ma, mb, a, (cudaStream_t)stream);
-  }
   if (make_map_2d(&mb, w, c, 9LL * c, c)) return CZ_ERR_CUDA;
   return launch_igemm(c, ma, mb, a, (cudaStream_t)stream);
 }
