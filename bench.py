@@ -170,7 +170,8 @@ def run_ours(args):
     eng = Engine(lib, f"cuda:{local}", n_games=games, sims_per_move=sims, leaves_per_round=K, noise_mode=1,
                  nn_filters=filters, nn_blocks=blocks, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
                  tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, max_game_length=100,
-                 max_nodes_per_game=args.nodes or max(4096, 24 * sims), seed=args.seed, rank=rank)
+                 max_nodes_per_game=args.nodes or max(4096, 24 * sims), seed=args.seed, rank=rank,
+                 nn_fp32_skip={"auto": None, "fp32": True, "fp16": False}[args.skip_stream])
     model = CChessModel(SimpleNamespace(model=SimpleNamespace(cnn_filter_num=filters, res_layer_num=blocks, value_fc_size=256,
                                                               cnn_first_filter_size=5, cnn_filter_size=3, input_depth=14)))
     model.build(seed=0)                      # random-init, Keras-equivalent (agent/model.py:32-66 defaults)
@@ -274,7 +275,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f16", "data": "synthetic (random-init Keras-equivalent weights, games from INIT_STATE)",
             "config": {"workload": f"{args.workload} = BASELINE.json configs[2]: {games} concurrent games/GPU, {sims} sims/move, "
                                    f"{filters}x{blocks} resnet", "games_per_gpu": games, "sims_per_move": sims,
-                       "leaves_per_round": K, "parallelism": f"dp{world} (games sharded, no data-path collective)",
+                       "leaves_per_round": K, "skip_stream": args.skip_stream, "parallelism": f"dp{world} (games sharded, no data-path collective)",
                        "l2": "inputs larger than L2 (activations ~1.2 GB/round, trees ~GBs)", "nn_positions": positions,
                        "games_finished": games_done, "records_gathered": gathered},
             "nn_positions_per_sec": None,
@@ -314,6 +315,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--skip-stream", default="auto", choices=["auto", "fp32", "fp16"],
+                    help="precision of the residual skip stream (auto = fp32 beyond 10 blocks: keeps the 1e-3 parity bound)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

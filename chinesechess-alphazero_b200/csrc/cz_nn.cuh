@@ -12,7 +12,7 @@ struct NnRuntime;
 size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch);
 // returns nullptr and sets cz_last_error on failure
 NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_batch, void* workspace, size_t bytes,
-                     void* stream, bool fp32_skip);
+                     void* stream, int fp32_skip_mode);
 void nn_destroy(NnRuntime*);
 int nn_set_weights(NnRuntime*, const cz_tensor_desc* descs, int n);
 bool nn_ready(const NnRuntime*);

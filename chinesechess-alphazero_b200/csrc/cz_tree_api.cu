@@ -324,7 +324,7 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
     const int maxb = cfg->n_games * cfg->leaves_per_round;
     e->nn_bytes = cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb);
     uint8_t* nnws = e->ws + ((used + 4095) & ~(size_t)4095);
-    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream, cfg->nn_fp32_skip != 0);
+    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream, cfg->nn_fp32_skip);
     if (!e->nn) { delete e; return CZ_ERR_CUDA; }
   }
 #else

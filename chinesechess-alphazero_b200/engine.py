@@ -21,7 +21,7 @@ class Engine:
     def __init__(self, lib=None, device=None, n_games=1, sims_per_move=800, leaves_per_round=8, virtual_loss=3,
                  max_nodes_per_game=None, max_edges_per_game=None, max_path=128, noise_mode=1, max_game_length=100,
                  nn_filters=0, nn_blocks=0, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
-                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0, nn_fp32_skip=False):
+                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0, nn_fp32_skip=None):
         self.lib = lib or get_lib()
         if device is None:
             device = 'cuda' if self.lib.is_cuda else 'cpu'
@@ -43,7 +43,7 @@ class Engine:
         cfg.tau_decay_rate, cfg.resign_threshold, cfg.enable_resign_rate = tau_decay_rate, resign_threshold, enable_resign_rate
         cfg.min_resign_turn, cfg.max_game_length = min_resign_turn, max_game_length
         cfg.seed, cfg.rank = seed, rank
-        cfg.nn_fp32_skip = 1 if nn_fp32_skip else 0
+        cfg.nn_fp32_skip = 0 if nn_fp32_skip is None else (1 if nn_fp32_skip else 2)   # None = auto (fp32 when blocks > 10)
         self.cfg = cfg
         nbytes = C.c_uint64(0)
         self.lib.call("cz_workspace_bytes", C.byref(cfg), C.byref(nbytes))

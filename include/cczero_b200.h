@@ -100,7 +100,8 @@ typedef struct cz_config {
   int32_t max_game_length;     /* play_config.max_game_length */
   uint64_t seed;               /* Philox key (seed, rank) for the on-device streams */
   int32_t rank;                /* data-parallel rank, selects the RNG sub-stream */
-  int32_t nn_fp32_skip;        /* 1: keep the residual (skip) stream in fp32 (value error of 20x256 6e-4 instead of 1.1e-3, ~+30 % time) */
+  int32_t nn_fp32_skip;        /* residual (skip) stream precision: 0 auto (fp32 when nn_blocks > 10), 1 fp32, 2 fp16.
+                                * fp32 keeps the value error of 20-block nets <= 6e-4 (fp16: up to 1.5e-3) for ~10 % time */
 } cz_config;
 
 /* Device workspace the caller must provide (a torch.uint8 CUDA tensor). */

