@@ -37,9 +37,11 @@ def _glorot(rng, shape, fan_in, fan_out):
     return rng.uniform(-lim, lim, size=shape).astype(np.float32)
 
 
-def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False):
+def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False, spread=1.0):
     """Keras-equivalent initialisation (glorot-uniform kernels, zero biases, BN gamma=1 beta=0 mean=0 var=1).
-    trained_like=True perturbs the BN statistics and biases so that folding bugs cannot hide."""
+    trained_like=True perturbs the BN statistics and biases so that folding bugs cannot hide; `spread` scales the
+    perturbation (1.0: gamma in [0.5,1.5], variance in [0.5,2] - a deep random net in that regime amplifies any
+    perturbation of its inputs several-fold per 10 blocks; 0.3 keeps the conditioning close to a Keras-initialised net)."""
     rng = np.random.RandomState(seed)
     w = {}
 
@@ -48,10 +50,10 @@ def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False):
 
     def bn(name, c):
         if trained_like:
-            w[name + "/gamma"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
-            w[name + "/beta"] = rng.uniform(-0.3, 0.3, c).astype(np.float32)
-            w[name + "/moving_mean"] = rng.uniform(-0.2, 0.2, c).astype(np.float32)
-            w[name + "/moving_variance"] = rng.uniform(0.5, 2.0, c).astype(np.float32)
+            w[name + "/gamma"] = rng.uniform(1 - 0.5 * spread, 1 + 0.5 * spread, c).astype(np.float32)
+            w[name + "/beta"] = rng.uniform(-0.3 * spread, 0.3 * spread, c).astype(np.float32)
+            w[name + "/moving_mean"] = rng.uniform(-0.2 * spread, 0.2 * spread, c).astype(np.float32)
+            w[name + "/moving_variance"] = np.exp(rng.uniform(-0.7 * spread, 0.7 * spread, c)).astype(np.float32)
         else:
             w[name + "/gamma"] = np.ones(c, np.float32)
             w[name + "/beta"] = np.zeros(c, np.float32)
