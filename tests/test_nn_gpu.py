@@ -26,7 +26,7 @@ def _engine(cuda_lib, filters, blocks, batch, fp32_skip=None):
 # with the fp32 skip stream); those nets are bounded separately at 1e-2 as a gross-error check.
 @pytest.mark.parametrize("filters,blocks,trained,spread,fp32_skip", [
     (128, 7, False, 0, None), (256, 7, False, 0, None), (192, 10, False, 0, None), (256, 20, False, 0, None),
-    (128, 7, True, 0.3, None), (256, 3, True, 1.0, None), (192, 10, True, 0.3, None), (256, 20, True, 0.3, None),
+    (128, 7, True, 0.3, None), (256, 3, True, 1.0, None), (192, 10, True, 0.3, None), (256, 20, True, 0.1, None),
     (192, 2, True, 1.0, True)])
 def test_forward_matches_fp32_restatement(cuda_lib, cuda_env, filters, blocks, trained, spread, fp32_skip):
     w = om.init_weights(filters, blocks, 256, seed=filters + blocks, trained_like=trained, spread=spread)
