@@ -27,40 +27,42 @@ CZ_KERNEL(k_begin)(EngineDev E, int sims_override) {
   if (g >= E.n_games) return;
   game_begin(E, g, sims_override, tree_smem());
 }
-CZ_KERNEL(k_wave)(EngineDev E) {
-  const int g = my_game();
-  if (g >= E.n_games) return;
+// The search kernels work on a game range [g0, g1) ("slot"): cz_search pipelines two halves of the games so the tree
+// work of one half overlaps the network evaluation of the other.  Per-game results do not depend on the split.
+CZ_KERNEL(k_wave)(EngineDev E, int g0, int g1) {
+  const int g = g0 + my_game();
+  if (g >= g1) return;
   game_wave(E, g, tree_smem());
 }
-CZ_KERNEL(k_apply)(EngineDev E, const float* policy, const float* value) {
-  const int g = my_game();
-  if (g >= E.n_games) return;
+CZ_KERNEL(k_apply)(EngineDev E, int g0, int g1, const float* policy, const float* value) {
+  const int g = g0 + my_game();
+  if (g >= g1) return;
   game_apply(E, g, policy, value, tree_smem());
 }
 // single warp: exclusive scan of the per-game leaf counts, totals[0] = leaves, totals[1] = any game busy
-CZ_KERNEL(k_scan)(EngineDev E) {
+CZ_KERNEL(k_scan)(EngineDev E, int gb, int ge, int slot) {
   int base = 0, busy = 0;
-  for (int g0 = 0; g0 < E.n_games; g0 += 32) {
+  for (int g0 = gb; g0 < ge; g0 += 32) {
     const int g = g0 + czs::lane();
-    const int n = g < E.n_games ? E.n_leaf[g] : 0;
+    const int n = g < ge ? E.n_leaf[g] : 0;
     int tot;
     const int off = czs::warp_excl_scan(n, &tot);
-    if (g < E.n_games) {
-      E.leaf_off[g] = base + off;
+    if (g < ge) {
+      E.leaf_off[g] = base + off;                      // offset inside this slot's dense list
       if (E.active[g] && (E.round_pending[g] > 0 || E.tasks_left[g] > 0)) busy = 1;
     }
     base += tot;
   }
   busy = czs::any(busy != 0) ? 1 : 0;
-  if (czs::lane() == 0) { E.totals[0] = base; E.totals[1] = busy; }
+  if (czs::lane() == 0) { E.totals[4 * slot] = base; E.totals[4 * slot + 1] = busy; }
 }
-CZ_KERNEL(k_gather)(EngineDev E) {
-  const int g = my_game();
-  if (g >= E.n_games) return;
+CZ_KERNEL(k_gather)(EngineDev E, int g0, int g1, uint8_t* dense) {
+  const int g = g0 + my_game();
+  if (g >= g1) return;
   const int n = E.n_leaf[g], off = E.leaf_off[g];
   for (int j = 0; j < n; ++j) {
     const uint8_t* s = E.leaf_board + ((size_t)g * E.K + j) * BOARD_STRIDE;
-    uint8_t* d = E.leaf_dense + (size_t)(off + j) * BOARD_STRIDE;
+    uint8_t* d = dense + (size_t)(off + j) * BOARD_STRIDE;
     if (czs::lane() < BOARD_STRIDE / 16) reinterpret_cast<uint4*>(d)[czs::lane()] = reinterpret_cast<const uint4*>(s)[czs::lane()];
   }
 }
@@ -184,6 +186,9 @@ struct cz_engine {
 #if !defined(CZ_EMUL)
   cznn::NnRuntime* nn;
   size_t nn_bytes;
+  cudaStream_t tree_stream;                                 // second stream for the pipelined search (NULL = off)
+  cudaEvent_t ev_ready[2], ev_done[2];
+  int32_t* h_totals;                                        // pinned [8]
 #endif
 };
 
@@ -214,7 +219,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.leaf_board = cv.take<uint8_t>(G * K * BOARD_STRIDE);
   d.resume_sim = cv.take<int32_t>(G * K); d.n_resume = cv.take<int32_t>(G);
   d.park_sim = cv.take<int32_t>(G * K); d.park_node = cv.take<int32_t>(G * K); d.n_park = cv.take<int32_t>(G);
-  d.leaf_off = cv.take<int32_t>(G); d.totals = cv.take<int32_t>(4);
+  d.leaf_off = cv.take<int32_t>(G); d.totals = cv.take<int32_t>(8);
   d.leaf_dense = cv.take<uint8_t>(G * K * BOARD_STRIDE);
   d.counters = cv.take<unsigned long long>(8);
   selfplay_carve(d.sp, cv, c);
@@ -268,6 +273,8 @@ int launch_ok(cz_engine* e, const char* what, int n = 1) {
 
 #define GAME_LAUNCH(e, kern, ...) \
   CZ_LAUNCH(kern, ((e)->cfg.n_games + kWarps - 1) / kWarps, kWarps, sizeof(TreeSmem) * kWarps, (e)->stream, __VA_ARGS__)
+#define RANGE_LAUNCH(e, st, g0, g1, kern, ...) \
+  CZ_LAUNCH(kern, ((g1) - (g0) + kWarps - 1) / kWarps, kWarps, sizeof(TreeSmem) * kWarps, st, __VA_ARGS__)
 
 }  // namespace
 
@@ -307,8 +314,19 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
   d.seed = cfg->seed; d.rank = cfg->rank;
   const size_t used = carve(e, e->ws);
 #if !defined(CZ_EMUL)
-  e->nn = nullptr; e->nn_bytes = 0;
+  e->nn = nullptr; e->nn_bytes = 0; e->tree_stream = nullptr; e->h_totals = nullptr;
   if (cudaSetDevice(cfg->device) != cudaSuccess) { delete e; return cz_fail(CZ_ERR_CUDA, "cz_create: cudaSetDevice(%d) failed", cfg->device); }
+  if (cfg->nn_filters > 0) {
+    const char* off = getenv("CZ_NO_PIPELINE");
+    if (!(off && off[0] == '1')) {
+      if (cudaStreamCreateWithFlags(&e->tree_stream, cudaStreamNonBlocking) != cudaSuccess) e->tree_stream = nullptr;
+      for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&e->ev_ready[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+      }
+    }
+    if (cudaMallocHost((void**)&e->h_totals, 8 * sizeof(int32_t)) != cudaSuccess) { delete e; return cz_fail(CZ_ERR_CUDA, "cz_create: cudaMallocHost failed"); }
+  }
 #endif
   // tables + initial state
   std::vector<int16_t> lut(8100);
@@ -338,6 +356,12 @@ void cz_destroy(cz_engine* e) {
   if (!e) return;
 #if !defined(CZ_EMUL)
   cznn::nn_destroy(e->nn);
+  if (e->tree_stream) {
+    cudaStreamSynchronize(e->tree_stream);
+    cudaStreamDestroy(e->tree_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(e->ev_ready[i]); cudaEventDestroy(e->ev_done[i]); }
+  }
+  if (e->h_totals) cudaFreeHost(e->h_totals);
 #endif
   delete e;
 }
@@ -409,9 +433,10 @@ int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {
 int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active) {
   if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_wave: null engine");
   if (e->last_leaves != 0) return cz_fail(CZ_ERR_STATE, "cz_search_wave: %d leaves of the previous wave were not applied", e->last_leaves);
-  GAME_LAUNCH(e, k_wave, e->d);
-  CZ_LAUNCH(k_scan, 1, 1, 0, e->stream, e->d);
-  GAME_LAUNCH(e, k_gather, e->d);
+  const int G = e->cfg.n_games;
+  RANGE_LAUNCH(e, e->stream, 0, G, k_wave, e->d, 0, G);
+  CZ_LAUNCH(k_scan, 1, 1, 0, e->stream, e->d, 0, G, 0);
+  RANGE_LAUNCH(e, e->stream, 0, G, k_gather, e->d, 0, G, e->d.leaf_dense);
   if (launch_ok(e, "cz_search_wave", 3)) return CZ_ERR_CUDA;
   int32_t t[4];
   czrt_copy(t, e->d.totals, sizeof(t), e->stream);
@@ -442,11 +467,70 @@ int cz_search_apply(cz_engine* e, const float* policy_dev, const float* value_de
   if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_apply: null engine");
   if (e->last_leaves == 0) return 0;
   if (!policy_dev || !value_dev) return cz_fail(CZ_ERR_ARG, "cz_search_apply: null evaluation");
-  GAME_LAUNCH(e, k_apply, e->d, policy_dev, value_dev);
+  RANGE_LAUNCH(e, e->stream, 0, e->cfg.n_games, k_apply, e->d, 0, e->cfg.n_games, policy_dev, value_dev);
   e->total_positions += (uint64_t)e->last_leaves;
   e->last_leaves = 0;
   return launch_ok(e, "cz_search_apply");
 }
+
+#if !defined(CZ_EMUL)
+namespace {
+// Two halves of the games ("slots") alternate between tree work (stream T) and network evaluation (the engine stream):
+//   T: wave/scan/gather(h)  -> host reads the leaf count -> N: forward(h) -> T: apply(h), wave(h) ...
+// while N evaluates one half the other half walks its trees, so the tensor cores never wait for the integer kernels.
+int search_pipelined(cz_engine* e) {
+  const int G = e->cfg.n_games, K = e->cfg.leaves_per_round;
+  const int mid = (G + 1) / 2;
+  const int gb[2] = {0, mid}, ge[2] = {mid, G};
+  uint8_t* dense[2] = {e->d.leaf_dense, e->d.leaf_dense + (size_t)mid * K * BOARD_STRIDE};
+  float* pol[2] = {e->policy_buf, e->policy_buf + (size_t)mid * K * CZ_N_LABELS};
+  float* val[2] = {e->value_buf, e->value_buf + (size_t)mid * K};
+  cudaStream_t T = e->tree_stream, N = e->stream;
+  cudaEvent_t ready[2] = {e->ev_ready[0], e->ev_ready[1]};   // gather(h) done on T
+  cudaEvent_t done[2] = {e->ev_done[0], e->ev_done[1]};      // forward(h) done on N
+  int n_in_flight[2] = {0, 0};
+  bool busy[2] = {true, true};
+  // everything queued on the engine stream so far (begin kernels) must precede the tree stream's first wave
+  cudaEventRecord(e->ev_done[0], N);
+  cudaStreamWaitEvent(T, e->ev_done[0], 0);
+  for (int turn = 0;; ++turn) {
+    const int h = turn & 1;
+    if (!busy[0] && !busy[1] && n_in_flight[0] == 0 && n_in_flight[1] == 0) break;
+    if (!busy[h] && n_in_flight[h] == 0) continue;
+    if (n_in_flight[h] > 0) {                                 // evaluation of this half is (being) computed on N
+      cudaStreamWaitEvent(T, done[h], 0);
+      RANGE_LAUNCH(e, T, gb[h], ge[h], k_apply, e->d, gb[h], ge[h], (const float*)pol[h], (const float*)val[h]);
+      e->total_positions += (uint64_t)n_in_flight[h];
+      e->launches += 1;
+      n_in_flight[h] = 0;
+    }
+    RANGE_LAUNCH(e, T, gb[h], ge[h], k_wave, e->d, gb[h], ge[h]);
+    CZ_LAUNCH(k_scan, 1, 1, 0, T, e->d, gb[h], ge[h], h);
+    RANGE_LAUNCH(e, T, gb[h], ge[h], k_gather, e->d, gb[h], ge[h], dense[h]);
+    cudaMemcpyAsync(e->h_totals + 4 * h, e->d.totals + 4 * h, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, T);
+    cudaEventRecord(ready[h], T);
+    e->launches += 3;
+    e->total_waves++;
+    if (cudaStreamSynchronize(T) != cudaSuccess) return cz_fail(CZ_ERR_CUDA, "cz_search: device failure in the tree stream");
+    const int n = e->h_totals[4 * h];
+    busy[h] = e->h_totals[4 * h + 1] != 0 || n > 0;
+    if (n > 0) {
+      cudaStreamWaitEvent(N, ready[h], 0);
+      const int rc = cznn::nn_forward_boards(e->nn, dense[h], n, pol[h], val[h]);
+      if (rc) return rc;
+      cudaEventRecord(done[h], N);
+      n_in_flight[h] = n;
+    }
+  }
+  // leave both streams quiescent and ordered for the caller
+  cudaEventRecord(ready[0], T);
+  cudaStreamWaitEvent(N, ready[0], 0);
+  const char* msg;
+  if (czrt_last_error(&msg)) return cz_fail(CZ_ERR_CUDA, "cz_search: %s", msg);
+  return 0;
+}
+}  // namespace
+#endif
 
 int cz_search(cz_engine* e, const cz_root_opts* opts) {
 #if defined(CZ_EMUL)
@@ -457,6 +541,7 @@ int cz_search(cz_engine* e, const cz_root_opts* opts) {
   if (!e->nn || !cznn::nn_ready(e->nn)) return cz_fail(CZ_ERR_STATE, "cz_search: network weights not set");
   int rc = cz_search_begin(e, opts);
   if (rc) return rc;
+  if (e->tree_stream && e->cfg.n_games >= 64) return search_pipelined(e);
   for (;;) {
     int32_t n = 0, busy = 0;
     if ((rc = cz_search_wave(e, &n, &busy))) return rc;

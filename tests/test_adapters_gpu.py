@@ -98,3 +98,33 @@ def test_selfplay_worker_writes_reference_records(cuda_lib, tmp_path):
             assert vv == val * (-1) ** i
             s = osenv.step(s, m)
     w.close()
+
+
+def test_pipelined_search_equals_sequential(cuda_lib):
+    """cz_search pipelines two halves of the games on two streams; per-game results must not depend on that."""
+    from cczero_b200.engine import Engine
+    from cczero_b200.model import CChessModel
+    cfg = _config("/tmp", filters=64, blocks=2)
+    weights = CChessModel(cfg).build(seed=9).torch_weights()
+
+    def run(no_pipeline):
+        os.environ["CZ_NO_PIPELINE"] = "1" if no_pipeline else "0"
+        try:
+            eng = Engine(cuda_lib, "cuda", n_games=96, sims_per_move=40, leaves_per_round=4, noise_mode=1, nn_filters=64,
+                         nn_blocks=2, seed=5)
+        finally:
+            os.environ.pop("CZ_NO_PIPELINE", None)
+        eng.set_weights(weights)
+        eng.reset()
+        out = []
+        for _ in range(3):
+            eng.search(None)
+            out.append([(eng.root(g)["n"], eng.root(g)["sum_n"]) for g in (0, 47, 48, 95)])
+            eng.play_move()
+        sims = eng.sims_run().tolist()
+        eng.close()
+        return out, sims
+
+    a, sa = run(False)
+    b, sb = run(True)
+    assert a == b and sa == sb
