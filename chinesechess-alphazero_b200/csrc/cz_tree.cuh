@@ -91,6 +91,7 @@ struct EngineDev {
   int32_t* totals;               // [4]: total leaves, any active, -, -
   uint8_t* leaf_dense;           // [G*K][96] leaves of all games, dense
   unsigned long long* counters;  // [8]
+  int32_t* gc_map;               // [G*ncap] scratch of game_compact: old node -> new node + 1 (0 = dropped)
   SelfplayDev sp;
 };
 
@@ -524,6 +525,100 @@ CZ_D void game_apply(const EngineDev& E, int g, const float* policy, const float
   czs::syncwarp();
 }
 
+// ------------------------------------------------------------------ pool compaction
+// Keep only the nodes reachable from `root` through cached child links (every node the searches below the current root
+// have walked to) and slide them, with their edges, to the front of the pools; rebuild the hash table.  The reference
+// never frees tree entries during a game (player.py:49, self_play.py:107); this is what the engine does INSTEAD of
+// dropping the whole table when a pool cannot hold the next search.  Statistics of every kept node are untouched.
+// Positions that were only reachable by transposition through an edge never walked from the kept subtree are dropped
+// and would be re-expanded if met again.  Returns the new root index.
+CZ_D int game_compact(const EngineDev& E, int g, int root) {
+  const int nn = E.n_nodes[g];
+  int32_t* map = E.gc_map + (size_t)g * E.ncap;
+  uint32_t* queue = E.hash + (size_t)g * E.hcap;            // the table is rebuilt below; borrow it as the BFS queue
+  czs::syncwarp();
+  for (int i = czs::lane(); i < nn; i += 32) map[i] = 0;
+  czs::syncwarp();
+  int kept = 0;
+  if (czs::lane() == 0) {                                    // breadth-first walk over child links
+    int head = 0, tail = 0;
+    queue[tail++] = (uint32_t)root; map[root] = 1;
+    while (head < tail) {
+      const int n = (int)queue[head++];
+      const size_t ni = (size_t)g * E.ncap + n;
+      const int L = (int)(E.node_meta[ni] & 0xff);
+      const size_t eo = (size_t)g * E.ecap + E.node_edge_off[ni];
+      for (int i = 0; i < L; ++i) {
+        const int c = E.edge_child[eo + i];
+        if (c >= 0 && map[c] == 0) { map[c] = 1; queue[tail++] = (uint32_t)c; }
+      }
+    }
+    kept = tail;
+  }
+  kept = czs::shfl(kept, 0);
+  czs::syncwarp();
+  // new indices in old order (so every move below goes towards lower addresses)
+  int cnt = 0;
+  for (int base = 0; base < nn; base += 32) {
+    const int i = base + czs::lane();
+    const bool k = i < nn && map[i] != 0;
+    const unsigned m = czs::ballot(k);
+    if (k) map[i] = cnt + czs::popc(m & ((1u << czs::lane()) - 1u)) + 1;
+    cnt += czs::popc(m);
+  }
+  czs::syncwarp();
+  // slide nodes and their edges
+  int ne = 0;
+  for (int i = 0; i < nn; ++i) {
+    const int j1 = map[i];
+    if (j1 == 0) continue;
+    const int j = j1 - 1;
+    const size_t si = (size_t)g * E.ncap + i, di = (size_t)g * E.ncap + j;
+    const int L = (int)(E.node_meta[si] & 0xff);
+    const size_t so = (size_t)g * E.ecap + E.node_edge_off[si], dof = (size_t)g * E.ecap + ne;
+    czs::syncwarp();
+    for (int b = 0; b < L; b += 32) {
+      const int k = b + czs::lane();
+      int n_ = 0, ch = 0; double w_ = 0; float p_ = 0; uint16_t mv = 0;
+      if (k < L) { n_ = E.edge_n[so + k]; w_ = E.edge_w[so + k]; p_ = E.edge_p[so + k]; mv = E.edge_move[so + k]; ch = E.edge_child[so + k]; }
+      czs::syncwarp();
+      if (k < L) {
+        if (ch >= 0) ch = map[ch] ? map[ch] - 1 : CHILD_UNKNOWN;
+        E.edge_n[dof + k] = n_; E.edge_w[dof + k] = w_; E.edge_p[dof + k] = p_; E.edge_move[dof + k] = mv; E.edge_child[dof + k] = ch;
+      }
+      czs::syncwarp();
+    }
+    if (czs::lane() == 0) {
+      const uint64_t k0 = E.node_key0[si], k1 = E.node_key1[si];
+      const int sn = E.node_sum_n[si]; const uint32_t meta = E.node_meta[si];
+      E.node_key0[di] = k0; E.node_key1[di] = k1; E.node_sum_n[di] = sn; E.node_meta[di] = meta; E.node_edge_off[di] = (uint32_t)ne;
+    }
+    ne += L;
+    czs::syncwarp();
+  }
+  // rebuild the table
+  uint32_t* h = E.hash + (size_t)g * E.hcap;
+  for (int i = czs::lane(); i < E.hcap; i += 32) h[i] = 0;
+  czs::syncwarp();
+  if (czs::lane() == 0) {
+    const uint32_t mask = (uint32_t)E.hcap - 1;
+    for (int j = 0; j < cnt; ++j) {
+      uint32_t s = (uint32_t)E.node_key0[(size_t)g * E.ncap + j] & mask;
+      while (h[s] != 0) s = (s + 1) & mask;
+      h[s] = (uint32_t)j + 1;
+    }
+    E.n_nodes[g] = cnt; E.n_edges[g] = ne;
+#if defined(CZ_EMUL)
+    E.counters[5] += 1;
+#else
+    atomicAdd(E.counters + 5, 1ULL);
+#endif
+  }
+  czs::syncwarp();
+  (void)kept;
+  return map[root] - 1;
+}
+
 // ------------------------------------------------------------------ begin: tree reuse and task count (action, :147-171)
 CZ_D void game_begin(const EngineDev& E, int g, int sims_override, TreeSmem* sm) {
   if (!E.active[g]) return;
@@ -537,8 +632,13 @@ CZ_D void game_begin(const EngineDev& E, int g, int sims_override, TreeSmem* sm)
   if (sims_override > 0) num_task = sims_override > done ? sims_override - done : 0;
   if (num_task < 0) num_task = 0;
   // pools must be able to hold this search; otherwise start from an empty table (counted)
-  const bool low = (E.ncap - E.n_nodes[g] < num_task + 2 || E.ecap - E.n_edges[g] < (num_task + 2) * 64) && E.n_nodes[g] > 0;
+  bool low = (E.ncap - E.n_nodes[g] < num_task + 2 || E.ecap - E.n_edges[g] < (num_task + 2) * 64) && E.n_nodes[g] > 0;
   czs::syncwarp();                                   // reads above complete before lane 0 rewrites the counters
+  if (low && root >= 0) {                            // keep what the game can still reach, drop the rest
+    root = game_compact(E, g, root);
+    low = E.ncap - E.n_nodes[g] < num_task + 2 || E.ecap - E.n_edges[g] < (num_task + 2) * 64;
+    czs::syncwarp();
+  }
   if (low) {
     uint32_t* h = E.hash + (size_t)g * E.hcap;
     for (int i = czs::lane(); i < E.hcap; i += 32) h[i] = 0;

@@ -137,6 +137,21 @@ CZ_KERNEL(k_set_roots)(EngineDev E, const uint8_t* boards) {
 CZ_KERNEL(k_noise_sample)(EngineDev E, int game, int n_moves, int count, double* out) {
   for (int i = czs::block_idx() * 32 + czs::lane(); i < count; i += 32 * 64) out[i] = dirichlet_first(E, game, (uint32_t)i, n_moves);
 }
+CZ_KERNEL(k_compact)(EngineDev E) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  TreeSmem* sm = tree_smem();
+  copy_board(E.root_board + (size_t)g * BOARD_STRIDE, sm->board);
+  uint64_t k0, k1;
+  board_key(sm->board, &k0, &k1);
+  const int root = tt_lookup(E, g, k0, k1);
+  if (root >= 0) {
+    const int nr = game_compact(E, g, root);
+    if (czs::lane() == 0) E.root_node[g] = nr;
+  } else {
+    clear_tree(E, g);
+  }
+}
 CZ_KERNEL(k_set_opts)(EngineDev E, const uint16_t* no_act, const uint8_t* inc, const uint8_t* act) {
   const int g = my_game();
   if (g >= E.n_games) return;
@@ -222,6 +237,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.leaf_off = cv.take<int32_t>(G); d.totals = cv.take<int32_t>(8);
   d.leaf_dense = cv.take<uint8_t>(G * K * BOARD_STRIDE);
   d.counters = cv.take<unsigned long long>(8);
+  d.gc_map = cv.take<int32_t>(G * N);
   selfplay_carve(d.sp, cv, c);
   e->init_board_dev = cv.take<uint8_t>(BOARD_STRIDE);
   e->opt_no_act = cv.take<uint8_t>(G * CZ_MAX_NO_ACT * 2); e->opt_inc = cv.take<uint8_t>(G); e->opt_act = cv.take<uint8_t>(G);
@@ -409,6 +425,14 @@ int cz_get_root_stats(cz_engine* e, int32_t* n_host, uint16_t* moves_host, int32
   czrt_copy(counts_host, e->stat_cnt, G * sizeof(int32_t), e->stream);
   if (sims_run_host) czrt_copy(sims_run_host, e->d.sims_run, G * sizeof(int32_t), e->stream);
   return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_get_root_stats: device failure") : 0;
+}
+
+int cz_compact(cz_engine* e) {
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_compact: null engine");
+  if (e->last_leaves != 0) return cz_fail(CZ_ERR_STATE, "cz_compact: a search is in flight");
+  GAME_LAUNCH(e, k_compact, e->d);
+  if (launch_ok(e, "cz_compact")) return CZ_ERR_CUDA;
+  return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_compact: device failure") : 0;
 }
 
 int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {

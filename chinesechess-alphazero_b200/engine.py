@@ -190,6 +190,9 @@ class Engine:
         self.download_root_stats(st)
         return st.sims.numpy()
 
+    def compact(self):
+        self.lib.call("cz_compact", self._h)
+
     def counters(self):
         a = np.zeros(8, dtype=np.uint64)
         self.lib.call("cz_get_counters", self._h, C.c_void_p(a.ctypes.data))

@@ -77,6 +77,7 @@ _SIGS = {
     "cz_set_roots": (C.c_int, [_P, _P]),
     "cz_get_roots": (C.c_int, [_P, _P]),
     "cz_get_root_stats": (C.c_int, [_P, _P, _P, _P, _P]),
+    "cz_compact": (C.c_int, [_P]),
     "cz_search_begin": (C.c_int, [_P, C.POINTER(CzRootOpts)]),
     "cz_search_wave": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cz_leaf_planes": (C.c_int, [_P, _P]),

@@ -168,8 +168,12 @@ int cz_get_root(cz_engine* e, int game, cz_root_info* out_host);
  * (0xFFFF padded), counts_host [n_games] legal-move counts, sims_run_host [n_games] or NULL.  Synchronises. */
 int cz_get_root_stats(cz_engine* e, int32_t* n_host, uint16_t* moves_host, int32_t* counts_host, int32_t* sims_run_host);
 
-/* Counters since cz_create: [0] simulations completed, [1] NN positions evaluated,
- * [2] wave iterations, [3] nodes created, [4] tree resets forced by pool overflow. */
+/* Compact every game's pools now: keep the nodes reachable from the current root (statistics untouched), drop the
+ * rest, rebuild the hash tables.  cz_search_begin does this on its own when a pool cannot hold the next search. */
+int cz_compact(cz_engine* e);
+
+/* Counters since cz_create: [0] simulations completed, [1] NN positions evaluated, [2] wave iterations,
+ * [4] whole-table resets (compaction was not enough / root unknown), [5] compactions. */
 int cz_get_counters(cz_engine* e, uint64_t* out_host /* [8] */);
 
 /* ------------------------------------------------------------------------------------------
