@@ -1,0 +1,95 @@
+"""Pin the oracle restatements to the REAL reference (read-only tree at /root/reference).  These tests run in the build
+container; on the GPU box the tree is absent and they skip — the committed golden vectors (tests/golden/, generated from
+the same reference by oracle/gen_golden*.py) carry the pin there."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import player as op
+from oracle import ref_import
+from oracle import senv as o
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+
+
+def test_env_restatement_on_random_playouts():
+    r = ref_import.senv()
+    lt = ref_import.lookup_tables()
+    assert o.ActionLabelsRed == lt.ActionLabelsRed
+    assert [o.flip_move(m) for m in o.ActionLabelsRed[:50]] == [lt.flip_move(m) for m in lt.ActionLabelsRed[:50]]
+    rng = random.Random(7)
+    n = 0
+    for g in range(25):
+        s = r.INIT_STATE
+        for ply in range(200):
+            lm = r.get_legal_moves(s)
+            assert o.get_legal_moves(s) == lm
+            assert o.done(s) == r.done(s) and o.done(s, need_check=True) == r.done(s, need_check=True)
+            assert (o.state_to_planes(s) == r.state_to_planes(s)).all()
+            assert o.has_attack_chessman(s) == r.has_attack_chessman(s) and o.fliped_state(s) == r.fliped_state(s)
+            if r.done(s)[0]:
+                break
+            m = rng.choice(lm)
+            if ply % 2 == 0:
+                assert o.will_check_or_catch(s, m) == r.will_check_or_catch(s, m)
+                assert o.be_catched(s, m) == r.be_catched(s, m)
+            assert o.new_step(s, m) == r.new_step(s, m)
+            s = r.step(s, m)
+            n += 1
+    assert n > 500
+
+
+def test_reference_smoke_vectors():
+    """The print-and-eyeball vectors of the reference's test.py, as assertions on the oracle."""
+    assert o.done('4s4/9/4e4/p8/2e2R2p/P5E2/8P/9/9/4S1E2') == (False, 0, None)
+    assert o.get_legal_moves('4s4/9/9/9/9/9/9/9/9/4S4') == ['4050', '4049', '4041', '4049', '4030', '4049']
+    s1 = o.step(o.INIT_STATE, '0001')
+    assert s1 == 'rkemsmek1/8r/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RKEMSMEKR'
+    assert o.step(s1, o.flip_move('7770')) == 'rkemsmekr/9/1c7/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/R8/1KEMSMEcR'
+    assert len(o.get_legal_moves(o.INIT_STATE)) == 44
+
+
+def _oracle_root(state, sims, k, seed):
+    pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.25, dirichlet_alpha=0.2,
+                       tau_decay_rate=0.98, virtual_loss=3, resign_threshold=-0.92, min_resign_turn=20)
+    np.random.seed(seed)
+    pl = op.OraclePlayer(pc, op.fake_evaluate_states)
+    a, _ = pl.action(state, 0)
+    return a, pl.tree[state]
+
+
+def test_player_restatement_equals_real_player_k1():
+    from oracle.ref_player_harness import real_player_moves
+    for sims, seed in ((80, 1), (150, 2)):
+        real = real_player_moves([(o.INIT_STATE, 0, None, False)], sims, seed)[0]
+        a, node = _oracle_root(o.INIT_STATE, sims, 1, seed)
+        got = {m: (int(e.n), float(e.w), float(e.q), float(e.p)) for m, e in node.a.items()}
+        assert a == real[0] and got == real[1] and node.sum_n == real[2]
+
+
+def test_canonical_schedule_is_statistically_the_threaded_player_k10():
+    """search_threads = 10: the real player is a racy thread pool (not reproducible); the canonical schedule must be
+    statistically indistinguishable from it.  Total-variation distance between root visit distributions: oracle-vs-real
+    must not exceed the real player's own run-to-run spread, and the seed-averaged distributions must agree."""
+    from oracle.ref_player_harness import real_player_moves
+    sims, k, seeds = 300, 10, range(5)
+    lm = o.get_legal_moves(o.INIT_STATE)
+
+    def real(seed):
+        r = real_player_moves([(o.INIT_STATE, 0, None, False)], sims, seed, search_threads=k)[0]
+        return np.array([r[1].get(m, (0,))[0] for m in lm], float)
+
+    def mine(seed):
+        _, node = _oracle_root(o.INIT_STATE, sims, k, seed)
+        return np.array([node.a[m].n if m in node.a else 0 for m in lm], float)
+
+    def tv(a, b):
+        return 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+
+    R, O = [real(s) for s in seeds], [mine(s) for s in seeds]
+    assert all(x.sum() == sims - 1 for x in R + O)
+    spread_real = np.mean([tv(R[i], R[j]) for i in seeds for j in seeds if i < j])
+    cross = np.mean([tv(R[i], O[j]) for i in seeds for j in seeds])
+    assert cross <= 1.5 * spread_real + 0.02, (cross, spread_real)
+    assert tv(sum(R), sum(O)) < 0.05
