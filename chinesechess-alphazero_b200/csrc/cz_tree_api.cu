@@ -137,6 +137,13 @@ CZ_KERNEL(k_set_roots)(EngineDev E, const uint8_t* boards) {
 CZ_KERNEL(k_noise_sample)(EngineDev E, int game, int n_moves, int count, double* out) {
   for (int i = czs::block_idx() * 32 + czs::lane(); i < count; i += 32 * 64) out[i] = dirichlet_first(E, game, (uint32_t)i, n_moves);
 }
+// single warp: counters[6] = OR of the per-game error flags, counters[7] = games with any flag set
+CZ_KERNEL(k_err_reduce)(EngineDev E) {
+  int orv = 0, cnt = 0;
+  for (int g = czs::lane(); g < E.n_games; g += 32) { const int f = E.game_err[g]; orv |= f; cnt += f != 0; }
+  for (int m = 16; m; m >>= 1) { orv |= czs::shfl_xor(orv, m); cnt += czs::shfl_xor(cnt, m); }
+  if (czs::lane() == 0) { E.counters[6] = (unsigned long long)orv; E.counters[7] = (unsigned long long)cnt; }
+}
 CZ_KERNEL(k_compact)(EngineDev E) {
   const int g = my_game();
   if (g >= E.n_games) return;
@@ -590,6 +597,7 @@ int cz_get_root(cz_engine* e, int game, cz_root_info* out) {
 int cz_get_counters(cz_engine* e, uint64_t* out) {
   if (!e || !out) return cz_fail(CZ_ERR_ARG, "cz_get_counters: bad argument");
   unsigned long long dc[8];
+  CZ_LAUNCH(k_err_reduce, 1, 1, 0, e->stream, e->d);
   czrt_copy(dc, e->d.counters, sizeof(dc), e->stream);
   if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_get_counters: device failure");
   std::vector<int32_t> sr(e->cfg.n_games);

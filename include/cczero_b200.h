@@ -173,7 +173,9 @@ int cz_get_root_stats(cz_engine* e, int32_t* n_host, uint16_t* moves_host, int32
 int cz_compact(cz_engine* e);
 
 /* Counters since cz_create: [0] simulations completed, [1] NN positions evaluated, [2] wave iterations,
- * [4] whole-table resets (compaction was not enough / root unknown), [5] compactions. */
+ * [4] whole-table resets (compaction was not enough / root unknown), [5] compactions,
+ * [6] OR of the per-game error flags (1 path longer than max_path, 2 pool exhausted inside a search, 4 host noise table
+ * exhausted, 8 node without a playable move), [7] number of games with a flag set.  Flags clear at cz_reset_games. */
 int cz_get_counters(cz_engine* e, uint64_t* out_host /* [8] */);
 
 /* ------------------------------------------------------------------------------------------

@@ -121,6 +121,7 @@ def compare_root(eng, game, pl, state):
         assert (n, w, float(np.float32(p))) == (en, ew, ep), (state, m, (n, w, p), (en, ew, ep))
     assert r["noise_used"] == pl.stats["noise_draws"]
     assert r["sims_run"] == pl.stats["sims"]
+    assert int(eng.counters()[6]) == 0 and int(eng.counters()[4]) == 0      # no error flag, no table reset
 
 
 def midgame_states(n, seed, lo=15, hi=80):
