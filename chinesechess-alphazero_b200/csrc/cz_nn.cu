@@ -464,8 +464,20 @@ struct Carver {
   }
 };
 
+// One network's folded weights (the arena holds two: best vs next generation, worker/evaluator.py:28-82).
+struct NetWeights {
+  __half* w_first; float* shift_first;
+  __half* w_conv;  float* shift_conv;
+  float *w6, *shift6, *wv1, *bv1, *wv2, *bv2;
+  __half* w_pol; float* b_pol;
+  CUtensorMap map_wpol;
+  std::vector<CUtensorMap> map_w, map_w_half;
+  bool ready;
+};
+
 struct NnRuntime {
   int filters, blocks, value_fc, max_batch;
+  NetWeights nets[2]; int n_nets, cur;     // the weight fields below alias nets[cur] (select_net / store_net)
   cudaStream_t stream;
   bool ready;
   uint64_t launches;
@@ -495,6 +507,24 @@ struct NnRuntime {
   double prof_ms, prof_flops; uint64_t prof_launches;
 };
 
+static void store_net(NnRuntime* r, int k) {
+  NetWeights& n = r->nets[k];
+  n.w_first = r->w_first; n.shift_first = r->shift_first; n.w_conv = r->w_conv; n.shift_conv = r->shift_conv;
+  n.w6 = r->w6; n.shift6 = r->shift6; n.wv1 = r->wv1; n.bv1 = r->bv1; n.wv2 = r->wv2; n.bv2 = r->bv2;
+  n.w_pol = r->w_pol; n.b_pol = r->b_pol; n.map_wpol = r->map_wpol; n.map_w = r->map_w; n.map_w_half = r->map_w_half;
+  n.ready = r->ready;
+}
+static void select_net(NnRuntime* r, int k) {
+  if (r->cur == k) return;
+  store_net(r, r->cur);
+  const NetWeights& n = r->nets[k];
+  r->w_first = n.w_first; r->shift_first = n.shift_first; r->w_conv = n.w_conv; r->shift_conv = n.shift_conv;
+  r->w6 = n.w6; r->shift6 = n.shift6; r->wv1 = n.wv1; r->bv1 = n.bv1; r->wv2 = n.wv2; r->bv2 = n.bv2;
+  r->w_pol = n.w_pol; r->b_pol = n.b_pol; r->map_wpol = n.map_wpol; r->map_w = n.map_w; r->map_w_half = n.map_w_half;
+  r->ready = n.ready;
+  r->cur = k;
+}
+
 static void prof_collect(NnRuntime* r) {
   for (size_t i = 0; i + 1 < r->ev_used; i += 2) {
     float ms = 0.f;
@@ -516,6 +546,7 @@ static void layout(NnRuntime* r, Carver& cv) {
   r->pol_feat = (__half*)cv.take(((size_t)r->max_batch + 128) * kPolK * sizeof(__half));
   r->logits = (float*)cv.take((size_t)r->max_batch * kPolN * sizeof(float));
   r->boards_tmp = (uint8_t*)cv.take((size_t)r->max_batch * CZ_BOARD_STRIDE);
+  for (int net = 0; net < r->n_nets; ++net) {
   r->w_first = (__half*)cv.take((size_t)25 * 14 * c * sizeof(__half));
   r->shift_first = (float*)cv.take(c * sizeof(float));
   r->w_conv = (__half*)cv.take((size_t)2 * r->blocks * 9 * c * c * sizeof(__half));
@@ -528,25 +559,32 @@ static void layout(NnRuntime* r, Carver& cv) {
   r->bv2 = (float*)cv.take(4 * sizeof(float));
   r->w_pol = (__half*)cv.take((size_t)kPolN * kPolK * sizeof(__half));
   r->b_pol = (float*)cv.take(kPolN * sizeof(float));
+  r->ready = false;
+  r->cur = net;
+  store_net(r, net);
+  }
+  if (r->n_nets > 1) { r->cur = r->n_nets - 1; select_net(r, 0); }
+  r->cur = 0;
   r->scratch = (float*)cv.take((size_t)2 * 256 * sizeof(float));
 }
 
-size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch) {
+size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch, int n_nets) {
   NnRuntime tmp;
-  tmp.filters = filters; tmp.blocks = blocks; tmp.value_fc = value_fc; tmp.max_batch = max_batch;
+  tmp.filters = filters; tmp.blocks = blocks; tmp.value_fc = value_fc; tmp.max_batch = max_batch; tmp.n_nets = n_nets; tmp.cur = 0;
   Carver cv{nullptr, 0, 0};
   layout(&tmp, cv);
   return cv.off + 4096;
 }
 
 NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_batch, void* workspace, size_t bytes,
-                     void* stream, int fp32_skip_mode) {
+                     void* stream, int fp32_skip_mode, int n_nets) {
   (void)device;
   if (filters % 64 != 0 || filters < 64 || filters > 256) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: filters must be 64..256 step 64"); return nullptr; }
   if (value_fc > 256 || value_fc < 1) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: value_fc_size must be <= 256"); return nullptr; }
-  if (bytes < nn_workspace_bytes(filters, blocks, value_fc, max_batch)) { cz_fail(CZ_ERR_ARG, "nn: workspace too small"); return nullptr; }
+  if (n_nets < 1 || n_nets > 2) { cz_fail(CZ_ERR_ARG, "nn: 1 or 2 networks"); return nullptr; }
+  if (bytes < nn_workspace_bytes(filters, blocks, value_fc, max_batch, n_nets)) { cz_fail(CZ_ERR_ARG, "nn: workspace too small"); return nullptr; }
   NnRuntime* r = new NnRuntime();
-  r->filters = filters; r->blocks = blocks; r->value_fc = value_fc; r->max_batch = max_batch;
+  r->filters = filters; r->blocks = blocks; r->value_fc = value_fc; r->max_batch = max_batch; r->n_nets = n_nets; r->cur = 0;
   r->stream = (cudaStream_t)stream; r->ready = false; r->launches = 0;
   // 0 = auto (fp32 skip stream for towers deeper than 10 blocks, where fp16 rounding of the skip stream pushes the value
   // error past 1e-3: measured 1.1e-3 .. 1.5e-3 at 20 blocks vs <= 6e-4 with fp32), 1 = always, 2 = never
@@ -568,12 +606,16 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   rc |= make_map_3d(&r->map_t, r->t, c, 9, rows, 9, 14);
   rc |= make_map_3d(&r->map_y, r->y, c, 9, rows, 9, 14);
   rc |= make_map_3d(&r->map_pf, r->pol_feat, kPolK, 1, (long long)max_batch + 128, 1, 128);
-  rc |= make_map_2d(&r->map_wpol, r->w_pol, kPolK, kPolN, 256);
-  r->map_w.resize(2 * blocks);
-  r->map_w_half.resize(2 * blocks);
-  for (int i = 0; i < 2 * blocks; ++i) {
-    rc |= make_map_2d(&r->map_w[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c);
-    rc |= make_map_2d(&r->map_w_half[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c / 2);
+  for (int net = n_nets - 1; net >= 0; --net) {
+    select_net(r, net);
+    rc |= make_map_2d(&r->map_wpol, r->w_pol, kPolK, kPolN, 256);
+    r->map_w.resize(2 * blocks);
+    r->map_w_half.resize(2 * blocks);
+    for (int i = 0; i < 2 * blocks; ++i) {
+      rc |= make_map_2d(&r->map_w[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c);
+      rc |= make_map_2d(&r->map_w_half[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c / 2);
+    }
+    store_net(r, net);
   }
   if (rc) { delete r; return nullptr; }
   // separator rows and padding must start as zeros
@@ -601,7 +643,12 @@ int nn_profile_read(NnRuntime* r, double* ms, uint64_t* launches, double* flops)
   r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0;
   return 0;
 }
-bool nn_ready(const NnRuntime* r) { return r && r->ready; }
+bool nn_ready(const NnRuntime* r) {
+  if (!r) return false;
+  for (int k = 0; k < r->n_nets; ++k)
+    if (!(k == r->cur ? r->ready : r->nets[k].ready)) return false;
+  return true;
+}
 uint64_t nn_launches(const NnRuntime* r) { return r ? r->launches : 0; }
 
 // ---- weights -----------------------------------------------------------------------------------
@@ -641,8 +688,10 @@ static int fold_bn(NnRuntime* r, const WeightSet& ws, const std::string& layer, 
   return 0;
 }
 
-int nn_set_weights(NnRuntime* r, const cz_tensor_desc* descs, int n) {
+int nn_set_weights(NnRuntime* r, int net, const cz_tensor_desc* descs, int n) {
   if (!r) return cz_fail(CZ_ERR_STATE, "cz_nn_set_weights: engine was created without a network (nn_filters = 0)");
+  if (net < 0 || net >= r->n_nets) return cz_fail(CZ_ERR_ARG, "cz_nn_set_weights: network %d of %d", net, r->n_nets);
+  select_net(r, net);
   WeightSet ws{descs, n};
   const int c = r->filters;
   cudaStream_t st = r->stream;
@@ -748,8 +797,10 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
   return 0;
 }
 
-int nn_forward_boards(NnRuntime* r, const uint8_t* boards, int batch, float* policy, float* value) {
-  if (!r || !r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
+int nn_forward_boards(NnRuntime* r, int net, const uint8_t* boards, int batch, float* policy, float* value) {
+  if (!r || net < 0 || net >= r->n_nets) return cz_fail(CZ_ERR_STATE, "no such network");
+  select_net(r, net);
+  if (!r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
   for (int off = 0; off < batch; off += r->max_batch) {
     const int n = batch - off < r->max_batch ? batch - off : r->max_batch;
     const int rc = forward_chunk(r, boards + (size_t)off * CZ_BOARD_STRIDE, n, policy + (size_t)off * kLabels, value + off);
@@ -758,8 +809,10 @@ int nn_forward_boards(NnRuntime* r, const uint8_t* boards, int batch, float* pol
   return 0;
 }
 
-int nn_forward_planes(NnRuntime* r, const float* planes, int batch, float* policy, float* value) {
-  if (!r || !r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
+int nn_forward_planes(NnRuntime* r, int net, const float* planes, int batch, float* policy, float* value) {
+  if (!r || net < 0 || net >= r->n_nets) return cz_fail(CZ_ERR_STATE, "no such network");
+  select_net(r, net);
+  if (!r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
   for (int off = 0; off < batch; off += r->max_batch) {
     const int n = batch - off < r->max_batch ? batch - off : r->max_batch;
     k_planes_to_boards<<<n, 96, 0, r->stream>>>(planes + (size_t)off * 14 * 90, r->boards_tmp, n);

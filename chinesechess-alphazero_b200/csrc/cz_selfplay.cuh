@@ -43,11 +43,49 @@ CZ_D void selfplay_start_game(const EngineDev& E, int g, uint8_t* board_smem) {
   czs::syncwarp();
 }
 
+// Arena (worker/evaluator.py:147-170): slots g and partner(g) are the two players' trees of game (g mod M).  The game with
+// running index idx = started*M + (g mod M) has player idx % 2 as red ("even: best = red, odd: best = black"); only the
+// slot of the player to move is active.
+CZ_D int arena_partner(const EngineDev& E, int g) { const int m = E.n_games / 2; return g < m ? g + m : g - m; }
+CZ_D int arena_mover_slot(const EngineDev& E, int g, int started, int turns) {
+  const int m = E.n_games / 2, i = g % m;
+  const int idx = started * m + i;
+  const int player = (idx + turns) & 1;             // red = player idx % 2 moves on even plies
+  return i + player * m;
+}
+
 CZ_D void selfplay_reset_game(const EngineDev& E, int g) {
   if (czs::lane() == 0) E.sp.games_started[g] = 0;
   czs::syncwarp();
   TreeSmem* sm = reinterpret_cast<TreeSmem*>(czs::dyn_smem()) + czs::warp_in_block();
   selfplay_start_game(E, g, sm->board);
+  if (E.arena && czs::lane() == 0) {
+    E.sp.enable_resign[g] = 0;                      // evaluator.py:157-160: enable_resign=False
+    E.active[g] = arena_mover_slot(E, g, 0, 0) == g ? 1 : 0;
+  }
+  czs::syncwarp();
+}
+
+// After slot g played a ply (game not over): hand the game to the partner slot — same position, counters, history and the
+// bans computed for the next mover — and flip which of the two is active.
+CZ_D void arena_handover(const EngineDev& E, int g, int turns_before, int turns_after) {
+  const SelfplayDev& sp = E.sp;
+  const int p = arena_partner(E, g);
+  czs::syncwarp();
+  for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) E.root_board[(size_t)p * BOARD_STRIDE + k] = E.root_board[(size_t)g * BOARD_STRIDE + k];
+  if (czs::lane() == 0) {
+    sp.turns[p] = sp.turns[g]; sp.no_eat[p] = sp.no_eat[g];
+    const size_t hg = (size_t)g * sp.hist_stride, hp = (size_t)p * sp.hist_stride;
+    for (int t = turns_before; t < turns_after; ++t) sp.hist_move[hp + t] = sp.hist_move[hg + t];
+    for (int t = turns_before + 1; t <= turns_after; ++t) { sp.hist_k0[hp + t] = sp.hist_k0[hg + t]; sp.hist_k1[hp + t] = sp.hist_k1[hg + t]; }
+    const int n = E.n_no_act[g];
+    E.n_no_act[p] = n;
+    for (int k = 0; k < n; ++k) E.no_act[(size_t)p * CZ_MAX_NO_ACT + k] = E.no_act[(size_t)g * CZ_MAX_NO_ACT + k];
+    E.increase_temp[p] = E.increase_temp[g];
+    E.n_no_act[g] = 0; E.increase_temp[g] = 0;
+    E.active[g] = 0; E.active[p] = 1;
+  }
+  czs::syncwarp();
 }
 
 CZ_D void clear_tree(const EngineDev& E, int g) {
@@ -183,9 +221,10 @@ CZ_D void game_play(const EngineDev& E, int g, const uint8_t* init_board, TreeSm
           const size_t hi = (size_t)g * sp.hist_stride + i;
           if (sp.hist_k0[hi] != k0 || sp.hist_k1[hi] != k1) continue;
           const move_t pm = sp.hist_move[hi];
+          if (E.arena) inc = true;                   // evaluator.py:176-178: any repetition raises the temperature
           if (will_check_or_catch(sm->board, pm, &sm->sc)) {
             if (n_ban < CZ_MAX_NO_ACT) { if (czs::lane() == 0) E.no_act[(size_t)g * CZ_MAX_NO_ACT + n_ban] = pm; ++n_ban; }
-          } else if (!be_catched(sm->board, pm, &sm->sc)) {
+          } else if (E.arena || !be_catched(sm->board, pm, &sm->sc)) {   // the evaluator has no be_catched exemption (:186-193)
             inc = true;
             if (++idle >= 3) { over = true; value = 0; flags |= REC_DRAW_RULE; }
           }
@@ -205,12 +244,13 @@ CZ_D void game_play(const EngineDev& E, int g, const uint8_t* init_board, TreeSm
     for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) E.root_board[(size_t)g * BOARD_STRIDE + k] = k < NSQ ? sm->board[k] : (uint8_t)0;
     if (czs::lane() == 0) sp.turns[g] = turns;
     czs::syncwarp();
+    if (E.arena) arena_handover(E, g, turns0, turns);
     return;
   }
   // ---- game over: result from red's view (:190-191), store rule (:194-200), record (:202-208)
   if (turns % 2 == 1) value = -value;
   bool store = true;
-  if (turns < 10) {
+  if (turns < 10 && !E.arena) {
     Rng r; r.init(E.seed, E.rank, (uint32_t)g, 4u, (uint32_t)sp.games_started[g]);
     store = r.uniform() > 0.9;
   }
@@ -225,7 +265,9 @@ CZ_D void game_play(const EngineDev& E, int g, const uint8_t* init_board, TreeSm
   slot = czs::shfl(slot, 0);
   if (slot < sp.rec_cap) {
     if (czs::lane() == 0) {
-      RecordHdr h; h.n_plies = turns; h.value_red = value; h.game_index = sp.games_started[g] * E.n_games + g;
+      RecordHdr h; h.n_plies = turns; h.value_red = value;
+      h.game_index = E.arena ? sp.games_started[g] * (E.n_games / 2) + g % (E.n_games / 2)
+                             : sp.games_started[g] * E.n_games + g;
       h.flags = flags | (store ? 0 : REC_NOT_STORED);
       sp.rec_hdr[slot] = h;
     }
@@ -238,6 +280,20 @@ CZ_D void game_play(const EngineDev& E, int g, const uint8_t* init_board, TreeSm
   czs::syncwarp();
   clear_tree(E, g);
   selfplay_start_game(E, g, sm->board);
+  if (E.arena) {                                     // both players start the next game of this pair with empty trees
+    const int p = arena_partner(E, g);
+    for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) E.root_board[(size_t)p * BOARD_STRIDE + k] = k < NSQ ? init_board[k] : (uint8_t)0;
+    if (czs::lane() == 0) { sp.games_started[p] = sp.games_started[g]; E.n_no_act[p] = 0; E.increase_temp[p] = 0; }
+    czs::syncwarp();
+    clear_tree(E, p);
+    selfplay_start_game(E, p, sm->board);
+    if (czs::lane() == 0) {
+      sp.enable_resign[g] = 0; sp.enable_resign[p] = 0;
+      const int mv = arena_mover_slot(E, g, sp.games_started[g], 0);
+      E.active[g] = mv == g ? 1 : 0; E.active[p] = mv == p ? 1 : 0;
+    }
+    czs::syncwarp();
+  }
 }
 
 }  // namespace cz

@@ -45,6 +45,7 @@ struct EngineDev {
   double c_puct, noise_eps, alpha, tau_decay, resign_threshold;
   int min_resign_turn, max_game_length;
   uint64_t seed; int rank;
+  int arena;                     // 1: slots g and g + G/2 are the two players' trees of one game (worker/evaluator.py)
   // ---- tables
   const int16_t* label_lut;      // [8100]
   // ---- per game: root + search bookkeeping

@@ -267,6 +267,7 @@ int check_cfg(const cz_config* c) {
   if (c->max_nodes_per_game < 16 || c->max_edges_per_game < 256 || c->max_path < 8)
     return cz_fail(CZ_ERR_ARG, "cz_config: pools too small");
   if (c->virtual_loss < 0 || c->max_plies < 2) return cz_fail(CZ_ERR_ARG, "cz_config: bad virtual_loss / max_plies");
+  if (c->arena && (c->n_games % 2)) return cz_fail(CZ_ERR_ARG, "cz_config: arena mode needs an even number of slots (two per game)");
   return 0;
 }
 
@@ -310,7 +311,7 @@ int cz_workspace_bytes(const cz_config* cfg, uint64_t* bytes) {
   size_t n = carve(&tmp, nullptr);
 #if !defined(CZ_EMUL)
   if (cfg->nn_filters > 0)
-    n += cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, cfg->n_games * cfg->leaves_per_round) + 4096;
+    n += cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, cfg->n_games * cfg->leaves_per_round, cfg->arena ? 2 : 1) + 4096;
 #endif
   *bytes = n;
   return 0;
@@ -334,7 +335,7 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
   d.noise_mode = cfg->noise_mode; d.max_plies = cfg->max_plies;
   d.c_puct = cfg->c_puct; d.noise_eps = cfg->noise_eps; d.alpha = cfg->dirichlet_alpha; d.tau_decay = cfg->tau_decay_rate;
   d.resign_threshold = cfg->resign_threshold; d.min_resign_turn = cfg->min_resign_turn; d.max_game_length = cfg->max_game_length;
-  d.seed = cfg->seed; d.rank = cfg->rank;
+  d.seed = cfg->seed; d.rank = cfg->rank; d.arena = cfg->arena ? 1 : 0;
   const size_t used = carve(e, e->ws);
 #if !defined(CZ_EMUL)
   e->nn = nullptr; e->nn_bytes = 0; e->tree_stream = nullptr; e->h_totals = nullptr;
@@ -363,9 +364,9 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
 #if !defined(CZ_EMUL)
   if (cfg->nn_filters > 0) {
     const int maxb = cfg->n_games * cfg->leaves_per_round;
-    e->nn_bytes = cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb);
+    e->nn_bytes = cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, cfg->arena ? 2 : 1);
     uint8_t* nnws = e->ws + ((used + 4095) & ~(size_t)4095);
-    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream, cfg->nn_fp32_skip);
+    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream, cfg->nn_fp32_skip, cfg->arena ? 2 : 1);
     if (!e->nn) { delete e; return CZ_ERR_CUDA; }
   }
 #else
@@ -547,7 +548,7 @@ int search_pipelined(cz_engine* e) {
     busy[h] = e->h_totals[4 * h + 1] != 0 || n > 0;
     if (n > 0) {
       cudaStreamWaitEvent(N, ready[h], 0);
-      const int rc = cznn::nn_forward_boards(e->nn, dense[h], n, pol[h], val[h]);
+      const int rc = cznn::nn_forward_boards(e->nn, e->cfg.arena ? h : 0, dense[h], n, pol[h], val[h]);   // arena: range h = player h's trees
       if (rc) return rc;
       cudaEventRecord(done[h], N);
       n_in_flight[h] = n;
@@ -572,12 +573,13 @@ int cz_search(cz_engine* e, const cz_root_opts* opts) {
   if (!e->nn || !cznn::nn_ready(e->nn)) return cz_fail(CZ_ERR_STATE, "cz_search: network weights not set");
   int rc = cz_search_begin(e, opts);
   if (rc) return rc;
-  if (e->tree_stream && e->cfg.n_games >= 64) return search_pipelined(e);
+  if (e->tree_stream && (e->cfg.n_games >= 64 || e->cfg.arena)) return search_pipelined(e);
+  if (e->cfg.arena) return cz_fail(CZ_ERR_STATE, "cz_search: arena mode needs the two-range pipeline (CZ_NO_PIPELINE is set)");
   for (;;) {
     int32_t n = 0, busy = 0;
     if ((rc = cz_search_wave(e, &n, &busy))) return rc;
     if (n > 0) {
-      if ((rc = cznn::nn_forward_boards(e->nn, e->d.leaf_dense, n, e->policy_buf, e->value_buf))) return rc;
+      if ((rc = cznn::nn_forward_boards(e->nn, 0, e->d.leaf_dense, n, e->policy_buf, e->value_buf))) return rc;
       if ((rc = cz_search_apply(e, e->policy_buf, e->value_buf))) return rc;
     }
     if (!busy) break;
@@ -616,15 +618,17 @@ int cz_launch_count(cz_engine* e, uint64_t* n) {
   return 0;
 }
 
-int cz_nn_set_weights(cz_engine* e, const cz_tensor_desc* descs, int32_t n) {
+int cz_nn_set_weights_net(cz_engine* e, int32_t net, const cz_tensor_desc* descs, int32_t n) {
 #if defined(CZ_EMUL)
-  (void)e; (void)descs; (void)n;
+  (void)e; (void)net; (void)descs; (void)n;
   return cz_fail(CZ_ERR_UNSUPPORTED, "cz_nn_set_weights: no tensor cores in the CPU emulation build");
 #else
   if (!e || !descs) return cz_fail(CZ_ERR_ARG, "cz_nn_set_weights: bad argument");
-  return cznn::nn_set_weights(e->nn, descs, n);
+  return cznn::nn_set_weights(e->nn, net, descs, n);
 #endif
 }
+
+int cz_nn_set_weights(cz_engine* e, const cz_tensor_desc* descs, int32_t n) { return cz_nn_set_weights_net(e, 0, descs, n); }
 
 int cz_nn_forward(cz_engine* e, const float* planes_dev, int32_t batch, float* policy_dev, float* value_dev) {
 #if defined(CZ_EMUL)
@@ -632,7 +636,7 @@ int cz_nn_forward(cz_engine* e, const float* planes_dev, int32_t batch, float* p
   return cz_fail(CZ_ERR_UNSUPPORTED, "cz_nn_forward: no tensor cores in the CPU emulation build");
 #else
   if (!e || !planes_dev || !policy_dev || !value_dev || batch < 0) return cz_fail(CZ_ERR_ARG, "cz_nn_forward: bad argument");
-  return cznn::nn_forward_planes(e->nn, planes_dev, batch, policy_dev, value_dev);
+  return cznn::nn_forward_planes(e->nn, 0, planes_dev, batch, policy_dev, value_dev);
 #endif
 }
 
@@ -642,7 +646,7 @@ int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch,
   return cz_fail(CZ_ERR_UNSUPPORTED, "cz_nn_forward_boards: no tensor cores in the CPU emulation build");
 #else
   if (!e || !boards_dev || !policy_dev || !value_dev || batch < 0) return cz_fail(CZ_ERR_ARG, "cz_nn_forward_boards: bad argument");
-  return cznn::nn_forward_boards(e->nn, boards_dev, batch, policy_dev, value_dev);
+  return cznn::nn_forward_boards(e->nn, 0, boards_dev, batch, policy_dev, value_dev);
 #endif
 }
 

@@ -21,7 +21,7 @@ class Engine:
     def __init__(self, lib=None, device=None, n_games=1, sims_per_move=800, leaves_per_round=8, virtual_loss=3,
                  max_nodes_per_game=None, max_edges_per_game=None, max_path=128, noise_mode=1, max_game_length=100,
                  nn_filters=0, nn_blocks=0, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
-                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0, nn_fp32_skip=None):
+                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0, nn_fp32_skip=None, arena=False):
         self.lib = lib or get_lib()
         if device is None:
             device = 'cuda' if self.lib.is_cuda else 'cpu'
@@ -43,6 +43,7 @@ class Engine:
         cfg.tau_decay_rate, cfg.resign_threshold, cfg.enable_resign_rate = tau_decay_rate, resign_threshold, enable_resign_rate
         cfg.min_resign_turn, cfg.max_game_length = min_resign_turn, max_game_length
         cfg.seed, cfg.rank = seed, rank
+        cfg.arena = 1 if arena else 0
         cfg.nn_fp32_skip = 0 if nn_fp32_skip is None else (1 if nn_fp32_skip else 2)   # None = auto (fp32 when blocks > 10)
         self.cfg = cfg
         nbytes = C.c_uint64(0)
@@ -235,8 +236,9 @@ class Engine:
         return out
 
     # ---- network
-    def set_weights(self, named_tensors):
-        """named_tensors: dict Keras-style name -> float32 tensor on self.device (Keras layouts)."""
+    def set_weights(self, named_tensors, net=0):
+        """named_tensors: dict Keras-style name -> float32 tensor on self.device (Keras layouts).  net = 1 is the second
+        (next-generation) network of an arena engine."""
         from .lib import CzTensorDesc
         arr = (CzTensorDesc * len(named_tensors))()
         keep = []
@@ -246,8 +248,9 @@ class Engine:
             arr[i].name = k.encode()
             arr[i].dev = t.data_ptr()
             arr[i].numel = t.numel()
-        self._weights_keep = keep
-        self.lib.call("cz_nn_set_weights", self._h, arr, len(named_tensors))
+        self._weights_keep = getattr(self, "_weights_keep", {})
+        self._weights_keep[net] = keep
+        self.lib.call("cz_nn_set_weights_net", self._h, net, arr, len(named_tensors))
 
     def nn_forward_planes(self, planes):
         n = planes.shape[0]

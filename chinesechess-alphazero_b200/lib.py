@@ -30,7 +30,7 @@ class CzConfig(C.Structure):
         ("c_puct", C.c_double), ("noise_eps", C.c_double), ("dirichlet_alpha", C.c_double),
         ("tau_decay_rate", C.c_double), ("resign_threshold", C.c_double), ("enable_resign_rate", C.c_double),
         ("min_resign_turn", C.c_int32), ("max_game_length", C.c_int32),
-        ("seed", C.c_uint64), ("rank", C.c_int32), ("nn_fp32_skip", C.c_int32),
+        ("seed", C.c_uint64), ("rank", C.c_int32), ("arena", C.c_int32), ("nn_fp32_skip", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -91,6 +91,7 @@ _SIGS = {
     "cz_drain_records": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "cz_record_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "cz_nn_set_weights": (C.c_int, [_P, C.POINTER(CzTensorDesc), C.c_int32]),
+    "cz_nn_set_weights_net": (C.c_int, [_P, C.c_int32, C.POINTER(CzTensorDesc), C.c_int32]),
     "cz_nn_forward": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "cz_nn_forward_boards": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "cz_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),

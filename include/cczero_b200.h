@@ -100,8 +100,12 @@ typedef struct cz_config {
   int32_t max_game_length;     /* play_config.max_game_length */
   uint64_t seed;               /* Philox key (seed, rank) for the on-device streams */
   int32_t rank;                /* data-parallel rank, selects the RNG sub-stream */
+  int32_t arena;               /* 1: evaluator arena (worker/evaluator.py:147-250): n_games = 2*M slots for M games; slot i holds
+                                * player 0's tree of game i, slot i+M player 1's; player p is evaluated by network p
+                                * (cz_nn_set_weights_net); the red side alternates with the game index; evaluator draw rules */
   int32_t nn_fp32_skip;        /* residual (skip) stream precision: 0 auto (fp32 when nn_blocks > 10), 1 fp32, 2 fp16.
                                 * fp32 keeps the value error of 20-block nets <= 6e-4 (fp16: up to 1.5e-3) for ~10 % time */
+  int32_t reserved;
 } cz_config;
 
 /* Device workspace the caller must provide (a torch.uint8 CUDA tensor). */
@@ -212,6 +216,8 @@ typedef struct cz_tensor_desc {
 } cz_tensor_desc;
 /* Fold BatchNorm (eps 1e-3) into fp16 GEMM operands and upload; weights stay caller-owned. */
 int cz_nn_set_weights(cz_engine* e, const cz_tensor_desc* descs, int32_t n);
+/* Second network of the arena (net 0 = best model, net 1 = next generation; evaluator.py:31-40). */
+int cz_nn_set_weights_net(cz_engine* e, int32_t net, const cz_tensor_desc* descs, int32_t n);
 /* predict_on_batch (api.py:62-64): planes_dev [B][14][10][9] f32 -> policy_dev [B][2086] f32
  * (softmax), value_dev [B] f32 (tanh). */
 int cz_nn_forward(cz_engine* e, const float* planes_dev, int32_t batch, float* policy_dev, float* value_dev);

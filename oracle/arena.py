@@ -1,0 +1,71 @@
+"""oracle/arena.py — CPU restatement of the evaluator's game loop.  TEST INFRASTRUCTURE.
+
+Restates worker/evaluator.py:147-250 (EvaluateWorker.start_game): two players with SEPARATE search trees alternate, the
+repetition rule has no be_catched exemption and raises the temperature on any repetition (:173-193), resignation is off
+(:157-160).  `draws_for(slot)` supplies the move sampler of the engine slot that plays the ply, so the device arena
+(csrc/cz_selfplay.cuh, E.arena) can be compared move for move.  Score bookkeeping of EvaluateWorker.start (:93-145) is
+`score_for_next_generation`.
+"""
+from . import senv
+from .player import OraclePlayer
+
+
+def play_arena_game(pc, evaluate0, evaluate1, idx, draws_for, m_games, max_game_length=100, env=senv, max_plies_guard=1000):
+    """idx = running game index; player idx % 2 is red (evaluator.py:163-170).  Returns dict(moves, value_red, turns, flags)."""
+    players = [OraclePlayer(pc, evaluate0, env=env, noise=(lambda n: 0.0) if pc.noise_eps == 0 else None),
+               OraclePlayer(pc, evaluate1, env=env, noise=(lambda n: 0.0) if pc.noise_eps == 0 else None)]
+    i = idx % m_games
+    state = env.INIT_STATE
+    history = [state]
+    value, turns, game_over, final_move = 0, 0, False, None
+    no_eat_count, check = 0, False
+    flags = 0
+    while not game_over and turns < max_plies_guard:
+        no_act, increase_temp = None, False
+        if not check and state in history[:-1]:
+            no_act, increase_temp, free_move = [], True, 0
+            for k in range(len(history) - 1):
+                if history[k] == state:
+                    if env.will_check_or_catch(state, history[k + 1]):
+                        no_act.append(history[k + 1])
+                    else:
+                        free_move += 1
+                        if free_move >= 3:
+                            game_over, value = True, 0
+                            flags |= 2
+                            break
+        if game_over:
+            break
+        p = (idx + turns) % 2                                  # red = player idx % 2 moves on even plies
+        player = players[p]
+        player.search(state, no_act, increase_temp)
+        node = player.tree[state]
+        action = draws_for(i + p * m_games).choose(node, no_act, turns, increase_temp, pc)
+        history.append(action)
+        state, no_eat = env.new_step(state, action)
+        turns += 1
+        no_eat_count = no_eat_count + 1 if no_eat else 0
+        history.append(state)
+        if no_eat_count >= 120 or turns / 2 >= max_game_length:
+            game_over, value = True, 0
+            flags |= 2
+        else:
+            game_over, value, final_move, check = env.done(state, need_check=True)
+            if not game_over and not env.has_attack_chessman(state):
+                game_over, value = True, 0
+                flags |= 2
+    if final_move:
+        history.append(final_move)
+        state = env.step(state, final_move)
+        turns += 1
+        value = -value
+        history.append(state)
+    if turns % 2 == 1:
+        value = -value
+    return {"moves": [history[2 * k + 1] for k in range(turns)], "value_red": value, "turns": turns, "flags": flags}
+
+
+def score_for_next_generation(value_red, idx):
+    """evaluator.py:127-137: score of the next-generation model (player 1); best model (player 0) is red when idx is even."""
+    score = 0 if value_red == -1 else (1 if value_red == 1 else 0.5)
+    return 1 - score if idx % 2 == 0 else score

@@ -128,3 +128,28 @@ def test_pipelined_search_equals_sequential(cuda_lib):
     a, sa = run(False)
     b, sb = run(True)
     assert a == b and sa == sb
+
+
+def test_evaluator_arena_two_networks(cuda_lib, tmp_path):
+    """worker/evaluator drop-in: two different networks, alternating colours, tallies add up."""
+    from cczero_b200.evaluator import EvaluateWorker
+    from cczero_b200.model import CChessModel
+    cfg = _config(str(tmp_path), sims=24, k=4)
+    cfg.play.tau_decay_rate = 0
+    cfg.play.noise_eps = 0.2
+    cfg.play.c_puct = 1
+    cfg.eval = SimpleNamespace(game_num=2)
+    bt, ng = CChessModel(cfg).build(seed=1), CChessModel(cfg).build(seed=2)
+    w = EvaluateWorker(cfg, bt, ng, n_games=6, concurrent_games=4, seed=3)
+    total, rw, rd, rf, bw, bd, bf = w.start()
+    assert rw + rd + rf + bw + bd + bf == 6
+    assert 0 <= total <= 6 and abs(total - (rw + bw + 0.5 * (rd + bd))) < 1e-9
+    assert int(w.engine.counters()[6]) == 0
+    w.close()
+    # identical networks on both sides and no randomness: the same game is played from both colours
+    cfg.play.noise_eps = 0
+    w = EvaluateWorker(cfg, bt, bt, n_games=4, concurrent_games=4, seed=3)
+    w.engine.selfplay(target_games=4, max_moves=0)
+    recs = sorted(w.engine.drain_records(), key=lambda r: r["game_index"])
+    assert recs[0]["moves"] == recs[1]["moves"] and recs[0]["value_red"] == recs[1]["value_red"]
+    w.close()
