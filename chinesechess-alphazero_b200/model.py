@@ -6,8 +6,9 @@ geometry from `config.model`.  The forward pass itself is the tensor-core pipeli
 (`cz_nn_set_weights` / `cz_nn_forward`), reached through `get_pipes()` exactly like the reference reaches Keras
 through CChessModelAPI.
 
-Weight files: `.npz` (one array per Keras weight name) next to a JSON config.  Reading Keras `.h5` files needs an
-HDF5 reader that this environment does not have; it is listed as a "next" row and `load()` says so.
+Weight files: the reference's own Keras `.h5` (read by the pure-Python HDF5 subset reader in keras_h5.py; geometry is
+inferred from the tensor names, so the Keras JSON config is not needed) or `.npz` (one array per Keras weight name)
+next to a small JSON config, which is what `save()` writes.
 """
 import hashlib
 import json
@@ -100,11 +101,17 @@ class CChessModel:
 
     def load(self, config_path, weight_path):
         """model.py:95-107.  `weight_path` must be an .npz written by `save()`."""
-        if not (os.path.exists(config_path) and os.path.exists(weight_path)):
+        if not os.path.exists(weight_path):
             return False
-        if weight_path.endswith(".h5"):
-            raise NotImplementedError("Keras .h5 weights need an HDF5 reader (not available here); convert to .npz "
-                                      "with Keras names first (SURVEY.md §8f row 3)")
+        if weight_path.endswith(".h5") or open(weight_path, "rb").read(8) == b"\x89HDF\r\n\x1a\n":
+            from .keras_h5 import read_keras_weights
+            self.weights = read_keras_weights(weight_path)
+            self._infer_geometry()
+            self.digest = self.fetch_digest(weight_path)
+            self.model = self
+            return True
+        if not os.path.exists(config_path):
+            return False
         with open(config_path, "rt") as f:
             cfg = json.load(f)
         mc = self.config.model
@@ -115,6 +122,16 @@ class CChessModel:
         self.digest = self.fetch_digest(weight_path)
         self.model = self
         return True
+
+    def _infer_geometry(self):
+        """cnn_filter_num / res_layer_num / value_fc_size from the tensors themselves (a Keras .h5 carries no config)."""
+        mc = self.config.model
+        k = next(v for n, v in self.weights.items() if n.startswith("input_conv") and n.endswith("/kernel"))
+        if k.shape[:3] != (5, 5, 14):
+            raise NotImplementedError(f"input convolution {k.shape}: only 5x5 on 14 planes is built")
+        mc.cnn_filter_num = int(k.shape[3])
+        mc.res_layer_num = max(int(n[3:n.index("_")]) for n in self.weights if n.startswith("res"))
+        mc.value_fc_size = int(self.weights["value_dense/bias"].shape[0])
 
     def save(self, config_path, weight_path):
         """model.py:109-115."""
