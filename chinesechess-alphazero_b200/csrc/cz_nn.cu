@@ -32,7 +32,11 @@ namespace cznn {
   } while (0)
 
 constexpr int kLabels = CZ_N_LABELS;
-constexpr int kPolK = 384;      // 360 policy features padded to 6 k-blocks
+constexpr int kPolK1 = 384;     // 360 policy features padded to 6 k-blocks
+constexpr int kPolK = 3 * kPolK1;  // the policy Dense runs as a split-precision GEMM on the tensor cores:
+                                   //   x = x_hi + x_lo, w = w_hi + w_lo (fp16 each); logits = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo
+                                   // laid out along K as A' = [x_hi | x_lo | x_hi], W' = [w_hi | w_hi | w_lo] -> one GEMM, ~fp32 accuracy
+                                   // (fp16 operands alone cost 1.1e-3 of policy probability on the reference's trained 192x10 net)
 constexpr int kPolN = 2304;     // 2086 labels padded to 9 N tiles of 256
 constexpr float kBnEps = 1e-3f;
 
@@ -337,9 +341,13 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
     }
   }
   __syncthreads();
-  for (int i = tid; i < npos * kPolK; i += 256) {
-    const int p = i / kPolK, k = i % kPolK;
-    pol_feat[(size_t)(b0 + p) * kPolK + k] = __float2half_rn(k < 360 ? feat[p][k / 90][k % 90] : 0.f);
+  for (int i = tid; i < npos * kPolK1; i += 256) {
+    const int p = i / kPolK1, k = i % kPolK1;
+    const float f = k < 360 ? feat[p][k / 90][k % 90] : 0.f;
+    const __half hi = __float2half_rn(f);
+    const __half lo = __float2half_rn(f - __half2float(hi));
+    __half* row = pol_feat + (size_t)(b0 + p) * kPolK;
+    row[k] = hi; row[kPolK1 + k] = lo; row[2 * kPolK1 + k] = hi;
   }
   float h[kHeadPos];
 #pragma unroll
@@ -440,12 +448,16 @@ __global__ void k_prep_1x1(const float* w, const float* scale, float* out, int c
     out[(size_t)co * ci_n + ci] = w[(size_t)ci * co_n + co] * scale[co];
   }
 }
-// Dense (in,out) [360][2086] -> [kPolN][kPolK] fp16 (zero padded), K-major
+// Dense (in,out) [360][2086] -> [kPolN][kPolK] fp16 (zero padded), K-major, split as [w_hi | w_hi | w_lo]
 __global__ void k_prep_policy(const float* w, __half* out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < (long long)kPolN * kPolK) {
-    const int k = (int)(i % kPolK), n = (int)(i / kPolK);
-    out[i] = __float2half_rn((k < 360 && n < kLabels) ? w[(size_t)k * kLabels + n] : 0.f);
+  if (i < (long long)kPolN * kPolK1) {
+    const int k = (int)(i % kPolK1), n = (int)(i / kPolK1);
+    const float f = (k < 360 && n < kLabels) ? w[(size_t)k * kLabels + n] : 0.f;
+    const __half hi = __float2half_rn(f);
+    const __half lo = __float2half_rn(f - __half2float(hi));
+    __half* row = out + (size_t)n * kPolK;
+    row[k] = hi; row[kPolK1 + k] = hi; row[2 * kPolK1 + k] = lo;
   }
 }
 __global__ void k_copy_pad(const float* src, float* dst, int n_src, int n_dst) {
@@ -724,7 +736,7 @@ int nn_set_weights(NnRuntime* r, int net, const cz_tensor_desc* descs, int n) {
   {
     NEED(k, "policy_out", "kernel", 360LL * kLabels);
     NEED(b, "policy_out", "bias", kLabels);
-    const long long nn = (long long)kPolN * kPolK;
+    const long long nn = (long long)kPolN * kPolK1;
     k_prep_policy<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>((const float*)k->dev, r->w_pol);
     k_copy_pad<<<(kPolN + 255) / 256, 256, 0, st>>>((const float*)b->dev, r->b_pol, kLabels, kPolN);
   }
