@@ -27,6 +27,7 @@ WORKLOADS = {
     # name: (games per GPU, sims/move, filters, blocks)
     "c3": (1024, 800, 256, 20),     # BASELINE.json configs[2]/[3] (per GPU)
     "c2": (256, 200, 128, 7),       # BASELINE.json configs[1]
+    "c5": (800, 1600, 256, 20),     # BASELINE.json configs[4]: arena, 400 paired games = 800 player slots, two networks
     "tiny": (32, 40, 64, 2),        # plumbing check
 }
 
@@ -171,11 +172,14 @@ def run_ours(args):
                  nn_filters=filters, nn_blocks=blocks, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
                  tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, max_game_length=100,
                  max_nodes_per_game=args.nodes or max(4096, 24 * sims), seed=args.seed, rank=rank,
-                 nn_fp32_skip={"auto": None, "fp32": True, "fp16": False}[args.skip_stream])
+                 nn_fp32_skip={"auto": None, "fp32": True, "fp16": False}[args.skip_stream], arena=args.workload == "c5")
     model = CChessModel(SimpleNamespace(model=SimpleNamespace(cnn_filter_num=filters, res_layer_num=blocks, value_fc_size=256,
                                                               cnn_first_filter_size=5, cnn_filter_size=3, input_depth=14)))
     model.build(seed=0)                      # random-init, Keras-equivalent (agent/model.py:32-66 defaults)
     eng.set_weights(model.torch_weights())
+    if args.workload == "c5":                # the arena's second network (next generation): another random init
+        model.build(seed=1)
+        eng.set_weights(model.torch_weights(), net=1)
     eng.reset()
 
     def barrier():
@@ -273,7 +277,8 @@ def run_ours(args):
             "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic (random-init Keras-equivalent weights, games from INIT_STATE)",
-            "config": {"workload": f"{args.workload} = BASELINE.json configs[2]: {games} concurrent games/GPU, {sims} sims/move, "
+            "config": {"workload": f"{args.workload} = BASELINE.json configs[{dict(c2=1, c3=2, c5=4).get(args.workload, '-')}]: {games} "
+                                   f"concurrent {'player slots (arena)' if args.workload == 'c5' else 'games'}/GPU, {sims} sims/move, "
                                    f"{filters}x{blocks} resnet", "games_per_gpu": games, "sims_per_move": sims,
                        "leaves_per_round": K, "skip_stream": args.skip_stream, "parallelism": f"dp{world} (games sharded, no data-path collective)",
                        "l2": "inputs larger than L2 (activations ~1.2 GB/round, trees ~GBs)", "nn_positions": positions,
