@@ -33,7 +33,7 @@ WORKLOADS = {
 
 
 # DRAM bytes per launch of the dominant kernel measured once with ncu (None where no capture exists)
-NCU_TRAFFIC = {("c3", 1024, 8): 7.83e8}
+NCU_TRAFFIC = {("c3", 1024, 8): 7.15e8}
 
 
 def net_flops(filters, blocks):
@@ -289,9 +289,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC.get((args.workload, games, K)),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of a full-batch "
-                                           "launch (profiles/r01b_igemm2_cta_pair_ncu_raw.csv); algorithmic bytes/launch = activations in + out "
-                                           "(+ skip) = 2 x 415 MB at 8192 boards x 256 ch",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full "
+                                           "(profiles/r01c_igemm2_final_ncu_raw.csv, ~4096-board launches of the two-range pipeline): conv1 "
+                                           "339 MB, conv2 with the fp32 skip stream 1090 MB, mean 715 MB = the algorithmic bytes (fp16 in/out "
+                                           "189 MB each, fp32 skip in/out 377 MB each)",
                          "kernel": "igemm::k_igemm2<C> (3x3 residual conv, tcgen05 cta_group::2)",
                          "launches": int(conv_launches), "avg_launch_ms": conv_ms / max(1.0, conv_launches / world),
                          "peak_source": peak_src, "share_of_step": conv_ms / ms},
