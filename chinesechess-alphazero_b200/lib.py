@@ -141,9 +141,17 @@ _lib = None
 
 
 def get_lib():
-    """The product library (CUDA).  Raises CzError when it has not been built."""
+    """The product library (CUDA).  Builds it with nvcc if the in-tree .so is missing (a fresh clone); raises CzError when
+    that is not possible.  There is no CPU fallback."""
     global _lib
     if _lib is None:
+        if not os.path.exists(CUDA_LIB_PATH):
+            try:
+                from . import build
+                build.build_cuda()
+            except Exception as e:       # no nvcc, compile error ...
+                raise CzError(f"native library missing and could not be built ({e}); run "
+                              "`python chinesechess-alphazero_b200/build.py cuda`") from e
         _lib = CzLib(CUDA_LIB_PATH)
         if not _lib.is_cuda:
             raise CzError("libcczero_b200.so is not a CUDA build")
