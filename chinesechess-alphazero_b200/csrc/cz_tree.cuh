@@ -16,7 +16,6 @@
 namespace cz {
 
 enum { CHILD_UNKNOWN = -1, CHILD_TERM_BASE = -2 };        // child <= -2: terminal, v = (-2 - child) - 1
-enum { SIM_IDLE = 0, SIM_LEAF = 1, SIM_PARKED = 2 };
 enum { NODE_WAITING = 1u << 8 };
 enum { GAME_ERR_PATH = 1, GAME_ERR_POOL = 2, GAME_ERR_NOISE = 4, GAME_ERR_NOMOVE = 8 };
 
@@ -336,23 +335,18 @@ CZ_D int descend(const EngineDev& E, int g, int sim, bool fresh, TreeSmem* sm, d
           *imm_value = 0.0;
           return OUT_IMMEDIATE;
         }
+        const int j = E.n_leaf[g];                   // leaf slot of this game (every lane reads before lane 0 bumps it)
+        czs::syncwarp();
         if (czs::lane() == 0) {
           if (parent_edge >= 0) E.edge_child[(size_t)g * E.ecap + parent_edge] = node;
           if (depth == 0) E.root_node[g] = node;
           E.sim_depth[si] = depth;
           E.sim_leaf_node[si] = node;
-          const int j = E.n_leaf[g];
           E.leaf_sim[(size_t)g * E.K + j] = sim;
           E.n_leaf[g] = j + 1;
         }
-        const int j = czs::shfl(E.n_leaf[g], 0) ;
-        (void)j;
-        czs::syncwarp();
-        {
-          const int jj = E.n_leaf[g] - 1;
-          uint8_t* lb = E.leaf_board + ((size_t)g * E.K + jj) * BOARD_STRIDE;
-          for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) lb[k] = k < NSQ ? sm->board[k] : (uint8_t)0;
-        }
+        uint8_t* lb = E.leaf_board + ((size_t)g * E.K + j) * BOARD_STRIDE;
+        for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) lb[k] = k < NSQ ? sm->board[k] : (uint8_t)0;
         czs::syncwarp();
         return OUT_LEAF;
       }
@@ -540,7 +534,6 @@ CZ_D int game_compact(const EngineDev& E, int g, int root) {
   czs::syncwarp();
   for (int i = czs::lane(); i < nn; i += 32) map[i] = 0;
   czs::syncwarp();
-  int kept = 0;
   if (czs::lane() == 0) {                                    // breadth-first walk over child links
     int head = 0, tail = 0;
     queue[tail++] = (uint32_t)root; map[root] = 1;
@@ -554,9 +547,7 @@ CZ_D int game_compact(const EngineDev& E, int g, int root) {
         if (c >= 0 && map[c] == 0) { map[c] = 1; queue[tail++] = (uint32_t)c; }
       }
     }
-    kept = tail;
   }
-  kept = czs::shfl(kept, 0);
   czs::syncwarp();
   // new indices in old order (so every move below goes towards lower addresses)
   int cnt = 0;
@@ -616,7 +607,6 @@ CZ_D int game_compact(const EngineDev& E, int g, int root) {
 #endif
   }
   czs::syncwarp();
-  (void)kept;
   return map[root] - 1;
 }
 

@@ -602,7 +602,6 @@ int cz_get_counters(cz_engine* e, uint64_t* out) {
   CZ_LAUNCH(k_err_reduce, 1, 1, 0, e->stream, e->d);
   czrt_copy(dc, e->d.counters, sizeof(dc), e->stream);
   if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_get_counters: device failure");
-  std::vector<int32_t> sr(e->cfg.n_games);
   out[0] = e->total_sims; out[1] = e->total_positions; out[2] = e->total_waves; out[3] = dc[3]; out[4] = dc[4];
   out[5] = dc[5]; out[6] = dc[6]; out[7] = dc[7];
   return 0;
