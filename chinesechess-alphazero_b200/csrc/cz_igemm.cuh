@@ -327,12 +327,12 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       uint32_t it = 0, tcount = 0;
       for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-        umma::mbar_wait_cluster(&tempty[acc], aph ^ 1);
+        umma::mbar_wait(&tempty[acc], aph ^ 1);       // cta-scope acquire: an acquire.cluster wait emits CCTL.IVALL (L1 flush)
         umma::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * N_TILE;
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
           const uint32_t s = it % kStages2, ph = (it / kStages2) & 1;
-          umma::mbar_wait_cluster(&full[s], ph);
+          umma::mbar_wait(&full[s], ph);
           umma::tc_fence_after();
           const uint32_t sA = umma::smem_u32(smem + s * C::kStageBytes);
           const uint64_t da = umma::smem_desc_sw128(sA);
