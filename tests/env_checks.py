@@ -107,3 +107,53 @@ def check_single_api(env):
     e = torch.empty((0, 96), dtype=torch.uint8, device=env.device)
     mv, cnt = env.movegen_batch(e)
     assert mv.shape[0] == 0 and cnt.shape[0] == 0
+
+
+EXTREME_STATES = [
+    '9/9/9/9/9/9/9/9/9/9',                                       # empty board: no kings at all
+    '4s4/9/9/9/9/9/9/9/9/9',                                     # side to move has no king
+    '9/9/9/9/9/9/9/9/9/4S4',                                     # opponent has no king
+    '3s5/9/9/9/9/9/9/9/9/4S4',                                   # bare kings, different files
+    'R2s4R/9/9/C7C/9/9/C7C/9/9/R3S3R',                           # rooks and cannons with long open lines (many moves)
+    'rkemsmekr/9/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RKEMSMEKR',
+    '4s4/4P4/9/9/9/9/9/9/4p4/4S4',                               # pawns next to the kings
+    '3ms4/4m4/4e4/9/2e6/6E2/9/4E4/4M4/4SM3',                     # only defenders left: no attacking piece
+    'r1e1s1e1r/4m4/2k1m1k2/p1p1C1p1p/9/9/P1P1P1P1P/2K1C1K2/9/R1EMSME1R',   # cannon pinning through two screens
+    '4s4/9/9/9/4R4/9/9/9/9/4S4',                                 # rook between the kings
+    '5s3/9/9/9/9/9/9/9/5r3/3S5',
+    'PPPPPPPPP/PPPPsPPPP/PPPPPPPPP/9/9/9/9/9/4S4/9',             # far more pawns than a real game can have
+]
+
+
+def check_extreme_positions(env):
+    """Hand-made boundary positions: missing kings, empty board, maximum mobility, piece counts outside real games."""
+    states = EXTREME_STATES
+    boards = env.boards_from_states(states)
+    mv, cnt = env.movegen_batch(boards)
+    mv = mv.cpu().numpy().view(np.uint16)
+    cnt = cnt.cpu().numpy()
+    out, fm = env.done_batch(boards, need_check=True)
+    out, fm = out.cpu().numpy(), fm.cpu().numpy().view(np.uint16)
+    planes = env.planes_batch(boards).cpu().numpy()
+    for i, s in enumerate(states):
+        ref_moves = osenv.get_legal_moves(s)
+        assert [u16_to_move(v) for v in mv[i, :cnt[i]]] == ref_moves, s
+        d = osenv.done(s, need_check=True)
+        assert (bool(out[i, 0]), int(out[i, 1])) == (d[0], d[1]), (s, out[i], d)
+        assert (None if fm[i] == 0xFFFF else u16_to_move(fm[i])) == d[2], s
+        if len(d) == 4:
+            assert bool(out[i, 2]) == d[3], s
+        assert (planes[i] == osenv.state_to_planes(s)).all(), s
+        assert env.has_attack_chessman(s) == osenv.has_attack_chessman(s), s
+        for m in ref_moves[:6]:
+            assert env.new_step(s, m) == osenv.new_step(s, m), (s, m)
+            if 's' in s and 'S' in s:
+                assert env.will_check_or_catch(s, m) == osenv.will_check_or_catch(s, m), (s, m)
+                assert env.be_catched(s, m) == osenv.be_catched(s, m), (s, m)
+    assert cnt.max() >= 60                                        # the mobility case really is large
+    # ragged / large batch: 20 000 boards in one call equal the same boards one by one
+    import torch
+    big = boards.repeat(1667, 1)[:20000]
+    mv2, cnt2 = env.movegen_batch(big)
+    assert torch.equal(cnt2.cpu(), torch.as_tensor(cnt).repeat(1667)[:20000])
+    assert torch.equal(mv2[12:24].cpu().view(torch.int16), torch.as_tensor(mv.view(np.int16)))

@@ -175,3 +175,35 @@ def check_terminal_and_repetition(lib, device):
             eng, _ = engine_search(lib, device, [s], sims, k, 40 + i, eps=0.25)
             compare_root(eng, 0, oracle_search(s, sims, k, 40 + i), s)
             eng.close()
+
+
+def check_multi_move_reuse_and_options(lib, device):
+    """Several plies with ONE engine / ONE oracle player (tree reuse, player.py:153-158) at K = 8, the `depth` argument
+    of action() (cz_root_opts.sims_override, player.py:160-161) and the `active` mask."""
+    sims, k = 120, 8
+    pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.0, dirichlet_alpha=0.2,
+                       tau_decay_rate=0.98, virtual_loss=3)
+    pl = op.OraclePlayer(pc, op.fake_evaluate_states, noise=lambda n: 0.0)
+    eng = Engine(lib, device, n_games=2, sims_per_move=sims, leaves_per_round=k, noise_mode=0, c_puct=1.5, noise_eps=0.0,
+                 tau_decay_rate=0.98)
+    other = midgame_states(1, 17)[0]
+    eng.reset([osenv.INIT_STATE, other])
+    state = osenv.INIT_STATE
+    for ply in range(4):
+        depth = 60 if ply == 2 else None                      # one ply searched with action(depth=60)
+        pl.stats["sims"] = 0
+        pl.stats["noise_draws"] = 0
+        pl.search(state, depth=depth)
+        eng.set_root(0, state)
+        eng.search_external(eval_planes, eng.make_opts(active=[1, 0], sims_override=depth or 0))
+        compare_root(eng, 0, pl, state)
+        assert eng.root(1)["moves"] == [] and eng.root(1)["sum_n"] == 0    # the inactive game was never touched
+        node = pl.tree[state]
+        best = max(node.legal_moves, key=lambda m: (node.a[m].n if m in node.a else 0))
+        state = osenv.step(state, best)
+    # now the second game alone
+    eng.search_external(eval_planes, eng.make_opts(active=[0, 1]))
+    pl2 = op.OraclePlayer(pc, op.fake_evaluate_states, noise=lambda n: 0.0)
+    pl2.search(other)
+    compare_root(eng, 1, pl2, other)
+    eng.close()

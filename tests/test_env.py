@@ -30,6 +30,15 @@ def test_emul_env_single_api(emul_env):
     env_checks.check_single_api(emul_env)
 
 
+def test_emul_env_extreme_positions(emul_env):
+    env_checks.check_extreme_positions(emul_env)
+
+
+@pytest.mark.gpu
+def test_cuda_env_extreme_positions(cuda_env):
+    env_checks.check_extreme_positions(cuda_env)
+
+
 @pytest.mark.gpu
 def test_cuda_env_golden(cuda_env, golden_env):
     env_checks.check_against_rows(cuda_env, golden_env["rows"])

@@ -38,6 +38,15 @@ def test_emul_terminal_and_repetition(emul_lib):
     sc.check_terminal_and_repetition(emul_lib, "cpu")
 
 
+def test_emul_multi_move_reuse_and_options(emul_lib):
+    sc.check_multi_move_reuse_and_options(emul_lib, "cpu")
+
+
+@pytest.mark.gpu
+def test_cuda_multi_move_reuse_and_options(cuda_lib):
+    sc.check_multi_move_reuse_and_options(cuda_lib, "cuda")
+
+
 @pytest.mark.gpu
 def test_cuda_golden_k1(cuda_lib):
     sc.check_golden_k1(cuda_lib, "cuda")
