@@ -115,8 +115,8 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     games, sims, filters, blocks = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    budget = max(5.0, min(40.0, 120.0 / max(1, args.steps + args.warmup)))
+    cores = int(os.environ.get("CZ_BENCH_CPU_PROCS", os.cpu_count() or 1))
+    budget = float(os.environ.get("CZ_BENCH_CPU_SECONDS", max(5.0, min(40.0, 120.0 / max(1, args.steps + args.warmup)))))
     vals = []
     for i in range(args.warmup + args.steps):
         v, n, dt = cpu_reference_sample(filters, blocks, sims, args.leaves, budget, cores)
