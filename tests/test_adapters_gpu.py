@@ -110,8 +110,8 @@ def test_pipelined_search_equals_sequential(cuda_lib):
     def run(no_pipeline):
         os.environ["CZ_NO_PIPELINE"] = "1" if no_pipeline else "0"
         try:
-            eng = Engine(cuda_lib, "cuda", n_games=96, sims_per_move=40, leaves_per_round=4, noise_mode=1, nn_filters=64,
-                         nn_blocks=2, seed=5)
+            eng = Engine(cuda_lib, "cuda", n_games=1024, sims_per_move=24, leaves_per_round=8, noise_mode=1, nn_filters=64,
+                         nn_blocks=2, seed=5, max_nodes_per_game=512)
         finally:
             os.environ.pop("CZ_NO_PIPELINE", None)
         eng.set_weights(weights)
@@ -119,7 +119,7 @@ def test_pipelined_search_equals_sequential(cuda_lib):
         out = []
         for _ in range(3):
             eng.search(None)
-            out.append([(eng.root(g)["n"], eng.root(g)["sum_n"]) for g in (0, 47, 48, 95)])
+            out.append([(eng.root(g)["n"], eng.root(g)["sum_n"]) for g in (0, 511, 512, 1023)])
             eng.play_move()
         sims = eng.sims_run().tolist()
         eng.close()
