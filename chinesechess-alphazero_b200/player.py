@@ -115,6 +115,19 @@ class CChessPlayer:
         my_action = int(np.random.choice(range(self.labels_n), p=self.apply_temperature(policy, turns)))
         return self.labels[my_action], list(policy)
 
+    def close_and_return_action(self, state, turns, no_act=None):
+        """player.py:88-106 (used by the UCI front end to stop an ongoing search): answer from the tree as it stands."""
+        root = self.engine.root(0)
+        policy, resign = self.calc_policy(root, turns, no_act)
+        if resign:
+            return None
+        if no_act is not None:
+            for act in no_act:
+                policy[self.move_lookup[act]] = 0
+        my_action = int(np.random.choice(range(self.labels_n), p=self.apply_temperature(policy, turns)))
+        value = self.debug.get(state, (None, 0))[1]
+        return self.labels[my_action], value, self.done_tasks // 100
+
     # ---- host-side tail of action(): player.py:375-406
     def calc_policy(self, root, turns, no_act):
         policy = np.zeros(self.labels_n)
@@ -130,6 +143,12 @@ class CChessPlayer:
         pc = self.play_config
         if max_q_value < getattr(pc, "resign_threshold", -1e9) and self.enable_resign and turns > getattr(pc, "min_resign_turn", 0):
             return policy, True
+        if self.debugging:                               # player.py:397-403: the five most visited moves
+            order = sorted(range(len(root["moves"])), key=lambda i: root["n"][i], reverse=True)[:5]
+            for i in order:
+                n, w = root["n"][i], root["w"][i]
+                if not (no_act and root["moves"][i] in no_act):
+                    self.search_results[root["moves"][i]] = (n, w / n if n else 0, root["p"][i])
         policy /= np.sum(policy)
         return policy, False
 

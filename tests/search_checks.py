@@ -76,6 +76,10 @@ def check_golden_k1(lib, device):
                     assert n == gn and w == gw and float(np.float32(p)) == gp, (case["name"], m, (n, w, p), (gn, gw, gp))
                 assert action == call["action"], (case["name"], action, call["action"])
                 assert abs(sum(policy) - 1.0) < 1e-9
+            # answering from the finished tree (close_and_return_action, player.py:88-106) is a legal move of the last state
+            last = case["calls"][-1]
+            got = player.close_and_return_action(last["state"], last["turns"], last["no_act"])
+            assert got is not None and got[0] in last["legal"]
         finally:
             player.close()
             srv.close()
