@@ -12,10 +12,12 @@ lib = get_lib()
 env = StaticEnv(lib, "cuda")
 states = [senv.INIT_STATE] + midgame_states(63, 3, lo=1, hi=120)
 planes = np.stack([senv.state_to_planes(s) for s in states])
+import sys as _s
+mode = {"fp16": False, "fp32": True, "ext8": "ext8", "auto": None}[_s.argv[1] if len(_s.argv) > 1 else "auto"]
 for f, b, trained in ((128, 7, False), (128, 7, True), (256, 7, False), (192, 10, True), (256, 20, False), (256, 20, True)):
     w = om.init_weights(f, b, 256, seed=1, trained_like=trained)
     rp, rv = om.forward(w, planes, b)
-    eng = Engine(lib, "cuda", n_games=64, sims_per_move=8, leaves_per_round=1, nn_filters=f, nn_blocks=b)
+    eng = Engine(lib, "cuda", n_games=64, sims_per_move=8, leaves_per_round=1, nn_filters=f, nn_blocks=b, nn_fp32_skip=mode)
     eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
     p, v = eng.nn_forward_boards(env.boards_from_states(states))
     p, v = p.cpu().numpy(), v.cpu().numpy()
