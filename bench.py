@@ -172,7 +172,7 @@ def run_ours(args):
                  nn_filters=filters, nn_blocks=blocks, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
                  tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, max_game_length=100,
                  max_nodes_per_game=args.nodes or max(4096, 24 * sims), seed=args.seed, rank=rank,
-                 nn_fp32_skip={"auto": None, "fp32": True, "fp16": False, "ext8": "ext8"}[args.skip_stream], arena=args.workload == "c5")
+                 nn_fp32_skip={"auto": None, "fp32": True, "fp16": False}[args.skip_stream], arena=args.workload == "c5")
     model = CChessModel(SimpleNamespace(model=SimpleNamespace(cnn_filter_num=filters, res_layer_num=blocks, value_fc_size=256,
                                                               cnn_first_filter_size=5, cnn_filter_size=3, input_depth=14)))
     model.build(seed=0)                      # random-init, Keras-equivalent (agent/model.py:32-66 defaults)
@@ -327,8 +327,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--skip-stream", default="auto", choices=["auto", "fp32", "fp16", "ext8"],
-                    help="precision of the residual skip stream (auto = fp16 + 8-bit extension from 10 blocks on: keeps the 1e-3 parity bound)")
+    ap.add_argument("--skip-stream", default="auto", choices=["auto", "fp32", "fp16"],
+                    help="precision of the residual skip stream (auto = fp32 beyond 10 blocks: keeps the 1e-3 parity bound)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -46,8 +46,6 @@ struct Args {
   const __half* residual;  // same layout as out (fp16) or null
   const float* residual32; // fp32 skip stream (takes precedence over `residual`) or null
   float* out32;            // optional fp32 copy of the output (the skip stream of the next block) or null
-  const uint8_t* res_e8;   // 8-bit mantissa extension of `residual` (skip = fp16 + e8 * ulp/256) or null
-  uint8_t* out_e8;         // 8-bit mantissa extension of the fp16 output or null
   void* out;
   uint32_t a_bytes;  // TMA bytes per A box
 };
@@ -256,23 +254,6 @@ struct Cfg2 {
   static_assert(N_TILE % 32 == 0 && N_TILE <= 256, "UMMA N constraint for M=256 and an even split of B");
 };
 
-// "ext8" skip stream: an fp16 value h plus a signed byte q holding the next 8 mantissa bits, v ~= h + q * ulp(h) / 256
-// (relative error 2^-19 instead of 2^-11).  Costs 1 byte per element each way instead of the 4 of an fp32 copy.
-__device__ __forceinline__ float ext8_scale(unsigned short hbits) {          // ulp(h) / 256 as a float
-  const int e = (hbits >> 10) & 31;
-  return __int_as_float(((e ? e : 1) + 94) << 23);                            // 2^(max(e,1) - 33)
-}
-__device__ __forceinline__ float ext8_inv_scale(unsigned short hbits) {
-  const int e = (hbits >> 10) & 31;
-  return __int_as_float((160 - (e ? e : 1)) << 23);                           // 2^(33 - max(e,1))
-}
-__device__ __forceinline__ unsigned ext8_encode(float v, __half h) {
-  const unsigned short hb = __half_as_ushort(h);
-  int q = __float2int_rn((v - __half2float(h)) * ext8_inv_scale(hb));
-  q = q < -128 ? -128 : (q > 127 ? 127 : q);
-  return (unsigned)(q & 0xff);
-}
-
 constexpr int kThreads2 = 384;             // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 
 template <int N_TILE>
@@ -386,10 +367,8 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const long long rbase = (long long)m_tile * kTileM + q * 32;     // first global pixel row of this warp
       const float* r32 = a.residual32 ? a.residual32 + rbase * a.ldo + cbeg : nullptr;
       const __half* r16 = (!a.residual32 && a.residual) ? a.residual + rbase * a.ldo + cbeg : nullptr;
-      const uint8_t* re8 = (r16 && a.res_e8) ? a.res_e8 + rbase * a.ldo + cbeg : nullptr;
       float4 nf[8];                                          // skip stream of the next chunk, line-coalesced
       uint4 nh[4];
-      uint2 ne[4];
       auto fetch = [&](int ch) {
         if (r32) {
 #pragma unroll
@@ -401,12 +380,6 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           for (int k = 0; k < 4; ++k)
             nh[k] = (rbase + r8 + 8 * k < a.rows) ? __ldg(reinterpret_cast<const uint4*>(r16 + (size_t)(r8 + 8 * k) * a.ldo + ch * 32 + c8))
                                                   : make_uint4(0u, 0u, 0u, 0u);
-          if (re8) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ne[k] = (rbase + r8 + 8 * k < a.rows) ? __ldg(reinterpret_cast<const uint2*>(re8 + (size_t)(r8 + 8 * k) * a.ldo + ch * 32 + c8))
-                                                    : make_uint2(0u, 0u);
-          }
         }
       };
       fetch(0);
@@ -423,18 +396,11 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         } else if (r16) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const unsigned short* hb = reinterpret_cast<const unsigned short*>(&nh[k]);
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __half2float(__ushort_as_half(hb[j]));
-            if (re8) {
-              const signed char* qb = reinterpret_cast<const signed char*>(&ne[k]);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += (float)qb[j] * ext8_scale(hb[j]);
-            }
+            const __half2* h = reinterpret_cast<const __half2*>(&nh[k]);
+            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
             float* d = S + (r8 + 8 * k) * kStageRow + c8;
-            *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            *reinterpret_cast<float4*>(d) = make_float4(f0.x, f0.y, f1.x, f1.y);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
           }
         }
         if (ch + 1 < kChunks) fetch(ch + 1);
@@ -472,16 +438,7 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             __half2* oh = reinterpret_cast<__half2*>(&ov);
             oh[0] = __floats2half2_rn(x0.x, x0.y); oh[1] = __floats2half2_rn(x0.z, x0.w);
             oh[2] = __floats2half2_rn(x1.x, x1.y); oh[3] = __floats2half2_rn(x1.z, x1.w);
-            if (rbase + r8 + 8 * k < a.rows) {
-              *reinterpret_cast<uint4*>(o16 + (size_t)(r8 + 8 * k) * a.ldo + c8) = ov;
-              if (a.out_e8) {
-                const __half* hh = reinterpret_cast<const __half*>(&ov);
-                uint2 ev;
-                ev.x = ext8_encode(x0.x, hh[0]) | ext8_encode(x0.y, hh[1]) << 8 | ext8_encode(x0.z, hh[2]) << 16 | ext8_encode(x0.w, hh[3]) << 24;
-                ev.y = ext8_encode(x1.x, hh[4]) | ext8_encode(x1.y, hh[5]) << 8 | ext8_encode(x1.z, hh[6]) << 16 | ext8_encode(x1.w, hh[7]) << 24;
-                *reinterpret_cast<uint2*>(a.out_e8 + (rbase + r8 + 8 * k) * a.ldo + c0 + c8) = ev;
-              }
-            }
+            if (rbase + r8 + 8 * k < a.rows) *reinterpret_cast<uint4*>(o16 + (size_t)(r8 + 8 * k) * a.ldo + c8) = ov;
           }
         }
         __syncwarp();

@@ -219,8 +219,8 @@ __device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 
 // phase 2: every thread owns two adjacent output channels and walks the lists (half2 loads, fp32 accumulate).
 // grid = batch, block = max(96, C/2) threads.  w: HWIO [5][5][14][C] fp16 (BN scale folded).
 __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
-                             const float* __restrict__ shift, __half* __restrict__ out, float* __restrict__ out32,
-                             uint8_t* __restrict__ out_e8, int c_out, int board_pixels) {
+                             const float* __restrict__ shift, __half* __restrict__ out, float* __restrict__ out32, int c_out,
+                             int board_pixels) {
   __shared__ int8_t pl[90];
   __shared__ uint16_t rows[90][26];
   __shared__ uint8_t cnt[90];
@@ -260,12 +260,7 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
       a0 += v.x; a1 += v.y;
     }
     a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
-    const __half2 hv = __floats2half2_rn(a0, a1);
-    *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = hv;
-    if (out_e8) {
-      const unsigned q = igemm::ext8_encode(a0, __low2half(hv)) | igemm::ext8_encode(a1, __high2half(hv)) << 8;
-      *reinterpret_cast<unsigned short*>(out_e8 + ((size_t)b * board_pixels + pix) * c_out + c) = (unsigned short)q;
-    }
+    *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = __floats2half2_rn(a0, a1);
     if (out32) *reinterpret_cast<float2*>(out32 + ((size_t)b * board_pixels + pix) * c_out + c) = make_float2(a0, a1);
   }
   for (int col = 90; col < board_pixels; ++col)
@@ -293,8 +288,8 @@ __global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __
 // A block handles kHeadPos positions so the 180 x H value weights are read once per group.
 // Phase 1: warp per pixel, lane owns 8 channels whose 6 x 8 folded weights sit in registers.
 constexpr int kHeadPos = 4;
-__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, const float* __restrict__ act32,
-                                                const uint8_t* __restrict__ act_e8, int c_in, int n_pos, int board_pixels,
+__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, const float* __restrict__ act32, int c_in, int n_pos,
+                                                int board_pixels,
                                                 const float* __restrict__ w6,      // [6][c_in], BN scale folded
                                                 const float* __restrict__ shift6,  // [6]
                                                 const float* __restrict__ wv1,     // [180][H]
@@ -329,15 +324,9 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
         x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w4.x; x[5] = w4.y; x[6] = w4.z; x[7] = w4.w;
       } else {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + cbase));
-        const unsigned short* hb = reinterpret_cast<const unsigned short*>(&v);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __half2float(__ushort_as_half(hb[j]));
-        if (act_e8) {
-          const uint2 ev = __ldg(reinterpret_cast<const uint2*>(act_e8 + ((size_t)(b0 + p) * board_pixels + pix) * c_in + cbase));
-          const signed char* qb = reinterpret_cast<const signed char*>(&ev);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] += (float)qb[j] * igemm::ext8_scale(hb[j]);
-        }
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
       }
 #pragma unroll
       for (int o = 0; o < 6; ++o)
@@ -507,8 +496,6 @@ struct NnRuntime {
   // activations
   __half *x, *t, *y, *pol_feat;
   float *x32, *y32;                      // fp32 skip stream (dense layout only)
-  uint8_t *xe8, *ye8;                    // 8-bit mantissa extension of x / y ("ext8" skip stream)
-  int skip_mode;                         // 0 fp16, 1 fp32 copy, 2 fp16 + ext8
   float* logits;
   uint8_t* boards_tmp;
   // weights
@@ -568,8 +555,6 @@ static void layout(NnRuntime* r, Carver& cv) {
   r->y = (__half*)cv.take(act);
   r->x32 = (float*)cv.take(act * 2);
   r->y32 = (float*)cv.take(act * 2);
-  r->xe8 = (uint8_t*)cv.take(act / 2);
-  r->ye8 = (uint8_t*)cv.take(act / 2);
   r->pol_feat = (__half*)cv.take(((size_t)r->max_batch + 128) * kPolK * sizeof(__half));
   r->logits = (float*)cv.take((size_t)r->max_batch * kPolN * sizeof(float));
   r->boards_tmp = (uint8_t*)cv.take((size_t)r->max_batch * CZ_BOARD_STRIDE);
@@ -616,11 +601,8 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   // 0 = auto (fp32 skip stream for towers of 10 blocks and more, where fp16 rounding of the skip stream pushes the outputs
   // past 1e-3: value 1.1e-3 .. 1.5e-3 at 20 random-init blocks vs <= 6e-4 with fp32; policy 1.6e-3 vs 9.8e-4 on the
   // reference's trained 192x10 net), 1 = always, 2 = never
-  //   3 = fp16 + 8-bit mantissa extension ("ext8": same accuracy class as fp32, +1 B/element each way instead of +4);
-  //   auto picks ext8 from 10 blocks on.
-  r->skip_mode = fp32_skip_mode == 1 ? 1 : fp32_skip_mode == 2 ? 0 : fp32_skip_mode == 3 ? 2 : (blocks >= 10 ? 2 : 0);
-  { const char* e = getenv("CZ_SKIP_MODE"); if (e && e[0] >= '0' && e[0] <= '2') r->skip_mode = e[0] - '0'; }
-  r->fp32_skip = r->skip_mode == 1;
+  r->fp32_skip = fp32_skip_mode == 1 || (fp32_skip_mode == 0 && blocks >= 10);
+  { const char* e = getenv("CZ_FP32_SKIP"); if (e && e[0] == '1') r->fp32_skip = true; if (e && e[0] == '0') r->fp32_skip = false; }
   r->profile = false; r->ev_used = 0; r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0;
   Carver cv{(uint8_t*)workspace, 0, bytes};
   layout(r, cv);
@@ -782,10 +764,9 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
   const int c = r->filters;
   cudaStream_t st = r->stream;
   const bool dense = r->board_pixels == 90;
-  const bool s32 = dense && r->skip_mode == 1, s8 = dense && r->skip_mode == 2;
+  const bool s32 = dense && r->fp32_skip;
   float *x32 = s32 ? r->x32 : nullptr, *y32 = s32 ? r->y32 : nullptr;
-  uint8_t *xe8 = s8 ? r->xe8 : nullptr, *ye8 = s8 ? r->ye8 : nullptr;
-  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, x32, xe8, c, r->board_pixels);
+  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, x32, c, r->board_pixels);
   CUtensorMap *ix = &r->imap_x, *iy = &r->imap_y;
   r->launches++;
   __half *x = r->x, *y = r->y;
@@ -807,9 +788,7 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
       igemm::Args d1 = conv_args_dense(n, c, a1.bias, nullptr, r->t, 1);
       igemm::Args d2 = conv_args_dense(n, c, a2.bias, x, y, 1);
       d2.residual32 = x32; d2.out32 = y32;
-      d2.res_e8 = xe8; d2.out_e8 = ye8;
       { float* t32 = x32; x32 = y32; y32 = t32; }
-      { uint8_t* t8 = xe8; xe8 = ye8; ye8 = t8; }
       if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
       if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
       CUtensorMap* ti = ix; ix = iy; iy = ti;
@@ -822,7 +801,7 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     CUtensorMap* tm = mx; mx = my; my = tm;
   }
   if (pe != (size_t)-1) cudaEventRecord(r->ev[pe + 1], st);
-  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, st>>>(x, x32, xe8, c, n, r->board_pixels, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
+  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, st>>>(x, x32, c, n, r->board_pixels, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
   igemm::Args ap = dense_args(n, kLabels, kPolN, kPolK, 256, r->b_pol, r->logits, kPolN);
   if (launch_igemm(256, r->map_pf, r->map_wpol, ap, st)) return CZ_ERR_CUDA;
   k_softmax<<<n, 256, 0, st>>>(r->logits, kPolN, policy);

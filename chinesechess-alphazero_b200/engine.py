@@ -44,8 +44,7 @@ class Engine:
         cfg.min_resign_turn, cfg.max_game_length = min_resign_turn, max_game_length
         cfg.seed, cfg.rank = seed, rank
         cfg.arena = 1 if arena else 0
-        # skip-stream precision: None = auto (ext8 from 10 blocks on), True = fp32 copy, False = fp16, "ext8" = fp16 + 8-bit extension
-        cfg.nn_fp32_skip = 0 if nn_fp32_skip is None else (3 if nn_fp32_skip == "ext8" else (1 if nn_fp32_skip else 2))
+        cfg.nn_fp32_skip = 0 if nn_fp32_skip is None else (1 if nn_fp32_skip else 2)   # None = auto (fp32 when blocks >= 10)
         self.cfg = cfg
         nbytes = C.c_uint64(0)
         self.lib.call("cz_workspace_bytes", C.byref(cfg), C.byref(nbytes))

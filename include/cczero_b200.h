@@ -103,9 +103,8 @@ typedef struct cz_config {
   int32_t arena;               /* 1: evaluator arena (worker/evaluator.py:147-250): n_games = 2*M slots for M games; slot i holds
                                 * player 0's tree of game i, slot i+M player 1's; player p is evaluated by network p
                                 * (cz_nn_set_weights_net); the red side alternates with the game index; evaluator draw rules */
-  int32_t nn_fp32_skip;        /* residual (skip) stream precision: 0 auto (ext8 when nn_blocks >= 10, else fp16), 1 fp32 copy,
-                                * 2 fp16, 3 ext8 = fp16 + 8-bit mantissa extension.  fp32 / ext8 keep the value error of 20-block
-                                * nets <= 6e-4 (fp16: up to 1.5e-3); ext8 moves 2 extra bytes per element and block, fp32 6 */
+  int32_t nn_fp32_skip;        /* residual (skip) stream precision: 0 auto (fp32 when nn_blocks >= 10), 1 fp32, 2 fp16.
+                                * fp32 keeps the value error of 20-block nets <= 6e-4 (fp16: up to 1.5e-3) for ~10 % time */
   int32_t reserved;
 } cz_config;
 

@@ -13,7 +13,7 @@ env = StaticEnv(lib, "cuda")
 states = [senv.INIT_STATE] + midgame_states(63, 3, lo=1, hi=120)
 planes = np.stack([senv.state_to_planes(s) for s in states])
 import sys as _s
-mode = {"fp16": False, "fp32": True, "ext8": "ext8", "auto": None}[_s.argv[1] if len(_s.argv) > 1 else "auto"]
+mode = {"fp16": False, "fp32": True, "auto": None}[_s.argv[1] if len(_s.argv) > 1 else "auto"]
 for f, b, trained in ((128, 7, False), (128, 7, True), (256, 7, False), (192, 10, True), (256, 20, False), (256, 20, True)):
     w = om.init_weights(f, b, 256, seed=1, trained_like=trained)
     rp, rv = om.forward(w, planes, b)
