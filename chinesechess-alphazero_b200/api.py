@@ -1,7 +1,7 @@
 """`CChessModelAPI` drop-in (reference: cchess_alphazero/agent/api.py:16-117): the batching prediction server.
 
 Same wire protocol as the reference, so UNMODIFIED reference players can be served by the B200 network:
-a client sends `list[np.float32[14,10,9]]` on its pipe end, the server answers `list[(np.float32[2086], float)]`
+a client sends `list[np.float32[14,10,9]]` (`[28,10,9]` for a use_history network) on its pipe end, the server answers `list[(np.float32[2086], float)]`
 in the same order (api.py:48-74 <-> player.py:118-120,131-140).  One daemon thread waits on every pipe, drains
 what is ready, runs ONE batched forward (`cz_nn_forward`: tensor-core pipeline) and scatters the results.
 
@@ -43,7 +43,8 @@ class CChessModelAPI:
             mc = self.config.model
             self.engine = Engine(self.lib, self.device, n_games=self.max_batch, sims_per_move=1, leaves_per_round=1,
                                  max_nodes_per_game=16, max_edges_per_game=256, max_path=8,
-                                 nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size)
+                                 nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size,
+                                 use_history=bool(getattr(self.agent_model, "use_history", False)))
             self.engine.set_weights(self.agent_model.torch_weights())
 
     def start(self, need_reload=True):

@@ -217,17 +217,21 @@ __device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 
 // The 14 input planes are one-hot, so an output pixel is the sum of <= 25 weight rows w[tap][plane(piece on the
 // tapped square)][:].  Phase 1: 90 threads list the occupied taps of their pixel (row index = tap*14 + plane);
 // phase 2: every thread owns two adjacent output channels and walks the lists (half2 loads, fp32 accumulate).
-// grid = batch, block = max(96, C/2) threads.  w: HWIO [5][5][14][C] fp16 (BN scale folded).
+// grid = batch, block = max(96, C/2) threads.  w: HWIO [5][5][in_planes][C] fp16 (BN scale folded).
+// in_planes = 28 (use_history, static_env.py:158-194): every board record is followed by the history board whose pieces
+// select planes 14-27; board_stride = bytes between records.
 __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
                              const float* __restrict__ shift, __half* __restrict__ out, float* __restrict__ out32, int c_out,
-                             int board_pixels) {
-  __shared__ int8_t pl[90];
-  __shared__ uint16_t rows[90][26];
+                             int board_pixels, int in_planes, int board_stride) {
+  __shared__ int8_t pl[2][90];
+  __shared__ uint16_t rows[90][52];
   __shared__ uint8_t cnt[90];
   const int b = blockIdx.x, t = threadIdx.x;
+  const int n_boards = in_planes / 14;
   if (t < 90) {
     const int r = t / 9, col = t % 9;
-    pl[t] = (int8_t)plane_of(boards[(size_t)b * CZ_BOARD_STRIDE + (9 - r) * 9 + col]);
+    for (int h = 0; h < n_boards; ++h)
+      pl[h][t] = (int8_t)plane_of(boards[(size_t)b * board_stride + h * CZ_BOARD_STRIDE + (9 - r) * 9 + col]);
   }
   __syncthreads();
   if (t < 90) {
@@ -239,8 +243,10 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
       for (int kw = 0; kw < 5; ++kw) {
         const int cc = col + kw - 2;
         if (cc < 0 || cc > 8) continue;
-        const int p = pl[rr * 9 + cc];
-        if (p >= 0) rows[t][n++] = (uint16_t)((kh * 5 + kw) * 14 + p);
+        for (int h = 0; h < n_boards; ++h) {
+          const int p = pl[h][rr * 9 + cc];
+          if (p >= 0) rows[t][n++] = (uint16_t)((kh * 5 + kw) * in_planes + h * 14 + p);
+        }
       }
     }
     cnt[t] = (uint8_t)n;
@@ -267,19 +273,22 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
     *reinterpret_cast<__half2*>(o + (size_t)col * c_out + c) = __floats2half2_rn(0.f, 0.f);          // separator row (strip layout)
 }
 
-// one-hot planes [B][14][10][9] f32 -> packed boards (inverse of state_to_planes)
-__global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __restrict__ boards, int n) {
+// one-hot planes [B][in_planes][10][9] f32 -> packed boards (inverse of state_to_planes / state_history_to_planes):
+// in_planes / 14 consecutive board records per position
+__global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __restrict__ boards, int n, int in_planes) {
   const int b = blockIdx.x;
   if (b >= n) return;
   const int t = threadIdx.x;
   if (t < 96) {
-    uint8_t code = 0;
-    if (t < 90) {
-      const int y = t / 9, x = t % 9, r = 9 - y;
-      for (int p = 0; p < 14; ++p)
-        if (planes[((size_t)b * 14 + p) * 90 + r * 9 + x] > 0.5f) code = (uint8_t)(p < 7 ? p + 1 : p + 2);
+    for (int h = 0; h < in_planes / 14; ++h) {
+      uint8_t code = 0;
+      if (t < 90) {
+        const int y = t / 9, x = t % 9, r = 9 - y;
+        for (int p = 0; p < 14; ++p)
+          if (planes[((size_t)b * in_planes + h * 14 + p) * 90 + r * 9 + x] > 0.5f) code = (uint8_t)(p < 7 ? p + 1 : p + 2);
+      }
+      boards[((size_t)b * (in_planes / 14) + h) * CZ_BOARD_STRIDE + t] = code;
     }
-    boards[(size_t)b * CZ_BOARD_STRIDE + t] = code;
   }
 }
 
@@ -498,6 +507,7 @@ struct NnRuntime {
   float *x32, *y32;                      // fp32 skip stream (dense layout only)
   float* logits;
   uint8_t* boards_tmp;
+  int in_planes;                         // 14, or 28 with use_history (board + history board per position)
   // weights
   __half* w_first; float* shift_first;
   __half* w_conv;  float* shift_conv;      // [2*blocks][9*C*C], [2*blocks][C]
@@ -557,9 +567,9 @@ static void layout(NnRuntime* r, Carver& cv) {
   r->y32 = (float*)cv.take(act * 2);
   r->pol_feat = (__half*)cv.take(((size_t)r->max_batch + 128) * kPolK * sizeof(__half));
   r->logits = (float*)cv.take((size_t)r->max_batch * kPolN * sizeof(float));
-  r->boards_tmp = (uint8_t*)cv.take((size_t)r->max_batch * CZ_BOARD_STRIDE);
+  r->boards_tmp = (uint8_t*)cv.take((size_t)r->max_batch * 2 * CZ_BOARD_STRIDE);
   for (int net = 0; net < r->n_nets; ++net) {
-  r->w_first = (__half*)cv.take((size_t)25 * 14 * c * sizeof(__half));
+  r->w_first = (__half*)cv.take((size_t)25 * 28 * c * sizeof(__half));
   r->shift_first = (float*)cv.take(c * sizeof(float));
   r->w_conv = (__half*)cv.take((size_t)2 * r->blocks * 9 * c * c * sizeof(__half));
   r->shift_conv = (float*)cv.take((size_t)2 * r->blocks * c * sizeof(float));
@@ -589,7 +599,7 @@ size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch, 
 }
 
 NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_batch, void* workspace, size_t bytes,
-                     void* stream, int fp32_skip_mode, int n_nets) {
+                     void* stream, int fp32_skip_mode, int n_nets, int in_planes) {
   (void)device;
   if (filters % 64 != 0 || filters < 64 || filters > 256) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: filters must be 64..256 step 64"); return nullptr; }
   if (value_fc > 256 || value_fc < 1) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: value_fc_size must be <= 256"); return nullptr; }
@@ -598,6 +608,7 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   NnRuntime* r = new NnRuntime();
   r->filters = filters; r->blocks = blocks; r->value_fc = value_fc; r->max_batch = max_batch; r->n_nets = n_nets; r->cur = 0;
   r->stream = (cudaStream_t)stream; r->ready = false; r->launches = 0;
+  r->in_planes = in_planes == 28 ? 28 : 14;
   // 0 = auto (fp32 skip stream for towers of 10 blocks and more, where fp16 rounding of the skip stream pushes the outputs
   // past 1e-3: value 1.1e-3 .. 1.5e-3 at 20 random-init blocks vs <= 6e-4 with fp32; policy 1.6e-3 vs 9.8e-4 on the
   // reference's trained 192x10 net), 1 = always, 2 = never
@@ -710,9 +721,9 @@ int nn_set_weights(NnRuntime* r, int net, const cz_tensor_desc* descs, int n) {
   cudaStream_t st = r->stream;
   float* scale = r->scratch;
   {
-    NEED(k, "input_conv", "kernel", 25LL * 14 * c);
+    NEED(k, "input_conv", "kernel", 25LL * r->in_planes * c);
     if (fold_bn(r, ws, "input_batchnorm", c, scale, r->shift_first)) return CZ_ERR_ARG;
-    const long long nn = 25LL * 14 * c;
+    const long long nn = 25LL * r->in_planes * c;
     k_prep_hwio<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>((const float*)k->dev, scale, r->w_first, nn, c);
   }
   for (int i = 0; i < r->blocks; ++i) {
@@ -766,7 +777,8 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
   const bool dense = r->board_pixels == 90;
   const bool s32 = dense && r->fp32_skip;
   float *x32 = s32 ? r->x32 : nullptr, *y32 = s32 ? r->y32 : nullptr;
-  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, x32, c, r->board_pixels);
+  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, x32, c, r->board_pixels, r->in_planes,
+                                                     (r->in_planes / 14) * CZ_BOARD_STRIDE);
   CUtensorMap *ix = &r->imap_x, *iy = &r->imap_y;
   r->launches++;
   __half *x = r->x, *y = r->y;
@@ -816,7 +828,7 @@ int nn_forward_boards(NnRuntime* r, int net, const uint8_t* boards, int batch, f
   if (!r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
   for (int off = 0; off < batch; off += r->max_batch) {
     const int n = batch - off < r->max_batch ? batch - off : r->max_batch;
-    const int rc = forward_chunk(r, boards + (size_t)off * CZ_BOARD_STRIDE, n, policy + (size_t)off * kLabels, value + off);
+    const int rc = forward_chunk(r, boards + (size_t)off * (r->in_planes / 14) * CZ_BOARD_STRIDE, n, policy + (size_t)off * kLabels, value + off);
     if (rc) return rc;
   }
   return 0;
@@ -828,7 +840,7 @@ int nn_forward_planes(NnRuntime* r, int net, const float* planes, int batch, flo
   if (!r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
   for (int off = 0; off < batch; off += r->max_batch) {
     const int n = batch - off < r->max_batch ? batch - off : r->max_batch;
-    k_planes_to_boards<<<n, 96, 0, r->stream>>>(planes + (size_t)off * 14 * 90, r->boards_tmp, n);
+    k_planes_to_boards<<<n, 96, 0, r->stream>>>(planes + (size_t)off * r->in_planes * 90, r->boards_tmp, n, r->in_planes);
     r->launches++;
     const int rc = forward_chunk(r, r->boards_tmp, n, policy + (size_t)off * kLabels, value + off);
     if (rc) return rc;

@@ -45,10 +45,14 @@ struct EngineDev {
   int min_resign_turn, max_game_length;
   uint64_t seed; int rank;
   int arena;                     // 1: slots g and g + G/2 are the two players' trees of one game (worker/evaluator.py)
+  int use_history;               // 28 input planes (static_env.py:158-194): every leaf carries a second board
+  int lb_stride;                 // bytes per leaf record: BOARD_STRIDE, or 2*BOARD_STRIDE (board, history board) with use_history
   // ---- tables
   const int16_t* label_lut;      // [8100]
   // ---- per game: root + search bookkeeping
   uint8_t* root_board;           // [G][96]
+  uint8_t* root_hist;            // [G][96] use_history: hist[-5] of action()'s `hist` argument (all empty = zero planes)
+  int32_t* root_has_hist;        // [G]     use_history: action() was given a non-empty `hist`
   int32_t* root_node;            // [G]
   int32_t* active;               // [G]
   int32_t* tasks_left;           // [G]
@@ -81,7 +85,7 @@ struct EngineDev {
   int32_t* sim_edge;             // [G*K*max_path]
   int32_t* leaf_sim;             // [G*K]
   int32_t* n_leaf;               // [G]
-  uint8_t* leaf_board;           // [G*K][96]
+  uint8_t* leaf_board;           // [G*K][lb_stride]
   int32_t* resume_sim;           // [G*K]
   int32_t* n_resume;             // [G]
   int32_t* park_sim;             // [G*K]
@@ -89,7 +93,7 @@ struct EngineDev {
   int32_t* n_park;               // [G]
   int32_t* leaf_off;             // [G]
   int32_t* totals;               // [4]: total leaves, any active, -, -
-  uint8_t* leaf_dense;           // [G*K][96] leaves of all games, dense
+  uint8_t* leaf_dense;           // [G*K][lb_stride] leaves of all games, dense
   unsigned long long* counters;  // [8]
   int32_t* gc_map;               // [G*ncap] scratch of game_compact: old node -> new node + 1 (0 = dropped)
   SelfplayDev sp;
@@ -345,8 +349,22 @@ CZ_D int descend(const EngineDev& E, int g, int sim, bool fresh, TreeSmem* sm, d
           E.leaf_sim[(size_t)g * E.K + j] = sim;
           E.n_leaf[g] = j + 1;
         }
-        uint8_t* lb = E.leaf_board + ((size_t)g * E.K + j) * BOARD_STRIDE;
+        uint8_t* lb = E.leaf_board + ((size_t)g * E.K + j) * E.lb_stride;
         for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) lb[k] = k < NSQ ? sm->board[k] : (uint8_t)0;
+        if (E.use_history) {
+          // expand_and_evaluate (player.py:322-334): planes 14-27 come from history[-5].  A descent that started at the
+          // root of an action() call that was given `hist` uses that list for every leaf it expands (is_root_node is
+          // never cleared, :198-221); otherwise the path: the position two plies above the leaf, none for depth < 2.
+          const uint8_t* hsrc = nullptr;
+          if (fresh && E.root_has_hist[g]) hsrc = E.root_hist + (size_t)g * BOARD_STRIDE;
+          else if (depth >= 2) {
+            copy_board(E.root_board + (size_t)g * BOARD_STRIDE, sm->sc.b0);
+            for (int l = 0; l < depth - 2; ++l)
+              step_flip(sm->sc.b0, E.edge_move[(size_t)g * E.ecap + E.sim_edge[so + l]], sm->sc.b0);
+            hsrc = sm->sc.b0;
+          }
+          for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) lb[BOARD_STRIDE + k] = (hsrc && k < NSQ) ? hsrc[k] : (uint8_t)0;
+        }
         czs::syncwarp();
         return OUT_LEAF;
       }

@@ -61,17 +61,21 @@ CZ_KERNEL(k_gather)(EngineDev E, int g0, int g1, uint8_t* dense) {
   if (g >= g1) return;
   const int n = E.n_leaf[g], off = E.leaf_off[g];
   for (int j = 0; j < n; ++j) {
-    const uint8_t* s = E.leaf_board + ((size_t)g * E.K + j) * BOARD_STRIDE;
-    uint8_t* d = dense + (size_t)(off + j) * BOARD_STRIDE;
-    if (czs::lane() < BOARD_STRIDE / 16) reinterpret_cast<uint4*>(d)[czs::lane()] = reinterpret_cast<const uint4*>(s)[czs::lane()];
+    const uint8_t* s = E.leaf_board + ((size_t)g * E.K + j) * E.lb_stride;
+    uint8_t* d = dense + (size_t)(off + j) * E.lb_stride;
+    if (czs::lane() < E.lb_stride / 16) reinterpret_cast<uint4*>(d)[czs::lane()] = reinterpret_cast<const uint4*>(s)[czs::lane()];
   }
 }
-CZ_KERNEL(k_planes_dense)(const uint8_t* boards, int n, float* planes) {
+CZ_KERNEL(k_planes_dense)(const uint8_t* boards, int n, float* planes, int lb_stride) {
   const int i = my_game();
   if (i >= n) return;
   TreeSmem* sm = tree_smem();
-  copy_board(boards + (size_t)i * BOARD_STRIDE, sm->board);
-  encode_planes_f32(sm->board, planes + (size_t)i * 14 * NSQ);
+  const int n_boards = lb_stride / BOARD_STRIDE;             // 2 with use_history: planes 14-27 = the history board
+  for (int h = 0; h < n_boards; ++h) {
+    copy_board(boards + (size_t)i * lb_stride + h * BOARD_STRIDE, sm->board);
+    encode_planes_f32(sm->board, planes + ((size_t)i * n_boards + h) * 14 * NSQ);
+    czs::syncwarp();
+  }
 }
 CZ_KERNEL(k_reset)(EngineDev E, const uint8_t* boards /* [G][96] or null */, const uint8_t* init_board, int clear_game /* -1 all */) {
   const int g = my_game();
@@ -85,6 +89,7 @@ CZ_KERNEL(k_reset)(EngineDev E, const uint8_t* boards /* [G][96] or null */, con
     E.n_nodes[g] = 0; E.n_edges[g] = 0; E.root_node[g] = -1;
     E.tasks_left[g] = 0; E.round_pending[g] = 0; E.n_leaf[g] = 0; E.n_park[g] = 0; E.n_resume[g] = 0;
     E.sims_run[g] = 0; E.noise_used[g] = 0; E.game_err[g] = 0; E.n_no_act[g] = 0; E.increase_temp[g] = 0; E.active[g] = 1;
+    E.root_has_hist[g] = 0;
   }
   czs::syncwarp();
   selfplay_reset_game(E, g);
@@ -159,9 +164,16 @@ CZ_KERNEL(k_compact)(EngineDev E) {
     clear_tree(E, g);
   }
 }
-CZ_KERNEL(k_set_opts)(EngineDev E, const uint16_t* no_act, const uint8_t* inc, const uint8_t* act) {
+CZ_KERNEL(k_set_opts)(EngineDev E, const uint16_t* no_act, const uint8_t* inc, const uint8_t* act, const uint8_t* hist,
+                      const uint8_t* hist_given) {
   const int g = my_game();
   if (g >= E.n_games) return;
+  if (E.use_history) {
+    const bool given = hist && hist_given && hist_given[g];
+    for (int k = czs::lane(); k < BOARD_STRIDE; k += 32)
+      E.root_hist[(size_t)g * BOARD_STRIDE + k] = (given && k < NSQ) ? hist[(size_t)g * BOARD_STRIDE + k] : (uint8_t)0;
+    if (czs::lane() == 0) E.root_has_hist[g] = given ? 1 : 0;
+  }
   if (czs::lane() == 0) {
     int n = 0;
     if (no_act) {
@@ -198,6 +210,7 @@ struct cz_engine {
   uint8_t* ws; size_t ws_bytes;
   uint8_t* init_board_dev;
   uint8_t* opt_no_act; uint8_t* opt_inc; uint8_t* opt_act;   // device staging for cz_root_opts
+  uint8_t* opt_hist; uint8_t* opt_hist_given;
   cz_root_info* root_info_dev;
   float* policy_buf; float* value_buf;                      // evaluator outputs for the built-in network
   uint8_t* board_stage;                                     // [G][96] staging for reset / set_root
@@ -225,6 +238,9 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.hcap = (int)H;
   d.label_lut = cv.take<int16_t>(8100);
   d.root_board = cv.take<uint8_t>(G * BOARD_STRIDE);
+  d.use_history = c.use_history ? 1 : 0;
+  d.lb_stride = d.use_history ? 2 * BOARD_STRIDE : BOARD_STRIDE;
+  d.root_hist = cv.take<uint8_t>(G * BOARD_STRIDE); d.root_has_hist = cv.take<int32_t>(G);
   d.root_node = cv.take<int32_t>(G); d.active = cv.take<int32_t>(G); d.tasks_left = cv.take<int32_t>(G);
   d.round_pending = cv.take<int32_t>(G); d.sims_run = cv.take<int32_t>(G); d.noise_used = cv.take<int32_t>(G);
   d.game_err = cv.take<int32_t>(G); d.no_act = cv.take<uint16_t>(G * CZ_MAX_NO_ACT); d.n_no_act = cv.take<int32_t>(G);
@@ -238,16 +254,17 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.sim_depth = cv.take<int32_t>(G * K); d.sim_leaf_node = cv.take<int32_t>(G * K);
   d.sim_node = cv.take<int32_t>(G * K * c.max_path); d.sim_edge = cv.take<int32_t>(G * K * c.max_path);
   d.leaf_sim = cv.take<int32_t>(G * K); d.n_leaf = cv.take<int32_t>(G);
-  d.leaf_board = cv.take<uint8_t>(G * K * BOARD_STRIDE);
+  d.leaf_board = cv.take<uint8_t>(G * K * d.lb_stride);
   d.resume_sim = cv.take<int32_t>(G * K); d.n_resume = cv.take<int32_t>(G);
   d.park_sim = cv.take<int32_t>(G * K); d.park_node = cv.take<int32_t>(G * K); d.n_park = cv.take<int32_t>(G);
   d.leaf_off = cv.take<int32_t>(G); d.totals = cv.take<int32_t>(8);
-  d.leaf_dense = cv.take<uint8_t>(G * K * BOARD_STRIDE);
+  d.leaf_dense = cv.take<uint8_t>(G * K * d.lb_stride);
   d.counters = cv.take<unsigned long long>(8);
   d.gc_map = cv.take<int32_t>(G * N);
   selfplay_carve(d.sp, cv, c);
   e->init_board_dev = cv.take<uint8_t>(BOARD_STRIDE);
   e->opt_no_act = cv.take<uint8_t>(G * CZ_MAX_NO_ACT * 2); e->opt_inc = cv.take<uint8_t>(G); e->opt_act = cv.take<uint8_t>(G);
+  e->opt_hist = cv.take<uint8_t>(G * BOARD_STRIDE); e->opt_hist_given = cv.take<uint8_t>(G);
   e->root_info_dev = cv.take<cz_root_info>(1);
   e->board_stage = cv.take<uint8_t>(G * BOARD_STRIDE);
   e->stat_n = cv.take<int32_t>(G * MAX_MOVES); e->stat_mv = cv.take<uint16_t>(G * MAX_MOVES); e->stat_cnt = cv.take<int32_t>(G);
@@ -366,7 +383,7 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
     const int maxb = cfg->n_games * cfg->leaves_per_round;
     e->nn_bytes = cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, cfg->arena ? 2 : 1);
     uint8_t* nnws = e->ws + ((used + 4095) & ~(size_t)4095);
-    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream, cfg->nn_fp32_skip, cfg->arena ? 2 : 1);
+    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream, cfg->nn_fp32_skip, cfg->arena ? 2 : 1, cfg->use_history ? 28 : 14);
     if (!e->nn) { delete e; return CZ_ERR_CUDA; }
   }
 #else
@@ -447,16 +464,22 @@ int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {
   if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_begin: null engine");
   const size_t G = e->cfg.n_games;
   const uint16_t* na = nullptr; const uint8_t* inc = nullptr; const uint8_t* act = nullptr;
+  const uint8_t* hist = nullptr; const uint8_t* hist_given = nullptr;
   int sims_override = 0;
   e->d.noise_table = nullptr; e->d.noise_stride = 0;
   if (opts) {
     if (opts->no_act_host) { czrt_copy(e->opt_no_act, opts->no_act_host, G * CZ_MAX_NO_ACT * 2, e->stream); na = (const uint16_t*)e->opt_no_act; }
     if (opts->increase_temp_host) { czrt_copy(e->opt_inc, opts->increase_temp_host, G, e->stream); inc = e->opt_inc; }
     if (opts->active_host) { czrt_copy(e->opt_act, opts->active_host, G, e->stream); act = e->opt_act; }
+    if (opts->root_hist_host && opts->root_hist_given_host) {
+      if (!e->cfg.use_history) return cz_fail(CZ_ERR_ARG, "cz_search_begin: root history given but the engine was created without use_history");
+      czrt_copy(e->opt_hist, opts->root_hist_host, G * BOARD_STRIDE, e->stream); hist = e->opt_hist;
+      czrt_copy(e->opt_hist_given, opts->root_hist_given_host, G, e->stream); hist_given = e->opt_hist_given;
+    }
     e->d.noise_table = opts->noise_dev; e->d.noise_stride = opts->noise_stride;
     sims_override = opts->sims_override;
   }
-  if (opts) GAME_LAUNCH(e, k_set_opts, e->d, na, inc, act);   // NULL keeps the options the game loop maintains
+  if (opts) GAME_LAUNCH(e, k_set_opts, e->d, na, inc, act, hist, hist_given);   // NULL keeps the options the game loop maintains
   GAME_LAUNCH(e, k_begin, e->d, sims_override);
   e->last_leaves = 0;
   return launch_ok(e, "cz_search_begin", 2);
@@ -485,14 +508,14 @@ int cz_leaf_planes(cz_engine* e, float* planes_dev) {
   const int n = e->last_leaves;
   if (n == 0) return 0;
   CZ_LAUNCH(k_planes_dense, (n + kWarps - 1) / kWarps, kWarps, sizeof(TreeSmem) * kWarps, e->stream,
-            (const uint8_t*)e->d.leaf_dense, n, planes_dev);
+            (const uint8_t*)e->d.leaf_dense, n, planes_dev, e->d.lb_stride);
   return launch_ok(e, "cz_leaf_planes");
 }
 
 int cz_leaf_boards(cz_engine* e, uint8_t* boards_dev) {
   if (!e || !boards_dev) return cz_fail(CZ_ERR_ARG, "cz_leaf_boards: bad argument");
   if (e->last_leaves == 0) return 0;
-  return czrt_copy(boards_dev, e->d.leaf_dense, (size_t)e->last_leaves * BOARD_STRIDE, e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_leaf_boards: copy failed") : 0;
+  return czrt_copy(boards_dev, e->d.leaf_dense, (size_t)e->last_leaves * e->d.lb_stride, e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_leaf_boards: copy failed") : 0;
 }
 
 int cz_search_apply(cz_engine* e, const float* policy_dev, const float* value_dev) {
@@ -514,7 +537,7 @@ int search_pipelined(cz_engine* e) {
   const int G = e->cfg.n_games, K = e->cfg.leaves_per_round;
   const int mid = (G + 1) / 2;
   const int gb[2] = {0, mid}, ge[2] = {mid, G};
-  uint8_t* dense[2] = {e->d.leaf_dense, e->d.leaf_dense + (size_t)mid * K * BOARD_STRIDE};
+  uint8_t* dense[2] = {e->d.leaf_dense, e->d.leaf_dense + (size_t)mid * K * e->d.lb_stride};
   float* pol[2] = {e->policy_buf, e->policy_buf + (size_t)mid * K * CZ_N_LABELS};
   float* val[2] = {e->value_buf, e->value_buf + (size_t)mid * K};
   cudaStream_t T = e->tree_stream, N = e->stream;

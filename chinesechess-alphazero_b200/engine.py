@@ -21,7 +21,8 @@ class Engine:
     def __init__(self, lib=None, device=None, n_games=1, sims_per_move=800, leaves_per_round=8, virtual_loss=3,
                  max_nodes_per_game=None, max_edges_per_game=None, max_path=128, noise_mode=1, max_game_length=100,
                  nn_filters=0, nn_blocks=0, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
-                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0, nn_fp32_skip=None, arena=False):
+                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0, nn_fp32_skip=None, arena=False,
+                 use_history=False):
         self.lib = lib or get_lib()
         if device is None:
             device = 'cuda' if self.lib.is_cuda else 'cpu'
@@ -45,6 +46,9 @@ class Engine:
         cfg.seed, cfg.rank = seed, rank
         cfg.arena = 1 if arena else 0
         cfg.nn_fp32_skip = 0 if nn_fp32_skip is None else (1 if nn_fp32_skip else 2)   # None = auto (fp32 when blocks >= 10)
+        cfg.use_history = 1 if use_history else 0
+        self.use_history = bool(use_history)
+        self.in_planes = 28 if use_history else 14
         self.cfg = cfg
         nbytes = C.c_uint64(0)
         self.lib.call("cz_workspace_bytes", C.byref(cfg), C.byref(nbytes))
@@ -86,9 +90,21 @@ class Engine:
         self.lib.call("cz_set_root", self._h, game, C.c_void_p(b.ctypes.data))
 
     # ---- search
-    def make_opts(self, no_act=None, increase_temp=None, active=None, noise=None, sims_override=0):
+    def make_opts(self, no_act=None, increase_temp=None, active=None, noise=None, sims_override=0, hist=None):
+        """hist (use_history engines): per game the `hist` list given to action() ([.., state, move, state]) or None."""
         o = CzRootOpts()
         keep = []
+        if hist is not None and any(h for h in hist):
+            hb = np.zeros((self.n_games, BOARD_STRIDE), dtype=np.uint8)
+            given = np.zeros(self.n_games, dtype=np.uint8)
+            for g, h in enumerate(hist):
+                if h:
+                    given[g] = 1
+                    if len(h) >= 5:
+                        hb[g] = state_to_board(h[-5])
+            keep += [hb, given]
+            o.root_hist_host = hb.ctypes.data
+            o.root_hist_given_host = given.ctypes.data
         if no_act is not None:
             a = np.full((self.n_games, MAX_NO_ACT), 0xFFFF, dtype=np.uint16)
             for g, lst in enumerate(no_act):
@@ -123,12 +139,12 @@ class Engine:
         return n.value, bool(busy.value)
 
     def leaf_planes(self, n):
-        planes = torch.empty((n, 14, 10, 9), dtype=torch.float32, device=self.device)
+        planes = torch.empty((n, self.in_planes, 10, 9), dtype=torch.float32, device=self.device)
         self.lib.call("cz_leaf_planes", self._h, _ptr(planes))
         return planes
 
     def leaf_boards(self, n):
-        b = torch.empty((n, BOARD_STRIDE), dtype=torch.uint8, device=self.device)
+        b = torch.empty((n, self.in_planes // 14 * BOARD_STRIDE), dtype=torch.uint8, device=self.device)
         self.lib.call("cz_leaf_boards", self._h, _ptr(b))
         return b
 

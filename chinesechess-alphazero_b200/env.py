@@ -185,6 +185,16 @@ class StaticEnv:
     def state_to_planes(self, state):
         return self.planes_batch(self.boards_from_states([state]))[0].cpu().numpy()
 
+    def state_history_to_planes(self, state, history):
+        """static_env.py:158-194: planes 0-13 = state, 14-27 = history[-5] when the list holds >= 5 entries, else zero."""
+        states = [state] + ([history[-5]] if history and len(history) >= 5 else [])
+        p = self.planes_batch(self.boards_from_states(states)).cpu().numpy()
+        out = np.zeros((28, 10, 9), dtype=np.float32)
+        out[:14] = p[0]
+        if len(states) == 2:
+            out[14:] = p[1]
+        return out
+
     def fliped_state(self, state):
         b = state_to_board(state)[:90]
         f = np.where(b[::-1] != 0, b[::-1] ^ 8, 0).astype(np.uint8)

@@ -30,7 +30,7 @@ class CzConfig(C.Structure):
         ("c_puct", C.c_double), ("noise_eps", C.c_double), ("dirichlet_alpha", C.c_double),
         ("tau_decay_rate", C.c_double), ("resign_threshold", C.c_double), ("enable_resign_rate", C.c_double),
         ("min_resign_turn", C.c_int32), ("max_game_length", C.c_int32),
-        ("seed", C.c_uint64), ("rank", C.c_int32), ("arena", C.c_int32), ("nn_fp32_skip", C.c_int32), ("pad_", C.c_int32),
+        ("seed", C.c_uint64), ("rank", C.c_int32), ("arena", C.c_int32), ("nn_fp32_skip", C.c_int32), ("use_history", C.c_int32),
     ]
 
 
@@ -39,6 +39,7 @@ class CzRootOpts(C.Structure):
         ("no_act_host", C.c_void_p), ("increase_temp_host", C.c_void_p), ("active_host", C.c_void_p),
         ("noise_dev", C.c_void_p), ("noise_stride", C.c_int64),
         ("sims_override", C.c_int32), ("reserved", C.c_int32),
+        ("root_hist_host", C.c_void_p), ("root_hist_given_host", C.c_void_p),
     ]
 
 

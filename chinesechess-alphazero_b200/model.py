@@ -70,9 +70,10 @@ class CChessModel:
 
         first = getattr(mc, "cnn_first_filter_size", 5)
         k = getattr(mc, "cnn_filter_size", 3)
-        if first != 5 or k != 3 or getattr(mc, "input_depth", 14) != 14:
-            raise NotImplementedError("the B200 path implements the 5x5 -> 3x3 residual tower on 14 input planes")
-        conv(f"input_conv-{first}-{f}", first, 14, f)
+        depth = getattr(mc, "input_depth", 14)        # 28 = the use_history network (data/model/model_128_l1_config.json)
+        if first != 5 or k != 3 or depth not in (14, 28):
+            raise NotImplementedError("the B200 path implements the 5x5 -> 3x3 residual tower on 14 or 28 input planes")
+        conv(f"input_conv-{first}-{f}", first, depth, f)
         bn("input_batchnorm", f)
         for i in range(1, blocks + 1):
             for j in (1, 2):
@@ -127,11 +128,20 @@ class CChessModel:
         """cnn_filter_num / res_layer_num / value_fc_size from the tensors themselves (a Keras .h5 carries no config)."""
         mc = self.config.model
         k = next(v for n, v in self.weights.items() if n.startswith("input_conv") and n.endswith("/kernel"))
-        if k.shape[:3] != (5, 5, 14):
-            raise NotImplementedError(f"input convolution {k.shape}: only 5x5 on 14 planes is built")
+        if k.shape[:2] != (5, 5) or k.shape[2] not in (14, 28):
+            raise NotImplementedError(f"input convolution {k.shape}: only 5x5 on 14 or 28 planes is built")
+        mc.input_depth = int(k.shape[2])
         mc.cnn_filter_num = int(k.shape[3])
         mc.res_layer_num = max(int(n[3:n.index("_")]) for n in self.weights if n.startswith("res"))
         mc.value_fc_size = int(self.weights["value_dense/bias"].shape[0])
+
+    @property
+    def use_history(self):
+        """What load_model returns next to the model (worker/self_play.py:29-46): the network reads 28 planes."""
+        if not self.weights:
+            return getattr(self.config.model, "input_depth", 14) == 28
+        k = next(v for n, v in self.weights.items() if n.startswith("input_conv") and n.endswith("/kernel"))
+        return int(k.shape[2]) == 28
 
     def save(self, config_path, weight_path):
         """model.py:109-115."""

@@ -11,7 +11,7 @@ that the global `np.random` stream is consumed exactly like the reference consum
     `np.random` state into a device table, lets the engine consume a prefix, then rewinds the generator
     and re-draws exactly the consumed prefix, leaving the stream where the reference would leave it.
   * evaluation: if `pipes` is given the leaves are sent through it with the reference wire protocol
-    (list of float32[14,10,9] -> list of (float32[2086], float), api.py:48-74), so the player works
+    (list of float32[14,10,9] ([28,10,9] with use_history) -> list of (float32[2086], float), api.py:48-74), so the player works
     against an unmodified CChessModelAPI; otherwise the engine's built-in tensor-core network is used.
 """
 import numpy as np
@@ -25,8 +25,7 @@ from .lib import get_lib
 class CChessPlayer:
     def __init__(self, config, search_tree=None, pipes=None, play_config=None, enable_resign=False, debugging=False,
                  uci=False, use_history=False, side=0, lib=None, device=None, weights=None, exact_noise=True):
-        if use_history:
-            raise NotImplementedError("28-plane history input is outside the built hot path (SURVEY.md §8f)")
+        self.use_history = use_history          # 28 input planes (static_env.py:158-194, player.py:326-334)
         self.config = config
         self.play_config = play_config or config.play
         self.lib = lib or get_lib()
@@ -59,7 +58,7 @@ class CChessPlayer:
             max_game_length=getattr(pc, "max_game_length", 100),
             max_nodes_per_game=max(4096, 8 * pc.simulation_num_per_move),
             nn_filters=mc.cnn_filter_num if (use_nn and mc) else 0, nn_blocks=mc.res_layer_num if (use_nn and mc) else 0,
-            nn_value_fc=mc.value_fc_size if (use_nn and mc) else 256)
+            nn_value_fc=mc.value_fc_size if (use_nn and mc) else 256, use_history=use_history)
         if use_nn:
             if weights is None:
                 raise ValueError("CChessPlayer without pipes needs `weights` (Keras-named tensors) for the built-in network")
@@ -94,7 +93,8 @@ class CChessPlayer:
             alpha = pc.dirichlet_alpha * np.ones(max(n_moves, 1))
             noise = np.array([np.random.dirichlet(alpha)[0] for _ in range(cap)], dtype=np.float64)[None, :]
         opts = eng.make_opts(no_act=[list(no_act)] if no_act else None, increase_temp=[1 if increase_temp else 0],
-                             noise=noise, sims_override=int(depth) if depth else 0)
+                             noise=noise, sims_override=int(depth) if depth else 0,
+                             hist=[list(hist)] if (self.use_history and hist) else None)
         if self.pipe is not None:
             eng.search_external(self._evaluate_through_pipe, opts)
         else:

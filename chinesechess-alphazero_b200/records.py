@@ -93,10 +93,12 @@ def read_game_data_from_file(path):
         return json.load(f)
 
 
-def expanding_data(data, env):
-    """expanding_data + convert_to_trainging_data (optimize.py:234-281, 14-plane path): one play record
+def expanding_data(data, env, use_history=False):
+    """expanding_data + convert_to_trainging_data (optimize.py:234-281): one play record
     `[init_state, [move, value], ...]` -> (planes f32 [T,14,10,9], one-hot policy f32 [T,2086], value f32 [T]).
-    The positions are replayed and encoded by the rules kernels (`env` is a StaticEnv)."""
+    use_history: planes f32 [T,28,10,9], planes 14-27 of sample i = the position of sample i-2 (history[0:2i+1][-5],
+    optimize.py:264-267), zero for the first two.  The positions are replayed and encoded by the rules kernels
+    (`env` is a StaticEnv)."""
     from .env import move_to_u16
     moves = [item[0] for item in data[1:]]
     values = np.asarray([item[1] for item in data[1:]], dtype=np.float32)
@@ -107,8 +109,12 @@ def expanding_data(data, env):
         boards, _ = env.step_batch(boards, env.moves_tensor([m]))
         seq.append(boards)
     if t == 0:
-        return (np.zeros((0, 14, 10, 9), np.float32), np.zeros((0, len(env.labels)), np.float32), values)
+        return (np.zeros((0, 28 if use_history else 14, 10, 9), np.float32), np.zeros((0, len(env.labels)), np.float32), values)
     planes = env.planes_batch(torch.cat(seq, dim=0)).cpu().numpy()
+    if use_history:
+        hist = np.zeros_like(planes)
+        hist[2:] = planes[:-2]
+        planes = np.concatenate([planes, hist], axis=1)
     policy = np.zeros((t, len(env.labels)), dtype=np.float32)
     lut = env.label_lut
     for i, m in enumerate(moves):

@@ -29,7 +29,7 @@ def load_model(config):
         model.build()
         os.makedirs(os.path.dirname(w_path), exist_ok=True)
         model.save(cfg_path, w_path)
-    return model, False
+    return model, model.use_history
 
 
 def start(config, games_per_process=128, max_games=None):
@@ -43,8 +43,6 @@ def start(config, games_per_process=128, max_games=None):
 class SelfPlayWorker:
     def __init__(self, config, pipes=None, pid=None, use_history=False, model=None, concurrent_games=None, lib=None,
                  device=None, seed=0, rank=0):
-        if use_history:
-            raise NotImplementedError("28-plane history input is outside the built hot path (SURVEY.md §8f)")
         self.config = config
         self.cur_pipes = pipes          # unused: evaluation happens inside the engine
         self.id = pid
@@ -63,7 +61,8 @@ class SelfPlayWorker:
             dirichlet_alpha=pc.dirichlet_alpha, tau_decay_rate=pc.tau_decay_rate, resign_threshold=pc.resign_threshold,
             enable_resign_rate=pc.enable_resign_rate, min_resign_turn=pc.min_resign_turn, max_game_length=pc.max_game_length,
             max_nodes_per_game=max(4096, 24 * pc.simulation_num_per_move),
-            nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size, seed=seed, rank=rank)
+            nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size, seed=seed, rank=rank,
+            use_history=use_history)    # the game loop never passes `hist` (self_play.py:124): path history only
         self.engine.set_weights(self.model.torch_weights())
         self.engine.reset()
         self.pending = []               # finished games not yet handed out by start_game

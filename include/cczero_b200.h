@@ -105,7 +105,8 @@ typedef struct cz_config {
                                 * (cz_nn_set_weights_net); the red side alternates with the game index; evaluator draw rules */
   int32_t nn_fp32_skip;        /* residual (skip) stream precision: 0 auto (fp32 when nn_blocks >= 10), 1 fp32, 2 fp16.
                                 * fp32 keeps the value error of 20-block nets <= 6e-4 (fp16: up to 1.5e-3) for ~10 % time */
-  int32_t reserved;
+  int32_t use_history;         /* CChessPlayer(use_history=True) (player.py:45,326-334): 28 input planes, planes 14-27 = the
+                                * position two plies earlier (static_env.py:158-194); leaf records become (board, history board) */
 } cz_config;
 
 /* Device workspace the caller must provide (a torch.uint8 CUDA tensor). */
@@ -134,6 +135,11 @@ typedef struct cz_root_opts {
   int64_t noise_stride;
   int32_t sims_override;           /* >0: depth argument of action() (player.py:160-161) */
   int32_t reserved;
+  /* use_history engines: the `hist` argument of action() (player.py:150-151,215-216).  root_hist_given_host [n_games]:
+   * 1 = a non-empty hist list was passed; root_hist_host [n_games][CZ_BOARD_STRIDE]: the position hist[-5] (all squares
+   * empty when the list holds fewer than 5 entries).  Both NULL = no hist (worker/self_play.py:124 never passes one). */
+  const uint8_t* root_hist_host;
+  const uint8_t* root_hist_given_host;
 } cz_root_opts;
 
 /* CChessPlayer.action up to the search (player.py:145-186), split so that an external
@@ -149,8 +155,8 @@ typedef struct cz_root_opts {
 /* opts == NULL keeps the per-game options the on-device game loop maintains (no_act / increase_temp). */
 int cz_search_begin(cz_engine* e, const cz_root_opts* opts);
 int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active);
-int cz_leaf_planes(cz_engine* e, float* planes_dev /* [n_leaves][14][10][9] */);
-int cz_leaf_boards(cz_engine* e, uint8_t* boards_dev /* [n_leaves][CZ_BOARD_STRIDE] */);
+int cz_leaf_planes(cz_engine* e, float* planes_dev /* [n_leaves][14][10][9]; [n_leaves][28][10][9] with use_history */);
+int cz_leaf_boards(cz_engine* e, uint8_t* boards_dev /* [n_leaves][CZ_BOARD_STRIDE]; [n_leaves][2][CZ_BOARD_STRIDE] with use_history */);
 int cz_search_apply(cz_engine* e, const float* policy_dev /* [n_leaves][2086] */, const float* value_dev /* [n_leaves] */);
 /* Whole search with the built-in network as evaluator (needs cz_nn_set_weights). Synchronises. */
 int cz_search(cz_engine* e, const cz_root_opts* opts);
@@ -218,10 +224,11 @@ typedef struct cz_tensor_desc {
 int cz_nn_set_weights(cz_engine* e, const cz_tensor_desc* descs, int32_t n);
 /* Second network of the arena (net 0 = best model, net 1 = next generation; evaluator.py:31-40). */
 int cz_nn_set_weights_net(cz_engine* e, int32_t net, const cz_tensor_desc* descs, int32_t n);
-/* predict_on_batch (api.py:62-64): planes_dev [B][14][10][9] f32 -> policy_dev [B][2086] f32
- * (softmax), value_dev [B] f32 (tanh). */
+/* predict_on_batch (api.py:62-64): planes_dev [B][14][10][9] f32 ([B][28][10][9] with use_history) -> policy_dev
+ * [B][2086] f32 (softmax), value_dev [B] f32 (tanh). */
 int cz_nn_forward(cz_engine* e, const float* planes_dev, int32_t batch, float* policy_dev, float* value_dev);
-/* Same from packed boards (plane encoding fused into the first convolution). */
+/* Same from packed boards (plane encoding fused into the first convolution); with use_history every position is two
+ * consecutive records: the board and the history board (all empty = zero planes). */
 int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch, float* policy_dev, float* value_dev);
 /* CUDA-event timing of the residual-tower tensor-core launches (the dominant kernel): switches the
  * bracketing on/off and returns + clears what accumulated since the last call: device milliseconds,

@@ -61,3 +61,6 @@ if __name__ == "__main__":
     elif what == "mcts":
         from oracle.gen_golden_mcts import gen_mcts
         gen_mcts()
+    elif what == "mcts_hist":
+        from oracle.gen_golden_mcts import gen_mcts_hist
+        gen_mcts_hist()

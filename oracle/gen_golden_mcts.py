@@ -82,3 +82,81 @@ def gen_mcts():
     with gzip.open(os.path.join(GOLD, "mcts_k1.json.gz"), "wt") as f:
         json.dump(out, f)
     print("mcts cases:", [(c["name"], [x["action"] for x in c["calls"]]) for c in cases])
+
+
+def _game_history(plies, seed):
+    """[s0, a0, s1, ..., s_plies] of a random playout that is not over."""
+    r = ref_import.senv()
+    rng = random.Random(seed)
+    while True:
+        s = r.INIT_STATE
+        hist = [s]
+        for _ in range(plies):
+            if r.done(s)[0]:
+                break
+            a = rng.choice(r.get_legal_moves(s))
+            s = r.step(s, a)
+            hist += [a, s]
+        if len(hist) == 2 * plies + 1 and not r.done(s)[0]:
+            return hist
+
+
+def gen_mcts_hist():
+    """use_history=True (28 input planes, static_env.py:158-194 / player.py:326-334): plane vectors and K=1 searches of the
+    real player, with and without the `hist` argument of action() -> tests/golden/mcts_k1_hist.json.gz."""
+    import numpy as np
+    r = ref_import.senv()
+    planes = []
+    for seed, plies in ((1, 1), (2, 2), (3, 7), (4, 30), (5, 55)):
+        h = _game_history(plies, seed)
+        p = r.state_history_to_planes(h[-1], h)
+        planes.append({"state": h[-1], "history": h[-5:], "nonzero": np.flatnonzero(p.reshape(-1)).tolist()})
+    h30, h41, h3 = _game_history(30, 11), _game_history(41, 12), _game_history(1, 13)
+    specs = [
+        dict(name="hist_init_80_nohist", seed=2, sims=80, calls=[(r.INIT_STATE, 0, None, False, None)]),
+        dict(name="hist_mid30_150", seed=4, sims=150, calls=[(h30[-1], 30, None, False, h30)]),
+        dict(name="hist_mid41_nohist_200", seed=6, sims=200, calls=[(h41[-1], 41, None, False, None)]),
+        dict(name="hist_short_60", seed=8, sims=60, calls=[(h3[-1], 1, None, False, h3)]),
+        dict(name="hist_mid41_no_act", seed=9, sims=120, calls=[(h41[-1], 41, "FIRST2", False, h41)]),
+    ]
+    cases = []
+    for sp in specs:
+        calls = []
+        for (s, t, na, inc, hi) in sp["calls"]:
+            if na == "FIRST2":
+                na = r.get_legal_moves(s)[:2]
+            calls.append((s, t, na, inc, hi))
+        res = real_player_moves(calls, sp["sims"], sp["seed"], use_history=True)
+        cases.append({"name": sp["name"], "seed": sp["seed"], "sims": sp["sims"],
+                      "calls": [{"state": c[0], "turns": c[1], "no_act": c[2], "increase_temp": c[3], "hist": c[4],
+                                 "action": a, "sum_n": sn, "legal": r.get_legal_moves(c[0]),
+                                 "edges": {m: list(v) for m, v in e.items()}}
+                                for c, (a, e, sn) in zip(calls, res)]})
+    # one player over three plies of a game with the growing game history passed in (uci.py:288)
+    from .ref_player_harness import FakeNetServer, make_config
+    pm = ref_import.player_module()
+    seed, sims = 29, 100
+    cfg = make_config(sims, 1)
+    srv = FakeNetServer()
+    np.random.seed(seed)
+    player = pm.CChessPlayer(cfg, pipes=srv.you, enable_resign=False, use_history=True)
+    hist = list(_game_history(6, 21))
+    s, t, seq = hist[-1], 6, []
+    for ply in range(3):
+        a, _ = player.action(s, t, hist=list(hist))
+        node = player.tree[s]
+        seq.append({"state": s, "turns": t, "no_act": None, "increase_temp": False, "hist": list(hist), "action": a,
+                    "sum_n": int(node.sum_n), "legal": r.get_legal_moves(s),
+                    "edges": {m: [int(x.n), float(x.w), float(x.q), float(x.p)] for m, x in node.a.items()}})
+        s = r.step(s, a)
+        hist += [a, s]
+        t += 1
+    player.close(wait=False)
+    srv.close()
+    cases.append({"name": "hist_three_plies_reuse", "seed": seed, "sims": sims, "calls": seq})
+    out = {"generator": "oracle/gen_golden_mcts.py:gen_mcts_hist", "reference": "NeymarL/ChineseChess-AlphaZero @7f45b0c agent/player.py",
+           "config": {"search_threads": 1, "c_puct": 1.5, "noise_eps": 0.25, "dirichlet_alpha": 0.2, "tau_decay_rate": 0.98,
+                      "virtual_loss": 3, "use_history": True}, "planes": planes, "cases": cases}
+    with gzip.open(os.path.join(GOLD, "mcts_k1_hist.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("hist cases:", [(c["name"], [x["action"] for x in c["calls"]]) for c in cases])

@@ -37,7 +37,7 @@ def _glorot(rng, shape, fan_in, fan_out):
     return rng.uniform(-lim, lim, size=shape).astype(np.float32)
 
 
-def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False, spread=1.0):
+def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False, spread=1.0, in_planes=14):
     """Keras-equivalent initialisation (glorot-uniform kernels, zero biases, BN gamma=1 beta=0 mean=0 var=1).
     trained_like=True perturbs the BN statistics and biases so that folding bugs cannot hide; `spread` scales the
     perturbation (1.0: gamma in [0.5,1.5], variance in [0.5,2] - a deep random net in that regime amplifies any
@@ -64,7 +64,7 @@ def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False, spre
         w[name + "/kernel"] = _glorot(rng, (cin, cout), cin, cout)
         w[name + "/bias"] = (rng.uniform(-0.1, 0.1, cout) if trained_like else np.zeros(cout)).astype(np.float32)
 
-    conv(f"input_conv-5-{filters}", 5, 14, filters)
+    conv(f"input_conv-5-{filters}", 5, in_planes, filters)     # 28 = the use_history variant (model_128_l1_config.json)
     bn("input_batchnorm", filters)
     for i in range(1, blocks + 1):
         for j in (1, 2):

@@ -67,10 +67,12 @@ class PlayConfig:
 
 
 class OraclePlayer:
-    """evaluate(list_of_states) -> list of (policy float32[2086], float value), same order."""
+    """evaluate(list_of_states) -> list of (policy float32[2086], float value), same order.
+    use_history (player.py:45,326-334): evaluate(list_of_states, list_of_history_states_or_None) instead; the second
+    list holds, per leaf, the state whose planes fill input planes 14-27 (None = zero planes)."""
 
     def __init__(self, play_config, evaluate, env=senv, tree=None, enable_resign=False, noise=None,
-                 evaluate_mode=False):
+                 evaluate_mode=False, use_history=False):
         self.pc = play_config
         self.evaluate = evaluate
         self.env = env
@@ -78,6 +80,7 @@ class OraclePlayer:
         self.labels = env.ActionLabelsRed
         self.move_lookup = {m: i for i, m in enumerate(self.labels)}
         self.enable_resign = enable_resign
+        self.use_history = use_history
         self.evaluate_mode = evaluate_mode      # config.opts.evaluate
         # noise(move_count) -> one Dirichlet(alpha * 1_n)[0] draw; default = the reference's call
         self.noise = noise or (lambda n: np.random.dirichlet(self.pc.dirichlet_alpha * np.ones(n))[0])
@@ -90,10 +93,12 @@ class OraclePlayer:
         self.stats = {"sims": 0, "positions": 0, "batches": 0, "noise_draws": 0}
 
     # ---- action(): player.py:145-196
-    def search(self, state, no_act=None, increase_temp=False, depth=None):
+    def search(self, state, no_act=None, increase_temp=False, depth=None, hist=None):
         self.root_state = state
         self.no_act = no_act
         self.increase_temp = increase_temp
+        if hist and len(hist) >= 5:                          # :150-151
+            hist = hist[-5:]
         done = self.tree[state].sum_n if state in self.tree else 0
         if no_act or increase_temp or done == self.pc.simulation_num_per_move:
             done = 0
@@ -108,11 +113,11 @@ class OraclePlayer:
                 self.num_task = min(k, all_tasks - k * it)
                 self.stats["sims"] += self.num_task
                 for _ in range(self.num_task):
-                    self.queue.append(("search", state, [state]))
+                    self.queue.append(("search", state, [state], hist))
                 self._drain_until_round_done()
 
-    def action(self, state, turns, no_act=None, depth=None, increase_temp=False):
-        self.search(state, no_act, increase_temp, depth)
+    def action(self, state, turns, no_act=None, depth=None, increase_temp=False, hist=None):
+        self.search(state, no_act, increase_temp, depth, hist)
         policy, resign = self.calc_policy(state, turns, no_act)
         if resign:
             return None, list(policy)
@@ -128,7 +133,7 @@ class OraclePlayer:
             while self.queue:
                 t = self.queue.popleft()
                 if t[0] == "search":
-                    self._mcts_search(t[1], t[2])
+                    self._mcts_search(t[1], t[2], t[3])
                 else:
                     self._update_tree(t[1], t[2], t[3])
             if self.num_task <= 0:
@@ -136,15 +141,21 @@ class OraclePlayer:
             if not self.buffer:
                 raise RuntimeError("oracle player: deadlock (no queued work, no pending evaluation)")
             batch = self.buffer[:256]
-            rets = self.evaluate([s for s, _ in batch])
+            if self.use_history:
+                rets = self.evaluate([s for s, _, _ in batch], [h for _, _, h in batch])
+            else:
+                rets = self.evaluate([s for s, _, _ in batch])
             self.stats["positions"] += len(batch)
             self.stats["batches"] += 1
-            for (s, hist), (p, v) in zip(batch, rets):
+            for (s, hist, _), (p, v) in zip(batch, rets):
                 self.queue.append(("update", p, float(v), hist))
             self.buffer = self.buffer[len(batch):]
 
     # ---- MCTS_search: player.py:198-260
-    def _mcts_search(self, state, history):
+    def _mcts_search(self, state, history, real_hist=None):
+        # real_hist: the `hist` argument of action(); only descents that START at the root carry it, and they use it
+        # for every leaf they expand whatever its depth (is_root_node is never cleared inside the loop, :198-221);
+        # simulations resumed by update_tree (:351-352) come without it.
         env = self.env
         while True:
             game_over, v, _ = env.done(state)
@@ -156,7 +167,9 @@ class OraclePlayer:
                 node.sum_n = 1
                 node.legal_moves = env.get_legal_moves(state)
                 node.waiting = True
-                self.buffer.append((state, history))       # expand_and_evaluate :322-338
+                src = real_hist if real_hist else history  # expand_and_evaluate :322-338
+                hist_state = src[-5] if (self.use_history and len(src) >= 5) else None
+                self.buffer.append((state, history, hist_state))
                 return
             if state in history[:-1]:
                 for i in range(len(history) - 1):
@@ -229,7 +242,7 @@ class OraclePlayer:
             node.p = p
             node.waiting = False
             for hist in node.visit:
-                self.queue.append(("search", state, hist))
+                self.queue.append(("search", state, hist, None))
             node.visit = []
         vl = self.pc.virtual_loss
         while len(history) > 0:
@@ -303,3 +316,8 @@ def fake_eval_from_planes(planes):
 
 def fake_evaluate_states(states, env=senv):
     return [fake_eval_from_planes(env.state_to_planes(s)) for s in states]
+
+
+def fake_evaluate_states_hist(states, hist_states, env=senv):
+    return [fake_eval_from_planes(env.state_history_to_planes(s, [h, None, None, None, s] if h else None))
+            for s, h in zip(states, hist_states)]

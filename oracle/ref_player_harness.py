@@ -41,18 +41,20 @@ def make_config(sims, search_threads=1, **over):
     return cfg
 
 
-def real_player_moves(states_and_opts, sims, seed, search_threads=1, **over):
-    """Run action() of ONE real player object over a list of (state, turns, no_act, increase_temp);
+def real_player_moves(states_and_opts, sims, seed, search_threads=1, use_history=False, **over):
+    """Run action() of ONE real player object over a list of (state, turns, no_act, increase_temp[, hist]);
     returns per call: (action, {move: (n, w, q, p)}, sum_n)."""
     pm = ref_import.player_module()
     cfg = make_config(sims, search_threads, **over)
     srv = FakeNetServer()
     np.random.seed(seed)
-    player = pm.CChessPlayer(cfg, pipes=srv.you, enable_resign=False)
+    player = pm.CChessPlayer(cfg, pipes=srv.you, enable_resign=False, use_history=use_history)
     out = []
     try:
-        for state, turns, no_act, inc in states_and_opts:
-            action, policy = player.action(state, turns, no_act, increase_temp=inc)
+        for call in states_and_opts:
+            state, turns, no_act, inc = call[:4]
+            hist = list(call[4]) if len(call) > 4 and call[4] is not None else None
+            action, policy = player.action(state, turns, no_act, increase_temp=inc, hist=hist)
             node = player.tree[state]
             edges = {m: (int(a.n), float(a.w), float(a.q), float(a.p)) for m, a in node.a.items()}
             out.append((action, edges, int(node.sum_n)))

@@ -13,11 +13,13 @@ from . import senv
 from .player import OraclePlayer
 
 
-def play_game(pc, evaluate, draws, max_game_length=100, enable_resign_rate=0.5, env=senv, max_plies_guard=1000):
+def play_game(pc, evaluate, draws, max_game_length=100, enable_resign_rate=0.5, env=senv, max_plies_guard=1000,
+              use_history=False):
     """Returns dict(moves, value_red, turns, flags, store).  `draws` supplies resign_lottery(), choose(...), store_lottery()."""
     enable_resign = draws.resign_lottery() > enable_resign_rate
     player = OraclePlayer(pc, evaluate, env=env, enable_resign=enable_resign,
-                          noise=(lambda n: 0.0) if pc.noise_eps == 0 else None)
+                          noise=(lambda n: 0.0) if pc.noise_eps == 0 else None, use_history=use_history)
+    # the game loop never hands its history to action() (self_play.py:124): history planes come from the search path only
     state = env.INIT_STATE
     history = [state]
     value, turns, game_over, final_move = 0, 0, False, None

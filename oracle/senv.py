@@ -253,6 +253,16 @@ def state_to_planes(state):
     return planes
 
 
+def state_history_to_planes(state, history):
+    """static_env.py:158-194: planes 0-13 = `state`, planes 14-27 = history[-5] (the position two plies
+    earlier, same side to move) when the history list [.., state, move, state, move, state] holds >= 5 entries."""
+    planes = np.zeros((28, 10, 9), dtype=np.float32)
+    planes[:14] = state_to_planes(state)
+    if history and len(history) >= 5:
+        planes[14:] = state_to_planes(history[-5])
+    return planes
+
+
 # ------------------------------------------------------------------ repetition rules
 def catch_set_codes(b, moves=None):
     res = set()

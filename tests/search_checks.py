@@ -17,8 +17,8 @@ from oracle import senv as osenv
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def load_mcts_golden():
-    with gzip.open(os.path.join(ROOT, "tests", "golden", "mcts_k1.json.gz"), "rt") as f:
+def load_mcts_golden(name="mcts_k1.json.gz"):
+    with gzip.open(os.path.join(ROOT, "tests", "golden", name), "rt") as f:
         return json.load(f)
 
 
@@ -57,17 +57,19 @@ def eval_planes(planes):
     return np.stack([o[0] for o in out]), np.array([o[1] for o in out], dtype=np.float32)
 
 
-def check_golden_k1(lib, device):
+def check_golden_k1(lib, device, use_history=False):
     """The drop-in CChessPlayer must reproduce the REAL reference player (search_threads=1): chosen move,
-    N, W, P of every root edge, for every call of every golden case (tests/golden/mcts_k1.json.gz)."""
-    gold = load_mcts_golden()
+    N, W, P of every root edge, for every call of every golden case (tests/golden/mcts_k1.json.gz; with use_history the
+    28-plane cases of mcts_k1_hist.json.gz, with and without the `hist` argument of action())."""
+    gold = load_mcts_golden("mcts_k1_hist.json.gz" if use_history else "mcts_k1.json.gz")
     for case in gold["cases"]:
         srv = FakeNetServer()
         np.random.seed(case["seed"])
-        player = CChessPlayer(make_config(case["sims"], 1), pipes=srv.you, lib=lib, device=device)
+        player = CChessPlayer(make_config(case["sims"], 1), pipes=srv.you, lib=lib, device=device, use_history=use_history)
         try:
             for call in case["calls"]:
-                action, policy = player.action(call["state"], call["turns"], call["no_act"], increase_temp=call["increase_temp"])
+                action, policy = player.action(call["state"], call["turns"], call["no_act"], increase_temp=call["increase_temp"],
+                                               hist=call.get("hist"))
                 root = player.engine.root(0)
                 assert root["moves"] == call["legal"], case["name"]
                 assert root["sum_n"] == call["sum_n"], (case["name"], root["sum_n"], call["sum_n"])
@@ -85,16 +87,16 @@ def check_golden_k1(lib, device):
             srv.close()
 
 
-def oracle_search(state, sims, k, seed, no_act=None, increase_temp=False, eps=0.25):
+def oracle_search(state, sims, k, seed, no_act=None, increase_temp=False, eps=0.25, use_history=False, hist=None):
     pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=eps, dirichlet_alpha=0.2,
                        tau_decay_rate=0.98, virtual_loss=3)
     np.random.seed(seed)
-    pl = op.OraclePlayer(pc, op.fake_evaluate_states)
-    pl.search(state, no_act, increase_temp)
+    pl = op.OraclePlayer(pc, op.fake_evaluate_states_hist if use_history else op.fake_evaluate_states, use_history=use_history)
+    pl.search(state, no_act, increase_temp, hist=hist)
     return pl
 
 
-def engine_search(lib, device, states, sims, k, seed, no_act=None, increase_temp=False, eps=0.25):
+def engine_search(lib, device, states, sims, k, seed, no_act=None, increase_temp=False, eps=0.25, use_history=False, hists=None):
     """All games share the seed: game g searches states[g] with its own copy of the oracle's noise stream."""
     g = len(states)
     tables = []
@@ -107,10 +109,11 @@ def engine_search(lib, device, states, sims, k, seed, no_act=None, increase_temp
     for i, t in enumerate(tables):
         noise[i, :len(t)] = t
     eng = Engine(lib, device, n_games=g, sims_per_move=sims, leaves_per_round=k, noise_mode=0, c_puct=1.5, noise_eps=eps,
-                 dirichlet_alpha=0.2, tau_decay_rate=0.98)
+                 dirichlet_alpha=0.2, tau_decay_rate=0.98, use_history=use_history)
     eng.reset(states)
     stats = eng.search_external(eval_planes, eng.make_opts(no_act=[no_act] * g if no_act else None,
-                                                           increase_temp=[1 if increase_temp else 0] * g, noise=noise))
+                                                           increase_temp=[1 if increase_temp else 0] * g, noise=noise,
+                                                           hist=hists))
     return eng, stats
 
 
@@ -143,6 +146,34 @@ def midgame_states(n, seed, lo=15, hi=80):
         if ok and not osenv.done(s)[0]:
             out.append(s)
     return out
+
+
+def game_history(plies, seed):
+    """[s0, a0, s1, ..., s_plies] of a random playout that is not over (the `history` list of worker/self_play.py:111-147)."""
+    rng = np.random.RandomState(seed)
+    while True:
+        s = osenv.INIT_STATE
+        hist = [s]
+        for _ in range(plies):
+            if osenv.done(s)[0]:
+                break
+            lm = osenv.get_legal_moves(s)
+            a = lm[rng.randint(len(lm))]
+            s = osenv.step(s, a)
+            hist += [a, s]
+        if len(hist) == 2 * plies + 1 and not osenv.done(s)[0]:
+            return hist
+
+
+def check_history_vs_oracle(lib, device, cases=((90, 1, 1), (160, 8, 2), (200, 16, 3))):
+    """use_history (28 planes): engine == oracle at any K, games with a long `hist`, a short one (< 5 entries) and none."""
+    for (sims, k, seed) in cases:
+        hists = [game_history(24 + seed, 50 + seed), game_history(1, 60 + seed), None, game_history(37, 70 + seed)]
+        states = [hists[0][-1], hists[1][-1], midgame_states(1, 80 + seed)[0], hists[3][-1]]
+        eng, _ = engine_search(lib, device, states, sims, k, seed, use_history=True, hists=hists)
+        for g, s in enumerate(states):
+            compare_root(eng, g, oracle_search(s, sims, k, seed, use_history=True, hist=hists[g]), s)
+        eng.close()
 
 
 def check_vs_oracle(lib, device, cases):

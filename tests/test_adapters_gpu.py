@@ -100,6 +100,50 @@ def test_selfplay_worker_writes_reference_records(cuda_lib, tmp_path):
     w.close()
 
 
+def test_history_network_builtin_search_and_worker(cuda_lib, tmp_path):
+    """use_history (28 planes): cz_search with the built-in network == the same search driven through cz_leaf_planes +
+    cz_nn_forward (the planes an external CChessModelAPI would see); the self-play worker runs on such a network."""
+    from cczero_b200.engine import Engine
+    from cczero_b200.model import CChessModel
+    from cczero_b200.self_play import SelfPlayWorker
+    from tests.search_checks import game_history
+    cfg = _config(str(tmp_path), sims=16, k=4)
+    cfg.model.input_depth = 28
+    model = CChessModel(cfg).build(seed=6)
+    assert model.use_history and model.weights["input_conv-5-64/kernel"].shape == (5, 5, 28, 64)
+    hists = [game_history(12, 3), None, game_history(2, 4)]
+    states = [hists[0][-1], osenv.INIT_STATE, hists[2][-1]]
+
+    def run(external):
+        eng = Engine(cuda_lib, "cuda", n_games=3, sims_per_move=64, leaves_per_round=8, noise_mode=1, nn_filters=64, nn_blocks=2,
+                     seed=5, use_history=True)
+        eng.set_weights(model.torch_weights())
+        eng.reset(states)
+        opts = eng.make_opts(hist=hists)
+        seen = []
+        if external:
+            def ev(planes):
+                t = torch.as_tensor(planes).cuda()
+                seen.append(t[:, 14:].abs().sum().item())
+                p, v = eng.nn_forward_planes(t)
+                return p.cpu().numpy(), v.cpu().numpy()
+            eng.search_external(ev, opts)
+        else:
+            eng.search(opts)
+        out = [(eng.root(g)["n"], eng.root(g)["w"]) for g in range(3)]
+        assert int(eng.counters()[6]) == 0
+        eng.close()
+        return out, seen
+    a, _ = run(False)
+    b, seen = run(True)
+    assert a == b and sum(seen) > 0
+    model.save(cfg.resource.model_best_config_path, cfg.resource.model_best_weight_path)
+    w = SelfPlayWorker(cfg, concurrent_games=4, seed=3, use_history=True, model=model)
+    recs = w.play_games(2)
+    assert len(recs) >= 2 and all(r["n_plies"] > 0 for r in recs)
+    w.close()
+
+
 def test_pipelined_search_equals_sequential(cuda_lib):
     """cz_search pipelines two halves of the games on two streams; per-game results must not depend on that."""
     from cczero_b200.engine import Engine

@@ -11,10 +11,10 @@ from tests.search_checks import midgame_states
 pytestmark = pytest.mark.gpu
 
 
-def _engine(cuda_lib, filters, blocks, batch, fp32_skip=None):
+def _engine(cuda_lib, filters, blocks, batch, fp32_skip=None, use_history=False):
     from cczero_b200.engine import Engine
     return Engine(cuda_lib, "cuda", n_games=batch, sims_per_move=8, leaves_per_round=1, nn_filters=filters,
-                  nn_blocks=blocks, nn_value_fc=256, nn_fp32_skip=fp32_skip)
+                  nn_blocks=blocks, nn_value_fc=256, nn_fp32_skip=fp32_skip, use_history=use_history)
 
 
 # Tolerance 1e-3 on policy probabilities and value (north_star), asserted on
@@ -73,6 +73,41 @@ def test_forward_chunks_and_batch_of_one(cuda_lib, cuda_env):
     assert torch.allclose(pol[4], p1[0], atol=1e-6) and torch.allclose(val[4], v1[0], atol=1e-6)
     ref_p, ref_v = om.forward(w, np.stack([osenv.state_to_planes(s) for s in states]), 2)
     assert np.abs(pol.cpu().numpy() - ref_p).max() < 1e-3 and np.abs(val.cpu().numpy() - ref_v).max() < 1e-3
+    eng.close()
+
+
+@pytest.mark.parametrize("filters,blocks,trained", [(128, 7, False), (192, 4, True)])
+def test_forward_28_planes_with_history(cuda_lib, cuda_env, filters, blocks, trained):
+    """use_history networks (data/model/model_128_l1_config.json: Input (28,10,9)): planes 14-27 = the position two plies
+    earlier or zero (static_env.py:158-194); the first convolution gathers from (board, history board) pairs."""
+    from tests.search_checks import game_history
+    w = om.init_weights(filters, blocks, 256, seed=5, trained_like=trained, spread=0.3, in_planes=28)
+    hists = [game_history(n, 100 + n) for n in (1, 2, 3, 9, 24, 40, 61)] + [None]
+    states = [h[-1] for h in hists[:-1]] + [osenv.INIT_STATE]
+    planes = np.stack([osenv.state_history_to_planes(s, h) for s, h in zip(states, hists)])
+    assert planes[3, 14:].sum() > 0 and planes[0, 14:].sum() == 0 and planes[-1, 14:].sum() == 0
+    ref_p, ref_v = om.forward(w, planes, blocks)
+    eng = _engine(cuda_lib, filters, blocks, 8, use_history=True)
+    eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    pol, val = eng.nn_forward_planes(torch.as_tensor(planes).cuda())
+    pairs = torch.zeros((len(states), 2, 96), dtype=torch.uint8, device="cuda")
+    pairs[:, 0] = cuda_env.boards_from_states(states)
+    for i, h in enumerate(hists):
+        if h and len(h) >= 5:
+            pairs[i, 1] = cuda_env.boards_from_states([h[-5]])[0]
+    pol2, val2 = eng.nn_forward_boards(pairs.reshape(len(states), 192))
+    torch.cuda.synchronize()
+    assert torch.equal(pol, pol2) and torch.equal(val, val2)
+    assert np.abs(pol.cpu().numpy() - ref_p).max() < 1e-3 and np.abs(val.cpu().numpy() - ref_v).max() < 1e-3
+    # the history planes matter: dropping them changes the output
+    pairs[:, 1] = 0
+    pol3, _ = eng.nn_forward_boards(pairs.reshape(len(states), 192))
+    assert not torch.equal(pol3[3], pol[3]) and torch.equal(pol3[0], pol[0])
+    eng.close()
+    # a 14-plane weight set is refused by a use_history engine and vice versa
+    eng = _engine(cuda_lib, filters, blocks, 8, use_history=False)
+    with pytest.raises(Exception):
+        eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
     eng.close()
 
 

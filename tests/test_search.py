@@ -22,8 +22,41 @@ def test_oracle_player_matches_golden_k1():
             assert a == call["action"] and node.sum_n == call["sum_n"]
 
 
+def test_oracle_player_matches_golden_k1_history():
+    """use_history=True: planes of static_env.state_history_to_planes and the real player's 28-plane searches."""
+    import numpy as np
+    from oracle import player as op
+    from oracle import senv
+    gold = sc.load_mcts_golden("mcts_k1_hist.json.gz")
+    for v in gold["planes"]:
+        p = senv.state_history_to_planes(v["state"], v["history"])
+        assert np.flatnonzero(p.reshape(-1)).tolist() == v["nonzero"]
+    for case in gold["cases"]:
+        pc = op.PlayConfig(simulation_num_per_move=case["sims"], search_threads=1, c_puct=1.5, noise_eps=0.25,
+                           dirichlet_alpha=0.2, tau_decay_rate=0.98, virtual_loss=3, resign_threshold=-0.92, min_resign_turn=20)
+        np.random.seed(case["seed"])
+        pl = op.OraclePlayer(pc, op.fake_evaluate_states_hist, use_history=True)
+        for call in case["calls"]:
+            a, _ = pl.action(call["state"], call["turns"], call["no_act"], increase_temp=call["increase_temp"], hist=call["hist"])
+            node = pl.tree[call["state"]]
+            got = {m: [int(e.n), float(e.w), float(e.q), float(e.p)] for m, e in node.a.items()}
+            assert got == call["edges"], case["name"]
+            assert a == call["action"] and node.sum_n == call["sum_n"]
+
+
 def test_emul_golden_k1(emul_lib):
     sc.check_golden_k1(emul_lib, "cpu")
+
+
+def test_emul_history(emul_lib):
+    sc.check_golden_k1(emul_lib, "cpu", use_history=True)
+    sc.check_history_vs_oracle(emul_lib, "cpu", cases=((90, 1, 1), (160, 8, 2)))
+
+
+@pytest.mark.gpu
+def test_cuda_history(cuda_lib):
+    sc.check_golden_k1(cuda_lib, "cuda", use_history=True)
+    sc.check_history_vs_oracle(cuda_lib, "cuda")
 
 
 def test_emul_vs_oracle(emul_lib):

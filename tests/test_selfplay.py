@@ -9,10 +9,11 @@ from oracle import senv as osenv
 from tests.search_checks import eval_planes
 
 
-def run_device_games(lib, device, n_games, sims, k, seed, want, max_game_length, tau_decay):
+def run_device_games(lib, device, n_games, sims, k, seed, want, max_game_length, tau_decay, use_history=False):
     eng = Engine(lib, device, n_games=n_games, sims_per_move=sims, leaves_per_round=k, noise_mode=1, noise_eps=0.0,
                  c_puct=1.5, tau_decay_rate=tau_decay, max_game_length=max_game_length, resign_threshold=-0.6,
-                 enable_resign_rate=0.5, min_resign_turn=4, seed=seed, max_nodes_per_game=sims * 2 * max_game_length + 64)
+                 enable_resign_rate=0.5, min_resign_turn=4, seed=seed, max_nodes_per_game=sims * 2 * max_game_length + 64,
+                 use_history=use_history)
     eng.reset()
     recs = []
     for _ in range(4 * max_game_length * (want // n_games + 2)):
@@ -26,8 +27,8 @@ def run_device_games(lib, device, n_games, sims, k, seed, want, max_game_length,
     return recs
 
 
-def check_selfplay(lib, device, n_games=3, sims=20, k=4, seed=11, want=6, max_game_length=25, tau_decay=0.9):
-    recs = run_device_games(lib, device, n_games, sims, k, seed, want, max_game_length, tau_decay)
+def check_selfplay(lib, device, n_games=3, sims=20, k=4, seed=11, want=6, max_game_length=25, tau_decay=0.9, use_history=False):
+    recs = run_device_games(lib, device, n_games, sims, k, seed, want, max_game_length, tau_decay, use_history)
     assert len(recs) >= want
     label_of = {m: i for i, m in enumerate(osenv.ActionLabelsRed)}
     pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.0, dirichlet_alpha=0.2,
@@ -35,8 +36,9 @@ def check_selfplay(lib, device, n_games=3, sims=20, k=4, seed=11, want=6, max_ga
     kinds = set()
     for r in recs:
         slot, started = r["game_index"] % n_games, r["game_index"] // n_games
-        ref = osp.play_game(pc, op.fake_evaluate_states, osp.DeviceDraws(seed, 0, slot, started, label_of),
-                            max_game_length=max_game_length, enable_resign_rate=0.5)
+        ref = osp.play_game(pc, op.fake_evaluate_states_hist if use_history else op.fake_evaluate_states,
+                            osp.DeviceDraws(seed, 0, slot, started, label_of),
+                            max_game_length=max_game_length, enable_resign_rate=0.5, use_history=use_history)
         assert r["moves"] == ref["moves"], (r["game_index"], r["moves"], ref["moves"])
         assert r["value_red"] == ref["value_red"] and r["n_plies"] == ref["turns"]
         assert (r["flags"] & 3) == ref["flags"] and bool(r["flags"] & 4) == (not ref["store"])
@@ -49,6 +51,11 @@ def test_emul_selfplay_matches_restated_game_loop(emul_lib):
     assert len(kinds) >= 1
 
 
+def test_emul_selfplay_with_history_planes(emul_lib):
+    """use_history=True: the device game loop feeds 28-plane leaves (path history only, self_play.py:124)."""
+    check_selfplay(emul_lib, "cpu", n_games=2, want=3, seed=5, use_history=True)
+
+
 def test_play_data_format():
     from cczero_b200.records import record_to_play_data
     d = record_to_play_data({"moves": ["7747", "7062", "1219"], "value_red": -1})
@@ -58,6 +65,11 @@ def test_play_data_format():
 @pytest.mark.gpu
 def test_cuda_selfplay_matches_restated_game_loop(cuda_lib):
     check_selfplay(cuda_lib, "cuda", n_games=4, want=8)
+
+
+@pytest.mark.gpu
+def test_cuda_selfplay_with_history_planes(cuda_lib):
+    check_selfplay(cuda_lib, "cuda", n_games=4, want=6, seed=5, use_history=True)
 
 
 def test_emul_expanding_data_matches_reference_layout(emul_env):
@@ -79,3 +91,11 @@ def test_emul_expanding_data_matches_reference_layout(emul_env):
         assert policy[i].sum() == 1 and policy[i, osenv.ActionLabelsRed.index(m)] == 1
         assert value[i] == (1 if i % 2 == 0 else -1)
         s = osenv.step(s, m)
+    # use_history (optimize.py:240-267): planes 14-27 of sample i = position i-2
+    planes28, policy28, _ = expanding_data(data, emul_env, use_history=True)
+    assert planes28.shape == (30, 28, 10, 9) and (policy28 == policy).all()
+    s, hist = osenv.INIT_STATE, [osenv.INIT_STATE]
+    for i, m in enumerate(moves):
+        assert (planes28[i] == osenv.state_history_to_planes(s, hist[0:2 * i + 1])).all()
+        s = osenv.step(s, m)
+        hist += [m, s]
