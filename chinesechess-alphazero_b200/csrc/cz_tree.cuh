@@ -72,6 +72,7 @@ struct EngineDev {
   int32_t* node_sum_n;
   uint32_t* node_edge_off;
   uint32_t* node_meta;           // nedge | flags
+  float* node_v;                 // network value of the node's position (player.py:349-350 `debug[state]`, read by the PV line)
   uint32_t* hash;                // [G*hcap] 0 = empty else node+1
   int32_t* edge_n;               // [G*ecap]
   double* edge_w;
@@ -506,7 +507,7 @@ CZ_D void game_apply(const EngineDev& E, int g, const float* policy, const float
     if (czs::lane() == 0) { for (int i = 0; i < L; ++i) all_p = all_p + sm->pr[i]; if (all_p == 0.f) all_p = 1.f; }
     all_p = czs::shfl(all_p, 0);
     for (int i = czs::lane(); i < L; i += 32) E.edge_p[eo + i] = sm->pr[i] / all_p;
-    if (czs::lane() == 0) E.node_meta[ni] &= ~(uint32_t)NODE_WAITING;
+    if (czs::lane() == 0) { E.node_meta[ni] &= ~(uint32_t)NODE_WAITING; E.node_v[ni] = value[off + j]; }
     czs::syncwarp();
     // simulations parked on this node re-enter the queue in park order (:351-353)
     const int np = E.n_park[g];
@@ -600,8 +601,9 @@ CZ_D int game_compact(const EngineDev& E, int g, int root) {
     }
     if (czs::lane() == 0) {
       const uint64_t k0 = E.node_key0[si], k1 = E.node_key1[si];
-      const int sn = E.node_sum_n[si]; const uint32_t meta = E.node_meta[si];
+      const int sn = E.node_sum_n[si]; const uint32_t meta = E.node_meta[si]; const float nv = E.node_v[si];
       E.node_key0[di] = k0; E.node_key1[di] = k1; E.node_sum_n[di] = sn; E.node_meta[di] = meta; E.node_edge_off[di] = (uint32_t)ne;
+      E.node_v[di] = nv;
     }
     ne += L;
     czs::syncwarp();
@@ -629,7 +631,8 @@ CZ_D int game_compact(const EngineDev& E, int g, int root) {
 }
 
 // ------------------------------------------------------------------ begin: tree reuse and task count (action, :147-171)
-CZ_D void game_begin(const EngineDev& E, int g, int sims_override, TreeSmem* sm) {
+// raw_tasks: run exactly sims_override simulations (the caller did the bookkeeping of player.py:153-165 itself)
+CZ_D void game_begin(const EngineDev& E, int g, int sims_override, bool raw_tasks, TreeSmem* sm) {
   if (!E.active[g]) return;
   copy_board(E.root_board + (size_t)g * BOARD_STRIDE, sm->board);
   uint64_t k0, k1;
@@ -639,6 +642,7 @@ CZ_D void game_begin(const EngineDev& E, int g, int sims_override, TreeSmem* sm)
   if (E.n_no_act[g] > 0 || E.increase_temp[g] || done == E.sims) done = 0;
   int num_task = E.sims - done;
   if (sims_override > 0) num_task = sims_override > done ? sims_override - done : 0;
+  if (raw_tasks) num_task = sims_override;
   if (num_task < 0) num_task = 0;
   // pools must be able to hold this search; otherwise start from an empty table (counted)
   bool low = (E.ncap - E.n_nodes[g] < num_task + 2 || E.ecap - E.n_edges[g] < (num_task + 2) * 64) && E.n_nodes[g] > 0;
@@ -662,6 +666,7 @@ CZ_D void game_begin(const EngineDev& E, int g, int sims_override, TreeSmem* sm)
     czs::syncwarp();
     root = -1;
     num_task = sims_override > 0 ? sims_override : E.sims;
+    if (raw_tasks) num_task = sims_override > 0 ? sims_override : 0;
   }
   if (czs::lane() == 0) {
     E.root_node[g] = root;
@@ -672,6 +677,54 @@ CZ_D void game_begin(const EngineDev& E, int g, int sims_override, TreeSmem* sm)
     E.n_leaf[g] = 0; E.n_park[g] = 0; E.n_resume[g] = 0;
   }
   czs::syncwarp();
+}
+
+// print_depth_info (player.py:408-450): the most visited line from the root.  At every node the LAST edge with the
+// largest N wins (`>=`, :421), the root skips no_act moves; the walk stops at a position that is not in the tree or was
+// never selected through (`len(node.a) == 0`, :418), or after max_len plies.  out_moves: canonical moves of the side to
+// move at each ply.  *out_value / *out_has_value: `debug[state]` of the position the walk ended on (:436-437).
+CZ_D int game_pv(const EngineDev& E, int g, int max_len, uint16_t* out_moves, float* out_value, int* out_has_value, TreeSmem* sm) {
+  copy_board(E.root_board + (size_t)g * BOARD_STRIDE, sm->board);
+  uint64_t k0, k1;
+  board_key(sm->board, &k0, &k1);
+  int node = tt_lookup(E, g, k0, k1);
+  int len = 0;
+  bool root = true;
+  while (len < max_len) {
+    if (node < 0) break;
+    const size_t ni = (size_t)g * E.ncap + node;
+    if (E.node_sum_n[ni] < 2) break;                 // expanded but never selected through: node.a is still empty
+    const int L = (int)(E.node_meta[ni] & 0xff);
+    const size_t eo = (size_t)g * E.ecap + E.node_edge_off[ni];
+    int best = -1, n = 0;
+    if (czs::lane() == 0) {
+      for (int i = 0; i < L; ++i) {
+        const int en = E.edge_n[eo + i];
+        if (en >= n) {
+          bool banned = false;
+          if (root) for (int k = 0; k < E.n_no_act[g]; ++k) banned |= E.no_act[(size_t)g * CZ_MAX_NO_ACT + k] == E.edge_move[eo + i];
+          if (banned) continue;
+          n = en; best = i;
+        }
+      }
+    }
+    best = czs::shfl(best, 0);
+    if (best < 0) break;
+    const move_t mv = E.edge_move[eo + best];
+    if (czs::lane() == 0) out_moves[len] = mv;
+    ++len;
+    step_flip(sm->board, mv, sm->board);
+    board_key(sm->board, &k0, &k1);
+    node = tt_lookup(E, g, k0, k1);
+    root = false;
+  }
+  if (czs::lane() == 0) {
+    const bool has = node >= 0 && !(E.node_meta[(size_t)g * E.ncap + node] & NODE_WAITING);
+    *out_has_value = has ? 1 : 0;
+    *out_value = has ? E.node_v[(size_t)g * E.ncap + node] : 0.f;
+  }
+  czs::syncwarp();
+  return len;
 }
 
 }  // namespace cz

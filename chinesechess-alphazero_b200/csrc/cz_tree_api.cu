@@ -22,10 +22,21 @@ constexpr int kWarps = 4;   // games per block
 CZ_D TreeSmem* tree_smem() { return reinterpret_cast<TreeSmem*>(czs::dyn_smem()) + czs::warp_in_block(); }
 CZ_D int my_game() { return czs::block_idx() * czs::warps_per_block() + czs::warp_in_block(); }
 
-CZ_KERNEL(k_begin)(EngineDev E, int sims_override) {
+CZ_KERNEL(k_begin)(EngineDev E, int sims_override, int raw_tasks) {
   const int g = my_game();
   if (g >= E.n_games) return;
-  game_begin(E, g, sims_override, tree_smem());
+  game_begin(E, g, sims_override, raw_tasks != 0, tree_smem());
+}
+// more simulations for the search cz_search_begin opened (same root options, noise table position and counters)
+CZ_KERNEL(k_more)(EngineDev E, int n_sims) {
+  const int g = my_game();
+  if (g >= E.n_games) return;
+  if (czs::lane() == 0 && E.active[g]) { E.tasks_left[g] = n_sims; E.round_pending[g] = 0; }
+}
+CZ_KERNEL(k_pv)(EngineDev E, int g, int max_len, cz_pv_info* out) {
+  float v; int has;
+  const int len = game_pv(E, g, max_len, out->moves, &v, &has, tree_smem());
+  if (czs::lane() == 0) { out->n_moves = len; out->value = v; out->has_value = has; }
 }
 // The search kernels work on a game range [g0, g1) ("slot"): cz_search pipelines two halves of the games so the tree
 // work of one half overlaps the network evaluation of the other.  Per-game results do not depend on the split.
@@ -211,6 +222,7 @@ struct cz_engine {
   uint8_t* init_board_dev;
   uint8_t* opt_no_act; uint8_t* opt_inc; uint8_t* opt_act;   // device staging for cz_root_opts
   uint8_t* opt_hist; uint8_t* opt_hist_given;
+  cz_pv_info* pv_dev;
   cz_root_info* root_info_dev;
   float* policy_buf; float* value_buf;                      // evaluator outputs for the built-in network
   uint8_t* board_stage;                                     // [G][96] staging for reset / set_root
@@ -248,6 +260,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.n_nodes = cv.take<int32_t>(G); d.n_edges = cv.take<int32_t>(G);
   d.node_key0 = cv.take<uint64_t>(G * N); d.node_key1 = cv.take<uint64_t>(G * N);
   d.node_sum_n = cv.take<int32_t>(G * N); d.node_edge_off = cv.take<uint32_t>(G * N); d.node_meta = cv.take<uint32_t>(G * N);
+  d.node_v = cv.take<float>(G * N);
   d.hash = cv.take<uint32_t>(G * H);
   d.edge_n = cv.take<int32_t>(G * Ecap); d.edge_w = cv.take<double>(G * Ecap); d.edge_p = cv.take<float>(G * Ecap);
   d.edge_move = cv.take<uint16_t>(G * Ecap); d.edge_child = cv.take<int32_t>(G * Ecap);
@@ -266,6 +279,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   e->opt_no_act = cv.take<uint8_t>(G * CZ_MAX_NO_ACT * 2); e->opt_inc = cv.take<uint8_t>(G); e->opt_act = cv.take<uint8_t>(G);
   e->opt_hist = cv.take<uint8_t>(G * BOARD_STRIDE); e->opt_hist_given = cv.take<uint8_t>(G);
   e->root_info_dev = cv.take<cz_root_info>(1);
+  e->pv_dev = cv.take<cz_pv_info>(1);
   e->board_stage = cv.take<uint8_t>(G * BOARD_STRIDE);
   e->stat_n = cv.take<int32_t>(G * MAX_MOVES); e->stat_mv = cv.take<uint16_t>(G * MAX_MOVES); e->stat_cnt = cv.take<int32_t>(G);
   if (c.nn_filters > 0) {
@@ -465,7 +479,7 @@ int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {
   const size_t G = e->cfg.n_games;
   const uint16_t* na = nullptr; const uint8_t* inc = nullptr; const uint8_t* act = nullptr;
   const uint8_t* hist = nullptr; const uint8_t* hist_given = nullptr;
-  int sims_override = 0;
+  int sims_override = 0, raw_tasks = 0;
   e->d.noise_table = nullptr; e->d.noise_stride = 0;
   if (opts) {
     if (opts->no_act_host) { czrt_copy(e->opt_no_act, opts->no_act_host, G * CZ_MAX_NO_ACT * 2, e->stream); na = (const uint16_t*)e->opt_no_act; }
@@ -478,11 +492,25 @@ int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {
     }
     e->d.noise_table = opts->noise_dev; e->d.noise_stride = opts->noise_stride;
     sims_override = opts->sims_override;
+    raw_tasks = opts->raw_tasks;
   }
   if (opts) GAME_LAUNCH(e, k_set_opts, e->d, na, inc, act, hist, hist_given);   // NULL keeps the options the game loop maintains
-  GAME_LAUNCH(e, k_begin, e->d, sims_override);
+  GAME_LAUNCH(e, k_begin, e->d, sims_override, raw_tasks);
   e->last_leaves = 0;
   return launch_ok(e, "cz_search_begin", 2);
+}
+
+int cz_set_noise_table(cz_engine* e, const double* noise_dev, int64_t noise_stride) {
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_set_noise_table: null engine");
+  e->d.noise_table = noise_dev; e->d.noise_stride = noise_stride;
+  return 0;
+}
+
+int cz_search_more(cz_engine* e, int32_t n_sims) {
+  if (!e || n_sims < 0) return cz_fail(CZ_ERR_ARG, "cz_search_more: bad argument");
+  if (e->last_leaves != 0) return cz_fail(CZ_ERR_STATE, "cz_search_more: %d leaves of the previous wave were not applied", e->last_leaves);
+  GAME_LAUNCH(e, k_more, e->d, n_sims);
+  return launch_ok(e, "cz_search_more");
 }
 
 int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active) {
@@ -619,6 +647,15 @@ int cz_get_root(cz_engine* e, int game, cz_root_info* out) {
   if (launch_ok(e, "cz_get_root")) return CZ_ERR_CUDA;
   czrt_copy(out, e->root_info_dev, sizeof(cz_root_info), e->stream);
   return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_get_root: device failure") : 0;
+}
+
+int cz_get_pv(cz_engine* e, int game, int32_t max_len, cz_pv_info* out) {
+  if (!e || !out || game < 0 || game >= e->cfg.n_games || max_len < 0 || max_len > CZ_MAX_PV)
+    return cz_fail(CZ_ERR_ARG, "cz_get_pv: bad argument");
+  CZ_LAUNCH(k_pv, 1, 1, sizeof(TreeSmem), e->stream, e->d, game, max_len, e->pv_dev);
+  if (launch_ok(e, "cz_get_pv")) return CZ_ERR_CUDA;
+  czrt_copy(out, e->pv_dev, sizeof(cz_pv_info), e->stream);
+  return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_get_pv: device failure") : 0;
 }
 
 int cz_get_counters(cz_engine* e, uint64_t* out) {

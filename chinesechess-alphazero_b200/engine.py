@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from .env import board_to_state, move_to_u16, state_to_board, u16_to_move
-from .lib import (BOARD_STRIDE, MAX_MOVES, MAX_NO_ACT, N_LABELS, CzConfig, CzRecordHdr, CzRootInfo, CzRootOpts,
+from .lib import (BOARD_STRIDE, MAX_MOVES, MAX_NO_ACT, N_LABELS, CzConfig, CzPvInfo, CzRecordHdr, CzRootInfo, CzRootOpts,
                   get_lib)
 
 
@@ -90,8 +90,9 @@ class Engine:
         self.lib.call("cz_set_root", self._h, game, C.c_void_p(b.ctypes.data))
 
     # ---- search
-    def make_opts(self, no_act=None, increase_temp=None, active=None, noise=None, sims_override=0, hist=None):
-        """hist (use_history engines): per game the `hist` list given to action() ([.., state, move, state]) or None."""
+    def make_opts(self, no_act=None, increase_temp=None, active=None, noise=None, sims_override=0, hist=None, raw_tasks=False):
+        """hist (use_history engines): per game the `hist` list given to action() ([.., state, move, state]) or None.
+        raw_tasks: run exactly sims_override simulations (the caller did action()'s done / depth bookkeeping)."""
         o = CzRootOpts()
         keep = []
         if hist is not None and any(h for h in hist):
@@ -127,6 +128,7 @@ class Engine:
             o.noise_dev = t.data_ptr()
             o.noise_stride = t.shape[1]
         o.sims_override = sims_override
+        o.raw_tasks = 1 if raw_tasks else 0
         self._keep = keep
         return o
 
@@ -170,6 +172,41 @@ class Engine:
             if not busy:
                 break
         return stats
+
+    def search_more(self, n_sims):
+        """n_sims more simulations inside the search search_begin opened (cz_search_more); run the wave loop after it."""
+        self.lib.call("cz_search_more", self._h, int(n_sims))
+
+    def set_noise_table(self, noise):
+        """Swap the Dirichlet table of the open search for a longer one (same leading draws)."""
+        t = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float64)).to(self.device)
+        assert t.dim() == 2 and t.shape[0] == self.n_games
+        self._keep.append(t)
+        self.lib.call("cz_set_noise_table", self._h, _ptr(t), t.shape[1])
+
+    def run_waves(self, evaluate_planes=None):
+        """The wave / evaluate / apply loop until every queued simulation is done; evaluate_planes as in search_external,
+        None = the built-in network (cz_nn_forward on the leaf planes)."""
+        n_pos = 0
+        while True:
+            n, busy = self.search_wave()
+            if n > 0:
+                if evaluate_planes is None:
+                    pol, val = self.nn_forward_boards(self.leaf_boards(n))
+                    self.search_apply(pol, val)
+                else:
+                    pol, val = evaluate_planes(self.leaf_planes(n).cpu().numpy())
+                    self.search_apply(torch.as_tensor(np.ascontiguousarray(pol, dtype=np.float32)).to(self.device),
+                                      torch.as_tensor(np.ascontiguousarray(val, dtype=np.float32)).to(self.device))
+                n_pos += n
+            if not busy:
+                return n_pos
+
+    def pv(self, game, max_len=20):
+        """print_depth_info's line (player.py:408-450): (moves as canonical strings per mover, value or None)."""
+        info = CzPvInfo()
+        self.lib.call("cz_get_pv", self._h, game, max_len, C.byref(info))
+        return [u16_to_move(info.moves[i]) for i in range(info.n_moves)], (float(info.value) if info.has_value else None)
 
     def search(self, opts=None):
         """Whole search with the built-in tensor-core network."""

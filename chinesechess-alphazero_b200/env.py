@@ -78,6 +78,22 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+# ---- UCI / FEN notation (static_env.py:224-228,380-388)
+_FEN_TO_STATE = str.maketrans("nNbBaAkK", "kKeEmMsS")      # FEN knight/bishop/advisor/king -> state letters k/e/m/s
+
+
+def fen_to_state(fen):
+    return fen.split(' ')[0].translate(_FEN_TO_STATE)
+
+
+def parse_ucci_move(move):
+    return str(ord(move[0]) - ord('a')) + move[1] + str(ord(move[2]) - ord('a')) + move[3]
+
+
+def to_uci_move(action):
+    return chr(ord('a') + int(action[0])) + action[1] + chr(ord('a') + int(action[2])) + action[3]
+
+
 class StaticEnv:
     """Rules engine bound to one library + device ('cuda' for the product)."""
 

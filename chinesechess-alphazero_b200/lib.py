@@ -38,7 +38,7 @@ class CzRootOpts(C.Structure):
     _fields_ = [
         ("no_act_host", C.c_void_p), ("increase_temp_host", C.c_void_p), ("active_host", C.c_void_p),
         ("noise_dev", C.c_void_p), ("noise_stride", C.c_int64),
-        ("sims_override", C.c_int32), ("reserved", C.c_int32),
+        ("sims_override", C.c_int32), ("raw_tasks", C.c_int32),
         ("root_hist_host", C.c_void_p), ("root_hist_given_host", C.c_void_p),
     ]
 
@@ -49,6 +49,13 @@ class CzRootInfo(C.Structure):
         ("moves", C.c_uint16 * MAX_MOVES), ("n", C.c_int32 * MAX_MOVES),
         ("w", C.c_double * MAX_MOVES), ("p", C.c_float * MAX_MOVES),
     ]
+
+
+MAX_PV = 32
+
+
+class CzPvInfo(C.Structure):
+    _fields_ = [("n_moves", C.c_int32), ("has_value", C.c_int32), ("value", C.c_float), ("moves", C.c_uint16 * MAX_PV)]
 
 
 class CzRecordHdr(C.Structure):
@@ -80,6 +87,9 @@ _SIGS = {
     "cz_get_root_stats": (C.c_int, [_P, _P, _P, _P, _P]),
     "cz_compact": (C.c_int, [_P]),
     "cz_search_begin": (C.c_int, [_P, C.POINTER(CzRootOpts)]),
+    "cz_search_more": (C.c_int, [_P, C.c_int32]),
+    "cz_set_noise_table": (C.c_int, [_P, _P, C.c_int64]),
+    "cz_get_pv": (C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(CzPvInfo)]),
     "cz_search_wave": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cz_leaf_planes": (C.c_int, [_P, _P]),
     "cz_leaf_boards": (C.c_int, [_P, _P]),

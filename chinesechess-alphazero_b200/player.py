@@ -13,18 +13,26 @@ that the global `np.random` stream is consumed exactly like the reference consum
   * evaluation: if `pipes` is given the leaves are sent through it with the reference wire protocol
     (list of float32[14,10,9] ([28,10,9] with use_history) -> list of (float32[2086], float), api.py:48-74), so the player works
     against an unmodified CChessModelAPI; otherwise the engine's built-in tensor-core network is used.
+  * UCI mode (`uci=True`, uci.py:207-209): action() runs its rounds (player.py:167-184) in slices that end exactly
+    where the reference prints an `info depth .. pv ..` line (`done_tasks // 100` changed), `infinite=True` searches
+    until `close_and_return_action` is called from another thread (uci.py:229-243).
 """
+import sys
+import threading
+from time import time
+
 import numpy as np
 import torch
 
 from .engine import Engine
-from .env import StaticEnv
+from .env import StaticEnv, flip_move, to_uci_move
 from .lib import get_lib
 
 
 class CChessPlayer:
     def __init__(self, config, search_tree=None, pipes=None, play_config=None, enable_resign=False, debugging=False,
-                 uci=False, use_history=False, side=0, lib=None, device=None, weights=None, exact_noise=True):
+                 uci=False, use_history=False, side=0, lib=None, device=None, weights=None, exact_noise=True,
+                 infinite_capacity=200000):
         self.use_history = use_history          # 28 input planes (static_env.py:158-194, player.py:326-334)
         self.config = config
         self.play_config = play_config or config.play
@@ -46,6 +54,10 @@ class CChessPlayer:
         self.search_results = {}
         self.done_tasks = 0
         self.exact_noise = exact_noise
+        self.info_stream = None            # where the `info depth` lines go (None = sys.stdout, like the reference's print)
+        self.infinite_capacity = infinite_capacity      # simulations an `infinite` search may run (node pool size)
+        self._stop = False
+        self._busy = threading.Lock()      # held while a search slice runs: close_and_return_action waits for it
         pc = self.play_config
         mc = getattr(config, "model", None)
         use_nn = pipes is None
@@ -56,7 +68,7 @@ class CChessPlayer:
             dirichlet_alpha=pc.dirichlet_alpha, tau_decay_rate=pc.tau_decay_rate,
             resign_threshold=getattr(pc, "resign_threshold", -1.0), min_resign_turn=getattr(pc, "min_resign_turn", 0),
             max_game_length=getattr(pc, "max_game_length", 100),
-            max_nodes_per_game=max(4096, 8 * pc.simulation_num_per_move),
+            max_nodes_per_game=max(4096, 8 * pc.simulation_num_per_move, (infinite_capacity + 64) if uci else 0),
             nn_filters=mc.cnn_filter_num if (use_nn and mc) else 0, nn_blocks=mc.res_layer_num if (use_nn and mc) else 0,
             nn_value_fc=mc.value_fc_size if (use_nn and mc) else 256, use_history=use_history)
         if use_nn:
@@ -67,66 +79,179 @@ class CChessPlayer:
 
     # ---- reference API
     def close(self, wait=True):
-        if self.engine is not None:
-            self.engine.close()
-            self.engine = None
+        self._stop = True
+        with self._busy:
+            if self.engine is not None:
+                self.engine.close()
+                self.engine = None
 
     def action(self, state, turns, no_act=None, depth=None, infinite=False, hist=None, increase_temp=False):
-        if infinite:
-            raise NotImplementedError("infinite analysis (uci.py) is outside the built hot path")
         pc = self.play_config
         eng = self.engine
-        self.root_state = state
-        self.no_act = no_act
-        self.increase_temp = increase_temp
-        if self._fresh:
-            eng.reset([state])
-            self._fresh = False
-        else:
-            eng.set_root(0, state)
-        noise, rng_state, n_moves = None, None, 0
-        if self.exact_noise and pc.noise_eps != 0:
-            n_moves = len(self.env.get_legal_moves(state))
-            sims = depth if depth else pc.simulation_num_per_move
-            rng_state = np.random.get_state()
-            cap = (sims + 2 * self.engine.K + 2) * max(n_moves, 1)
-            alpha = pc.dirichlet_alpha * np.ones(max(n_moves, 1))
-            noise = np.array([np.random.dirichlet(alpha)[0] for _ in range(cap)], dtype=np.float64)[None, :]
-        opts = eng.make_opts(no_act=[list(no_act)] if no_act else None, increase_temp=[1 if increase_temp else 0],
-                             noise=noise, sims_override=int(depth) if depth else 0,
-                             hist=[list(hist)] if (self.use_history and hist) else None)
-        if self.pipe is not None:
-            eng.search_external(self._evaluate_through_pipe, opts)
-        else:
-            eng.search(opts)
-        root = eng.root(0)
-        self.done_tasks += root["sims_run"]
-        if rng_state is not None:
-            np.random.set_state(rng_state)
-            alpha = pc.dirichlet_alpha * np.ones(max(n_moves, 1))
-            for _ in range(root["noise_used"]):
-                np.random.dirichlet(alpha)
-        policy, resign = self.calc_policy(root, turns, no_act)
-        if resign:
-            return None, list(policy)
-        if no_act is not None:
-            for act in no_act:
-                policy[self.move_lookup[act]] = 0
-        my_action = int(np.random.choice(range(self.labels_n), p=self.apply_temperature(policy, turns)))
-        return self.labels[my_action], list(policy)
+        with self._busy:
+            self._stop = False
+            self.root_state = state
+            self.no_act = no_act
+            self.increase_temp = increase_temp
+            if self._fresh:
+                eng.reset([state])
+                self._fresh = False
+            else:
+                eng.set_root(0, state)
+            # task count: player.py:153-165
+            done = eng.root(0)["sum_n"]
+            if no_act or increase_temp or done == pc.simulation_num_per_move:
+                done = 0
+            self.done_tasks = done
+            num_task = pc.simulation_num_per_move - done
+            if depth:
+                num_task = depth - done if depth > done else 0
+            if infinite:
+                num_task = min(100000, self.infinite_capacity)
+            self._noise_begin(state, num_task)
+        start_time = time()
+        shown = 0
+        k = self.config.play.search_threads
+        left, first = num_task, True
+        while left > 0 and not self._stop:
+            with self._busy:
+                if self._stop or self.engine is None:
+                    break
+                # the rounds up to the next `info depth` line (or all of them outside UCI mode)
+                n = left
+                if self.uci or infinite:
+                    n, dt = 0, self.done_tasks
+                    while n < left:
+                        r = min(k, left - n)
+                        n += r
+                        dt += r
+                        if dt // 100 != shown:
+                            break
+                self._noise_reserve(n, search_open=not first)
+                if first:
+                    opts = eng.make_opts(no_act=[list(no_act)] if no_act else None, increase_temp=[1 if increase_temp else 0],
+                                         noise=self._noise_table, sims_override=n, raw_tasks=True,
+                                         hist=[list(hist)] if (self.use_history and hist) else None)
+                    eng.search_begin(opts)
+                    first = False
+                else:
+                    eng.search_more(n)
+                eng.run_waves(self._evaluate_through_pipe if self.pipe is not None else None)
+                self.done_tasks += n
+                left -= n
+                if self.uci and shown != self.done_tasks // 100:      # player.py:180-184
+                    shown = self.done_tasks // 100
+                    self._remember_root_value(state)
+                    self.print_depth_info(state, turns, start_time, self.debug[state][1], no_act)
+        with self._busy:
+            if self._stop or self.engine is None:                      # close_and_return_action answered already
+                if self.engine is not None:
+                    self._noise_end(eng.root(0)["noise_used"])
+                return None, None
+            if first:                                                  # nothing to search: still a valid (empty) search
+                eng.search_begin(eng.make_opts(no_act=[list(no_act)] if no_act else None,
+                                               increase_temp=[1 if increase_temp else 0], sims_override=0, raw_tasks=True))
+            root = eng.root(0)
+            self._noise_end(root["noise_used"])
+            if self.debugging or self.uci:
+                self._remember_root_value(state, root)
+            policy, resign = self.calc_policy(root, turns, no_act)
+            if resign:
+                return None, list(policy)
+            if no_act is not None:
+                for act in no_act:
+                    policy[self.move_lookup[act]] = 0
+            my_action = int(np.random.choice(range(self.labels_n), p=self.apply_temperature(policy, turns)))
+            return self.labels[my_action], list(policy)
+
+    # ---- root Dirichlet noise with the reference's np.random consumption (player.py:304)
+    def _noise_begin(self, state, num_task):
+        self._noise_table, self._rng_state, self._noise_rows, self._n_moves = None, None, 0, 0
+        if self.exact_noise and self.play_config.noise_eps != 0 and num_task > 0:
+            self._n_moves = max(len(self.env.get_legal_moves(state)), 1)
+            self._rng_state = np.random.get_state()
+            self._noise_table = np.zeros((1, 0))
+            self._noise_sims = 0
+
+    def _noise_reserve(self, n_sims, search_open):
+        """Make sure the table holds the draws `n_sims` more simulations can consume (one draw per legal move per root
+        selection; parked simulations select again).  `np.random.dirichlet(alpha, size=m)` draws the same stream as m calls."""
+        if self._rng_state is None:
+            return
+        self._noise_sims += n_sims
+        want = (self._noise_sims + 2 * self.engine.K + 2) * self._n_moves
+        if want > self._noise_rows:
+            more = max(want - self._noise_rows, 64 * self._n_moves)
+            alpha = self.play_config.dirichlet_alpha * np.ones(self._n_moves)
+            new = np.random.dirichlet(alpha, size=more)[:, 0]
+            self._noise_table = np.concatenate([self._noise_table, new[None, :]], axis=1)
+            self._noise_rows += more
+            if search_open:                                            # swap the table of the running search
+                self.engine.set_noise_table(self._noise_table)
+
+    def _noise_end(self, used):
+        """Rewind np.random and draw exactly what the search consumed, leaving the stream where the reference leaves it."""
+        if self._rng_state is not None:
+            np.random.set_state(self._rng_state)
+            if used:
+                np.random.dirichlet(self.play_config.dirichlet_alpha * np.ones(self._n_moves), size=used)
+            self._rng_state = None
+
+    def _remember_root_value(self, state, root=None):
+        """debug[state] = (p, v) (player.py:349-350) for the root: v = the network's value of the root position."""
+        _, v = self.engine.pv(0, 0)
+        self.debug[state] = ((root or self.engine.root(0))["p"], v if v is not None else 0)
+
+    # ---- player.py:408-450
+    def print_depth_info(self, state, turns, start_time, value, no_act):
+        depth = self.done_tasks // 100
+        end_time = time()
+        moves, end_value = self.engine.pv(0, 20)
+        pv = ""
+        for mv in moves:
+            if turns % 2 == 1:
+                mv = flip_move(mv)
+            pv += " " + to_uci_move(mv)
+            turns += 1
+        if end_value is not None:
+            value = end_value
+            if turns % 2 != self.side:
+                value = -value
+        score = int(value * 1000)
+        duration = max(end_time - start_time, 1e-9)
+        nps = int(depth * 100 / duration) * 1000
+        output = f"info depth {depth} score {score} time {int(duration * 1000)} pv" + pv + f" nps {nps}"
+        out = self.info_stream or sys.stdout
+        print(output, file=out)
+        out.flush()
 
     def close_and_return_action(self, state, turns, no_act=None):
-        """player.py:88-106 (used by the UCI front end to stop an ongoing search): answer from the tree as it stands."""
-        root = self.engine.root(0)
-        policy, resign = self.calc_policy(root, turns, no_act)
-        if resign:
-            return None
-        if no_act is not None:
-            for act in no_act:
-                policy[self.move_lookup[act]] = 0
-        my_action = int(np.random.choice(range(self.labels_n), p=self.apply_temperature(policy, turns)))
-        value = self.debug.get(state, (None, 0))[1]
-        return self.labels[my_action], value, self.done_tasks // 100
+        """player.py:88-106 (used by the UCI front end to stop an ongoing search): answer from the tree as it stands.
+        A running action() finishes its current slice of rounds, then returns (None, None)."""
+        self._stop = True
+        with self._busy:
+            root = self.engine.root(0)
+            if (self.debugging or self.uci) and state not in self.debug and root["sum_n"] > 0:
+                self._remember_root_value(state, root)
+            policy, resign = self.calc_policy(root, turns, no_act)
+            if resign:
+                return None
+            if no_act is not None:
+                for act in no_act:
+                    policy[self.move_lookup[act]] = 0
+            my_action = int(np.random.choice(range(self.labels_n), p=self.apply_temperature(policy, turns)))
+            value = self.debug.get(state, (None, 0))[1]
+            return self.labels[my_action], value, self.done_tasks // 100
+
+    def engine_child_stats(self, state):
+        """[(move, N)] of `state`'s node, [] if it is not in the tree or was never selected through (what iterating
+        `search_tree[state].a` yields in uci.py:303-311).  Moves the engine's root: only for a player that is done searching."""
+        with self._busy:
+            self.engine.set_root(0, state)
+            r = self.engine.root(0)
+            if r["sum_n"] < 2:
+                return []
+            return list(zip(r["moves"], r["n"]))
 
     # ---- host-side tail of action(): player.py:375-406
     def calc_policy(self, root, turns, no_act):

@@ -134,7 +134,8 @@ typedef struct cz_root_opts {
   const double* noise_dev;         /* noise_mode 0: [n_games][noise_stride] Dirichlet[0] draws in call order */
   int64_t noise_stride;
   int32_t sims_override;           /* >0: depth argument of action() (player.py:160-161) */
-  int32_t reserved;
+  int32_t raw_tasks;               /* 1: run exactly sims_override simulations; the caller did the bookkeeping of
+                                    * player.py:153-165 (done / depth / infinite) itself (UCI front end) */
   /* use_history engines: the `hist` argument of action() (player.py:150-151,215-216).  root_hist_given_host [n_games]:
    * 1 = a non-empty hist list was passed; root_hist_host [n_games][CZ_BOARD_STRIDE]: the position hist[-5] (all squares
    * empty when the list holds fewer than 5 entries).  Both NULL = no hist (worker/self_play.py:124 never passes one). */
@@ -158,6 +159,13 @@ int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active);
 int cz_leaf_planes(cz_engine* e, float* planes_dev /* [n_leaves][14][10][9]; [n_leaves][28][10][9] with use_history */);
 int cz_leaf_boards(cz_engine* e, uint8_t* boards_dev /* [n_leaves][CZ_BOARD_STRIDE]; [n_leaves][2][CZ_BOARD_STRIDE] with use_history */);
 int cz_search_apply(cz_engine* e, const float* policy_dev /* [n_leaves][2086] */, const float* value_dev /* [n_leaves] */);
+/* n_sims more simulations for every active game inside the search cz_search_begin opened: same root options, the noise
+ * table continues where it stopped, sims_run / noise_used keep counting.  Follow with the wave / apply loop.  Lets a host
+ * loop run action()'s rounds (player.py:167-184) in slices: `go infinite` / movetime stops, `info depth` lines between. */
+int cz_search_more(cz_engine* e, int32_t n_sims);
+/* Replace the Dirichlet table of the open search (noise_mode 0) by a longer one holding the same draws plus more; the
+ * per-game read position is kept.  Host-side only. */
+int cz_set_noise_table(cz_engine* e, const double* noise_dev, int64_t noise_stride);
 /* Whole search with the built-in network as evaluator (needs cz_nn_set_weights). Synchronises. */
 int cz_search(cz_engine* e, const cz_root_opts* opts);
 
@@ -173,6 +181,17 @@ typedef struct cz_root_info {
 } cz_root_info;
 /* node.a of the root (read by calc_policy, player.py:375-406).  Synchronises. */
 int cz_get_root(cz_engine* e, int game, cz_root_info* out_host);
+
+#define CZ_MAX_PV 32
+typedef struct cz_pv_info {
+  int32_t n_moves;
+  int32_t has_value;               /* the position the line ends on has been evaluated (`state in self.debug`, player.py:436) */
+  float value;                     /* its network value, from its side to move */
+  uint16_t moves[CZ_MAX_PV];       /* canonical moves, each from its mover's point of view */
+} cz_pv_info;
+/* print_depth_info (player.py:408-450): most-visited line from the root of `game` (last maximum wins, the root skips its
+ * no_act moves), at most max_len <= CZ_MAX_PV plies.  Synchronises. */
+int cz_get_pv(cz_engine* e, int game, int32_t max_len, cz_pv_info* out_host);
 
 /* Visit counts of every root after a search: n_host [n_games][CZ_MAX_MOVES], moves_host likewise
  * (0xFFFF padded), counts_host [n_games] legal-move counts, sims_run_host [n_games] or NULL.  Synchronises. */

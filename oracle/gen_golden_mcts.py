@@ -160,3 +160,56 @@ def gen_mcts_hist():
     with gzip.open(os.path.join(GOLD, "mcts_k1_hist.json.gz"), "wt") as f:
         json.dump(out, f)
     print("hist cases:", [(c["name"], [x["action"] for x in c["calls"]]) for c in cases])
+
+
+def gen_uci_info():
+    """`info depth` lines of the REAL player in UCI mode (uci=True, debugging=True; player.py:180-184,408-450) at
+    search_threads=1 -> tests/golden/uci_info_k1.json.gz.  Wall-clock fields (time, nps) are dropped."""
+    import contextlib
+    import io
+    import re
+    import numpy as np
+    from .ref_player_harness import FakeNetServer, make_config
+    r = ref_import.senv()
+    pm = ref_import.player_module()
+    h31, h44 = _game_history(31, 41), _game_history(44, 42)
+    specs = [
+        dict(name="uci_init_320", seed=1, sims=320, state=r.INIT_STATE, turns=0, no_act=None, depth=None, hist=[r.INIT_STATE], use_history=False),
+        dict(name="uci_black_31_depth3", seed=2, sims=800, state=h31[-1], turns=31, no_act=None, depth=300, hist=h31, use_history=False),
+        dict(name="uci_red_44_no_act", seed=3, sims=250, state=h44[-1], turns=44, no_act="FIRST2", depth=None, hist=h44, use_history=False),
+        dict(name="uci_black_31_history_planes", seed=4, sims=230, state=h31[-1], turns=31, no_act=None, depth=None, hist=h31, use_history=True),
+    ]
+    cases = []
+    for sp in specs:
+        cfg = make_config(sp["sims"], 1)
+        srv = FakeNetServer()
+        np.random.seed(sp["seed"])
+        no_act = r.get_legal_moves(sp["state"])[:2] if sp["no_act"] == "FIRST2" else sp["no_act"]
+        player = pm.CChessPlayer(cfg, pipes=srv.you, enable_resign=False, debugging=True, uci=True,
+                                 use_history=sp["use_history"], side=sp["turns"] % 2)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            action, _ = player.action(sp["state"], sp["turns"], no_act=no_act, depth=sp["depth"], hist=list(sp["hist"]))
+        node = player.tree[sp["state"]]
+        lines = []
+        for ln in buf.getvalue().splitlines():
+            m = re.match(r"info depth (\d+) score (-?\d+) time \d+ pv(.*) nps -?\d+$", ln)
+            assert m, ln
+            lines.append([int(m.group(1)), int(m.group(2)), m.group(3)])
+        value = float(player.debug[sp["state"]][1])
+        cases.append({"name": sp["name"], "seed": sp["seed"], "sims": sp["sims"], "state": sp["state"], "turns": sp["turns"],
+                      "no_act": no_act, "depth": sp["depth"], "hist": list(sp["hist"]), "use_history": sp["use_history"],
+                      "action": action, "done_tasks": int(player.done_tasks), "root_value": value, "info": lines,
+                      "legal": r.get_legal_moves(sp["state"]), "sum_n": int(node.sum_n),
+                      "edges": {m: [int(x.n), float(x.w), float(x.q), float(x.p)] for m, x in node.a.items()}})
+        player.close(wait=False)
+        srv.close()
+    notation = {"fen": "rnbakabnr/9/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RNBAKABNR w - - 0 1",
+                "fen_state": r.fen_to_state("rnbakabnr/9/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RNBAKABNR w - - 0 1"),
+                "ucci": [[m, r.parse_ucci_move(m)] for m in ("h2e2", "b9c7", "a0a1", "i9i0")],
+                "uci": [[m, r.to_uci_move(m)] for m in ("7242", "1927", "0001", "8980")]}
+    out = {"generator": "oracle/gen_golden_mcts.py:gen_uci_info", "reference": "NeymarL/ChineseChess-AlphaZero @7f45b0c agent/player.py",
+           "cases": cases, "notation": notation}
+    with gzip.open(os.path.join(GOLD, "uci_info_k1.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("uci cases:", [(c["name"], c["action"], c["info"]) for c in cases])

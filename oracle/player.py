@@ -72,7 +72,7 @@ class OraclePlayer:
     list holds, per leaf, the state whose planes fill input planes 14-27 (None = zero planes)."""
 
     def __init__(self, play_config, evaluate, env=senv, tree=None, enable_resign=False, noise=None,
-                 evaluate_mode=False, use_history=False):
+                 evaluate_mode=False, use_history=False, uci=False, side=0, debugging=False):
         self.pc = play_config
         self.evaluate = evaluate
         self.env = env
@@ -81,6 +81,10 @@ class OraclePlayer:
         self.move_lookup = {m: i for i, m in enumerate(self.labels)}
         self.enable_resign = enable_resign
         self.use_history = use_history
+        self.uci, self.side, self.debugging = uci, side, debugging
+        self.debug = {}                         # state -> (p, v) of every evaluated position when debugging (:349-350)
+        self.info = []                          # (depth, score, pv string) of every `info depth` line (:408-450)
+        self.done_tasks = 0
         self.evaluate_mode = evaluate_mode      # config.opts.evaluate
         # noise(move_count) -> one Dirichlet(alpha * 1_n)[0] draw; default = the reference's call
         self.noise = noise or (lambda n: np.random.dirichlet(self.pc.dirichlet_alpha * np.ones(n))[0])
@@ -93,7 +97,8 @@ class OraclePlayer:
         self.stats = {"sims": 0, "positions": 0, "batches": 0, "noise_draws": 0}
 
     # ---- action(): player.py:145-196
-    def search(self, state, no_act=None, increase_temp=False, depth=None, hist=None):
+    def search(self, state, no_act=None, increase_temp=False, depth=None, hist=None, turns=0, infinite=False, stop=None):
+        """stop(): polled between rounds when `infinite` (the reference's close_and_return_action sets job_done)."""
         self.root_state = state
         self.no_act = no_act
         self.increase_temp = increase_temp
@@ -102,22 +107,64 @@ class OraclePlayer:
         done = self.tree[state].sum_n if state in self.tree else 0
         if no_act or increase_temp or done == self.pc.simulation_num_per_move:
             done = 0
+        self.done_tasks = done
         num_task = self.pc.simulation_num_per_move - done
         if depth:
             num_task = depth - done if depth > done else 0
+        if infinite:
+            num_task = 100000
+        shown = 0
         if num_task > 0:
             k = self.pc.search_threads
             all_tasks = num_task
             batch = all_tasks // k + (1 if all_tasks % k else 0)
             for it in range(batch):
+                if stop is not None and stop():
+                    break
                 self.num_task = min(k, all_tasks - k * it)
+                self.done_tasks += self.num_task
                 self.stats["sims"] += self.num_task
                 for _ in range(self.num_task):
                     self.queue.append(("search", state, [state], hist))
                 self._drain_until_round_done()
+                if self.uci and shown != self.done_tasks // 100:             # :180-184
+                    shown = self.done_tasks // 100
+                    self.info.append(self.depth_info(state, turns, self.debug[state][1], no_act))
 
-    def action(self, state, turns, no_act=None, depth=None, increase_temp=False, hist=None):
-        self.search(state, no_act, increase_temp, depth, hist)
+    # ---- print_depth_info: player.py:408-450 (returns (depth, score, " m1 m2 ...") instead of printing; time and nps
+    #      are wall-clock and left out)
+    def depth_info(self, state, turns, value, no_act):
+        env = self.env
+        pv = ""
+        i = 0
+        root = True
+        while i < 20:
+            node = self.tree.get(state)
+            if node is None or len(node.a) == 0:
+                break
+            bestmove, n = None, 0
+            for mov, a in node.a.items():
+                if a.n >= n:
+                    if root and no_act and mov in no_act:
+                        continue
+                    n, bestmove = a.n, mov
+            if bestmove is None:
+                break
+            state = env.step(state, bestmove)
+            root = False
+            if turns % 2 == 1:
+                bestmove = env.flip_move(bestmove)
+            pv += " " + env.to_uci_move(bestmove)
+            i += 1
+            turns += 1
+        if state in self.debug:
+            _, value = self.debug[state]
+            if turns % 2 != self.side:
+                value = -value
+        return (self.done_tasks // 100, int(value * 1000), pv)
+
+    def action(self, state, turns, no_act=None, depth=None, increase_temp=False, hist=None, infinite=False, stop=None):
+        self.search(state, no_act, increase_temp, depth, hist, turns, infinite, stop)
         policy, resign = self.calc_policy(state, turns, no_act)
         if resign:
             return None, list(policy)
@@ -241,6 +288,8 @@ class OraclePlayer:
             node = self.tree[state]
             node.p = p
             node.waiting = False
+            if self.debugging:
+                self.debug[state] = (p, v)
             for hist in node.visit:
                 self.queue.append(("search", state, hist, None))
             node.visit = []

@@ -263,6 +263,22 @@ def state_history_to_planes(state, history):
     return planes
 
 
+# ------------------------------------------------------------------ UCI / FEN notation (static_env.py:224-228,380-388)
+_FEN_TO_STATE = str.maketrans("nNbBaAkK", "kKeEmMsS")      # FEN knight/bishop/advisor/king -> state k/e/m/s (common.py:32-47)
+
+
+def fen_to_state(fen):
+    return fen.split(' ')[0].translate(_FEN_TO_STATE)
+
+
+def parse_ucci_move(move):
+    return str(ord(move[0]) - ord('a')) + move[1] + str(ord(move[2]) - ord('a')) + move[3]
+
+
+def to_uci_move(action):
+    return chr(ord('a') + int(action[0])) + action[1] + chr(ord('a') + int(action[2])) + action[3]
+
+
 # ------------------------------------------------------------------ repetition rules
 def catch_set_codes(b, moves=None):
     res = set()
