@@ -211,6 +211,7 @@ def run_ours(args):
         step_device()
     # ---- device-resident timing
     eng.nn_profile(True)
+    st0 = eng.search_stats()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local)
     barrier()
@@ -230,6 +231,7 @@ def run_ours(args):
     conv_ms, conv_launches, conv_flops = eng.nn_profile(False)
     launches = eng.launch_count() - launches0
     positions = int(eng.counters()[1])
+    st1 = eng.search_stats()
     # ---- NCCL gather of finished play records (the only inter-GPU traffic of the path), timed with the step region
     gathered = 0
     if world > 1:
@@ -305,6 +307,18 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        # the byte model of the tree kernels evaluated on what rank 0's timed region actually did
+        d_sims = max(1, st1["sims"] - st0["sims"])
+        depth = (st1["path_edges"] - st0["path_edges"]) / d_sims
+        legal = st1["edges_stored"] / max(1, st1["nodes_stored"])
+        expand = (st1["nodes_created"] - st0["nodes_created"]) / d_sims
+        line["search_stats"] = {
+            "mean_path_edges": depth, "mean_legal_moves": legal, "no_network_rate": (st1["no_network"] - st0["no_network"]) / d_sims,
+            "expansions_per_sim": expand,
+            "tree_bytes_per_sim": depth * (32 + 14 * legal) + depth * 24 + depth * 90 + expand * ((32 + 22 * legal) + 90 + 2 * legal
+                                                                                                + 96 + 4 * 2086),
+            "note": "algorithmic HBM bytes of the integer kernels per simulation: select reads + virtual-loss/backup RMW + board "
+                    "replay per path edge; per expansion node+edge write, movegen, leaf record, policy row read by k_apply"}
         line["nn_positions_per_sec"] = (conv_flops / (2.0 * 90 * 9 * filters * filters * 2 * blocks)) / (ms * 1e-3)
         print(json.dumps(line))
     eng.close()

@@ -96,6 +96,8 @@ struct EngineDev {
   int32_t* totals;               // [4]: total leaves, any active, -, -
   uint8_t* leaf_dense;           // [G*K][lb_stride] leaves of all games, dense
   unsigned long long* counters;  // [8]
+  unsigned long long* stat;      // [G][4] since cz_create: simulations backed up, sum of their path lengths, simulations
+                                 //        that ended without the network (terminal / repetition / error), nodes created
   int32_t* gc_map;               // [G*ncap] scratch of game_compact: old node -> new node + 1 (0 = dropped)
   SelfplayDev sp;
 };
@@ -208,6 +210,7 @@ CZ_D int node_create(const EngineDev& E, int g, uint64_t k0, uint64_t k1, const 
     E.node_edge_off[ni] = (uint32_t)ne;
     E.node_meta[ni] = (uint32_t)L | NODE_WAITING;
     E.n_nodes[g] = nn + 1; E.n_edges[g] = ne + L;
+    E.stat[(size_t)g * 4 + 3] += 1;
   }
   czs::syncwarp();
   tt_insert(E, g, k0, nn);
@@ -289,6 +292,7 @@ CZ_D void backup(const EngineDev& E, int g, int sim, double v) {
     const size_t so = ((size_t)g * E.K + sim) * E.max_path;
     const int depth = E.sim_depth[(size_t)g * E.K + sim];
     const double vl = (double)E.vl;
+    E.stat[(size_t)g * 4 + 0] += 1; E.stat[(size_t)g * 4 + 1] += (unsigned long long)depth;
     for (int l = depth - 1; l >= 0; --l) {
       v = -v;
       const size_t e = (size_t)g * E.ecap + E.sim_edge[so + l];
@@ -476,6 +480,7 @@ CZ_D void game_wave(const EngineDev& E, int g, TreeSmem* sm) {
     if (czs::lane() == 0) {
       E.round_pending[g] -= n_imm;
       E.sims_run[g] += n_imm;
+      E.stat[(size_t)g * 4 + 2] += (unsigned long long)n_imm;
     }
     czs::syncwarp();
     if (E.n_leaf[g] > 0 || E.round_pending[g] > 0) return;   // evaluations outstanding

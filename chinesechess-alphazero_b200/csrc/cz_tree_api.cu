@@ -160,6 +160,22 @@ CZ_KERNEL(k_err_reduce)(EngineDev E) {
   for (int m = 16; m; m >>= 1) { orv |= czs::shfl_xor(orv, m); cnt += czs::shfl_xor(cnt, m); }
   if (czs::lane() == 0) { E.counters[6] = (unsigned long long)orv; E.counters[7] = (unsigned long long)cnt; }
 }
+// single warp: sums of the per-game search statistics; out[4] = edges of the nodes currently stored, out[5] = those nodes
+CZ_KERNEL(k_stat_reduce)(EngineDev E, unsigned long long* out) {
+  unsigned long long a[6] = {0, 0, 0, 0, 0, 0};
+  for (int g = czs::lane(); g < E.n_games; g += 32) {
+    for (int k = 0; k < 4; ++k) a[k] += E.stat[(size_t)g * 4 + k];
+    a[4] += (unsigned long long)E.n_edges[g]; a[5] += (unsigned long long)E.n_nodes[g];
+  }
+  for (int k = 0; k < 6; ++k) {
+    uint32_t lo = (uint32_t)a[k], hi = (uint32_t)(a[k] >> 32);
+    for (int m = 16; m; m >>= 1) {
+      const unsigned long long o = ((unsigned long long)czs::shfl_xor(hi, m) << 32) | czs::shfl_xor(lo, m);
+      a[k] += o; lo = (uint32_t)a[k]; hi = (uint32_t)(a[k] >> 32);
+    }
+    if (czs::lane() == 0) out[k] = a[k];
+  }
+}
 CZ_KERNEL(k_compact)(EngineDev E) {
   const int g = my_game();
   if (g >= E.n_games) return;
@@ -223,6 +239,7 @@ struct cz_engine {
   uint8_t* opt_no_act; uint8_t* opt_inc; uint8_t* opt_act;   // device staging for cz_root_opts
   uint8_t* opt_hist; uint8_t* opt_hist_given;
   cz_pv_info* pv_dev;
+  unsigned long long* stat_out;
   cz_root_info* root_info_dev;
   float* policy_buf; float* value_buf;                      // evaluator outputs for the built-in network
   uint8_t* board_stage;                                     // [G][96] staging for reset / set_root
@@ -273,6 +290,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.leaf_off = cv.take<int32_t>(G); d.totals = cv.take<int32_t>(8);
   d.leaf_dense = cv.take<uint8_t>(G * K * d.lb_stride);
   d.counters = cv.take<unsigned long long>(8);
+  d.stat = cv.take<unsigned long long>(G * 4);
   d.gc_map = cv.take<int32_t>(G * N);
   selfplay_carve(d.sp, cv, c);
   e->init_board_dev = cv.take<uint8_t>(BOARD_STRIDE);
@@ -280,6 +298,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   e->opt_hist = cv.take<uint8_t>(G * BOARD_STRIDE); e->opt_hist_given = cv.take<uint8_t>(G);
   e->root_info_dev = cv.take<cz_root_info>(1);
   e->pv_dev = cv.take<cz_pv_info>(1);
+  e->stat_out = cv.take<unsigned long long>(8);
   e->board_stage = cv.take<uint8_t>(G * BOARD_STRIDE);
   e->stat_n = cv.take<int32_t>(G * MAX_MOVES); e->stat_mv = cv.take<uint16_t>(G * MAX_MOVES); e->stat_cnt = cv.take<int32_t>(G);
   if (c.nn_filters > 0) {
@@ -391,6 +410,7 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
   init_board(ib);
   czrt_copy(e->init_board_dev, ib, BOARD_STRIDE, e->stream);
   czrt_memset(d.counters, 0, 8 * sizeof(unsigned long long), e->stream);
+  czrt_memset(d.stat, 0, (size_t)cfg->n_games * 4 * sizeof(unsigned long long), e->stream);
   czrt_sync(e->stream);
 #if !defined(CZ_EMUL)
   if (cfg->nn_filters > 0) {
@@ -656,6 +676,17 @@ int cz_get_pv(cz_engine* e, int game, int32_t max_len, cz_pv_info* out) {
   if (launch_ok(e, "cz_get_pv")) return CZ_ERR_CUDA;
   czrt_copy(out, e->pv_dev, sizeof(cz_pv_info), e->stream);
   return czrt_sync(e->stream) ? cz_fail(CZ_ERR_CUDA, "cz_get_pv: device failure") : 0;
+}
+
+int cz_get_search_stats(cz_engine* e, uint64_t* out) {
+  if (!e || !out) return cz_fail(CZ_ERR_ARG, "cz_get_search_stats: bad argument");
+  CZ_LAUNCH(k_stat_reduce, 1, 1, 0, e->stream, e->d, e->stat_out);
+  if (launch_ok(e, "cz_get_search_stats")) return CZ_ERR_CUDA;
+  unsigned long long h[6];
+  czrt_copy(h, e->stat_out, sizeof(h), e->stream);
+  if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_get_search_stats: device failure");
+  for (int k = 0; k < 6; ++k) out[k] = h[k];
+  return 0;
 }
 
 int cz_get_counters(cz_engine* e, uint64_t* out) {

@@ -208,6 +208,13 @@ class Engine:
         self.lib.call("cz_get_pv", self._h, game, max_len, C.byref(info))
         return [u16_to_move(info.moves[i]) for i in range(info.n_moves)], (float(info.value) if info.has_value else None)
 
+    def search_stats(self):
+        """cz_get_search_stats as a dict (totals since the engine was created)."""
+        a = np.zeros(6, dtype=np.uint64)
+        self.lib.call("cz_get_search_stats", self._h, C.c_void_p(a.ctypes.data))
+        sims, depth, imm, created, edges, nodes = (int(x) for x in a)
+        return {"sims": sims, "path_edges": depth, "no_network": imm, "nodes_created": created, "edges_stored": edges, "nodes_stored": nodes}
+
     def search(self, opts=None):
         """Whole search with the built-in tensor-core network."""
         self.lib.call("cz_search", self._h, C.byref(opts) if opts is not None else None)

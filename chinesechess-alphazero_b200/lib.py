@@ -97,6 +97,7 @@ _SIGS = {
     "cz_search": (C.c_int, [_P, C.POINTER(CzRootOpts)]),
     "cz_get_root": (C.c_int, [_P, C.c_int, C.POINTER(CzRootInfo)]),
     "cz_get_counters": (C.c_int, [_P, _P]),
+    "cz_get_search_stats": (C.c_int, [_P, _P]),
     "cz_play_move": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "cz_selfplay": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "cz_drain_records": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),

@@ -201,6 +201,12 @@ int cz_get_root_stats(cz_engine* e, int32_t* n_host, uint16_t* moves_host, int32
  * rest, rebuild the hash tables.  cz_search_begin does this on its own when a pool cannot hold the next search. */
 int cz_compact(cz_engine* e);
 
+/* Search statistics summed over all games since cz_create, for checking the byte model of the tree kernels (SURVEY.md
+ * §8d): out[0] simulations backed up, out[1] sum of their path lengths (edges), out[2] simulations that ended without
+ * the network (terminal, repetition, error), out[3] nodes created (= positions sent to the network), out[4] edges and
+ * out[5] nodes currently stored (mean legal moves per node = out[4]/out[5]).  Synchronises. */
+int cz_get_search_stats(cz_engine* e, uint64_t* out /* [6] */);
+
 /* Counters since cz_create: [0] simulations completed, [1] NN positions evaluated, [2] wave iterations,
  * [4] whole-table resets (compaction was not enough / root unknown), [5] compactions,
  * [6] OR of the per-game error flags (1 path longer than max_path, 2 pool exhausted inside a search, 4 host noise table

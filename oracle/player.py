@@ -94,7 +94,7 @@ class OraclePlayer:
         self.queue = deque()
         self.buffer = []                        # (state, history) awaiting evaluation
         self.num_task = 0
-        self.stats = {"sims": 0, "positions": 0, "batches": 0, "noise_draws": 0}
+        self.stats = {"sims": 0, "positions": 0, "batches": 0, "noise_draws": 0, "path_edges": 0, "no_network": 0}
 
     # ---- action(): player.py:145-196
     def search(self, state, no_act=None, increase_temp=False, depth=None, hist=None, turns=0, infinite=False, stop=None):
@@ -283,6 +283,8 @@ class OraclePlayer:
 
     # ---- update_tree: player.py:340-373
     def _update_tree(self, p, v, history):
+        self.stats["path_edges"] += len(history) // 2
+        self.stats["no_network"] += 1 if p is None else 0
         state = history.pop()
         if p is not None:
             node = self.tree[state]

@@ -181,9 +181,19 @@ def check_vs_oracle(lib, device, cases):
     for (sims, k, seed, n_states) in cases:
         states = [osenv.INIT_STATE] + midgame_states(n_states - 1, seed)
         eng, stats = engine_search(lib, device, states, sims, k, seed)
+        tot = {"sims": 0, "path_edges": 0, "no_network": 0, "positions": 0}
         for g, s in enumerate(states):
             pl = oracle_search(s, sims, k, seed)
             compare_root(eng, g, pl, s)
+            for key in tot:
+                tot[key] += pl.stats[key]
+            # the most visited line (print_depth_info, player.py:408-450) read back through cz_get_pv
+            _, _, pv = pl.depth_info(s, 0, 0.0, None)
+            moves, _ = eng.pv(g, 20)
+            assert "".join(" " + osenv.to_uci_move(osenv.flip_move(m) if i % 2 else m) for i, m in enumerate(moves)) == pv
+        st = eng.search_stats()                          # the counters behind bench.py's byte-model figures
+        assert (st["sims"], st["path_edges"], st["no_network"], st["nodes_created"]) == \
+               (tot["sims"], tot["path_edges"], tot["no_network"], tot["positions"]), (st, tot)
         eng.close()
 
 
