@@ -646,7 +646,9 @@ int cz_search(cz_engine* e, const cz_root_opts* opts) {
   if (rc) return rc;
   // two half-ranges only pay when each half still fills the tensor cores (>= 4096 leaves per round); the arena always
   // needs them (one range per network)
-  if (e->tree_stream && ((long long)e->cfg.n_games * e->cfg.leaves_per_round >= 8192 || e->cfg.arena)) return search_pipelined(e);
+  const char* force = getenv("CZ_FORCE_PIPELINE");                 // test hook: the two-range path at any size
+  if (e->tree_stream && ((long long)e->cfg.n_games * e->cfg.leaves_per_round >= 8192 || e->cfg.arena || (force && force[0] == '1')))
+    return search_pipelined(e);
   if (e->cfg.arena) return cz_fail(CZ_ERR_STATE, "cz_search: arena mode needs the two-range pipeline (CZ_NO_PIPELINE is set)");
   for (;;) {
     int32_t n = 0, busy = 0;

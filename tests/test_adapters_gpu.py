@@ -114,10 +114,11 @@ def test_history_network_builtin_search_and_worker(cuda_lib, tmp_path):
     hists = [game_history(12, 3), None, game_history(2, 4)]
     states = [hists[0][-1], osenv.INIT_STATE, hists[2][-1]]
 
-    def run(external):
+    def run(external, pipelined=False):
         eng = Engine(cuda_lib, "cuda", n_games=3, sims_per_move=64, leaves_per_round=8, noise_mode=1, nn_filters=64, nn_blocks=2,
                      seed=5, use_history=True)
         eng.set_weights(model.torch_weights())
+        os.environ["CZ_FORCE_PIPELINE"] = "1" if pipelined else "0"
         eng.reset(states)
         opts = eng.make_opts(hist=hists)
         seen = []
@@ -136,7 +137,9 @@ def test_history_network_builtin_search_and_worker(cuda_lib, tmp_path):
         return out, seen
     a, _ = run(False)
     b, seen = run(True)
-    assert a == b and sum(seen) > 0
+    c, _ = run(False, pipelined=True)                    # the two-range pipeline carries the 192-byte leaf records too
+    os.environ.pop("CZ_FORCE_PIPELINE", None)
+    assert a == b == c and sum(seen) > 0
     model.save(cfg.resource.model_best_config_path, cfg.resource.model_best_weight_path)
     w = SelfPlayWorker(cfg, concurrent_games=4, seed=3, use_history=True, model=model)
     recs = w.play_games(2)
