@@ -124,3 +124,22 @@ def expanding_data(data, env, use_history=False):
             raise ValueError(f"move {m} is not an action label")
         policy[i, lab] = 1
     return planes, policy, values
+
+
+def flip_policy(pol, env):
+    """lookup_tables.py:134-141: re-index a 2086-vector from black's move labels to red's
+    (out[i] = pol[index of flip_move(label_i)])."""
+    from .env import flip_move
+    if not hasattr(env, "_unflipped_index"):
+        lookup = {m: i for i, m in enumerate(env.labels)}
+        env._unflipped_index = np.asarray([lookup[flip_move(m)] for m in env.labels])
+    return np.asarray(pol)[env._unflipped_index]
+
+
+def build_policy(action, flip, env):
+    """optimize.py:283-292 / self_play.py:253-262: one-hot over the action labels, optionally seen from the other side."""
+    policy = np.zeros(len(env.labels))
+    policy[env.labels.index(action)] = 1
+    if flip:
+        policy = flip_policy(policy, env)
+    return list(policy)

@@ -99,3 +99,15 @@ def test_emul_expanding_data_matches_reference_layout(emul_env):
         assert (planes28[i] == osenv.state_history_to_planes(s, hist[0:2 * i + 1])).all()
         s = osenv.step(s, m)
         hist += [m, s]
+
+
+def test_flip_policy_matches_reference_definition(emul_env):
+    """lookup_tables.py:134-141: Unflipped_index = [ActionLabelsRed.index(x) for x in ActionLabelsBlack]."""
+    from cczero_b200.records import build_policy, flip_policy
+    red = osenv.ActionLabelsRed
+    black = [osenv.flip_move(m) for m in red]
+    pol = np.random.RandomState(1).rand(len(red))
+    want = np.asarray([pol[red.index(x)] for x in black])
+    assert (flip_policy(pol, emul_env) == want).all()
+    p = build_policy("7747", True, emul_env)
+    assert sum(p) == 1 and p[red.index(osenv.flip_move("7747"))] == 1
