@@ -361,10 +361,27 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const int r8 = lane >> 2, c8 = (lane & 3) * 8;           // fp16 view: rows r8 + 8k, 8 halves at column c8
     const int cbeg = half * (N_TILE / 2);
     uint32_t tcount = 0;
+    // The skip stream of a tile is one contiguous block (kTileM pixels x N channels).  With only a chunk per warp in
+    // flight its loads were DRAM-latency bound (ncu: conv2 with the fp32 stream 17 us per tile vs 14.8 us of MMA), so
+    // one warp pulls the block of the NEXT tile into L2 a whole tile ahead; the chunk loads then hit L2.
+    auto prefetch_skip = [&](int pr) {
+      if (warp != 4 || pr >= pairs || !(a.residual32 || a.residual)) return;
+      const long long row0 = (long long)(2 * pr + (int)rank) * kTileM;
+      const long long nrow = a.rows - row0 < kTileM ? a.rows - row0 : kTileM;
+      if (nrow <= 0) return;
+      const size_t esz = a.residual32 ? 4 : 2;
+      const char* base = (a.residual32 ? reinterpret_cast<const char*>(a.residual32) : reinterpret_cast<const char*>(a.residual)) +
+                         (size_t)row0 * a.ldo * esz;
+      const size_t total = (size_t)nrow * a.ldo * esz;           // multiple of 16: ldo is a multiple of 64 channels
+      for (size_t off = (size_t)lane * 16384; off < total; off += 32 * 16384)
+        umma::l2_prefetch_bulk(base + off, (uint32_t)(total - off < 16384 ? total - off : 16384));
+    };
+    prefetch_skip(cluster_id);
     for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
       const int m_tile = 2 * pair + (int)rank;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       const long long rbase = (long long)m_tile * kTileM + q * 32;     // first global pixel row of this warp
+      prefetch_skip(pair + n_clusters);
       const float* r32 = a.residual32 ? a.residual32 + rbase * a.ldo + cbeg : nullptr;
       const __half* r16 = (!a.residual32 && a.residual) ? a.residual + rbase * a.ldo + cbeg : nullptr;
       float4 nf[8];                                          // skip stream of the next chunk, line-coalesced

@@ -136,6 +136,11 @@ __device__ __forceinline__ uint32_t mapa_shared(const void* p, uint32_t rank) {
 // Remote arrive without memory-ordering side effects.  The epilogue only has to order its TMEM reads before the arrive
 // (tcgen05.wait::ld + tcgen05.fence::before_thread_sync do that); a .release.cluster arrive compiles to
 // MEMBAR.ALL.GPU + ERRBAR and makes every thread wait for the tile's global stores (21 % of epilogue stall samples in ncu).
+// Pull `bytes` (multiple of 16) of global memory into L2 ahead of use; no destination, no completion to wait for.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
