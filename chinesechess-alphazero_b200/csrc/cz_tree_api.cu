@@ -501,6 +501,8 @@ int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {
   const uint8_t* hist = nullptr; const uint8_t* hist_given = nullptr;
   int sims_override = 0, raw_tasks = 0;
   e->d.noise_table = nullptr; e->d.noise_stride = 0;
+  if (opts && opts->struct_bytes != (int)sizeof(cz_root_opts))
+    return cz_fail(CZ_ERR_ARG, "cz_root_opts: struct_bytes mismatch (%d vs %d)", opts->struct_bytes, (int)sizeof(cz_root_opts));
   if (opts) {
     if (opts->no_act_host) { czrt_copy(e->opt_no_act, opts->no_act_host, G * CZ_MAX_NO_ACT * 2, e->stream); na = (const uint16_t*)e->opt_no_act; }
     if (opts->increase_temp_host) { czrt_copy(e->opt_inc, opts->increase_temp_host, G, e->stream); inc = e->opt_inc; }

@@ -94,6 +94,7 @@ class Engine:
         """hist (use_history engines): per game the `hist` list given to action() ([.., state, move, state]) or None.
         raw_tasks: run exactly sims_override simulations (the caller did action()'s done / depth bookkeeping)."""
         o = CzRootOpts()
+        o.struct_bytes = C.sizeof(CzRootOpts)
         keep = []
         if hist is not None and any(h for h in hist):
             hb = np.zeros((self.n_games, BOARD_STRIDE), dtype=np.uint8)

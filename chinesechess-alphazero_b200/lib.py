@@ -36,6 +36,7 @@ class CzConfig(C.Structure):
 
 class CzRootOpts(C.Structure):
     _fields_ = [
+        ("struct_bytes", C.c_int32), ("reserved", C.c_int32),
         ("no_act_host", C.c_void_p), ("increase_temp_host", C.c_void_p), ("active_host", C.c_void_p),
         ("noise_dev", C.c_void_p), ("noise_stride", C.c_int64),
         ("sims_override", C.c_int32), ("raw_tasks", C.c_int32),

@@ -127,6 +127,8 @@ int cz_set_roots(cz_engine* e, const uint8_t* boards_host);
 int cz_get_roots(cz_engine* e, uint8_t* boards_host);
 
 typedef struct cz_root_opts {
+  int32_t struct_bytes;            /* sizeof(cz_root_opts): checked like cz_config.struct_bytes */
+  int32_t reserved;
   /* per game, may be NULL for "none" */
   const uint16_t* no_act_host;     /* [n_games][CZ_MAX_NO_ACT] moves banned at the root, 0xFFFF-terminated */
   const uint8_t* increase_temp_host; /* [n_games] */
