@@ -53,6 +53,11 @@ CZ_D int popc(unsigned x) { return __builtin_popcount(x); }
 CZ_D int ffs(unsigned x) { return __builtin_ffs((int)x); }          // 1-based, 0 if none
 CZ_D int fls(unsigned x) { return x ? 32 - __builtin_clz(x) : 0; }  // 1-based msb, 0 if none
 CZ_D double dsqrt(double x) { return sqrt(x); }
+// fast single-precision transcendentals of the root-noise sampler (statistical parity only, never bit-compared)
+CZ_D float flog(float x) { return logf(x); }
+CZ_D float fcos(float x) { return cosf(x); }
+CZ_D float fpow(float x, float y) { return powf(x, y); }
+CZ_D float fsqrt(float x) { return sqrtf(x); }
 template <class T> CZ_D T ldg(const T* p) { return *p; }
 }  // namespace czs
 
@@ -78,6 +83,10 @@ CZ_D int popc(unsigned x) { return __popc(x); }
 CZ_D int ffs(unsigned x) { return __ffs((int)x); }
 CZ_D int fls(unsigned x) { return 32 - __clz((int)x); }
 CZ_D double dsqrt(double x) { return __dsqrt_rn(x); }
+CZ_D float flog(float x) { return __logf(x); }
+CZ_D float fcos(float x) { return __cosf(x); }
+CZ_D float fpow(float x, float y) { return __powf(x, y); }
+CZ_D float fsqrt(float x) { return __fsqrt_rn(x); }
 template <class T> CZ_D T ldg(const T* p) { return __ldg(p); }
 }  // namespace czs
 #endif

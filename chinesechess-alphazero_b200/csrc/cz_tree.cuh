@@ -136,21 +136,28 @@ struct Rng {                     // a private stream: key = (seed, rank), counte
     const uint64_t a = next(), b = next();
     return ((double)(((a << 32) | b) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
   }
-  CZ_DM double normal() {
-    const double u1 = uniform(), u2 = uniform();
-    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+  // The root-noise sampler below works in single precision with the SFU transcendentals: the draws only have to be
+  // Beta(alpha, (L-1) alpha) distributed (tests/test_noise.py), and in fp64 (log / cos / pow slow paths) they were 35 %
+  // of all instructions k_wave executed (ncu source view, profiles/).  uniform() above stays fp64: the move / resign /
+  // store lotteries are restated bit for bit by oracle/selfplay.py.
+  CZ_DM float uniform_f() {      // (0,1), 24 bits, never 0 or 1
+    return ((float)(next() >> 8) + 0.5f) * (1.0f / 16777216.0f);
   }
-  CZ_DM double gamma(double a) { // Marsaglia-Tsang, with the a < 1 boost
-    double boost = 1.0;
-    if (a < 1.0) { boost = pow(uniform(), 1.0 / a); a += 1.0; }
-    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  CZ_DM float normal_f() {
+    const float u1 = uniform_f(), u2 = uniform_f();
+    return czs::fsqrt(-2.0f * czs::flog(u1)) * czs::fcos(6.2831853f * u2);
+  }
+  CZ_DM float gamma_f(float a) { // Marsaglia-Tsang, with the a < 1 boost
+    float boost = 1.0f;
+    if (a < 1.0f) { boost = czs::fpow(uniform_f(), 1.0f / a); a += 1.0f; }
+    const float d = a - 1.0f / 3.0f, c = 1.0f / czs::fsqrt(9.0f * d);
     for (int it = 0; it < 64; ++it) {
-      const double x = normal();
-      double v = 1.0 + c * x;
-      if (v <= 0.0) continue;
+      const float x = normal_f();
+      float v = 1.0f + c * x;
+      if (v <= 0.0f) continue;
       v = v * v * v;
-      const double u = uniform();
-      if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v * boost;
+      const float u = uniform_f();
+      if (czs::flog(u) < 0.5f * x * x + d - d * v + d * czs::flog(v)) return d * v * boost;
     }
     return d * boost;
   }
@@ -158,11 +165,11 @@ struct Rng {                     // a private stream: key = (seed, rank), counte
 // first component of Dirichlet(alpha * 1_n): Gamma(alpha) / (Gamma(alpha) + Gamma((n-1) alpha))
 CZ_D double dirichlet_first(const EngineDev& E, int game, uint32_t index, int n) {
   Rng r; r.init(E.seed, E.rank, (uint32_t)game, 1u, index);
-  const double g1 = r.gamma(E.alpha);
+  const float g1 = r.gamma_f((float)E.alpha);
   if (n <= 1) return 1.0;
-  const double g2 = r.gamma(E.alpha * (double)(n - 1));
-  const double s = g1 + g2;
-  return s > 0.0 ? g1 / s : 0.0;
+  const float g2 = r.gamma_f((float)E.alpha * (float)(n - 1));
+  const float s = g1 + g2;
+  return s > 0.0f ? (double)(g1 / s) : 0.0;
 }
 
 // ------------------------------------------------------------------ transposition table
