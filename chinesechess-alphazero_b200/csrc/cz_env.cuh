@@ -120,15 +120,28 @@ struct EmitSink {
 };
 
 // Ordered pseudo-legal move list of the side to move (static_env.py:256-321).
-// Squares are scanned y-major then x (== ascending sq); lanes own squares lane, lane+32,
-// lane+64 and a warp scan keeps the reference order.  Returns the count (<= MAX_MOVES).
+// The reference scans squares y-major then x (== ascending sq) and emits each piece's moves in turn.  Here the own
+// pieces are compacted in that order (three ballots over the 90 squares) and piece k goes to lane k % 32, so one pass
+// of count / scan / emit serves up to 32 pieces (a legal position has at most 16) instead of one pass per 32 SQUARES
+// with mostly idle lanes.  Returns the count (<= MAX_MOVES).
 CZ_D int movegen(const uint8_t* b, move_t* list) {
-  int base = 0;
+  unsigned own[3];
   for (int j = 0; j < 3; ++j) {
     const int sq = j * 32 + czs::lane();
-    const uint8_t c = sq < NSQ ? b[sq] : (uint8_t)0;
+    own[j] = czs::ballot(sq < NSQ && pc_own(b[sq]));
+  }
+  const int n0 = czs::popc(own[0]), n1 = czs::popc(own[1]), n2 = czs::popc(own[2]);
+  const int pieces = n0 + n1 + n2;
+  int base = 0;
+  for (int first = 0; first < pieces; first += 32) {
+    const int k = first + czs::lane();                       // this lane's piece, in scan order
+    int sq = -1;
+    if (k < n0) sq = czs::nth_set_bit(own[0], k);
+    else if (k < n0 + n1) sq = 32 + czs::nth_set_bit(own[1], k - n0);
+    else if (k < pieces) sq = 64 + czs::nth_set_bit(own[2], k - n0 - n1);
+    const uint8_t c = sq >= 0 ? b[sq] : (uint8_t)0;
     int cnt = 0;
-    if (pc_own(c)) { CountSink cs{0}; gen_piece(b, sq, c, cs); cnt = cs.n; }
+    if (sq >= 0) { CountSink cs{0}; gen_piece(b, sq, c, cs); cnt = cs.n; }
     int tot;
     const int off = czs::warp_excl_scan(cnt, &tot);
     if (cnt) { EmitSink es{list, base + off, sq}; gen_piece(b, sq, c, es); }

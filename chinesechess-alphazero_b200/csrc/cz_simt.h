@@ -52,6 +52,10 @@ template <class T> CZ_D T shfl(T v, int src) {
 CZ_D int popc(unsigned x) { return __builtin_popcount(x); }
 CZ_D int ffs(unsigned x) { return __builtin_ffs((int)x); }          // 1-based, 0 if none
 CZ_D int fls(unsigned x) { return x ? 32 - __builtin_clz(x) : 0; }  // 1-based msb, 0 if none
+CZ_D int nth_set_bit(unsigned x, int n) {                            // position of the n-th (0-based) set bit, -1 if none
+  for (int i = 0; i < 32; ++i) if ((x >> i) & 1u) { if (n == 0) return i; --n; }
+  return -1;
+}
 CZ_D double dsqrt(double x) { return sqrt(x); }
 // fast single-precision transcendentals of the root-noise sampler (statistical parity only, never bit-compared)
 CZ_D float flog(float x) { return logf(x); }
@@ -82,6 +86,7 @@ template <class T> CZ_D T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v
 CZ_D int popc(unsigned x) { return __popc(x); }
 CZ_D int ffs(unsigned x) { return __ffs((int)x); }
 CZ_D int fls(unsigned x) { return 32 - __clz((int)x); }
+CZ_D int nth_set_bit(unsigned x, int n) { const unsigned r = __fns(x, 0u, n + 1); return r == 0xffffffffu ? -1 : (int)r; }
 CZ_D double dsqrt(double x) { return __dsqrt_rn(x); }
 CZ_D float flog(float x) { return __logf(x); }
 CZ_D float fcos(float x) { return __cosf(x); }
