@@ -153,7 +153,9 @@ class Engine:
 
     def search_apply(self, policy, value):
         assert policy.dtype == torch.float32 and value.dtype == torch.float32
-        self._keep.append((policy, value))
+        # hold the evaluation of the last few waves (the kernels read them stream-ordered; a long `go infinite` search
+        # must not accumulate one tensor pair per wave)
+        self._apply_keep = (getattr(self, "_apply_keep", []) + [(policy, value)])[-4:]
         self.lib.call("cz_search_apply", self._h, _ptr(policy), _ptr(value))
 
     def search_external(self, evaluate_planes, opts=None):
@@ -182,7 +184,7 @@ class Engine:
         """Swap the Dirichlet table of the open search for a longer one (same leading draws)."""
         t = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float64)).to(self.device)
         assert t.dim() == 2 and t.shape[0] == self.n_games
-        self._keep.append(t)
+        self._noise_keep = (getattr(self, "_noise_keep", []) + [t])[-2:]     # the previous table may still be read by a queued kernel
         self.lib.call("cz_set_noise_table", self._h, _ptr(t), t.shape[1])
 
     def run_waves(self, evaluate_planes=None):

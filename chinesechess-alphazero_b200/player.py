@@ -181,9 +181,9 @@ class CChessPlayer:
         self._noise_sims += n_sims
         want = (self._noise_sims + 2 * self.engine.K + 2) * self._n_moves
         if want > self._noise_rows:
-            more = max(want - self._noise_rows, 64 * self._n_moves)
+            more = max(want - self._noise_rows, 64 * self._n_moves, self._noise_rows)     # at least double: O(log) re-uploads
             alpha = self.play_config.dirichlet_alpha * np.ones(self._n_moves)
-            new = np.random.dirichlet(alpha, size=more)[:, 0]
+            new = np.concatenate([np.random.dirichlet(alpha, size=min(16384, more - i))[:, 0] for i in range(0, more, 16384)])
             self._noise_table = np.concatenate([self._noise_table, new[None, :]], axis=1)
             self._noise_rows += more
             if search_open:                                            # swap the table of the running search
@@ -193,8 +193,11 @@ class CChessPlayer:
         """Rewind np.random and draw exactly what the search consumed, leaving the stream where the reference leaves it."""
         if self._rng_state is not None:
             np.random.set_state(self._rng_state)
-            if used:
-                np.random.dirichlet(self.play_config.dirichlet_alpha * np.ones(self._n_moves), size=used)
+            alpha = self.play_config.dirichlet_alpha * np.ones(self._n_moves)
+            while used > 0:                                            # in slices: a long search consumed millions of draws
+                m = min(used, 16384)
+                np.random.dirichlet(alpha, size=m)
+                used -= m
             self._rng_state = None
 
     def _remember_root_value(self, state, root=None):
