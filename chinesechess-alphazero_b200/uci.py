@@ -1,20 +1,92 @@
-"""UCI / UCCI front end (reference: cchess_alphazero/uci.py:40-331) on top of the drop-in `CChessPlayer`.
+"""UCI / UCCI front end on top of the drop-in `CChessPlayer` (behaviour of the reference's cchess_alphazero/uci.py:40-331).
 
-Same command set and output as the reference: `uci`, `ucinewgame`, `setoption name gpu|Threads value x`, `isready`,
-`position {fen <fen> | startpos} [moves ...]`, `fen ...`, `go [depth x] [movetime|time x] [wtime x] [btime x] [infinite]`,
-`stop`, `quit`; answers `info depth .. score .. time .. pv .. nps ..` while thinking (printed by the player,
-player.py:408-450), then `info depth .. score .. time .. nps ..` and `bestmove <m> [ponder <m>]` (uci.py:293-327).
+Wire behaviour kept from the reference:
+  uci            -> id / option lines, `uciok`; loads the network                       (uci.py:71-88)
+  ucinewgame     -> start position                                                       (uci.py:90-95)
+  setoption name gpu|Threads value <x>                                                   (uci.py:97-110)
+  isready        -> `readyok`                                                            (uci.py:112-116)
+  position {fen <fen> w|b - - <half> <full> | startpos} [moves m1 m2 ...] , fen ...      (uci.py:118-174)
+  go [depth d] [movetime|time ms] [wtime ms] [btime ms] [infinite]                      (uci.py:177-227)
+                 -> `info depth .. score .. time .. pv .. nps ..` while thinking (printed by the player,
+                    player.py:408-450), then `info depth .. score .. time .. nps ..` and
+                    `bestmove <m> [ponder <m>]`                                          (uci.py:293-327)
+  stop           -> answer from the tree as it stands                                    (uci.py:229-243)
+  quit
 
-Differences that do not show on the wire: one search engine on the GPU instead of a thread pool; by default the leaves
-are evaluated by the built-in tensor-core network (`use_pipes=True` goes through CChessModelAPI's pipe like uci.py:205).
+What differs does not show on the wire: the search runs in one GPU engine instead of a thread pool, and by default the
+leaves are evaluated by the built-in tensor-core network (`use_pipes=True` / `pipes_factory` go through a pipe like
+uci.py:205).
 """
 import sys
+from dataclasses import dataclass
 from threading import Thread, Timer
 from time import time
+from typing import Optional
 
 from .env import INIT_STATE, StaticEnv, fen_to_state, flip_move, parse_ucci_move, to_uci_move
 from .lib import get_lib
 from .player import CChessPlayer
+
+ID_LINES = ('id name CCZero', 'id author https://cczero.org', 'id version 2.4',
+            'option name gpu spin default 0 min 0 max 7', 'option name Threads spin default 10 min 0 max 1024', 'uciok')
+
+
+@dataclass
+class GoLimits:
+    """What a `go` line asks for (uci.py:198-221)."""
+    depth: Optional[int] = None        # simulations = 100 x the UCI depth
+    infinite: bool = True
+    seconds: Optional[float] = None    # stop after this long
+
+    @classmethod
+    def parse(cls, words, red_to_move):
+        lim = cls()
+        for key, val in zip(words, words[1:] + [None]):
+            if key == 'depth':
+                lim.depth, lim.infinite = int(val) * 100, False
+            elif key in ('movetime', 'time'):
+                lim.seconds = int(val) / 1000
+            elif key == 'infinite':
+                lim.infinite = True
+            elif (key == 'wtime' and red_to_move) or (key == 'btime' and not red_to_move):
+                lim.seconds, lim.depth, lim.infinite = int(val) / 1000, 3000, False     # own clock: at most 3000 simulations
+        return lim
+
+
+class Position:
+    """Board + game history in the reference's canonical form: `state` is seen by the side to move, `history` is
+    [state, move, state, ...] with every move written from its mover's side (uci.py:118-169)."""
+
+    def __init__(self, env):
+        self.env = env
+        self.reset()
+
+    def reset(self):
+        self.state, self.red_to_move, self.turns = INIT_STATE, True, 0
+        self.history = [INIT_STATE]
+
+    def set_fen(self, fen, side, fullmove):
+        state = fen_to_state(fen)
+        self.env.get_legal_moves(state)               # raises on garbage
+        self.history = [state]
+        self.red_to_move = side != 'b'
+        self.turns = (int(fullmove) - 1) * 2 + (0 if self.red_to_move else 1)
+        self.state = state if self.red_to_move else self.env.fliped_state(state)
+
+    def push(self, ucci_move):
+        action = parse_ucci_move(ucci_move)
+        if not self.red_to_move:
+            action = flip_move(action)
+        self.state = self.env.step(self.state, action)
+        self.history += [action, self.state]
+        self.red_to_move = not self.red_to_move
+        self.turns += 1
+
+    def repeated_replies(self):
+        """Moves that were played from this very position earlier in the game (None if it is new)."""
+        if self.state not in self.history[:-1]:
+            return None
+        return [self.history[i + 1] for i in range(len(self.history) - 1) if self.history[i] == self.state]
 
 
 class UCI:
@@ -24,196 +96,72 @@ class UCI:
         self.lib = lib or get_lib()
         self.device = device
         self.env = StaticEnv(self.lib, device)
-        self.stdin = stdin or sys.stdin
-        self.stdout = stdout or sys.stdout
+        self.stdin, self.stdout = stdin or sys.stdin, stdout or sys.stdout
         self.model = model
         self.use_pipes = use_pipes or pipes_factory is not None
         self.pipes_factory = pipes_factory       # () -> Connection; default: model.get_pipes(need_reload=False)
         self.infinite_capacity = infinite_capacity
-        self.args = None
-        self.state = None
-        self.is_red_turn = None
+        self.pos = Position(self.env)
+        self.args = []
         self.player = None
         self.is_ready = False
-        self.remain_time = None
-        self.history = None
-        self.turns = 0
+        self.use_history = False
         self.start_time = None
         self.t = None
-        self.use_history = False
         self.search_worker = None
+
+    # attribute names of the reference object, for callers that read them
+    state = property(lambda self: self.pos.state)
+    history = property(lambda self: self.pos.history)
+    turns = property(lambda self: self.pos.turns)
+    is_red_turn = property(lambda self: self.pos.red_to_move)
 
     def _print(self, text):
         print(text, file=self.stdout)
         self.stdout.flush()
 
-    # ---- uci.py:59-69
     def main(self):
         for line in self.stdin:
-            cmd = line.strip()
-            if not cmd:
+            words = line.split()
+            if not words:
                 continue
-            cmds = cmd.split(' ')
-            self.args = cmds[1:]
-            method = getattr(self, 'cmd_' + cmds[0], None)
-            if method is not None:
-                if method() == "quit":
-                    return
+            handler = getattr(self, 'cmd_' + words[0], None)
+            self.args = words[1:]
+            if handler is not None and handler() == "quit":
+                return
 
-    # ---- uci.py:71-88
+    # ---- session
     def cmd_uci(self):
-        self._print('id name CCZero')
-        self._print('id author https://cczero.org')
-        self._print('id version 2.4')
-        self._print('option name gpu spin default 0 min 0 max 7')
-        self._print('option name Threads spin default 10 min 0 max 1024')
-        self._print('uciok')
+        for ln in ID_LINES:
+            self._print(ln)
         self.use_history = self.load_model()
+        self.pos.reset()
         self.is_ready = True
-        self.turns = 0
-        self.remain_time = None
-        self.state = INIT_STATE
-        self.history = [self.state]
-        self.is_red_turn = True
 
     def cmd_ucinewgame(self):
-        self.state = INIT_STATE
-        self.history = [self.state]
+        self.pos.reset()
         self.is_ready = True
-        self.is_red_turn = True
 
-    # ---- uci.py:97-110
     def cmd_setoption(self):
-        if len(self.args) > 3:
-            name = self.args[1]
-            if name == 'gpu':
-                self.device = f"cuda:{int(self.args[3])}" if self.lib.is_cuda else self.device
-            if name == 'Threads':
-                self.config.play.search_threads = int(self.args[3])
+        if len(self.args) < 4:
+            return
+        name, value = self.args[1], self.args[3]
+        if name == 'gpu' and self.lib.is_cuda:
+            self.device = f"cuda:{int(value)}"
+        elif name == 'Threads':
+            self.config.play.search_threads = int(value)
 
     def cmd_isready(self):
         if self.is_ready:
             self._print('readyok')
-
-    # ---- uci.py:118-169
-    def cmd_position(self):
-        if not self.is_ready:
-            return
-        move_idx = -1
-        if len(self.args) > 0:
-            if self.args[0] == 'fen':
-                try:
-                    self.state = fen_to_state(self.args[1])
-                    self.env.get_legal_moves(self.state)
-                except Exception:
-                    return
-                self.history = [self.state]
-                if self.args[2] == 'b':
-                    self.state = self.env.fliped_state(self.state)
-                    self.is_red_turn = False
-                    self.turns = (int(self.args[6]) - 1) * 2 + 1
-                else:
-                    self.is_red_turn = True
-                    self.turns = (int(self.args[6]) - 1) * 2
-                if len(self.args) > 7 and self.args[7] == 'moves':
-                    move_idx = 8
-            elif self.args[0] == 'startpos':
-                self.state = INIT_STATE
-                self.is_red_turn = True
-                self.history = [self.state]
-                self.turns = 0
-                if len(self.args) > 1 and self.args[1] == 'moves':
-                    move_idx = 2
-            elif self.args[0] == 'moves':
-                move_idx = 1
-        else:
-            self.state = INIT_STATE
-            self.is_red_turn = True
-            self.history = [self.state]
-            self.turns = 0
-        if move_idx != -1:
-            for i in range(move_idx, len(self.args)):
-                action = parse_ucci_move(self.args[i])
-                if not self.is_red_turn:
-                    action = flip_move(action)
-                self.history.append(action)
-                self.state = self.env.step(self.state, action)
-                self.is_red_turn = not self.is_red_turn
-                self.turns += 1
-                self.history.append(self.state)
-
-    def cmd_fen(self):
-        self.args.insert(0, 'fen')
-        self.cmd_position()
-
-    # ---- uci.py:177-227
-    def cmd_go(self):
-        if not self.is_ready:
-            return
-        self.start_time = time()
-        self.t = None
-        depth = None
-        infinite = True
-        self.remain_time = None
-        pipes = None
-        if self.use_pipes:
-            if self.pipes_factory is not None:
-                pipes = self.pipes_factory()
-            else:
-                self.model.close_pipes()
-                pipes = self.model.get_pipes(need_reload=False)
-        self.player = CChessPlayer(self.config, search_tree=None, pipes=pipes, enable_resign=False, debugging=True, uci=True,
-                                   use_history=self.use_history, side=self.turns % 2, lib=self.lib, device=self.device,
-                                   weights=None if pipes is not None else self.model.torch_weights(),
-                                   infinite_capacity=self.infinite_capacity)
-        self.player.info_stream = self.stdout
-        for i in range(len(self.args)):
-            if self.args[i] == 'depth':
-                depth = int(self.args[i + 1]) * 100
-                infinite = False
-            if self.args[i] == 'movetime' or self.args[i] == 'time':
-                self.remain_time = int(self.args[i + 1]) / 1000
-            if self.args[i] == 'infinite':
-                infinite = True
-            if self.args[i] == 'wtime' and self.is_red_turn:
-                self.remain_time = int(self.args[i + 1]) / 1000
-                depth = 3000
-                infinite = False
-            if self.args[i] == 'btime' and not self.is_red_turn:
-                self.remain_time = int(self.args[i + 1]) / 1000
-                depth = 3000
-                infinite = False
-        self.search_worker = Thread(target=self.search_action, args=(self.player, depth, infinite), daemon=True)
-        self.search_worker.start()
-        if self.remain_time:
-            self.t = Timer(max(self.remain_time - 0.01, 0.0), self.cmd_stop)
-            self.t.start()
-
-    # ---- uci.py:229-243
-    def cmd_stop(self):
-        if not self.is_ready:
-            return
-        player, self.player = self.player, None
-        if player is None:
-            return
-        no_act = None
-        if self.state in self.history[:-1]:
-            no_act = []
-            for i in range(len(self.history) - 1):
-                if self.history[i] == self.state:
-                    no_act.append(self.history[i + 1])
-        got = player.close_and_return_action(self.state, self.turns, no_act)
-        if got is not None:
-            self.info_best_move(player, *got)
-        self._release(player)
 
     def cmd_quit(self):
         if self.t:
             self.t.cancel()
         return "quit"
 
-    # ---- uci.py:245-263
     def load_model(self):
+        """uci.py:245-263: the best model, or a fresh one; returns whether it reads 28 planes."""
         if self.model is None:
             from .model import CChessModel
             self.model = CChessModel(self.config)
@@ -222,26 +170,86 @@ class UCI:
                 self.model.build()
         return bool(self.model.use_history)
 
-    # ---- uci.py:265-291
-    def search_action(self, player, depth, infinite):
-        no_act = None
-        res = self.env.done(self.state, need_check=True)
-        check = res[3] if len(res) > 3 else False
-        if not check and self.state in self.history[:-1]:
-            no_act = []
-            for i in range(len(self.history) - 1):
-                if self.history[i] == self.state:
-                    if self.env.will_check_or_catch(self.state, self.history[i + 1]):
-                        no_act.append(self.history[i + 1])
-        action, _ = player.action(self.state, self.turns, no_act=no_act, depth=depth, infinite=infinite, hist=self.history)
-        if self.player is not player:          # `stop` answered meanwhile (close_and_return_action)
+    # ---- position
+    def cmd_position(self):
+        if not self.is_ready:
+            return
+        a = self.args
+        moves_at = None
+        if not a or a[0] == 'startpos':
+            self.pos.reset()
+            if len(a) > 1 and a[1] == 'moves':
+                moves_at = 2
+        elif a[0] == 'fen':
+            try:
+                self.pos.set_fen(a[1], a[2], a[6])
+            except Exception:
+                return
+            if len(a) > 7 and a[7] == 'moves':
+                moves_at = 8
+        elif a[0] == 'moves':
+            moves_at = 1
+        for mv in (a[moves_at:] if moves_at is not None else []):
+            self.pos.push(mv)
+
+    def cmd_fen(self):
+        self.args = ['fen'] + self.args
+        self.cmd_position()
+
+    # ---- search
+    def cmd_go(self):
+        if not self.is_ready:
+            return
+        self.start_time = time()
+        limits = GoLimits.parse(self.args, self.pos.red_to_move)
+        pipes = None
+        if self.use_pipes:
+            if self.pipes_factory is not None:
+                pipes = self.pipes_factory()
+            else:
+                self.model.close_pipes()
+                pipes = self.model.get_pipes(need_reload=False)
+        # a new player (and tree) per `go`, like uci.py:205-209
+        self.player = CChessPlayer(self.config, search_tree=None, pipes=pipes, enable_resign=False, debugging=True, uci=True,
+                                   use_history=self.use_history, side=self.pos.turns % 2, lib=self.lib, device=self.device,
+                                   weights=None if pipes is not None else self.model.torch_weights(),
+                                   infinite_capacity=self.infinite_capacity)
+        self.player.info_stream = self.stdout
+        self.search_worker = Thread(target=self._think, args=(self.player, limits), daemon=True)
+        self.search_worker.start()
+        self.t = None
+        if limits.seconds:
+            self.t = Timer(max(limits.seconds - 0.01, 0.0), self.cmd_stop)
+            self.t.start()
+
+    def _think(self, player, limits):
+        """uci.py:265-291: ban the replies that would repeat the position with a check or a chase, search, report."""
+        pos = self.pos
+        res = self.env.done(pos.state, need_check=True)
+        in_check = res[3] if len(res) > 3 else False
+        replies = None if in_check else pos.repeated_replies()
+        no_act = None if replies is None else [m for m in replies if self.env.will_check_or_catch(pos.state, m)]
+        action, _ = player.action(pos.state, pos.turns, no_act=no_act, depth=limits.depth, infinite=limits.infinite,
+                                  hist=pos.history)
+        if self.player is not player:          # `stop` answered meanwhile
             return
         self.player = None
         if self.t:
             self.t.cancel()
         if action is not None:
-            _, value = player.debug[self.state]
-            self.info_best_move(player, action, value, player.done_tasks // 100)
+            self._report(player, action, player.debug[pos.state][1], player.done_tasks // 100)
+        self._release(player)
+
+    def cmd_stop(self):
+        """uci.py:229-243: every earlier reply from this position is banned, the tree answers as it stands."""
+        if not self.is_ready:
+            return
+        player, self.player = self.player, None
+        if player is None:
+            return
+        got = player.close_and_return_action(self.pos.state, self.pos.turns, self.pos.repeated_replies())
+        if got is not None:
+            self._report(player, *got)
         self._release(player)
 
     def _release(self, player):
@@ -249,30 +257,20 @@ class UCI:
         if self.use_pipes and self.pipes_factory is None:
             self.model.close_pipes()
 
-    # ---- uci.py:293-327
-    def info_best_move(self, player, action, value, depth):
-        end_time = time()
-        if not self.is_red_turn:
-            value = -value
-        score = int(value * 1000)
-        duration = max(end_time - self.start_time, 1e-9)
-        nps = int(depth * 100 / duration) * 1000
-        self._print(f"info depth {depth} score {score} time {int(duration * 1000)} nps {nps}")
-        # the most visited reply, if the position after `action` is in the tree (first maximum, uci.py:305-311)
-        ponder = None
-        child = player.engine_child_stats(self.env.step(self.state, action))
-        cnt = 0
-        for mov, n in child:
-            if n > cnt:
-                ponder, cnt = mov, n
-        if not self.is_red_turn:
-            action = flip_move(action)
-        output = f"bestmove {to_uci_move(action)}"
+    def _report(self, player, action, value, depth):
+        """uci.py:293-327: summary line, best move in board coordinates, the most visited reply as ponder move."""
+        red = self.pos.red_to_move
+        elapsed = max(time() - self.start_time, 1e-9)
+        score = int((value if red else -value) * 1000)
+        self._print(f"info depth {depth} score {score} time {int(elapsed * 1000)} nps {int(depth * 100 / elapsed) * 1000}")
+        ponder, best_n = None, 0
+        for mov, n in player.engine_child_stats(self.env.step(self.pos.state, action)):
+            if n > best_n:                      # first maximum (uci.py:305-311)
+                ponder, best_n = mov, n
+        out = "bestmove " + to_uci_move(action if red else flip_move(action))
         if ponder:
-            if self.is_red_turn:
-                ponder = flip_move(ponder)
-            output += f" ponder {to_uci_move(ponder)}"
-        self._print(output)
+            out += " ponder " + to_uci_move(flip_move(ponder) if red else ponder)
+        self._print(out)
 
 
 def main(config):
