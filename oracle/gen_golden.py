@@ -61,6 +61,9 @@ if __name__ == "__main__":
     elif what == "mcts":
         from oracle.gen_golden_mcts import gen_mcts
         gen_mcts()
+    elif what == "endgames":
+        from oracle.gen_golden_mcts import gen_mcts_endgames
+        gen_mcts_endgames()
     elif what == "uci":
         from oracle.gen_golden_mcts import gen_uci_info
         gen_uci_info()

@@ -213,3 +213,27 @@ def gen_uci_info():
     with gzip.open(os.path.join(GOLD, "uci_info_k1.json.gz"), "wt") as f:
         json.dump(out, f)
     print("uci cases:", [(c["name"], c["action"], c["info"]) for c in cases])
+
+
+def gen_mcts_endgames():
+    """K=1 searches of the real player on sparse endgames, where simulations run into terminal positions and IN-PATH
+    repetitions (player.py:223-234: will_check_or_catch / be_catched verdicts) all the time -> mcts_k1_endgames.json.gz."""
+    r = ref_import.senv()
+    endings = ['3s5/9/9/9/4r4/9/9/4R4/9/4S4', '4s4/4m4/9/9/9/9/2R6/9/4M4/3S1r3', '2e1s4/4m4/4e4/9/9/9/9/4C4/4M4/3S5',
+               '3s5/4m4/9/9/9/p8/9/4C4/4M4/4S4', '3s5/9/9/9/9/9/2k6/9/4R4/4S4', '5s3/9/9/2p6/9/9/6P2/9/9/3S5']
+    endings = [s for s in endings if not r.done(s)[0]]
+    assert len(endings) >= 5
+    cases = []
+    for i, s in enumerate(endings):
+        for sims in (200, 500):
+            res = real_player_moves([(s, 60 + i, None, False)], sims, 100 + i)
+            a, e, sn = res[0]
+            cases.append({"name": f"endgame{i}_{sims}", "seed": 100 + i, "sims": sims,
+                          "calls": [{"state": s, "turns": 60 + i, "no_act": None, "increase_temp": False, "action": a, "sum_n": sn,
+                                     "legal": r.get_legal_moves(s), "edges": {m: list(v) for m, v in e.items()}}]})
+    out = {"generator": "oracle/gen_golden_mcts.py:gen_mcts_endgames", "reference": "NeymarL/ChineseChess-AlphaZero @7f45b0c agent/player.py",
+           "config": {"search_threads": 1, "c_puct": 1.5, "noise_eps": 0.25, "dirichlet_alpha": 0.2, "tau_decay_rate": 0.98,
+                      "virtual_loss": 3}, "cases": cases}
+    with gzip.open(os.path.join(GOLD, "mcts_k1_endgames.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("endgame cases:", [(c["name"], c["calls"][0]["action"], c["calls"][0]["sum_n"]) for c in cases])

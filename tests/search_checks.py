@@ -57,11 +57,11 @@ def eval_planes(planes):
     return np.stack([o[0] for o in out]), np.array([o[1] for o in out], dtype=np.float32)
 
 
-def check_golden_k1(lib, device, use_history=False):
+def check_golden_k1(lib, device, use_history=False, name=None):
     """The drop-in CChessPlayer must reproduce the REAL reference player (search_threads=1): chosen move,
     N, W, P of every root edge, for every call of every golden case (tests/golden/mcts_k1.json.gz; with use_history the
     28-plane cases of mcts_k1_hist.json.gz, with and without the `hist` argument of action())."""
-    gold = load_mcts_golden("mcts_k1_hist.json.gz" if use_history else "mcts_k1.json.gz")
+    gold = load_mcts_golden(name or ("mcts_k1_hist.json.gz" if use_history else "mcts_k1.json.gz"))
     for case in gold["cases"]:
         srv = FakeNetServer()
         np.random.seed(case["seed"])
