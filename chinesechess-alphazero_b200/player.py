@@ -167,7 +167,8 @@ class CChessPlayer:
     # ---- root Dirichlet noise with the reference's np.random consumption (player.py:304)
     def _noise_begin(self, state, num_task):
         self._noise_table, self._rng_state, self._noise_rows, self._n_moves = None, None, 0, 0
-        if self.exact_noise and self.play_config.noise_eps != 0 and num_task > 0:
+        # the reference draws one Dirichlet sample per legal move per root selection even when noise_eps == 0 (:304)
+        if self.exact_noise and num_task > 0:
             self._n_moves = max(len(self.env.get_legal_moves(state)), 1)
             self._rng_state = np.random.get_state()
             self._noise_table = np.zeros((1, 0))

@@ -12,8 +12,9 @@ from .player import OraclePlayer
 
 def play_arena_game(pc, evaluate0, evaluate1, idx, draws_for, m_games, max_game_length=100, env=senv, max_plies_guard=1000):
     """idx = running game index; player idx % 2 is red (evaluator.py:163-170).  Returns dict(moves, value_red, turns, flags)."""
-    players = [OraclePlayer(pc, evaluate0, env=env, noise=(lambda n: 0.0) if pc.noise_eps == 0 else None),
-               OraclePlayer(pc, evaluate1, env=env, noise=(lambda n: 0.0) if pc.noise_eps == 0 else None)]
+    # the reference draws its Dirichlet sample even when eps == 0 (player.py:304): keep that when replaying its RNG
+    quiet = (lambda n: 0.0) if (pc.noise_eps == 0 and not hasattr(draws_for(0), "choose_with_player")) else None
+    players = [OraclePlayer(pc, evaluate0, env=env, noise=quiet), OraclePlayer(pc, evaluate1, env=env, noise=quiet)]
     i = idx % m_games
     state = env.INIT_STATE
     history = [state]
@@ -40,7 +41,11 @@ def play_arena_game(pc, evaluate0, evaluate1, idx, draws_for, m_games, max_game_
         player = players[p]
         player.search(state, no_act, increase_temp)
         node = player.tree[state]
-        action = draws_for(i + p * m_games).choose(node, no_act, turns, increase_temp, pc)
+        draws = draws_for(i + p * m_games)
+        if hasattr(draws, "choose_with_player"):            # the reference's own np.random.choice (oracle/ref_worker_harness.py)
+            action = draws.choose_with_player(player, state, turns, no_act, increase_temp)
+        else:
+            action = draws.choose(node, no_act, turns, increase_temp, pc)
         history.append(action)
         state, no_eat = env.new_step(state, action)
         turns += 1

@@ -61,6 +61,12 @@ if __name__ == "__main__":
     elif what == "mcts":
         from oracle.gen_golden_mcts import gen_mcts
         gen_mcts()
+    elif what == "games":
+        from oracle.gen_golden_games import gen_games
+        gen_games()
+    elif what == "eps0":
+        from oracle.gen_golden_mcts import gen_mcts_eps0
+        gen_mcts_eps0()
     elif what == "endgames":
         from oracle.gen_golden_mcts import gen_mcts_endgames
         gen_mcts_endgames()

@@ -237,3 +237,36 @@ def gen_mcts_endgames():
     with gzip.open(os.path.join(GOLD, "mcts_k1_endgames.json.gz"), "wt") as f:
         json.dump(out, f)
     print("endgame cases:", [(c["name"], c["calls"][0]["action"], c["calls"][0]["sum_n"]) for c in cases])
+
+
+def gen_mcts_eps0():
+    """noise_eps = 0: the reference still calls np.random.dirichlet once per legal move per root selection (player.py:304),
+    so the position of the np.random stream after the search - and with it the sampled move - depends on it
+    -> mcts_k1_eps0.json.gz (three plies of one game, moves sampled with tau > 0)."""
+    import numpy as np
+    from .ref_player_harness import FakeNetServer, make_config
+    r = ref_import.senv()
+    pm = ref_import.player_module()
+    seed, sims = 31, 90
+    cfg = make_config(sims, 1, noise_eps=0.0)
+    srv = FakeNetServer()
+    np.random.seed(seed)
+    player = pm.CChessPlayer(cfg, pipes=srv.you, enable_resign=False)
+    s, t, seq = r.INIT_STATE, 0, []
+    for ply in range(4):
+        a, _ = player.action(s, t)
+        node = player.tree[s]
+        seq.append({"state": s, "turns": t, "no_act": None, "increase_temp": False, "action": a, "sum_n": int(node.sum_n),
+                    "legal": r.get_legal_moves(s),
+                    "edges": {m: [int(x.n), float(x.w), float(x.q), float(x.p)] for m, x in node.a.items()}})
+        s = r.step(s, a)
+        t += 1
+    tail = float(np.random.rand())
+    player.close(wait=False)
+    srv.close()
+    out = {"generator": "oracle/gen_golden_mcts.py:gen_mcts_eps0", "reference": "NeymarL/ChineseChess-AlphaZero @7f45b0c agent/player.py",
+           "config": {"search_threads": 1, "c_puct": 1.5, "noise_eps": 0.0, "dirichlet_alpha": 0.2, "tau_decay_rate": 0.98, "virtual_loss": 3},
+           "cases": [{"name": "eps0_four_plies", "seed": seed, "sims": sims, "calls": seq, "rand_after": tail}]}
+    with gzip.open(os.path.join(GOLD, "mcts_k1_eps0.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("eps0:", [c["action"] for c in seq], tail)

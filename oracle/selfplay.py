@@ -18,7 +18,8 @@ def play_game(pc, evaluate, draws, max_game_length=100, enable_resign_rate=0.5, 
     """Returns dict(moves, value_red, turns, flags, store).  `draws` supplies resign_lottery(), choose(...), store_lottery()."""
     enable_resign = draws.resign_lottery() > enable_resign_rate
     player = OraclePlayer(pc, evaluate, env=env, enable_resign=enable_resign,
-                          noise=(lambda n: 0.0) if pc.noise_eps == 0 else None, use_history=use_history)
+                          noise=(lambda n: 0.0) if (pc.noise_eps == 0 and not hasattr(draws, "choose_with_player")) else None,
+                          use_history=use_history)     # the reference draws its Dirichlet sample even when eps == 0 (:304)
     # the game loop never hands its history to action() (self_play.py:124): history planes come from the search path only
     state = env.INIT_STATE
     history = [state]
@@ -34,7 +35,10 @@ def play_game(pc, evaluate, draws, max_game_length=100, enable_resign_rate=0.5, 
             flags |= 1
             break
         node = player.tree[state]
-        action = draws.choose(node, no_act, turns, increase_temp, pc)
+        if hasattr(draws, "choose_with_player"):            # the reference's own np.random.choice (oracle/ref_worker_harness.py)
+            action = draws.choose_with_player(player, state, turns, no_act, increase_temp)
+        else:
+            action = draws.choose(node, no_act, turns, increase_temp, pc)
         history.append(action)
         state, no_eat = env.new_step(state, action)
         turns += 1

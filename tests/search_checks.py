@@ -62,10 +62,12 @@ def check_golden_k1(lib, device, use_history=False, name=None):
     N, W, P of every root edge, for every call of every golden case (tests/golden/mcts_k1.json.gz; with use_history the
     28-plane cases of mcts_k1_hist.json.gz, with and without the `hist` argument of action())."""
     gold = load_mcts_golden(name or ("mcts_k1_hist.json.gz" if use_history else "mcts_k1.json.gz"))
+    eps = gold["config"].get("noise_eps", 0.25)
     for case in gold["cases"]:
         srv = FakeNetServer()
         np.random.seed(case["seed"])
-        player = CChessPlayer(make_config(case["sims"], 1), pipes=srv.you, lib=lib, device=device, use_history=use_history)
+        player = CChessPlayer(make_config(case["sims"], 1, noise_eps=eps), pipes=srv.you, lib=lib, device=device,
+                              use_history=use_history)
         try:
             for call in case["calls"]:
                 action, policy = player.action(call["state"], call["turns"], call["no_act"], increase_temp=call["increase_temp"],
@@ -79,6 +81,8 @@ def check_golden_k1(lib, device, use_history=False, name=None):
                 assert action == call["action"], (case["name"], action, call["action"])
                 assert abs(sum(policy) - 1.0) < 1e-9
             # answering from the finished tree (close_and_return_action, player.py:88-106) is a legal move of the last state
+            if "rand_after" in case:                     # the np.random stream stands where the reference left it
+                assert float(np.random.rand()) == case["rand_after"]
             last = case["calls"][-1]
             got = player.close_and_return_action(last["state"], last["turns"], last["no_act"])
             assert got is not None and got[0] in last["legal"]

@@ -93,3 +93,29 @@ def test_canonical_schedule_is_statistically_the_threaded_player_k10():
     cross = np.mean([tv(R[i], O[j]) for i in seeds for j in seeds])
     assert cross <= 1.5 * spread_real + 0.02, (cross, spread_real)
     assert tv(sum(R), sum(O)) < 0.05
+
+
+def test_game_loop_restatements_replay_live_reference_games():
+    """The unmodified SelfPlayWorker.start_game / EvaluateWorker.start_game (Keras/TensorFlow imports satisfied by empty
+    stand-ins, oracle/ref_worker_harness.py) against oracle/selfplay.py and oracle/arena.py, fresh seeds."""
+    import random
+    from oracle import arena as oarena
+    from oracle import ref_worker_harness as h
+    from oracle import selfplay as osp
+    play = dict(max_game_length=20, tau_decay_rate=0.98, noise_eps=0.25, enable_resign_rate=0.1, resign_threshold=-0.5, min_resign_turn=4)
+    pc = op.PlayConfig(simulation_num_per_move=16, search_threads=1, c_puct=1.5, noise_eps=0.25, dirichlet_alpha=0.2,
+                       tau_decay_rate=0.98, virtual_loss=3, resign_threshold=-0.5, min_resign_turn=4)
+    for seed in (41, 42):
+        g = h.real_selfplay_game(seed, 16, **play)
+        random.seed(seed)
+        np.random.seed(seed)
+        r = osp.play_game(pc, op.fake_evaluate_states, h.ReferenceDraws(), max_game_length=20, enable_resign_rate=0.1)
+        assert (r["turns"], r["value_red"], r["store"], r["final_state"]) == (g["turns"], g["value_red"], g["store"], g["final_state"])
+        assert g["moves"] is None or g["moves"] == r["moves"]
+    for seed, idx in ((43, 0), (44, 1)):
+        g = h.real_arena_game(seed, idx, 16, **play)
+        random.seed(seed)
+        np.random.seed(seed)
+        d = h.ReferenceDraws()
+        r = oarena.play_arena_game(pc, op.fake_evaluate_states, op.fake_evaluate_states, idx, lambda slot: d, 1, max_game_length=20)
+        assert (r["turns"], r["value_red"]) == (g["turns"], g["value_red"]) and r["moves"][:len(g["moves"])] == g["moves"]

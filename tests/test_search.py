@@ -4,7 +4,7 @@ import pytest
 from tests import search_checks as sc
 
 
-@pytest.mark.parametrize("name", ["mcts_k1.json.gz", "mcts_k1_endgames.json.gz"])
+@pytest.mark.parametrize("name", ["mcts_k1.json.gz", "mcts_k1_endgames.json.gz", "mcts_k1_eps0.json.gz"])
 def test_oracle_player_matches_golden_k1(name):
     """oracle/player.py against the fixtures recorded from the REAL reference CChessPlayer (mid-game searches; sparse
     endgames full of terminal positions and in-path repetitions, player.py:204-208,223-234)."""
@@ -13,7 +13,8 @@ def test_oracle_player_matches_golden_k1(name):
     gold = sc.load_mcts_golden(name)
     loops = 0
     for case in gold["cases"]:
-        pc = op.PlayConfig(simulation_num_per_move=case["sims"], search_threads=1, c_puct=1.5, noise_eps=0.25,
+        pc = op.PlayConfig(simulation_num_per_move=case["sims"], search_threads=1, c_puct=1.5,
+                           noise_eps=gold["config"]["noise_eps"],
                            dirichlet_alpha=0.2, tau_decay_rate=0.98, virtual_loss=3, resign_threshold=-0.92, min_resign_turn=20)
         np.random.seed(case["seed"])
         pl = op.OraclePlayer(pc, op.fake_evaluate_states)
@@ -23,6 +24,8 @@ def test_oracle_player_matches_golden_k1(name):
             got = {m: [int(e.n), float(e.w), float(e.q), float(e.p)] for m, e in node.a.items()}
             assert got == call["edges"], case["name"]
             assert a == call["action"] and node.sum_n == call["sum_n"]
+        if "rand_after" in case:
+            assert float(np.random.rand()) == case["rand_after"]
         loops += pl.stats["no_network"]
     if "endgames" in name:
         assert loops > 500          # the cases do run into terminal / repeated positions all the time
@@ -53,6 +56,7 @@ def test_oracle_player_matches_golden_k1_history():
 def test_emul_golden_k1(emul_lib):
     sc.check_golden_k1(emul_lib, "cpu")
     sc.check_golden_k1(emul_lib, "cpu", name="mcts_k1_endgames.json.gz")
+    sc.check_golden_k1(emul_lib, "cpu", name="mcts_k1_eps0.json.gz")
 
 
 def test_emul_history(emul_lib):
@@ -91,6 +95,7 @@ def test_cuda_multi_move_reuse_and_options(cuda_lib):
 def test_cuda_golden_k1(cuda_lib):
     sc.check_golden_k1(cuda_lib, "cuda")
     sc.check_golden_k1(cuda_lib, "cuda", name="mcts_k1_endgames.json.gz")
+    sc.check_golden_k1(cuda_lib, "cuda", name="mcts_k1_eps0.json.gz")
 
 
 @pytest.mark.gpu
