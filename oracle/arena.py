@@ -5,6 +5,9 @@ repetition rule has no be_catched exemption and raises the temperature on any re
 (:157-160).  `draws_for(slot)` supplies the move sampler of the engine slot that plays the ply, so the device arena
 (csrc/cz_selfplay.cuh, E.arena) can be compared move for move.  Score bookkeeping of EvaluateWorker.start (:93-145) is
 `score_for_next_generation`.
+
+Pinned: replays whole games of the REAL, unmodified EvaluateWorker.start_game move for move when the random decisions come
+from the reference's own generators (tests/golden/games_k1.json.gz, tests/test_games_golden.py).
 """
 from . import senv
 from .player import OraclePlayer

@@ -4,6 +4,10 @@ Restates worker/self_play.py:95-212 (SelfPlayWorker.start_game) for ONE game aro
 random decisions of the reference (resign lottery :102-105, move sampling player.py:195, store lottery :194-200)
 injectable, so the device loop (csrc/cz_selfplay.cuh), which draws them from Philox streams, can be compared move
 for move.  `DeviceDraws` re-implements those Philox draws and the device's sampling arithmetic in Python.
+
+Pinned: with the random decisions taken from the reference's own generators (ref_worker_harness.ReferenceDraws) this
+loop replays whole games of the REAL, unmodified SelfPlayWorker.start_game move for move (tests/golden/games_k1.json.gz,
+tests/test_games_golden.py; live in tests/test_oracle_vs_reference.py).
 """
 import math
 
