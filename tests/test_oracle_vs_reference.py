@@ -119,3 +119,44 @@ def test_game_loop_restatements_replay_live_reference_games():
         d = h.ReferenceDraws()
         r = oarena.play_arena_game(pc, op.fake_evaluate_states, op.fake_evaluate_states, idx, lambda slot: d, 1, max_game_length=20)
         assert (r["turns"], r["value_red"]) == (g["turns"], g["value_red"]) and r["moves"][:len(g["moves"])] == g["moves"]
+
+
+def test_drop_in_player_searches_through_the_real_model_api(emul_lib):
+    """The reference's own CChessModelAPI (agent/api.py:16-74, unmodified; a stand-in object plays the Keras model) serves
+    the drop-in CChessPlayer over its Pipe: the wire protocol of player.py:118-140 <-> api.py:48-74 is what the product
+    speaks.  Result == the oracle search with the same evaluator."""
+    from contextlib import nullcontext
+    from types import SimpleNamespace
+    from oracle import ref_worker_harness as h
+    from cczero_b200.player import CChessPlayer
+    from tests import search_checks as sc
+    h.worker_modules()                                   # installs the Keras / TensorFlow import stand-ins
+    from cchess_alphazero.agent.api import CChessModelAPI
+
+    class FakeKeras:
+        def predict_on_batch(self, data):
+            out = [op.fake_eval_from_planes(p) for p in data]
+            return np.stack([o[0] for o in out]), np.array([[o[1]] for o in out], dtype=np.float32)
+    agent_model = SimpleNamespace(model=FakeKeras(), graph=SimpleNamespace(as_default=lambda: nullcontext()))
+    cfg = ref_import.config("mini")
+    cfg.internet.distributed = False
+    api = CChessModelAPI(cfg, agent_model)
+    api.start(need_reload=False)
+    pipe = api.get_pipe(need_reload=False)
+    sims, k, seed = 120, 4, 9
+    np.random.seed(seed)
+    player = CChessPlayer(sc.make_config(sims, k), pipes=pipe, lib=emul_lib, device="cpu")
+    state = sc.midgame_states(1, 21)[0]
+    action, policy = player.action(state, 33)
+    root = player.engine.root(0)
+    np.random.seed(seed)
+    pl = op.OraclePlayer(op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.25, dirichlet_alpha=0.2,
+                                       tau_decay_rate=0.98, virtual_loss=3), op.fake_evaluate_states)
+    a2, pol2 = pl.action(state, 33)
+    node = pl.tree[state]
+    assert action == a2 and list(policy) == list(pol2)
+    assert root["n"] == [node.a[m].n if m in node.a else 0 for m in root["moves"]]
+    api.done = True                                      # stop the reference's server thread before its pipe goes away
+    import time
+    time.sleep(0.05)
+    player.close()
