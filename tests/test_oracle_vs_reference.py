@@ -160,3 +160,23 @@ def test_drop_in_player_searches_through_the_real_model_api(emul_lib):
     import time
     time.sleep(0.05)
     player.close()
+
+
+def test_expanding_data_matches_the_real_trainer_side(emul_env):
+    """records.expanding_data vs the reference's worker/optimize.py:234-281 (unmodified; Keras imports stubbed) on one
+    golden game record, 14 and 28 planes."""
+    import gzip
+    import json
+    import os
+    from oracle import ref_worker_harness as h
+    from cczero_b200.records import expanding_data, record_to_play_data
+    h.worker_modules()
+    import cchess_alphazero.worker.optimize as ropt
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with gzip.open(os.path.join(root, "tests", "golden", "games_k1.json.gz"), "rt") as f:
+        game = next(g for g in json.load(f)["games"] if g["kind"] == "selfplay" and g["result"]["moves"] and g["result"]["value_red"] != 0)
+    data = record_to_play_data({"moves": game["result"]["moves"], "value_red": game["result"]["value_red"]})
+    for use_history in (False, True):
+        rs, rp, rv = ropt.expanding_data(data, use_history)
+        s, p, v = expanding_data(data, emul_env, use_history=use_history)
+        assert s.shape == rs.shape and (s == rs).all() and (p == rp).all() and (v == rv).all()
