@@ -37,7 +37,8 @@ def _glorot(rng, shape, fan_in, fan_out):
     return rng.uniform(-lim, lim, size=shape).astype(np.float32)
 
 
-def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False, spread=1.0, in_planes=14):
+def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False, spread=1.0, in_planes=14, policy_filters=4,
+                 value_filters=2):
     """Keras-equivalent initialisation (glorot-uniform kernels, zero biases, BN gamma=1 beta=0 mean=0 var=1).
     trained_like=True perturbs the BN statistics and biases so that folding bugs cannot hide; `spread` scales the
     perturbation (1.0: gamma in [0.5,1.5], variance in [0.5,2] - a deep random net in that regime amplifies any
@@ -70,12 +71,14 @@ def init_weights(filters, blocks, value_fc=256, seed=0, trained_like=False, spre
         for j in (1, 2):
             conv(f"res{i}_conv{j}-3-{filters}", 3, filters, filters)
             bn(f"res{i}_batchnorm{j}", filters)
-    conv("policy_conv-1-2", 1, filters, 4)
-    bn("policy_batchnorm", 4)
-    dense("policy_out", 360, N_LABELS)
-    conv("value_conv-1-4", 1, filters, 2)
-    bn("value_batchnorm", 2)
-    dense("value_dense", 180, value_fc)
+    # agent/model.py:47-61 builds 4 policy and 2 value channels; the older JSON configs under data/model/ (128f, 256f,
+    # 128_l1) still carry the head widths of earlier versions (policy 2 or 32, value 4) under the same layer names
+    conv("policy_conv-1-2", 1, filters, policy_filters)
+    bn("policy_batchnorm", policy_filters)
+    dense("policy_out", 90 * policy_filters, N_LABELS)
+    conv("value_conv-1-4", 1, filters, value_filters)
+    bn("value_batchnorm", value_filters)
+    dense("value_dense", 90 * value_filters, value_fc)
     dense("value_out", value_fc, 1)
     return w
 

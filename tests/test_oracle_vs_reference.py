@@ -180,3 +180,29 @@ def test_expanding_data_matches_the_real_trainer_side(emul_env):
         rs, rp, rv = ropt.expanding_data(data, use_history)
         s, p, v = expanding_data(data, emul_env, use_history=use_history)
         assert s.shape == rs.shape and (s == rs).all() and (p == rp).all() and (v == rv).all()
+
+
+def test_network_restatement_matches_the_shipped_keras_graph():
+    """oracle/model.py (restated from agent/model.py) vs the layer graph Keras itself wrote for the shipped networks
+    (data/model/model_best_config.json + model_best_weight.h5; model_128_l1_config.json = the 28-plane variant), executed
+    by oracle/keras_graph.py."""
+    import os
+    from cczero_b200.keras_h5 import read_keras_weights
+    from oracle import keras_graph, model as om
+    from tests.search_checks import game_history, midgame_states
+    mdir = os.path.join(ref_import.REF_ROOT, "data", "model")
+    w = read_keras_weights(os.path.join(mdir, "model_best_weight.h5"))
+    states = [o.INIT_STATE] + midgame_states(11, 4, lo=2, hi=110)
+    planes = np.stack([o.state_to_planes(s) for s in states])
+    gp, gv = keras_graph.run(os.path.join(mdir, "model_best_config.json"), w, planes)
+    rp, rv = om.forward(w, planes, 10)
+    assert gp.shape == (12, 2086) and np.abs(gp - rp).max() < 2e-6 and np.abs(gv[:, 0] - rv).max() < 2e-6
+    assert gp.max() > 0.2                                        # a trained, peaked policy - not a degenerate comparison
+    # the 28-plane variant (Input (28,10,9), 7 blocks x 128): random weights under the names of that config
+    # (that legacy file keeps the head widths of an earlier model version: 32 policy / 4 value channels)
+    w28 = om.init_weights(128, 7, 256, seed=2, trained_like=True, spread=0.5, in_planes=28, policy_filters=32, value_filters=4)
+    hists = [game_history(n, 30 + n) for n in (2, 5, 17, 40)]
+    p28 = np.stack([o.state_history_to_planes(h[-1], h) for h in hists])
+    gp, gv = keras_graph.run(os.path.join(mdir, "model_128_l1_config.json"), w28, p28)
+    rp, rv = om.forward(w28, p28, 7)
+    assert np.abs(gp - rp).max() < 2e-6 and np.abs(gv[:, 0] - rv).max() < 2e-6
