@@ -139,7 +139,9 @@ class UCI:
         self.is_ready = True
 
     def cmd_ucinewgame(self):
-        self.pos.reset()
+        turns = self.pos.turns                   # the reference leaves its move counter alone here (uci.py:90-95);
+        self.pos.reset()                         # the `position` command that follows sets it
+        self.pos.turns = turns
         self.is_ready = True
 
     def cmd_setoption(self):

@@ -61,6 +61,9 @@ if __name__ == "__main__":
     elif what == "mcts":
         from oracle.gen_golden_mcts import gen_mcts
         gen_mcts()
+    elif what == "uci_session":
+        from oracle.gen_golden_uci import gen_uci_session
+        gen_uci_session()
     elif what == "games":
         from oracle.gen_golden_games import gen_games
         gen_games()

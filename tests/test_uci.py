@@ -200,6 +200,46 @@ def check_uci_session(lib, device):
         srv.close()
 
 
+def check_uci_session_against_real_front_end(lib, device):
+    """tests/golden/uci_session_k1.json.gz: a session with the REAL reference uci.UCI (search_threads = 1, fake network).
+    cczero_b200/uci.py must print the same lines (clock fields stripped) and hold the same position after every command."""
+    import re
+    from types import SimpleNamespace
+    from cczero_b200.uci import UCI
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "uci_session_k1.json.gz"), "rt") as f:
+        gold = json.load(f)
+    p = gold["play"]
+    cfg = sc.make_config(p["simulation_num_per_move"], p["search_threads"], **{k: v for k, v in p.items()
+                                                                                if k not in ("simulation_num_per_move", "search_threads")})
+    servers = []
+
+    def pipes_factory():
+        servers.append(sc.FakeNetServer())
+        return servers[-1].you
+    out = _Lines()
+    u = UCI(cfg, model=SimpleNamespace(use_history=False), lib=lib, device=device, stdout=out, pipes_factory=pipes_factory,
+            infinite_capacity=4000)
+    for step in gold["steps"]:
+        n0 = len(out.lines)
+        parts = step["cmd"].split(' ')
+        u.args = parts[1:]
+        if step["seed"] is not None:
+            np.random.seed(step["seed"])
+        getattr(u, 'cmd_' + parts[0])()
+        if parts[0] == "go":
+            out.wait_for("bestmove", n0)
+            u.search_worker.join(30)
+        got = [re.sub(r" nps -?\d+", "", re.sub(r" time \d+", "", ln)) for ln in out.lines[n0:]]
+        assert got == step["out"], (step["cmd"], got, step["out"])
+        assert (u.state, u.turns, u.is_red_turn) == (step["state"], step["turns"], step["is_red_turn"]), step["cmd"]
+    for srv in servers:
+        srv.close()
+
+
+def test_emul_uci_session_equals_real_front_end(emul_lib):
+    check_uci_session_against_real_front_end(emul_lib, "cpu")
+
+
 def test_emul_uci_session(emul_lib):
     check_uci_session(emul_lib, "cpu")
 
@@ -217,3 +257,4 @@ def test_cuda_player_uci(cuda_lib):
     check_player_uci(cuda_lib, "cuda")
     check_infinite_and_stop(cuda_lib, "cuda")
     check_uci_session(cuda_lib, "cuda")
+    check_uci_session_against_real_front_end(cuda_lib, "cuda")
