@@ -20,6 +20,20 @@ def score_for_next_generation(value_red, idx):
     return 1 - score if idx % 2 == 0 else score
 
 
+def tally_games(results):
+    """EvaluateWorker.start's bookkeeping (evaluator.py:93-145) over (game index, red's result) pairs:
+    (total_score, red_new_win, red_new_draw, red_new_fail, black_new_win, black_new_draw, black_new_fail)."""
+    tally = {"red": [0, 0, 0], "black": [0, 0, 0]}           # next generation as red / black: win, draw, fail
+    total = 0
+    for idx, v in results:
+        ng_is_red = idx % 2 == 1
+        ng_result = v if ng_is_red else -v                   # +1 win, 0 draw, -1 fail for the next generation
+        tally["red" if ng_is_red else "black"][{1: 0, 0: 1, -1: 2}[ng_result]] += 1
+        total += score_for_next_generation(v, idx)
+    r, b = tally["red"], tally["black"]
+    return (total, r[0], r[1], r[2], b[0], b[1], b[2])
+
+
 class EvaluateWorker:
     def __init__(self, config, model_bt, model_ng, n_games=None, concurrent_games=None, lib=None, device=None, seed=0):
         self.config = config
@@ -40,21 +54,13 @@ class EvaluateWorker:
     def start(self):
         """Returns (total_score, red_new_win, red_new_draw, red_new_fail, black_new_win, black_new_draw, black_new_fail)
         like EvaluateWorker.start (evaluator.py:93-145), over the first `n_games` finished games."""
-        tally = {"red": [0, 0, 0], "black": [0, 0, 0]}       # next generation as red / black: win, draw, fail
-        total, done = 0.0, 0
-        while done < self.n_games:
+        results = []
+        while len(results) < self.n_games:
             self.engine.selfplay(target_games=1, max_moves=0)
             for rec in self.engine.drain_records():
-                if done >= self.n_games:
-                    break
-                idx, v = rec["game_index"], rec["value_red"]
-                ng_is_red = idx % 2 == 1
-                ng_result = v if ng_is_red else -v               # +1 win, 0 draw, -1 fail for the next generation
-                tally["red" if ng_is_red else "black"][{1: 0, 0: 1, -1: 2}[ng_result]] += 1
-                total += score_for_next_generation(v, idx)
-                done += 1
-        r, b = tally["red"], tally["black"]
-        return (total, r[0], r[1], r[2], b[0], b[1], b[2])
+                if len(results) < self.n_games:
+                    results.append((rec["game_index"], rec["value_red"]))
+        return tally_games(results)
 
     def close(self):
         self.engine.close()

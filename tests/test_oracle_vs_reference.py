@@ -206,3 +206,23 @@ def test_network_restatement_matches_the_shipped_keras_graph():
     gp, gv = keras_graph.run(os.path.join(mdir, "model_128_l1_config.json"), w28, p28)
     rp, rv = om.forward(w28, p28, 7)
     assert np.abs(gp - rp).max() < 2e-6 and np.abs(gv[:, 0] - rv).max() < 2e-6
+
+
+def test_evaluator_tally_matches_the_real_worker():
+    """EvaluateWorker.start's win / draw / fail bookkeeping and score (evaluator.py:93-145, unmodified) over canned game
+    results vs cczero_b200.evaluator.tally_games."""
+    from oracle import ref_worker_harness as h
+    from cczero_b200.evaluator import tally_games
+    _, ev = h.worker_modules()
+    cfg = ref_import.config("mini")
+    results = [1, -1, 0, 1, 1, -1, 0, 0, -1, 1, 1, -1]
+    cfg.eval.game_num = len(results)
+    w = ev.EvaluateWorker(cfg, pid=0)
+    w.start_game = lambda idx: (results[idx], 40)
+    sleep = ev.sleep
+    ev.sleep = lambda s: None
+    try:
+        want = w.start()
+    finally:
+        ev.sleep = sleep
+    assert tuple(want) == tuple(tally_games(list(enumerate(results))))
