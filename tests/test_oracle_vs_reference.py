@@ -121,6 +121,7 @@ def test_game_loop_restatements_replay_live_reference_games():
         assert (r["turns"], r["value_red"]) == (g["turns"], g["value_red"]) and r["moves"][:len(g["moves"])] == g["moves"]
 
 
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")          # api.py:68 float(array) under numpy 2
 def test_drop_in_player_searches_through_the_real_model_api(emul_lib):
     """The reference's own CChessModelAPI (agent/api.py:16-74, unmodified; a stand-in object plays the Keras model) serves
     the drop-in CChessPlayer over its Pipe: the wire protocol of player.py:118-140 <-> api.py:48-74 is what the product
