@@ -52,6 +52,13 @@ def gen_games():
         play = dict(BASE, **over)
         g = real_selfplay_game(seed, sims, **play)
         games.append({"kind": "selfplay", "seed": seed, "sims": sims, "play": play, "result": g, "deterministic": _deterministic(play, g)})
+    # use_history = True: 28-plane leaves (the game loop passes no `hist`, self_play.py:124)
+    for seed, sims, over in ((21, 20, dict(max_game_length=40)),
+                             (22, 22, dict(max_game_length=100, tau_decay_rate=0.0, noise_eps=0.0, enable_resign_rate=0.0))):
+        play = dict(BASE, **over)
+        g = real_selfplay_game(seed, sims, use_history=True, **play)
+        games.append({"kind": "selfplay", "seed": seed, "sims": sims, "play": play, "result": g, "use_history": True,
+                      "deterministic": _deterministic(play, g)})
     for seed, idx, sims, over in ARENA:
         play = dict(BASE, **over)
         g = real_arena_game(seed, idx, sims, **play)

@@ -103,13 +103,13 @@ def _config(sims, **play):
     return cfg
 
 
-def real_selfplay_game(seed, sims, **play):
+def real_selfplay_game(seed, sims, use_history=False, **play):
     """One SelfPlayWorker.start_game.  Returns dict(moves, value_red, turns, store, final_state, increase_temp_used)."""
     sp, _ = worker_modules()
     pm = ref_import.player_module()
     cfg = _config(sims, **play)
     srv = FakeNetServer()
-    worker = sp.SelfPlayWorker(cfg, pipes=[srv.you], pid=0)
+    worker = sp.SelfPlayWorker(cfg, pipes=[srv.you], pid=0, use_history=use_history)
     saved, temps = [], []
     worker.save_play_data = lambda idx, data: saved.append(data)
     worker.remove_play_data = lambda: None

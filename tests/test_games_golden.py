@@ -59,8 +59,10 @@ def test_restated_game_loops_replay_the_real_games():
         want = g["result"]
         d = _HostDraws()
         if g["kind"] == "selfplay":
-            r = osp.play_game(_pc(g), op.fake_evaluate_states, d, max_game_length=g["play"]["max_game_length"],
-                              enable_resign_rate=g["play"]["enable_resign_rate"])
+            hist = bool(g.get("use_history"))
+            r = osp.play_game(_pc(g), op.fake_evaluate_states_hist if hist else op.fake_evaluate_states, d,
+                              max_game_length=g["play"]["max_game_length"], enable_resign_rate=g["play"]["enable_resign_rate"],
+                              use_history=hist)
             assert (r["turns"], r["value_red"], r["store"], r["final_state"]) == \
                    (want["turns"], want["value_red"], want["store"], want["final_state"]), (g["seed"], g["sims"])
             if want["moves"] is not None:
@@ -82,7 +84,8 @@ def check_device_loop_replays_real_games(lib, device):
         eng = Engine(lib, device, n_games=2 if arena else 1, sims_per_move=g["sims"], leaves_per_round=1, noise_mode=1,
                      noise_eps=0.0, c_puct=p["c_puct"], tau_decay_rate=0.0, max_game_length=p["max_game_length"],
                      resign_threshold=p["resign_threshold"], enable_resign_rate=0.0, min_resign_turn=p["min_resign_turn"], seed=1,
-                     max_nodes_per_game=g["sims"] * 2 * p["max_game_length"] + 64, arena=arena)
+                     max_nodes_per_game=g["sims"] * 2 * p["max_game_length"] + 64, arena=arena,
+                     use_history=bool(g.get("use_history")))
         eng.reset()
         recs = []
         for _ in range(want_records * (2 * p["max_game_length"] + 4)):
@@ -96,7 +99,7 @@ def check_device_loop_replays_real_games(lib, device):
         return recs
     det = [g for g in _games() if g["deterministic"]]
     sp = [g for g in det if g["kind"] == "selfplay"]
-    assert len(sp) >= 3
+    assert len(sp) >= 3 and any(g.get("use_history") for g in sp)
     for g in sp:
         rec = play(g, False, 1)[0]
         want = g["result"]
