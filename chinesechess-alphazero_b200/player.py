@@ -29,6 +29,27 @@ from .env import StaticEnv, flip_move, to_uci_move
 from .lib import get_lib
 
 
+class EdgeView:
+    """ActionState as callers read it (player.py:28-33)."""
+    __slots__ = ("n", "w", "q", "p")
+
+    def __init__(self, n, w, p):
+        self.n, self.w, self.p = n, w, p
+        self.q = w / n if n else 0
+
+
+class NodeView:
+    """VisitState as callers read it (player.py:17-25): `a` maps move -> EdgeView in legal-move order."""
+
+    def __init__(self, root):
+        self.sum_n = root["sum_n"]
+        self.legal_moves = list(root["moves"])
+        self.a = {m: EdgeView(n, w, p) for m, n, w, p in zip(root["moves"], root["n"], root["w"], root["p"])} if root["sum_n"] > 1 else {}
+        self.p = None
+        self.waiting = False
+        self.visit = []
+
+
 class CChessPlayer:
     def __init__(self, config, search_tree=None, pipes=None, play_config=None, enable_resign=False, debugging=False,
                  uci=False, use_history=False, side=0, lib=None, device=None, weights=None, exact_noise=True,
@@ -49,7 +70,10 @@ class CChessPlayer:
         self.increase_temp = False
         self.no_act = None
         self.root_state = None
-        self.tree = {}                 # the tree lives in device memory; kept for attribute compatibility
+        # The tree lives in device memory.  `search_tree` is the caller's dict (uci.py:205-209 reads the node of the position
+        # after the best move out of it for its ponder move): in UCI mode the root and its children are mirrored into it
+        # after every action() (`_mirror_tree`); other callers only hand it back to the next player, which cz_set_root covers.
+        self.tree = search_tree if search_tree is not None else {}
         self.debug = {}
         self.search_results = {}
         self.done_tasks = 0
@@ -155,6 +179,8 @@ class CChessPlayer:
             self._noise_end(root["noise_used"])
             if self.debugging or self.uci:
                 self._remember_root_value(state, root)
+            if self.uci:
+                self._mirror_tree(state, root)
             policy, resign = self.calc_policy(root, turns, no_act)
             if resign:
                 return None, list(policy)
@@ -237,6 +263,8 @@ class CChessPlayer:
             root = self.engine.root(0)
             if (self.debugging or self.uci) and state not in self.debug and root["sum_n"] > 0:
                 self._remember_root_value(state, root)
+            if self.uci and root["sum_n"] > 0:
+                self._mirror_tree(state, root)
             policy, resign = self.calc_policy(root, turns, no_act)
             if resign:
                 return None
@@ -246,6 +274,19 @@ class CChessPlayer:
             my_action = int(np.random.choice(range(self.labels_n), p=self.apply_temperature(policy, turns)))
             value = self.debug.get(state, (None, 0))[1]
             return self.labels[my_action], value, self.done_tasks // 100
+
+    def _mirror_tree(self, state, root):
+        """tree[state] and tree[child] for every expanded child of the root, as NodeView objects (call with _busy held)."""
+        self.tree[state] = NodeView(root)
+        for mov, n in zip(root["moves"], root["n"]):
+            if n <= 0:
+                continue
+            child = self.env.step(state, mov)
+            self.engine.set_root(0, child)
+            r = self.engine.root(0)
+            if r["sum_n"] > 0:
+                self.tree[child] = NodeView(r)
+        self.engine.set_root(0, state)
 
     def engine_child_stats(self, state):
         """[(move, N)] of `state`'s node, [] if it is not in the tree or was never selected through (what iterating

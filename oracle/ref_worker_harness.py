@@ -103,8 +103,10 @@ def _config(sims, **play):
     return cfg
 
 
-def real_selfplay_game(seed, sims, use_history=False, **play):
-    """One SelfPlayWorker.start_game.  Returns dict(moves, value_red, turns, store, final_state, increase_temp_used)."""
+def real_selfplay_game(seed, sims, use_history=False, player_factory=None, **play):
+    """One SelfPlayWorker.start_game.  Returns dict(moves, value_red, turns, store, final_state, increase_temp_used).
+    player_factory: class / callable put in place of the module's `CChessPlayer` name (the import swap of
+    INTEGRATION.md §3) - the reference's own loop then drives that player."""
     sp, _ = worker_modules()
     pm = ref_import.player_module()
     cfg = _config(sims, **play)
@@ -119,19 +121,23 @@ def real_selfplay_game(seed, sims, use_history=False, **play):
         temps.append(bool(increase_temp))
         return orig_action(self, state, turns, no_act, depth, infinite, hist, increase_temp)
     pm.CChessPlayer.action = spy
+    sp_player = sp.CChessPlayer
+    if player_factory is not None:
+        sp.CChessPlayer = player_factory
     random.seed(seed)
     np.random.seed(seed)
     try:
         v, turns, state, store = worker.start_game(1, defaultdict(pm.VisitState))
     finally:
         pm.CChessPlayer.action = orig_action
+        sp.CChessPlayer = sp_player
         srv.close()
     moves = [m for m, _ in saved[0][1:]] if saved else None
     return {"moves": moves, "value_red": v, "turns": turns, "store": bool(store), "final_state": state,
             "increase_temp_used": any(temps)}
 
 
-def real_arena_game(seed, idx, sims, **play):
+def real_arena_game(seed, idx, sims, player_factory=None, **play):
     """One EvaluateWorker.start_game (two players, separate trees; both served by the fake network)."""
     _, ev = worker_modules()
     pm = ref_import.player_module()
@@ -150,12 +156,31 @@ def real_arena_game(seed, idx, sims, **play):
         moves.append(a)
         return a, p
     pm.CChessPlayer.action = spy
+    ev_player = ev.CChessPlayer
+    if player_factory is not None:
+        cfg.play.simulation_num_per_move = sims          # (the real player reads it per call; a swapped-in one at creation)
+
+        class Recording:                                 # same bookkeeping as the spy, around the swapped-in player
+            def __init__(self, *a, **k):
+                cfg.play.simulation_num_per_move = sims
+                self.p = player_factory(*a, **k)
+
+            def action(self, state, turns, no_act=None, increase_temp=False):
+                temps.append(bool(increase_temp))
+                a, pol = self.p.action(state, turns, no_act=no_act, increase_temp=increase_temp)
+                moves.append(a)
+                return a, pol
+
+            def close(self, wait=True):
+                self.p.close()
+        ev.CChessPlayer = Recording
     random.seed(seed)
     np.random.seed(seed)
     try:
         value, turns = worker.start_game(idx)
     finally:
         pm.CChessPlayer.action = orig_action
+        ev.CChessPlayer = ev_player
         ev.randint = ev_randint
         s1.close()
         s2.close()

@@ -227,3 +227,94 @@ def test_evaluator_tally_matches_the_real_worker():
     finally:
         ev.sleep = sleep
     assert tuple(want) == tuple(tally_games(list(enumerate(results))))
+
+
+def test_reference_game_loops_drive_the_drop_in_player(emul_lib):
+    """INTEGRATION.md §3, literally: the name `CChessPlayer` inside the reference's worker modules is rebound to
+    cczero_b200.player.CChessPlayer and the UNMODIFIED SelfPlayWorker.start_game / EvaluateWorker.start_game play whole
+    games with it.  Since the drop-in consumes np.random exactly like the reference player, every golden game - sampled
+    moves, resignations, repetition bans included - must come out identical."""
+    import gzip
+    import json
+    import os
+    from functools import partial
+    from oracle import ref_worker_harness as h
+    from cczero_b200.player import CChessPlayer
+    factory = partial(CChessPlayer, lib=emul_lib, device="cpu")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with gzip.open(os.path.join(root, "tests", "golden", "games_k1.json.gz"), "rt") as f:
+        games = json.load(f)["games"]
+    done = 0
+    for g in games:
+        want = g["result"]
+        if want["turns"] > 60:                           # keep the CPU tier short: the long games are covered elsewhere
+            continue
+        if g["kind"] == "selfplay":
+            r = h.real_selfplay_game(g["seed"], g["sims"], use_history=bool(g.get("use_history")), player_factory=factory, **g["play"])
+            assert (r["moves"], r["value_red"], r["turns"], r["store"], r["final_state"]) == \
+                   (want["moves"], want["value_red"], want["turns"], want["store"], want["final_state"]), (g["seed"], g["sims"])
+        else:
+            r = h.real_arena_game(g["seed"], g["idx"], g["sims"], player_factory=factory, **g["play"])
+            assert (r["moves"], r["value_red"], r["turns"]) == (want["moves"], want["value_red"], want["turns"])
+        done += 1
+    assert done >= 8
+
+
+def test_reference_uci_front_end_drives_the_drop_in_player(emul_lib):
+    """The REAL uci.UCI class with `CChessPlayer` rebound to the drop-in: the golden session (recorded with the real
+    player) must come out line for line."""
+    import contextlib
+    import gzip
+    import io
+    import json
+    import os
+    import sys
+    import time
+    from functools import partial
+    from oracle import gen_golden_uci as gu
+    from oracle import ref_worker_harness as h
+    from oracle.ref_player_harness import FakeNetServer
+    from cczero_b200.player import CChessPlayer
+    h.worker_modules()
+    err = sys.stderr
+    import cchess_alphazero.uci as ruci
+    sys.stderr = err
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with gzip.open(os.path.join(root, "tests", "golden", "uci_session_k1.json.gz"), "rt") as f:
+        gold = json.load(f)
+    cfg = ruci.config
+    for k, v in gold["play"].items():
+        setattr(cfg.play, k, v)
+    servers = []
+
+    class FakeModel:
+        def get_pipes(self, need_reload=True):
+            servers.append(FakeNetServer())
+            return servers[-1].you
+
+        def close_pipes(self):
+            pass
+    u = ruci.UCI(cfg)
+    u.load_model = lambda config_file=None: (setattr(u, "model", FakeModel()) or False)
+    real_player, real_ssc = ruci.CChessPlayer, ruci.set_session_config
+    ruci.set_session_config = lambda **k: None
+    ruci.CChessPlayer = partial(CChessPlayer, lib=emul_lib, device="cpu", infinite_capacity=4000)
+    try:
+        for step in gold["steps"]:
+            buf = io.StringIO()
+            parts = step["cmd"].split(" ")
+            u.args = parts[1:]
+            if step["seed"] is not None:
+                np.random.seed(step["seed"])
+            with contextlib.redirect_stdout(buf):
+                getattr(u, "cmd_" + parts[0])()
+                if parts[0] == "go":
+                    t0 = time.time()
+                    while "bestmove" not in buf.getvalue() and time.time() - t0 < 120:
+                        time.sleep(0.02)
+                    time.sleep(0.1)
+            assert [gu.strip_clock(x) for x in buf.getvalue().splitlines()] == step["out"], step["cmd"]
+    finally:
+        ruci.CChessPlayer, ruci.set_session_config = real_player, real_ssc
+        for s in servers:
+            s.close()
