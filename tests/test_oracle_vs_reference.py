@@ -318,3 +318,24 @@ def test_reference_uci_front_end_drives_the_drop_in_player(emul_lib):
         ruci.CChessPlayer, ruci.set_session_config = real_player, real_ssc
         for s in servers:
             s.close()
+
+
+def test_reference_player_runs_on_the_drop_in_rules_engine(emul_env):
+    """The other import swap of INTEGRATION.md §3: `senv` inside the reference's agent/player.py rebound to
+    cczero_b200.env.StaticEnv - the REAL player must search exactly as it does on its own static_env."""
+    from oracle.ref_player_harness import real_player_moves
+    from tests.search_checks import load_mcts_golden
+    pm = ref_import.player_module()
+    gold = {c["name"]: c for c in load_mcts_golden()["cases"]}
+    hist = {c["name"]: c for c in load_mcts_golden("mcts_k1_hist.json.gz")["cases"]}
+    own = pm.senv
+    pm.senv = emul_env
+    try:
+        for case, use_history in ((gold["init_60"], False), (gold["mid2_no_act"], False), (hist["hist_mid30_150"], True)):
+            calls = [(c["state"], c["turns"], c["no_act"], c["increase_temp"], c.get("hist")) for c in case["calls"]]
+            res = real_player_moves(calls, case["sims"], case["seed"], use_history=use_history)
+            for (a, edges, sum_n), c in zip(res, case["calls"]):
+                assert a == c["action"] and sum_n == c["sum_n"]
+                assert {m: list(v) for m, v in edges.items()} == c["edges"]
+    finally:
+        pm.senv = own
