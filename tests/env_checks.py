@@ -122,7 +122,66 @@ EXTREME_STATES = [
     '4s4/9/9/9/4R4/9/9/9/9/4S4',                                 # rook between the kings
     '5s3/9/9/9/9/9/9/9/5r3/3S5',
     'PPPPPPPPP/PPPPsPPPP/PPPPPPPPP/9/9/9/9/9/4S4/9',             # far more pawns than a real game can have
+    'PPPPPPPPP/PPPPsPPPP/PPPPPPPPP/PPPPPPPPP/PPPP1PPPP/9/9/9/4S4/9',    # 44 own pieces: more than one warp of pieces
+    'ppppppppp/pppp1pppp/ppppppppp/ppppppppp/pppp1pppp/R8/9/9/4S4/4s4',  # ... and of opposing ones
 ]
+
+
+def random_boards(n, seed):
+    """Arbitrary (mostly unreachable) positions: both kings somewhere in their palaces, a random subset of the other 30
+    pieces on random squares."""
+    rng = np.random.RandomState(seed)
+    own = "RRKKEEMMCCPPPPP"
+    out = []
+    for _ in range(n):
+        sq = [None] * 90
+        ks = [(y, x) for y in range(3) for x in range(3, 6)]
+        y, x = ks[rng.randint(9)]
+        sq[y * 9 + x] = 'S'
+        y, x = ks[rng.randint(9)]
+        sq[(9 - y) * 9 + x] = 's'
+        for side in (own, own.lower()):
+            for c in side:
+                if rng.rand() < 0.6:
+                    k = rng.randint(90)
+                    if sq[k] is None:
+                        sq[k] = c
+        rows = []
+        for y in range(9, -1, -1):
+            row, gap = "", 0
+            for x in range(9):
+                c = sq[y * 9 + x]
+                if c is None:
+                    gap += 1
+                else:
+                    row += (str(gap) if gap else "") + c
+                    gap = 0
+            rows.append(row + (str(gap) if gap else ""))
+        out.append("/".join(rows))
+    return out
+
+
+def check_random_boards(env, n=400, seed=12):
+    states = random_boards(n, seed)
+    boards = env.boards_from_states(states)
+    mv, cnt = env.movegen_batch(boards)
+    mv, cnt = mv.cpu().numpy().view(np.uint16), cnt.cpu().numpy()
+    out, fm = env.done_batch(boards, need_check=True)
+    out, fm = out.cpu().numpy(), fm.cpu().numpy().view(np.uint16)
+    planes = env.planes_batch(boards).cpu().numpy()
+    for i, s in enumerate(states):
+        ref_moves = osenv.get_legal_moves(s)
+        assert [u16_to_move(v) for v in mv[i, :cnt[i]]] == ref_moves, s
+        d = osenv.done(s, need_check=True)
+        assert (bool(out[i, 0]), int(out[i, 1])) == (d[0], d[1]) and (None if fm[i] == 0xFFFF else u16_to_move(fm[i])) == d[2], s
+        if len(d) == 4:
+            assert bool(out[i, 2]) == d[3], s
+        assert (planes[i] == osenv.state_to_planes(s)).all(), s
+        if i % 8 == 0 and ref_moves and not d[0]:
+            m = ref_moves[(i // 8) % len(ref_moves)]
+            assert env.new_step(s, m) == osenv.new_step(s, m), (s, m)
+            assert env.will_check_or_catch(s, m) == osenv.will_check_or_catch(s, m), (s, m)
+            assert env.be_catched(s, m) == osenv.be_catched(s, m), (s, m)
 
 
 def check_extreme_positions(env):
@@ -153,7 +212,9 @@ def check_extreme_positions(env):
     assert cnt.max() >= 60                                        # the mobility case really is large
     # ragged / large batch: 20 000 boards in one call equal the same boards one by one
     import torch
-    big = boards.repeat(1667, 1)[:20000]
+    k = len(states)
+    reps = 20000 // k + 1
+    big = boards.repeat(reps, 1)[:20000]
     mv2, cnt2 = env.movegen_batch(big)
-    assert torch.equal(cnt2.cpu(), torch.as_tensor(cnt).repeat(1667)[:20000])
-    assert torch.equal(mv2[12:24].cpu().view(torch.int16), torch.as_tensor(mv.view(np.int16)))
+    assert torch.equal(cnt2.cpu(), torch.as_tensor(cnt).repeat(reps)[:20000])
+    assert torch.equal(mv2[k:2 * k].cpu().view(torch.int16), torch.as_tensor(mv.view(np.int16)))

@@ -34,9 +34,14 @@ def test_emul_env_extreme_positions(emul_env):
     env_checks.check_extreme_positions(emul_env)
 
 
+def test_emul_env_random_boards(emul_env):
+    env_checks.check_random_boards(emul_env)
+
+
 @pytest.mark.gpu
 def test_cuda_env_extreme_positions(cuda_env):
     env_checks.check_extreme_positions(cuda_env)
+    env_checks.check_random_boards(cuda_env, n=2000, seed=13)
 
 
 @pytest.mark.gpu

@@ -339,3 +339,19 @@ def test_reference_player_runs_on_the_drop_in_rules_engine(emul_env):
                 assert {m: list(v) for m, v in edges.items()} == c["edges"]
     finally:
         pm.senv = own
+
+
+def test_env_restatement_on_arbitrary_boards():
+    """Unreachable positions (random pieces on random squares, piece counts no game can have): oracle == real static_env."""
+    from tests.env_checks import EXTREME_STATES, random_boards
+    r = ref_import.senv()
+    for s in random_boards(600, 5) + [x for x in EXTREME_STATES if 's' in x and 'S' in x]:
+        lm = r.get_legal_moves(s)
+        assert o.get_legal_moves(s) == lm, s
+        assert o.done(s) == r.done(s) and o.done(s, need_check=True) == r.done(s, need_check=True), s
+        assert (o.state_to_planes(s) == r.state_to_planes(s)).all() and o.has_attack_chessman(s) == r.has_attack_chessman(s)
+        if lm and not r.done(s)[0]:
+            m = lm[len(s) % len(lm)]
+            assert o.new_step(s, m) == r.new_step(s, m), (s, m)
+            assert o.will_check_or_catch(s, m) == r.will_check_or_catch(s, m), (s, m)
+            assert o.be_catched(s, m) == r.be_catched(s, m), (s, m)
