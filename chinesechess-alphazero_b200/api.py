@@ -70,37 +70,36 @@ class CChessModelAPI:
                 self.last_error = e
                 logger.error(f"prediction worker: {e!r}")
 
+    def _collect(self):
+        """Every request waiting on any pipe, as (connection, list of planes), in arrival order per pipe."""
+        requests = []
+        for conn in connection.wait(self.pipes, timeout=0.001):
+            try:
+                while conn.poll():
+                    requests.append((conn, conn.recv()))
+            except EOFError:                             # the player went away
+                conn.close()
+                if conn in self.pipes:
+                    self.pipes.remove(conn)
+        return requests
+
     def _serve_once(self):
-        if self._last_check + 600 < time() and self.need_reload:
+        now = time()
+        if self.need_reload and now - self._last_check > 600:      # api.py:42-44
             self.try_reload_model()
-            self._last_check = time()
-        ready = connection.wait(self.pipes, timeout=0.001)
-        if not ready:
+            self._last_check = now
+        requests = self._collect()
+        if not requests:
             return
-        data, result_pipes, data_len = [], [], []
-        for pipe in ready:
-            while pipe.poll():
-                try:
-                    tmp = pipe.recv()
-                except EOFError:
-                    pipe.close()
-                    if pipe in self.pipes:
-                        self.pipes.remove(pipe)
-                    break
-                data.extend(tmp)
-                data_len.append(len(tmp))
-                result_pipes.append(pipe)
-        if not data:
-            return
-        planes = torch.from_numpy(np.asarray(data, dtype=np.float32)).to(self.engine.device)
-        pol, val = self.engine.nn_forward_planes(planes)
-        policy_ary, value_ary = pol.cpu().numpy(), val.cpu().numpy()
-        self.positions += len(data)
+        batch = np.asarray([p for _, planes in requests for p in planes], dtype=np.float32)
+        pol, val = self.engine.nn_forward_planes(torch.from_numpy(batch).to(self.engine.device))     # ONE forward for all of them
+        policy, value = pol.cpu().numpy(), val.cpu().numpy()
+        self.positions += len(batch)
         self.batches += 1
-        k = 0
-        for pipe, n in zip(result_pipes, data_len):
-            pipe.send([(policy_ary[k + i], float(value_ary[k + i])) for i in range(n)])
-            k += n
+        offset = 0
+        for conn, planes in requests:                    # one reply per request, same order (api.py:65-74)
+            conn.send([(policy[offset + i], float(value[offset + i])) for i in range(len(planes))])
+            offset += len(planes)
 
     def try_reload_model(self, config_file=None):
         rc = getattr(self.config, "resource", None)
