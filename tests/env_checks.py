@@ -127,11 +127,11 @@ EXTREME_STATES = [
 ]
 
 
-def random_boards(n, seed):
+def random_boards(n, seed, own="RRKKEEMMCCPPPPP"):
     """Arbitrary (mostly unreachable) positions: both kings somewhere in their palaces, a random subset of the other 30
-    pieces on random squares."""
+    pieces on random squares.  (Advisors / elephants on squares they can never reach make moves outside the 2086 action
+    labels: fine for the rules, a KeyError for the reference's search - pass own="RRKKCCPPPPP" for search tests.)"""
     rng = np.random.RandomState(seed)
-    own = "RRKKEEMMCCPPPPP"
     out = []
     for _ in range(n):
         sq = [None] * 90

@@ -180,6 +180,43 @@ def check_history_vs_oracle(lib, device, cases=((90, 1, 1), (160, 8, 2), (200, 1
         eng.close()
 
 
+def check_search_fuzz(lib, device, n_cases=10, seed=2024):
+    """Seeded random configurations (simulations, K, c_puct, noise_eps, virtual loss) on random positions - reachable
+    mid-games, sparse endgames and arbitrary boards with up to ~80 legal moves (three 32-lane chunks in select): engine ==
+    oracle bit for bit."""
+    from tests.env_checks import random_boards
+    rng = np.random.RandomState(seed)
+    pool = midgame_states(6, seed % 1000, lo=5, hi=150) + [s for s in random_boards(60, seed, own="RRKKCCPPPPP") if not osenv.done(s)[0]][:8] + \
+        ['3s5/9/9/9/9/9/9/9/9/4S4', '5s3/9/9/9/9/9/9/9/5r3/3S5'] + \
+        ['R2msm2R/4m4/9/C7C/9/9/C7C/9/9/R3S3R', 'R2msm2R/4m4/9/C7C/9/4R4/C7C/9/9/R3S3R',        # 67 and 82 legal moves
+         'R2msm2R/4m4/9/C7C/1R5R1/9/C7C/9/9/R3S3R']                                                # 97
+    assert max(len(osenv.get_legal_moves(s)) for s in pool) > 96
+    for case in range(n_cases):
+        sims, k = int(rng.choice([17, 40, 75, 130])), int(rng.choice([1, 2, 3, 8, 16, 40]))
+        c_puct, eps, vl = float(rng.choice([0.5, 1.5, 5.0])), float(rng.choice([0.0, 0.25, 1.0])), int(rng.choice([1, 3]))
+        states = [pool[i] for i in rng.choice(len(pool), size=2, replace=False)] + [pool[-1 - case % 3]]
+        tables = []
+        for s in states:
+            L = len(osenv.get_legal_moves(s))
+            np.random.seed(case)
+            tables.append([np.random.dirichlet(0.2 * np.ones(L))[0] for _ in range((sims + 2 * k + 2) * L)])
+        noise = np.zeros((len(states), max(len(t) for t in tables)))
+        for i, t in enumerate(tables):
+            noise[i, :len(t)] = t
+        eng = Engine(lib, device, n_games=len(states), sims_per_move=sims, leaves_per_round=k, virtual_loss=vl, noise_mode=0,
+                     c_puct=c_puct, noise_eps=eps, dirichlet_alpha=0.2, tau_decay_rate=0.98)
+        eng.reset(states)
+        eng.search_external(eval_planes, eng.make_opts(noise=noise))
+        for g, s in enumerate(states):
+            pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=c_puct, noise_eps=eps, dirichlet_alpha=0.2,
+                               tau_decay_rate=0.98, virtual_loss=vl)
+            np.random.seed(case)
+            pl = op.OraclePlayer(pc, op.fake_evaluate_states)
+            pl.search(s)
+            compare_root(eng, g, pl, s)
+        eng.close()
+
+
 def check_vs_oracle(lib, device, cases):
     """Canonical K-round schedule: engine == oracle restatement bit for bit (N, W, P, sum_n, noise draws)."""
     for (sims, k, seed, n_states) in cases:

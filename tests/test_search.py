@@ -74,6 +74,15 @@ def test_emul_vs_oracle(emul_lib):
     sc.check_vs_oracle(emul_lib, "cpu", [(100, 1, 1, 2), (150, 4, 2, 3), (240, 8, 3, 3), (300, 16, 4, 2), (130, 40, 5, 2)])
 
 
+def test_emul_search_fuzz(emul_lib):
+    sc.check_search_fuzz(emul_lib, "cpu", n_cases=8)
+
+
+@pytest.mark.gpu
+def test_cuda_search_fuzz(cuda_lib):
+    sc.check_search_fuzz(cuda_lib, "cuda", n_cases=24, seed=77)
+
+
 def test_emul_no_act_and_temp(emul_lib):
     sc.check_no_act_and_temp(emul_lib, "cpu")
 
