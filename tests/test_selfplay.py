@@ -51,6 +51,14 @@ def test_emul_selfplay_matches_restated_game_loop(emul_lib):
     assert len(kinds) >= 1
 
 
+def test_emul_selfplay_other_configurations(emul_lib):
+    """More shapes of the device game loop against the restated one: K = 1 and K > simulations, no temperature decay
+    (always arg-max), long temperature schedule, short and longer games."""
+    check_selfplay(emul_lib, "cpu", n_games=2, sims=12, k=1, seed=3, want=3, max_game_length=14, tau_decay=0.0)
+    check_selfplay(emul_lib, "cpu", n_games=2, sims=10, k=16, seed=4, want=2, max_game_length=18, tau_decay=0.99)
+    check_selfplay(emul_lib, "cpu", n_games=1, sims=30, k=8, seed=8, want=2, max_game_length=30, tau_decay=0.5)
+
+
 def test_emul_selfplay_with_history_planes(emul_lib):
     """use_history=True: the device game loop feeds 28-plane leaves (path history only, self_play.py:124)."""
     check_selfplay(emul_lib, "cpu", n_games=2, want=3, seed=5, use_history=True)
@@ -65,6 +73,13 @@ def test_play_data_format():
 @pytest.mark.gpu
 def test_cuda_selfplay_matches_restated_game_loop(cuda_lib):
     check_selfplay(cuda_lib, "cuda", n_games=4, want=8)
+
+
+@pytest.mark.gpu
+def test_cuda_selfplay_other_configurations(cuda_lib):
+    check_selfplay(cuda_lib, "cuda", n_games=8, sims=12, k=1, seed=3, want=8, max_game_length=14, tau_decay=0.0)
+    check_selfplay(cuda_lib, "cuda", n_games=8, sims=10, k=16, seed=4, want=8, max_game_length=18, tau_decay=0.99)
+    check_selfplay(cuda_lib, "cuda", n_games=4, sims=60, k=8, seed=8, want=4, max_game_length=60, tau_decay=0.5)
 
 
 @pytest.mark.gpu
