@@ -59,3 +59,28 @@ def test_prediction_server_batches_and_scatters():
     assert len(recv(pipes[1])) == 1
     api.close()
     assert not api.thread.is_alive() or api.done
+
+
+def test_hot_reload_follows_the_digest(tmp_path):
+    """api.py:76-88: when the best-model file changes (sha256 digest), the server loads it and re-uploads the weights."""
+    from cczero_b200.api import CChessModelAPI
+    from cczero_b200.model import CChessModel
+    res = SimpleNamespace(model_best_config_path=str(tmp_path / "cfg.json"), model_best_weight_path=str(tmp_path / "w.npz"))
+    cfg = SimpleNamespace(model=SimpleNamespace(cnn_filter_num=64, res_layer_num=1, value_fc_size=256, cnn_first_filter_size=5,
+                                                cnn_filter_size=3, input_depth=14), resource=res)
+    model = CChessModel(cfg).build(seed=1)
+    model.save(res.model_best_config_path, res.model_best_weight_path)
+    uploads = []
+    eng = StubEngine()
+    eng.set_weights = lambda w: uploads.append(float(w["value_out/kernel"].sum()))
+    api = CChessModelAPI(cfg, model, lib=SimpleNamespace(is_cuda=False), device="cpu")
+    api.engine = eng
+    api.try_reload_model()
+    assert uploads == []                                        # same digest: nothing to do
+    other = CChessModel(cfg).build(seed=2)
+    other.save(res.model_best_config_path, res.model_best_weight_path)
+    api.try_reload_model()
+    assert len(uploads) == 1 and model.digest == other.digest
+    assert uploads[0] == float(other.weights["value_out/kernel"].sum())
+    api.try_reload_model()
+    assert len(uploads) == 1
