@@ -86,6 +86,19 @@ def fen_to_state(fen):
     return fen.split(' ')[0].translate(_FEN_TO_STATE)
 
 
+_STATE_TO_FEN = str.maketrans("kKeEmMsS", "nNbBaAkK")
+
+
+def state_to_fen(state, turns):
+    """static_env.py:215-243: FEN of the position; on black's turns (odd) the canonical state is turned back to the
+    board's orientation (rows reversed, each row mirrored, colours swapped) and the side-to-move field becomes b."""
+    fen = state.translate(_STATE_TO_FEN)
+    if turns % 2 == 0:
+        return f"{fen} w - - 0 {turns}"
+    rows = ["".join(c.swapcase() for c in reversed(row)) for row in reversed(fen.split('/'))]
+    return "/".join(rows) + f" b - - 0 {turns}"
+
+
 def parse_ucci_move(move):
     return str(ord(move[0]) - ord('a')) + move[1] + str(ord(move[2]) - ord('a')) + move[3]
 

@@ -50,6 +50,15 @@ def test_reference_smoke_vectors():
     assert len(o.get_legal_moves(o.INIT_STATE)) == 44
 
 
+def test_fen_helpers_match_reference():
+    from cczero_b200 import env as penv
+    r = ref_import.senv()
+    s = '4s4/9/4e4/p8/2e2R2p/P5E2/8P/9/9/4S1E2'
+    for st, t in ((o.INIT_STATE, 0), (o.step(o.INIT_STATE, '0001'), 1), (s, 7), (s, 10)):
+        assert o.state_to_fen(st, t) == r.state_to_fen(st, t) == penv.state_to_fen(st, t)
+        assert o.fen_to_state(r.state_to_fen(st, t)) == r.fen_to_state(r.state_to_fen(st, t))
+
+
 def _oracle_root(state, sims, k, seed):
     pc = op.PlayConfig(simulation_num_per_move=sims, search_threads=k, c_puct=1.5, noise_eps=0.25, dirichlet_alpha=0.2,
                        tau_decay_rate=0.98, virtual_loss=3, resign_threshold=-0.92, min_resign_turn=20)
