@@ -86,8 +86,8 @@ class CChessModelAPI:
     def _serve_once(self):
         now = time()
         if self.need_reload and now - self._last_check > 600:      # api.py:42-44
+            self._last_check = now                                 # before the attempt: a failing reload is retried in 600 s, not every loop
             self.try_reload_model()
-            self._last_check = now
         requests = self._collect()
         if not requests:
             return
@@ -107,9 +107,25 @@ class CChessModelAPI:
             return
         path = rc.model_best_weight_path
         digest = self.agent_model.fetch_digest(path)
-        if digest and digest != self.agent_model.digest:
-            if self.agent_model.load(rc.model_best_config_path, path):
-                self.engine.set_weights(self.agent_model.torch_weights())
+        if not digest or digest == self.agent_model.digest:
+            return
+        # Load into a scratch model first: the served model object (weights, digest, geometry) changes only after the
+        # engine accepted the new weights, so a half-written file or a different geometry leaves the old network serving
+        # AND the old digest in place (the next check tries again).
+        import copy
+        cand = type(self.agent_model)(copy.deepcopy(self.config))
+        try:
+            if not cand.load(rc.model_best_config_path, path):
+                return
+            cm, mc = cand.config.model, self.config.model
+            geo = lambda m: (m.cnn_filter_num, m.res_layer_num, m.value_fc_size, getattr(m, "input_depth", 14))
+            if geo(cm) != geo(mc):
+                raise ValueError(f"new weight file has geometry {geo(cm)}, the serving engine was built for {geo(mc)}")
+            self.engine.set_weights(cand.torch_weights())
+        except Exception as e:
+            logger.error(f"reload of {path} failed, keeping the current weights: {e!r}")
+            return
+        self.agent_model.weights, self.agent_model.digest = cand.weights, cand.digest
 
     def close(self):
         self.done = True

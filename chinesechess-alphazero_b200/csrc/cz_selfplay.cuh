@@ -15,6 +15,8 @@ inline void selfplay_carve(SelfplayDev& sp, CarverT& cv, const CfgT& c) {
   sp.hist_stride = (int32_t)S;
   sp.turns = cv.template take<int32_t>(G); sp.no_eat = cv.template take<int32_t>(G);
   sp.enable_resign = cv.template take<int32_t>(G); sp.games_started = cv.template take<int32_t>(G);
+  sp.sims_game = cv.template take<int32_t>(G); sp.retired = cv.template take<int32_t>(G);
+  sp.game_quota = c.game_quota; sp.playouts_lo = c.playouts_lo; sp.playouts_hi = c.playouts_hi;
   sp.hist_k0 = cv.template take<uint64_t>(G * S); sp.hist_k1 = cv.template take<uint64_t>(G * S);
   sp.hist_move = cv.template take<uint16_t>(G * S);
   sp.rec_cap = (int32_t)(2 * G < 64 ? 64 : 2 * G);
@@ -37,6 +39,13 @@ CZ_D void selfplay_start_game(const EngineDev& E, int g, uint8_t* board_smem) {
     Rng r; r.init(E.seed, E.rank, (uint32_t)g, 3u, (uint32_t)idx);
     sp.enable_resign[g] = r.uniform() > sp.enable_resign_rate ? 1 : 0;
     sp.turns[g] = 0; sp.no_eat[g] = 0;
+    // evaluator.py:153-154: `playouts = randint(8, 12) * 100` once per game; both player slots of a game draw the same value
+    int sg = 0;
+    if (E.arena && sp.playouts_lo > 0 && sp.playouts_hi >= sp.playouts_lo) {
+      Rng q; q.init(E.seed, E.rank, (uint32_t)(g % (E.n_games / 2)), 5u, (uint32_t)idx);
+      sg = (sp.playouts_lo + (int)(q.next() % (uint32_t)(sp.playouts_hi - sp.playouts_lo + 1))) * 100;
+    }
+    sp.sims_game[g] = sg;
     sp.hist_k0[(size_t)g * sp.hist_stride] = k0;
     sp.hist_k1[(size_t)g * sp.hist_stride] = k1;
   }
@@ -54,14 +63,22 @@ CZ_D int arena_mover_slot(const EngineDev& E, int g, int started, int turns) {
   return i + player * m;
 }
 
+// running index of the game a slot plays after `started` earlier ones: the i-th of M (arena) / G concurrent games
+CZ_D int game_index_of(const EngineDev& E, int g, int started) {
+  return E.arena ? started * (E.n_games / 2) + g % (E.n_games / 2) : started * E.n_games + g;
+}
+
 CZ_D void selfplay_reset_game(const EngineDev& E, int g) {
-  if (czs::lane() == 0) E.sp.games_started[g] = 0;
+  if (czs::lane() == 0) { E.sp.games_started[g] = 0; E.sp.retired[g] = 0; }
   czs::syncwarp();
   TreeSmem* sm = reinterpret_cast<TreeSmem*>(czs::dyn_smem()) + czs::warp_in_block();
   selfplay_start_game(E, g, sm->board);
   if (E.arena && czs::lane() == 0) {
     E.sp.enable_resign[g] = 0;                      // evaluator.py:157-160: enable_resign=False
     E.active[g] = arena_mover_slot(E, g, 0, 0) == g ? 1 : 0;
+  }
+  if (E.sp.game_quota > 0 && game_index_of(E, g, 0) >= E.sp.game_quota && czs::lane() == 0) {   // more slots than games
+    E.sp.retired[g] = 1; E.active[g] = 0;
   }
   czs::syncwarp();
 }
@@ -263,16 +280,35 @@ CZ_D void game_play(const EngineDev& E, int g, const uint8_t* init_board, TreeSm
 #endif
   }
   slot = czs::shfl(slot, 0);
+  if (slot >= sp.rec_cap && czs::lane() == 0) {      // ring full: counted, never silent (cz_get_counters [3])
+#if defined(CZ_EMUL)
+    E.counters[3] += 1;
+#else
+    atomicAdd(E.counters + 3, 1ULL);
+#endif
+  }
   if (slot < sp.rec_cap) {
     if (czs::lane() == 0) {
       RecordHdr h; h.n_plies = turns; h.value_red = value;
-      h.game_index = E.arena ? sp.games_started[g] * (E.n_games / 2) + g % (E.n_games / 2)
-                             : sp.games_started[g] * E.n_games + g;
+      h.game_index = game_index_of(E, g, sp.games_started[g]);
       h.flags = flags | (store ? 0 : REC_NOT_STORED);
       sp.rec_hdr[slot] = h;
     }
     for (int i = czs::lane(); i < turns; i += 32)
       sp.rec_moves[(size_t)slot * sp.hist_stride + i] = sp.hist_move[(size_t)g * sp.hist_stride + i];
+  }
+  // ---- quota reached: the slot (both player slots of an arena game) retires with an empty tree
+  if (sp.game_quota > 0 && game_index_of(E, g, sp.games_started[g] + 1) >= sp.game_quota) {
+    if (czs::lane() == 0) { sp.retired[g] = 1; E.active[g] = 0; E.n_no_act[g] = 0; E.increase_temp[g] = 0; }
+    czs::syncwarp();
+    clear_tree(E, g);
+    if (E.arena) {
+      const int p = arena_partner(E, g);
+      if (czs::lane() == 0) { sp.retired[p] = 1; E.active[p] = 0; E.n_no_act[p] = 0; E.increase_temp[p] = 0; }
+      czs::syncwarp();
+      clear_tree(E, p);
+    }
+    return;
   }
   // ---- restart the slot from the initial position with an empty tree
   for (int k = czs::lane(); k < BOARD_STRIDE; k += 32) E.root_board[(size_t)g * BOARD_STRIDE + k] = k < NSQ ? init_board[k] : (uint8_t)0;

@@ -27,6 +27,8 @@ struct SelfplayDev {
   int32_t* no_eat;         // [G] consecutive non-capturing plies
   int32_t* enable_resign;  // [G]
   int32_t* games_started;  // [G] games begun in this slot (RNG stream + game index)
+  int32_t* sims_game;      // [G] simulations per move of the game in this slot (evaluator.py:153-154), 0 = EngineDev::sims
+  int32_t* retired;        // [G] 1 = the slot reached cz_config.game_quota and plays no further game
   uint64_t* hist_k0;       // [G][hist_stride] keys of the states s_0..s_turns
   uint64_t* hist_k1;
   uint16_t* hist_move;     // [G][hist_stride] actions a_0..a_{turns-1}
@@ -35,6 +37,7 @@ struct SelfplayDev {
   int32_t* rec_count;      // [1] records in the ring
   int32_t* finished;       // [1] games finished by the last cz_play_move
   int32_t rec_cap, hist_stride;
+  int32_t game_quota, playouts_lo, playouts_hi;
   double enable_resign_rate;
 };
 
@@ -650,9 +653,10 @@ CZ_D void game_begin(const EngineDev& E, int g, int sims_override, bool raw_task
   uint64_t k0, k1;
   board_key(sm->board, &k0, &k1);
   int root = tt_lookup(E, g, k0, k1);
+  const int sims = E.sp.sims_game[g] > 0 ? E.sp.sims_game[g] : E.sims;   // play_config.simulation_num_per_move of this game
   int done = root >= 0 ? E.node_sum_n[(size_t)g * E.ncap + root] : 0;
-  if (E.n_no_act[g] > 0 || E.increase_temp[g] || done == E.sims) done = 0;
-  int num_task = E.sims - done;
+  if (E.n_no_act[g] > 0 || E.increase_temp[g] || done == sims) done = 0;
+  int num_task = sims - done;
   if (sims_override > 0) num_task = sims_override > done ? sims_override - done : 0;
   if (raw_tasks) num_task = sims_override;
   if (num_task < 0) num_task = 0;
@@ -677,7 +681,7 @@ CZ_D void game_begin(const EngineDev& E, int g, int sims_override, bool raw_task
     }
     czs::syncwarp();
     root = -1;
-    num_task = sims_override > 0 ? sims_override : E.sims;
+    num_task = sims_override > 0 ? sims_override : sims;
     if (raw_tasks) num_task = sims_override > 0 ? sims_override : 0;
   }
   if (czs::lane() == 0) {

@@ -212,7 +212,7 @@ CZ_KERNEL(k_set_opts)(EngineDev E, const uint16_t* no_act, const uint8_t* inc, c
     }
     E.n_no_act[g] = n;
     E.increase_temp[g] = inc ? inc[g] : 0;
-    E.active[g] = act ? act[g] : 1;
+    E.active[g] = E.sp.retired[g] ? 0 : (act ? act[g] : 1);
   }
 }
 
@@ -244,7 +244,9 @@ struct cz_engine {
   float* policy_buf; float* value_buf;                      // evaluator outputs for the built-in network
   uint8_t* board_stage;                                     // [G][96] staging for reset / set_root
   int32_t* stat_n; uint16_t* stat_mv; int32_t* stat_cnt;    // staging for cz_get_root_stats
+  int32_t* sims_stage;                                      // [G] staging for cz_set_game_sims
   int last_leaves;
+  int ring_count;                                           // finished-game records in the device ring (as of the last cz_play_move)
   uint64_t launches;
   uint64_t total_sims, total_positions, total_waves;
 #if !defined(CZ_EMUL)
@@ -300,6 +302,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   e->pv_dev = cv.take<cz_pv_info>(1);
   e->stat_out = cv.take<unsigned long long>(8);
   e->board_stage = cv.take<uint8_t>(G * BOARD_STRIDE);
+  e->sims_stage = cv.take<int32_t>(G);
   e->stat_n = cv.take<int32_t>(G * MAX_MOVES); e->stat_mv = cv.take<uint16_t>(G * MAX_MOVES); e->stat_cnt = cv.take<int32_t>(G);
   if (c.nn_filters > 0) {
     e->policy_buf = cv.take<float>(G * K * (size_t)CZ_N_LABELS);
@@ -317,6 +320,11 @@ int check_cfg(const cz_config* c) {
   if (c->max_nodes_per_game < 16 || c->max_edges_per_game < 256 || c->max_path < 8)
     return cz_fail(CZ_ERR_ARG, "cz_config: pools too small");
   if (c->virtual_loss < 0 || c->max_plies < 2) return cz_fail(CZ_ERR_ARG, "cz_config: bad virtual_loss / max_plies");
+  // the per-game history and record rows hold max_plies + 4 entries; the game loop writes up to 2*max_game_length (+1)
+  if (c->max_game_length < 1 || c->max_plies < 2 * c->max_game_length)
+    return cz_fail(CZ_ERR_ARG, "cz_config: max_game_length >= 1 and max_plies >= 2*max_game_length required (%d, %d)", c->max_game_length, c->max_plies);
+  if (c->game_quota < 0 || c->playouts_lo < 0 || c->playouts_hi < c->playouts_lo)
+    return cz_fail(CZ_ERR_ARG, "cz_config: bad game_quota / playouts range");
   if (c->arena && (c->n_games % 2)) return cz_fail(CZ_ERR_ARG, "cz_config: arena mode needs an even number of slots (two per game)");
   return 0;
 }
@@ -377,7 +385,7 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
   e->cfg = *cfg;
   e->stream = (cz_stream_t)stream;
   e->ws = (uint8_t*)workspace; e->ws_bytes = workspace_bytes;
-  e->launches = 0; e->last_leaves = 0; e->total_sims = e->total_positions = e->total_waves = 0;
+  e->launches = 0; e->last_leaves = 0; e->ring_count = 0; e->total_sims = e->total_positions = e->total_waves = 0;
   EngineDev& d = e->d;
   memset(&d, 0, sizeof(d));
   d.n_games = cfg->n_games; d.sims = cfg->sims_per_move; d.K = cfg->leaves_per_round; d.vl = cfg->virtual_loss;
@@ -699,7 +707,7 @@ int cz_get_counters(cz_engine* e, uint64_t* out) {
   CZ_LAUNCH(k_err_reduce, 1, 1, 0, e->stream, e->d);
   czrt_copy(dc, e->d.counters, sizeof(dc), e->stream);
   if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_get_counters: device failure");
-  out[0] = e->total_sims; out[1] = e->total_positions; out[2] = e->total_waves; out[3] = dc[3]; out[4] = dc[4];
+  out[0] = e->total_sims; out[1] = e->total_positions; out[2] = e->total_waves; out[3] = dc[3]; out[4] = dc[4];   // [3] records dropped
   out[5] = dc[5]; out[6] = dc[6]; out[7] = dc[7];
   return 0;
 }

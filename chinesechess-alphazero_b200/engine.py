@@ -22,7 +22,7 @@ class Engine:
                  max_nodes_per_game=None, max_edges_per_game=None, max_path=128, noise_mode=1, max_game_length=100,
                  nn_filters=0, nn_blocks=0, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
                  tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0, nn_fp32_skip=None, arena=False,
-                 use_history=False):
+                 use_history=False, game_quota=0, playouts=None):
         self.lib = lib or get_lib()
         if device is None:
             device = 'cuda' if self.lib.is_cuda else 'cpu'
@@ -47,6 +47,8 @@ class Engine:
         cfg.arena = 1 if arena else 0
         cfg.nn_fp32_skip = 0 if nn_fp32_skip is None else (1 if nn_fp32_skip else 2)   # None = auto (fp32 when blocks >= 10)
         cfg.use_history = 1 if use_history else 0
+        cfg.game_quota = int(game_quota or 0)        # > 0: play exactly the games with running index < game_quota, then retire
+        cfg.playouts_lo, cfg.playouts_hi = (playouts or (0, 0))   # arena: per-game randint(lo, hi) * 100 simulations per move
         self.use_history = bool(use_history)
         self.in_planes = 28 if use_history else 14
         self.cfg = cfg
@@ -283,6 +285,22 @@ class Engine:
         g, s = C.c_int32(0), C.c_int64(0)
         self.lib.call("cz_selfplay", self._h, target_games, max_moves, C.byref(g), C.byref(s))
         return g.value, s.value
+
+    def set_game_sims(self, sims):
+        """Per-slot simulations per move of the games now running (0 = the engine default): the per-game
+        `config.play.simulation_num_per_move` of evaluator.py:153-154."""
+        a = np.ascontiguousarray(np.asarray(sims, dtype=np.int32))
+        assert a.shape == (self.n_games,)
+        self.lib.call("cz_set_game_sims", self._h, C.c_void_p(a.ctypes.data))
+
+    def any_active(self):
+        """False once every slot has retired (cz_config.game_quota reached)."""
+        return bool(self.active_flags().any())
+
+    def active_flags(self):
+        a = np.zeros(self.n_games, dtype=np.int32)
+        self.lib.call("cz_get_active", self._h, C.c_void_p(a.ctypes.data))
+        return a
 
     def drain_records(self, cap=None):
         cap = cap or max(64, 2 * self.n_games)

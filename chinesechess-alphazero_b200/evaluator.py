@@ -35,32 +35,42 @@ def tally_games(results):
 
 
 class EvaluateWorker:
-    def __init__(self, config, model_bt, model_ng, n_games=None, concurrent_games=None, lib=None, device=None, seed=0):
+    def __init__(self, config, model_bt, model_ng, n_games=None, concurrent_games=None, lib=None, device=None, seed=0,
+                 playouts=(8, 12)):
+        """playouts: every game draws `randint(lo, hi) * 100` simulations per move when it starts (evaluator.py:153-154);
+        None = config.play.simulation_num_per_move for every game."""
         self.config = config
         pc, mc = config.play, config.model
         self.n_games = n_games or config.eval.game_num * pc.max_processes
         m = concurrent_games or min(self.n_games, 512)
         self.m = m
+        sims_max = playouts[1] * 100 if playouts else pc.simulation_num_per_move
         self.engine = Engine(
             lib or get_lib(), device, n_games=2 * m, sims_per_move=pc.simulation_num_per_move,
             leaves_per_round=pc.search_threads, virtual_loss=getattr(pc, "virtual_loss", 3), noise_mode=1, c_puct=pc.c_puct,
             noise_eps=pc.noise_eps, dirichlet_alpha=getattr(pc, "dirichlet_alpha", 0.2), tau_decay_rate=pc.tau_decay_rate,
-            enable_resign_rate=0.0, max_game_length=pc.max_game_length, max_nodes_per_game=max(4096, 16 * pc.simulation_num_per_move),
-            nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size, seed=seed, arena=True)
+            enable_resign_rate=0.0, max_game_length=pc.max_game_length, max_nodes_per_game=max(4096, 16 * sims_max),
+            nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size, seed=seed, arena=True,
+            game_quota=self.n_games, playouts=playouts)   # exactly the games 0 .. n_games-1, each played to its end
         self.engine.set_weights(model_bt.torch_weights(), net=0)
         self.engine.set_weights(model_ng.torch_weights(), net=1)
         self.engine.reset()
 
     def start(self):
         """Returns (total_score, red_new_win, red_new_draw, red_new_fail, black_new_win, black_new_draw, black_new_fail)
-        like EvaluateWorker.start (evaluator.py:93-145), over the first `n_games` finished games."""
-        results = []
+        like EvaluateWorker.start (evaluator.py:93-145): the games with running index 0 .. n_games-1 (`for idx in
+        range(game_num)`, :104), every one played to its end — a slot whose next game would be past the quota retires
+        (cz_config.game_quota) instead of starting games nobody counts, so quick decisive games are not over-sampled."""
+        results = {}
         while len(results) < self.n_games:
-            self.engine.selfplay(target_games=1, max_moves=0)
-            for rec in self.engine.drain_records():
-                if len(results) < self.n_games:
-                    results.append((rec["game_index"], rec["value_red"]))
-        return tally_games(results)
+            done, sims = self.engine.selfplay(target_games=self.n_games - len(results), max_moves=0)
+            recs = self.engine.drain_records()
+            for rec in recs:
+                assert rec["game_index"] < self.n_games and rec["game_index"] not in results
+                results[rec["game_index"]] = rec["value_red"]
+            if not recs and sims == 0:
+                raise RuntimeError(f"arena stalled: {len(results)} of {self.n_games} games finished and no slot is active")
+        return tally_games(sorted(results.items()))
 
     def close(self):
         self.engine.close()

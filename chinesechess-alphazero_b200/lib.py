@@ -31,6 +31,7 @@ class CzConfig(C.Structure):
         ("tau_decay_rate", C.c_double), ("resign_threshold", C.c_double), ("enable_resign_rate", C.c_double),
         ("min_resign_turn", C.c_int32), ("max_game_length", C.c_int32),
         ("seed", C.c_uint64), ("rank", C.c_int32), ("arena", C.c_int32), ("nn_fp32_skip", C.c_int32), ("use_history", C.c_int32),
+        ("game_quota", C.c_int32), ("playouts_lo", C.c_int32), ("playouts_hi", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -101,6 +102,10 @@ _SIGS = {
     "cz_get_search_stats": (C.c_int, [_P, _P]),
     "cz_play_move": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "cz_selfplay": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "cz_set_game_sims": (C.c_int, [_P, _P]),
+    "cz_get_active": (C.c_int, [_P, _P]),
+    "cz_record_layout": (C.c_int, [_P, _P]),
+    "cz_clear_records": (C.c_int, [_P]),
     "cz_drain_records": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "cz_record_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "cz_nn_set_weights": (C.c_int, [_P, C.POINTER(CzTensorDesc), C.c_int32]),

@@ -66,9 +66,36 @@ class RootStage:
         return self.boards.numel() + self.n.numel() * 4 + self.moves.numel() * 2 + self.counts.numel() * 4 + self.sims.numel() * 4
 
 
-def gather_records(engine, dist, world):
-    """NCCL all_gather of the finished-game record ring of every rank: the only inter-GPU traffic of the
-    path.  The ring lives inside the engine's workspace tensor, so the collective reads it in place."""
+def decode_ring(ring_u8, count, layout):
+    """A record ring as the collective delivered it (uint8 tensor / array) -> the dicts `Engine.drain_records` returns."""
+    from .env import u16_to_move
+    cap, stride, moves_off, _ = layout
+    raw = ring_u8.cpu().numpy() if hasattr(ring_u8, "cpu") else np.asarray(ring_u8)
+    count = min(int(count), cap)
+    hdr = raw[:cap * 16].view(np.int32).reshape(cap, 4)
+    moves = raw[moves_off:moves_off + cap * stride * 2].view(np.uint16).reshape(cap, stride)
+    out = []
+    for i in range(count):
+        n_plies, value_red, game_index, flags = (int(x) for x in hdr[i])
+        out.append({"n_plies": n_plies, "value_red": value_red, "game_index": game_index, "flags": flags,
+                    "moves": [u16_to_move(int(v)) for v in moves[i, :n_plies]]})
+    return out
+
+
+def record_layout(engine):
+    import ctypes as C
+    a = np.zeros(4, dtype=np.int64)
+    engine.lib.call("cz_record_layout", engine._h, C.c_void_p(a.ctypes.data))
+    return tuple(int(x) for x in a)
+
+
+def gather_records(engine, dist, world, decode_on=0, clear=True):
+    """all_gather (NCCL on GPUs, gloo in the CPU tests) of the finished-game record ring of every rank — SURVEY.md §8e:
+    the only inter-GPU traffic of the path, the analogue of the reference uploading its play-data files
+    (worker/self_play.py:228-241).  The ring lives inside the engine's workspace tensor, so the collective reads it in
+    place; every rank must call this at the same point of its loop.  Returns (records, total): on rank `decode_on` the
+    decoded records of ALL ranks as [(rank, record dict), ...] (None elsewhere: other ranks only forward), and the
+    number of records gathered.  clear=True empties the local ring afterwards (its content now lives on rank decode_on)."""
     import ctypes as C
     ptr, nbytes, ready = C.c_void_p(0), C.c_uint64(0), C.c_int32(0)
     engine.lib.call("cz_record_buffer", engine._h, C.byref(ptr), C.byref(nbytes), C.byref(ready))
@@ -77,9 +104,20 @@ def gather_records(engine, dist, world):
     count = torch.tensor([ready.value], device=engine.device, dtype=torch.int32)
     counts = [torch.zeros_like(count) for _ in range(world)]
     dist.all_gather(counts, count)
-    rings = [torch.empty_like(ring) for _ in range(world)]
-    dist.all_gather(rings, ring)
-    return int(sum(int(c.item()) for c in counts))
+    counts = [int(c.item()) for c in counts]
+    total = sum(counts)
+    records = None
+    if total > 0:                               # same decision on every rank (they all hold the same counts)
+        rings = [torch.empty_like(ring) for _ in range(world)]
+        dist.all_gather(rings, ring)
+        if dist.get_rank() == decode_on:
+            layout = record_layout(engine)
+            records = [(r, rec) for r in range(world) for rec in decode_ring(rings[r], counts[r], layout)]
+    elif dist.get_rank() == decode_on:
+        records = []
+    if clear:
+        engine.lib.call("cz_clear_records", engine._h)
+    return records, total
 
 
 # ---- trainer-side view of the records (worker/optimize.py:223-292, lib/data_helper.py:11-24) -------------------

@@ -32,17 +32,49 @@ def load_model(config):
     return model, model.use_history
 
 
-def start(config, games_per_process=128, max_games=None):
-    """self_play.py:48-60."""
-    model, use_history = load_model(config)
-    worker = SelfPlayWorker(config, pipes=None, pid=0, use_history=use_history, model=model,
-                            concurrent_games=config.play.max_processes * games_per_process)
-    return worker.start(max_games=max_games)
+def start(config, games_per_process=128, max_games=None, flush_plies=8, lib=None, device=None, evaluate_planes=None):
+    """self_play.py:48-60.  The reference fans out over `max_processes` OS processes that share one prediction thread;
+    here one process drives one GPU, and data parallelism is one process per GPU under `torchrun` (RANK / LOCAL_RANK /
+    WORLD_SIZE in the environment): rank r plays its own `max_processes x games_per_process` concurrent games on GPU
+    LOCAL_RANK with its own Philox sub-stream (engine rank r) — no data-path collective.  Every `flush_plies` plies the
+    ranks all_gather their finished-game rings (NCCL over NVLink; gloo on CPU) and rank 0 decodes them and writes the
+    reference's play-data files (worker/self_play.py:202-232): the other ranks never touch the disk.
+    Returns the number of games stored by this launch (rank 0; the others return the same total)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    model, use_history = load_model(config) if rank == 0 or world == 1 else (None, None)
+    if world == 1:
+        worker = SelfPlayWorker(config, pipes=None, pid=0, use_history=use_history, model=model, lib=lib, device=device,
+                                concurrent_games=config.play.max_processes * games_per_process)
+        return worker.start(max_games=max_games)
+    import torch
+    import torch.distributed as dist
+    on_gpu = device is None and torch.cuda.is_available()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if on_gpu:
+        torch.cuda.set_device(local)
+        device = f"cuda:{local}"
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl" if on_gpu else "gloo", **({"device_id": torch.device(device)} if on_gpu else {}))
+    try:
+        if rank != 0:                                      # rank 0 built / loaded the model (and wrote it): the others read it after
+            dist.barrier()
+            model, use_history = load_model(config)
+        else:
+            dist.barrier()
+        worker = SelfPlayWorker(config, pipes=None, pid=rank, use_history=use_history, model=model, lib=lib, device=device,
+                                concurrent_games=config.play.max_processes * games_per_process, rank=rank,
+                                external_evaluator=evaluate_planes is not None)
+        return worker.start_distributed(dist, world, max_games=max_games, flush_plies=flush_plies, evaluate_planes=evaluate_planes)
+    finally:
+        if created:
+            dist.destroy_process_group()
 
 
 class SelfPlayWorker:
     def __init__(self, config, pipes=None, pid=None, use_history=False, model=None, concurrent_games=None, lib=None,
-                 device=None, seed=0, rank=0):
+                 device=None, seed=0, rank=0, external_evaluator=False):
         self.config = config
         self.cur_pipes = pipes          # unused: evaluation happens inside the engine
         self.id = pid
@@ -52,7 +84,7 @@ class SelfPlayWorker:
         self.lib = lib or get_lib()
         pc, mc = config.play, config.model
         self.model = model
-        if self.model is None:
+        if self.model is None and not external_evaluator:
             self.model, _ = load_model(config)
         g = concurrent_games or max(1, pc.max_processes)
         self.engine = Engine(
@@ -61,12 +93,15 @@ class SelfPlayWorker:
             dirichlet_alpha=pc.dirichlet_alpha, tau_decay_rate=pc.tau_decay_rate, resign_threshold=pc.resign_threshold,
             enable_resign_rate=pc.enable_resign_rate, min_resign_turn=pc.min_resign_turn, max_game_length=pc.max_game_length,
             max_nodes_per_game=max(4096, 24 * pc.simulation_num_per_move),
-            nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size, seed=seed, rank=rank,
+            nn_filters=0 if external_evaluator else mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size,
+            seed=seed, rank=rank,
             use_history=use_history)    # the game loop never passes `hist` (self_play.py:124): path history only
-        self.engine.set_weights(self.model.torch_weights())
+        if not external_evaluator:      # external evaluator: the leaves go to a caller-supplied function (CPU test tier)
+            self.engine.set_weights(self.model.torch_weights())
         self.engine.reset()
         self.pending = []               # finished games not yet handed out by start_game
-        self.games_written = 0
+        self.games_written = 0          # play-data files written
+        self.games_stored = 0           # games handed to save_play_data (its idx, self_play.py:199)
         self.env = None
 
     # ---- self_play.py:72-93
@@ -80,6 +115,38 @@ class SelfPlayWorker:
             if store:
                 idx += 1
         return idx - 1
+
+    def start_distributed(self, dist, world, max_games=None, flush_plies=8, evaluate_planes=None):
+        """One rank of the data-parallel launch: play `flush_plies` plies, gather every rank's finished-game ring, rank 0
+        stores the games (running file index over all ranks).  All ranks leave the loop together: the stop test only uses
+        the gathered totals.  evaluate_planes: external evaluator (CPU tests with the emulator build); None = built-in net."""
+        from .records import gather_records
+        stored = 0
+        self.gather_ms = 0.0
+        while max_games is None or stored < max_games:
+            if evaluate_planes is None:
+                self.engine.selfplay(target_games=0, max_moves=flush_plies)
+            else:
+                for _ in range(flush_plies):
+                    self.engine.search_external(evaluate_planes, None)
+                    self.engine.play_move()
+            t0 = time()
+            recs, total = gather_records(self.engine, dist, world)
+            self.gather_ms += 1e3 * (time() - t0)
+            n_stored = 0
+            if recs is not None:                           # rank 0: decode + write (self_play.py:202-227)
+                for r, rec in recs:
+                    if not (rec["flags"] & 4):
+                        self.games_stored += 1
+                        n_stored += 1
+                        self.save_play_data(self.games_stored, record_to_play_data(rec))
+            # every rank needs the stored count for the common stop test: it is a function of the gathered records'
+            # flags, which only rank 0 decoded -> broadcast one integer
+            import torch
+            t = torch.tensor([n_stored], dtype=torch.int64, device=self.engine.device)
+            dist.broadcast(t, src=0)
+            stored += int(t.item())
+        return stored
 
     # ---- self_play.py:95-212: returns (v, turns, state, store) of the next finished game
     def start_game(self, idx, search_tree):
@@ -100,9 +167,10 @@ class SelfPlayWorker:
         while len(out) < n:
             self.engine.selfplay(target_games=n - len(out), max_moves=0)
             out.extend(self.engine.drain_records())
-        for i, rec in enumerate(out):
+        for rec in out:
             if not (rec["flags"] & 4):
-                self.save_play_data(self.games_written + 1, record_to_play_data(rec))
+                self.games_stored += 1
+                self.save_play_data(self.games_stored, record_to_play_data(rec))
         return out
 
     # ---- self_play.py:214-227

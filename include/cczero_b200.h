@@ -107,6 +107,12 @@ typedef struct cz_config {
                                 * fp32 keeps the value error of 20-block nets <= 6e-4 (fp16: up to 1.5e-3) for ~10 % time */
   int32_t use_history;         /* CChessPlayer(use_history=True) (player.py:45,326-334): 28 input planes, planes 14-27 = the
                                 * position two plies earlier (static_env.py:158-194); leaf records become (board, history board) */
+  int32_t game_quota;          /* > 0: the on-device game loop plays exactly the games with running index < game_quota (the
+                                * `for idx in range(game_num)` of evaluator.py:104 / a bounded self-play run): a slot whose next
+                                * game index would reach the quota retires instead of restarting.  0 = restart for ever */
+  int32_t playouts_lo;         /* arena, > 0: every game draws its own simulations per move = randint(playouts_lo, playouts_hi) * 100 */
+  int32_t playouts_hi;         /*   when it starts (evaluator.py:153-154: randint(8, 12) * 100), from the Philox stream of the game */
+  int32_t reserved0;
 } cz_config;
 
 /* Device workspace the caller must provide (a torch.uint8 CUDA tensor). */
@@ -210,6 +216,7 @@ int cz_compact(cz_engine* e);
 int cz_get_search_stats(cz_engine* e, uint64_t* out /* [6] */);
 
 /* Counters since cz_create: [0] simulations completed, [1] NN positions evaluated, [2] wave iterations,
+ * [3] finished-game records dropped because the ring was full (0 unless cz_play_move was driven without draining),
  * [4] whole-table resets (compaction was not enough / root unknown), [5] compactions,
  * [6] OR of the per-game error flags (1 path longer than max_path, 2 pool exhausted inside a search, 4 host noise table
  * exhausted, 8 node without a playable move), [7] number of games with a flag set.  Flags clear at cz_reset_games. */
@@ -223,7 +230,9 @@ int cz_get_counters(cz_engine* e, uint64_t* out_host /* [8] */);
  * move and value signs (:177-191).  Finished games are recorded and restarted from INIT_STATE.
  * n_finished counts games that ended in this call.  Synchronises. */
 int cz_play_move(cz_engine* e, int32_t* n_finished);
-/* Search + play until `target_games` games finished or `max_moves` plies were played. */
+/* Search + play until `target_games` games finished or `max_moves` plies were played.  Also returns early (with what it
+ * did so far) when the finished-game ring could not take another ply's worth of records — drain it and call again — and
+ * when every slot has retired (cz_config.game_quota). */
 int cz_selfplay(cz_engine* e, int32_t target_games, int32_t max_moves, int32_t* games_done, int64_t* sims_done);
 
 typedef struct cz_record_hdr {
@@ -236,8 +245,20 @@ typedef struct cz_record_hdr {
  * (moves as seen by the side that played them, i.e. the strings self_play.py:132 appends).
  * Returns the number drained in *n.  Synchronises. */
 int cz_drain_records(cz_engine* e, cz_record_hdr* hdr_host, uint16_t* moves_host, int32_t cap, int32_t* n);
+/* Simulations per move of the games currently in the slots (per-game `simulation_num_per_move`, evaluator.py:153-154):
+ * sims_host [n_games], 0 = cz_config.sims_per_move.  A slot keeps its value until its game ends.  Stream-ordered. */
+int cz_set_game_sims(cz_engine* e, const int32_t* sims_host);
+/* Which slots will search / play next: active_host [n_games] (arena: the slot of the player to move; 0 everywhere once
+ * every slot has retired under cz_config.game_quota).  Synchronises. */
+int cz_get_active(cz_engine* e, int32_t* active_host);
 /* Device-side view of the same ring (for the NCCL gather of play records). */
 int cz_record_buffer(cz_engine* e, void** dev_ptr, uint64_t* bytes, int32_t* n_ready);
+/* Layout of that ring for a peer that received it through the collective: out[0] = ring capacity in records, out[1] = uint16
+ * slots per record row, out[2] = byte offset of the move rows inside the buffer (the headers start at 0, 16 bytes each),
+ * out[3] = total bytes.  Host-only. */
+int cz_record_layout(cz_engine* e, int64_t* out /* [4] */);
+/* Forget the records in the ring (after a gather shipped them).  Stream-ordered. */
+int cz_clear_records(cz_engine* e);
 
 /* ------------------------------------------------------------------------------------------
  * Policy + value network — agent/model.py:32-83 behind agent/api.py:37-74

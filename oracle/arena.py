@@ -13,8 +13,18 @@ from . import senv
 from .player import OraclePlayer
 
 
-def play_arena_game(pc, evaluate0, evaluate1, idx, draws_for, m_games, max_game_length=100, env=senv, max_plies_guard=1000):
-    """idx = running game index; player idx % 2 is red (evaluator.py:163-170).  Returns dict(moves, value_red, turns, flags)."""
+def play_arena_game(pc, evaluate0, evaluate1, idx, draws_for, m_games, max_game_length=100, env=senv, max_plies_guard=1000,
+                    playouts=None):
+    """idx = running game index; player idx % 2 is red (evaluator.py:163-170).  Returns dict(moves, value_red, turns, flags).
+    playouts: (lo, hi) -> the game first draws `randint(lo, hi) * 100` simulations per move for BOTH players
+    (evaluator.py:153-154 rebinds config.play.simulation_num_per_move before the players are created), through
+    `draws_for(slot).playouts(lo, hi)`; None = pc.simulation_num_per_move as given."""
+    sims_game = None
+    if playouts is not None:
+        import copy
+        sims_game = draws_for(idx % m_games).playouts(*playouts)
+        pc = copy.copy(pc)
+        pc.simulation_num_per_move = sims_game
     # the reference draws its Dirichlet sample even when eps == 0 (player.py:304): keep that when replaying its RNG
     quiet = (lambda n: 0.0) if (pc.noise_eps == 0 and not hasattr(draws_for(0), "choose_with_player")) else None
     players = [OraclePlayer(pc, evaluate0, env=env, noise=quiet), OraclePlayer(pc, evaluate1, env=env, noise=quiet)]
@@ -70,7 +80,8 @@ def play_arena_game(pc, evaluate0, evaluate1, idx, draws_for, m_games, max_game_
         history.append(state)
     if turns % 2 == 1:
         value = -value
-    return {"moves": [history[2 * k + 1] for k in range(turns)], "value_red": value, "turns": turns, "flags": flags}
+    return {"moves": [history[2 * k + 1] for k in range(turns)], "value_red": value, "turns": turns, "flags": flags,
+            "playouts": sims_game}
 
 
 def score_for_next_generation(value_red, idx):

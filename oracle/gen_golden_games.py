@@ -38,6 +38,14 @@ ARENA = [
     (4, 1, 24, dict(max_game_length=100, tau_decay_rate=0.0, noise_eps=0.0)),
     (5, 0, 16, dict(max_game_length=100, noise_eps=0.0)),
 ]
+# arena games run EXACTLY as written: `playouts = randint(8, 12) * 100` (evaluator.py:153-154) from the seeded `random`
+# module sets the simulations per move of the game.  Short by max_game_length (800-1200 pure-Python simulations per ply).
+ARENA_REAL = [
+    # (seed, idx, overrides)
+    (11, 0, dict(max_game_length=5, tau_decay_rate=0.0, noise_eps=0.0)),
+    (12, 1, dict(max_game_length=4, tau_decay_rate=0.0, noise_eps=0.0)),
+    (17, 0, dict(max_game_length=3)),
+]
 BASE = dict(tau_decay_rate=0.98, noise_eps=0.25, enable_resign_rate=0.1, resign_threshold=-0.5, min_resign_turn=4, c_puct=1.5,
             dirichlet_alpha=0.2, virtual_loss=3)
 
@@ -63,16 +71,24 @@ def gen_games():
         play = dict(BASE, **over)
         g = real_arena_game(seed, idx, sims, **play)
         games.append({"kind": "arena", "seed": seed, "idx": idx, "sims": sims, "play": play, "result": g,
-                      "deterministic": _deterministic(play, g)})
+                      "deterministic": _deterministic(play, g), "playouts_patched": True})
+    for seed, idx, over in ARENA_REAL:
+        play = dict(BASE, **over)
+        g = real_arena_game(seed, idx, None, **play)
+        assert g["playouts"] in (800, 900, 1000, 1100, 1200)
+        games.append({"kind": "arena", "seed": seed, "idx": idx, "sims": g["playouts"], "play": play, "result": g,
+                      "deterministic": play["tau_decay_rate"] == 0.0 and play["noise_eps"] == 0.0 and not g["increase_temp_used"],
+                      "playouts_patched": False})
     # deterministic arena games (no repetition): scan seeds-independent settings (the game does not depend on the seed)
     for sims in (18, 20, 22, 26, 28, 30, 34):
-        if sum(1 for x in games if x["kind"] == "arena" and x["deterministic"]) >= 2:
+        if sum(1 for x in games if x["kind"] == "arena" and x["deterministic"] and x["playouts_patched"]) >= 2:
             break
         play = dict(BASE, max_game_length=100, tau_decay_rate=0.0, noise_eps=0.0)
         for idx in (0, 1):
             g = real_arena_game(0, idx, sims, **play)
             if _deterministic(play, g):
-                games.append({"kind": "arena", "seed": 0, "idx": idx, "sims": sims, "play": play, "result": g, "deterministic": True})
+                games.append({"kind": "arena", "seed": 0, "idx": idx, "sims": sims, "play": play, "result": g, "deterministic": True,
+                              "playouts_patched": True})
     out = {"generator": "oracle/gen_golden_games.py", "reference": "NeymarL/ChineseChess-AlphaZero @7f45b0c worker/self_play.py, worker/evaluator.py",
            "search_threads": 1, "games": games}
     with gzip.open(os.path.join(GOLD, "games_k1.json.gz"), "wt") as f:

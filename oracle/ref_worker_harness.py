@@ -84,6 +84,9 @@ class ReferenceDraws:
     def store_lottery(self):
         return random.random()
 
+    def playouts(self, lo, hi):
+        return random.randint(lo, hi) * 100              # evaluator.py:12,153: `from random import randint`
+
     def choose_with_player(self, player, state, turns, no_act, increase_temp):
         player.increase_temp = increase_temp
         policy, _ = player.calc_policy(state, turns, no_act)
@@ -138,19 +141,23 @@ def real_selfplay_game(seed, sims, use_history=False, player_factory=None, **pla
 
 
 def real_arena_game(seed, idx, sims, player_factory=None, **play):
-    """One EvaluateWorker.start_game (two players, separate trees; both served by the fake network)."""
+    """One EvaluateWorker.start_game (two players, separate trees; both served by the fake network).
+    sims = None: the game runs exactly as written — `playouts = randint(8, 12) * 100` (evaluator.py:153-154) drawn from the
+    seeded `random` module decides the simulations per move; the drawn value is returned as "playouts".
+    sims = <int>: TEST-SPEED DEVICE for the long rule-coverage games only — the per-game draw still happens but the players
+    are made to search `sims` simulations (800-1200 simulations x 100 plies of pure-Python search would take minutes per
+    game); such games are flagged "playouts_patched" in the fixture."""
     _, ev = worker_modules()
     pm = ref_import.player_module()
-    cfg = _config(sims, **play)
+    cfg = _config(sims or 0, **play)
     s1, s2 = FakeNetServer(), FakeNetServer()
     worker = ev.EvaluateWorker(cfg, pipes1=[s1.you], pipes2=[s2.you], pid=0)
-    ev_randint = ev.randint
-    ev.randint = lambda a, b: 0                    # playouts = randint(8, 12) * 100 (:152-153) -> set below instead
     moves, temps = [], []
     orig_action = pm.CChessPlayer.action
 
     def spy(self, state, turns, no_act=None, depth=None, infinite=False, hist=None, increase_temp=False):
-        self.play_config.simulation_num_per_move = sims
+        if sims is not None:
+            self.play_config.simulation_num_per_move = sims
         temps.append(bool(increase_temp))
         a, p = orig_action(self, state, turns, no_act, depth, infinite, hist, increase_temp)
         moves.append(a)
@@ -158,11 +165,10 @@ def real_arena_game(seed, idx, sims, player_factory=None, **play):
     pm.CChessPlayer.action = spy
     ev_player = ev.CChessPlayer
     if player_factory is not None:
-        cfg.play.simulation_num_per_move = sims          # (the real player reads it per call; a swapped-in one at creation)
-
         class Recording:                                 # same bookkeeping as the spy, around the swapped-in player
             def __init__(self, *a, **k):
-                cfg.play.simulation_num_per_move = sims
+                if sims is not None:                     # (the real player reads it per call; a swapped-in one at creation)
+                    cfg.play.simulation_num_per_move = sims
                 self.p = player_factory(*a, **k)
 
             def action(self, state, turns, no_act=None, increase_temp=False):
@@ -181,7 +187,7 @@ def real_arena_game(seed, idx, sims, player_factory=None, **play):
     finally:
         pm.CChessPlayer.action = orig_action
         ev.CChessPlayer = ev_player
-        ev.randint = ev_randint
         s1.close()
         s2.close()
-    return {"moves": moves, "value_red": value, "turns": turns, "increase_temp_used": any(temps)}
+    return {"moves": moves, "value_red": value, "turns": turns, "increase_temp_used": any(temps),
+            "playouts": cfg.play.simulation_num_per_move if sims is None else None}

@@ -105,6 +105,14 @@ def philox4x32(c, k):
     return [c0, c1, c2, c3]
 
 
+def philox_first_word(seed, rank, game, purpose, index):
+    """First Rng::next() of the stream (csrc/cz_tree.cuh Rng): buf[3] of the first Philox block."""
+    M = 0xFFFFFFFF
+    k0 = ((seed & M) ^ ((rank * 0x632BE5AB) & M)) & M
+    k1 = (((seed >> 32) & M) + 0x1234567 * rank) & M
+    return philox4x32((game & M, purpose & M, index & M, 0), (k0, k1))[3]
+
+
 def philox_uniform(seed, rank, game, purpose, index):
     """First Rng::uniform() of the stream (csrc/cz_tree.cuh Rng): buf[3] is the high word, buf[2] the low word."""
     M = 0xFFFFFFFF
@@ -127,6 +135,11 @@ class DeviceDraws:
 
     def store_lottery(self):
         return philox_uniform(self.seed, self.rank, self.game, 4, self.started)
+
+    def playouts(self, lo, hi):
+        """Arena: simulations per move of the game this slot starts (selfplay_start_game; `game` must be the game's first
+        slot, i.e. slot % M, so that both player slots agree)."""
+        return (lo + philox_first_word(self.seed, self.rank, self.game, 5, self.started) % (hi - lo + 1)) * 100
 
     def choose(self, node, no_act, turns, increase_temp, pc):
         moves = node.legal_moves

@@ -84,3 +84,34 @@ def test_hot_reload_follows_the_digest(tmp_path):
     assert uploads[0] == float(other.weights["value_out/kernel"].sum())
     api.try_reload_model()
     assert len(uploads) == 1
+
+
+def test_failed_reload_keeps_serving_and_retries(tmp_path):
+    """A weight file the engine refuses (other geometry) or that is half written must leave the served model, its digest
+    and its geometry untouched — the next check tries again instead of believing the reload happened."""
+    from cczero_b200.api import CChessModelAPI
+    from cczero_b200.model import CChessModel
+    res = SimpleNamespace(model_best_config_path=str(tmp_path / "cfg.json"), model_best_weight_path=str(tmp_path / "w.npz"))
+    mk = lambda f: SimpleNamespace(model=SimpleNamespace(cnn_filter_num=f, res_layer_num=1, value_fc_size=256, cnn_first_filter_size=5,
+                                                         cnn_filter_size=3, input_depth=14), resource=res)
+    cfg = mk(64)
+    model = CChessModel(cfg).build(seed=1)
+    model.save(res.model_best_config_path, res.model_best_weight_path)
+    digest0 = model.digest
+    uploads = []
+    eng = StubEngine()
+    eng.set_weights = lambda w: uploads.append(1)
+    api = CChessModelAPI(cfg, model, lib=SimpleNamespace(is_cuda=False), device="cpu")
+    api.engine = eng
+    CChessModel(mk(128)).build(seed=2).save(res.model_best_config_path, res.model_best_weight_path)     # other geometry
+    api.try_reload_model()
+    assert uploads == [] and model.digest == digest0 and cfg.model.cnn_filter_num == 64
+    assert model.weights["input_conv-5-64/kernel"].shape[-1] == 64
+    with open(res.model_best_weight_path, "wb") as f:                                                   # half-written file
+        f.write(b"PK\x03\x04 not a zip")
+    api.try_reload_model()
+    assert uploads == [] and model.digest == digest0
+    good = CChessModel(mk(64)).build(seed=3)
+    good.save(res.model_best_config_path, res.model_best_weight_path)
+    api.try_reload_model()
+    assert uploads == [1] and model.digest == good.digest

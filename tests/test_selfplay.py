@@ -126,3 +126,81 @@ def test_flip_policy_matches_reference_definition(emul_env):
     assert (flip_policy(pol, emul_env) == want).all()
     p = build_policy("7747", True, emul_env)
     assert sum(p) == 1 and p[red.index(osenv.flip_move("7747"))] == 1
+
+
+# ---- bounded runs, the record ring, file batching (host logic + device bookkeeping on the emulator)
+def _engine(lib, device, n_games, sims=6, k=4, max_game_length=3, **kw):
+    return Engine(lib, device, n_games=n_games, sims_per_move=sims, leaves_per_round=k, noise_mode=1, noise_eps=0.0,
+                  tau_decay_rate=0.9, max_game_length=max_game_length, enable_resign_rate=0.0, seed=5,
+                  max_nodes_per_game=256, **kw)
+
+
+def _play_all(eng, guard=400):
+    recs = []
+    for _ in range(guard):
+        eng.search_external(eval_planes, None)
+        eng.play_move()
+        recs += eng.drain_records()
+        if not eng.any_active():
+            break
+    return recs
+
+
+def test_emul_game_quota_plays_each_index_once(emul_lib):
+    """cz_config.game_quota: exactly the games 0 .. quota-1 are played, each to its end, then every slot retires."""
+    eng = _engine(emul_lib, "cpu", n_games=4, game_quota=10)
+    recs = _play_all(eng)
+    assert sorted(r["game_index"] for r in recs) == list(range(10))
+    assert all(r["n_plies"] <= 7 for r in recs) and sum(r["n_plies"] == 6 for r in recs) >= 8   # max_game_length = 3: 6-ply draws
+    eng.close()
+    eng = _engine(emul_lib, "cpu", n_games=4, game_quota=3)          # more slots than games: slot 3 never plays
+    assert sorted(r["game_index"] for r in _play_all(eng)) == [0, 1, 2]
+    eng.close()
+
+
+def test_config_rejects_short_record_rows(emul_lib):
+    """max_plies must cover 2*max_game_length (the history / record rows are written up to that index)."""
+    import ctypes as C
+    from cczero_b200.lib import CzConfig, CzError
+    eng = _engine(emul_lib, "cpu", n_games=1)
+    cfg = CzConfig.from_buffer_copy(eng.cfg)
+    eng.close()
+    cfg.max_plies = 2 * cfg.max_game_length - 1
+    n = C.c_uint64(0)
+    with pytest.raises(CzError, match="max_plies"):
+        emul_lib.call("cz_workspace_bytes", C.byref(cfg), C.byref(n))
+
+
+def test_emul_record_ring_is_never_silently_overrun(emul_lib):
+    """cz_selfplay returns early while the ring can still take a ply's worth of finished games; driving cz_play_move
+    without draining past the ring capacity fails loudly and counts the dropped records."""
+    from cczero_b200.lib import CzError
+    eng = _engine(emul_lib, "cpu", n_games=40, sims=2, k=2, max_game_length=1)       # every game ends after 2 plies; ring = 80
+    with pytest.raises(CzError, match="dropped"):
+        for _ in range(8):                                                            # 40 records per 2 plies, never drained
+            eng.search_external(eval_planes, None)
+            eng.play_move()
+    assert int(eng.counters()[3]) > 0                                                 # counted, not silent
+    assert len(eng.drain_records()) == 80                                             # what fitted is intact
+    eng.close()
+
+
+def test_play_data_files_with_several_games_per_file(tmp_path):
+    """with nb_game_in_file = 5 (configs/normal.py) a file must be written every 5 stored games."""
+    from types import SimpleNamespace
+    from cczero_b200.self_play import SelfPlayWorker
+    w = SelfPlayWorker.__new__(SelfPlayWorker)
+    w.config = SimpleNamespace(play_data=SimpleNamespace(nb_game_in_file=5),
+                               resource=SimpleNamespace(play_data_dir=str(tmp_path), play_data_filename_tmpl="play_%s.json"))
+    w.buffer, w.games_written, w.games_stored, w.pending, w.pid = [], 0, 0, [], 0
+    recs = [{"moves": ["7747", "7062"], "value_red": 1, "flags": 0, "n_plies": 2, "game_index": i} for i in range(12)]
+    recs[3]["flags"] = 4                                                              # not stored (short-game lottery)
+    w.pending = list(recs)
+    w.engine = None
+    out = w.play_games(12)
+    assert len(out) == 12 and w.games_stored == 11 and w.games_written == 2
+    import glob, json
+    files = sorted(glob.glob(str(tmp_path / "play_*.json")))
+    assert len(files) == 2
+    assert all(len(json.load(open(f))) == 5 * 3 for f in files)                      # 5 games x (init state + 2 moves)
+    assert len(w.buffer) == 3                                                         # the 11th game waits for the next file
