@@ -2,20 +2,21 @@
 """bench.py — MCTS simulations/s of the B200 self-play hot path (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
-  python bench.py --impl reference ...                      CPU arm: the reference's algorithm (oracle port) on host cores
+  python bench.py --impl reference ...                      CPU arm: the reference's OWN `run.py self` plumbing on host cores
 
 A "step" is one move of self-play for every concurrent game: a full PUCT search (sims/move simulations per game,
 tree walk + leaf evaluation by the residual network + backup, all on the device) followed by the on-device move
 selection / adjudication.  Workload = BASELINE.json configs[2] (the one the metric is quoted on: 1024 concurrent
 games per GPU, 800 sims/move, 20x256 resnet, random-init weights, games from INIT_STATE; weak scaling: every rank
-runs its own 1024 games).  Prints ONE JSON line on rank 0.
+runs its own 1024 games).  Prints ONE JSON line on rank 0; at N = 1 that line also carries `secondary` (short runs of
+BASELINE configs[1] and configs[4], each with its own roofline) and `cpu_baseline`.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -30,14 +31,19 @@ WORKLOADS = {
     "c5": (800, 1600, 256, 20),     # BASELINE.json configs[4]: arena, 400 paired games = 800 player slots, two networks
     "tiny": (32, 40, 64, 2),        # plumbing check
 }
+CONFIG_INDEX = dict(c2=1, c3=2, c5=4)
 
-
-# DRAM bytes per launch of the dominant kernel measured once with ncu (None where no capture exists)
+# DRAM bytes per launch of the dominant kernel measured once with ncu --set full (None where no capture exists); see profiles/
 NCU_TRAFFIC = {("c3", 1024, 8): 7.15e8}
 
 
 def net_flops(filters, blocks):
     return 2 * 90 * (350 * filters + blocks * 18 * filters * filters + 6 * filters) + 2 * (360 * 2086 + 180 * 256 + 256)
+
+
+def workload_text(name, games, sims, filters, blocks):
+    return (f"{name} = BASELINE.json configs[{CONFIG_INDEX.get(name, '-')}]: {games} concurrent "
+            f"{'player slots (arena)' if name == 'c5' else 'games'}/GPU, {sims} sims/move, {filters}x{blocks} resnet")
 
 
 def measured_peaks():
@@ -100,14 +106,63 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_sample(filters, blocks, sims, k, budget_s, procs):
-    """The reference's algorithm on the host cores: `procs` single-threaded workers (the reference's own scaling knob is
-    processes, worker/self_play.py:55-60), each the oracle port of agent/player.py + static_env.py with the fp32 PyTorch
-    restatement of agent/model.py as predict_on_batch, self-playing from INIT_STATE for ~budget_s seconds.
-    Returns (aggregate sims/s, simulations, mean window seconds)."""
+# The reference's own plumbing (oracle/ref_selfplay_bench.py: unmodified self_play.start -> SelfPlayWorker / CChessPlayer <->
+# Pipe <-> CChessModelAPI thread, byte-compiled from /root/reference into oracle/_ref by __graft_entry__.build()).  The ONE
+# prediction thread of the reference is its bottleneck on a CPU, so it gets half of the host threads as torch intra-op
+# threads and the player processes a quarter (they mostly wait on their pipes); both numbers are reported.
+def cpu_layout():
+    cores = os.cpu_count() or 1
+    procs = int(os.environ.get("CZ_BENCH_CPU_PROCS", max(1, cores // 4)))
+    nn_threads = int(os.environ.get("CZ_BENCH_CPU_NN_THREADS", max(1, cores // 2)))
+    return cores, procs, nn_threads
+
+
+def ref_conf(sims, filters, blocks, k):
+    play = {"simulation_num_per_move": sims, "search_threads": k, "c_puct": 1.5, "noise_eps": 0.15, "dirichlet_alpha": 0.2,
+            "tau_decay_rate": 0.9, "virtual_loss": 3, "resign_threshold": -0.98, "enable_resign_rate": 0.5, "min_resign_turn": 40,
+            "max_game_length": 100}
+    model = {"cnn_filter_num": filters, "res_layer_num": blocks, "value_fc_size": 256}
+    return play, model
+
+
+def reference_windows(sims, filters, blocks, k, n_windows, window_s, warm_windows=0, free_nn=False, config_type="normal"):
+    """Runs the reference self-play ONCE (persistent process pool) and samples it in windows.
+    Returns (list of (sims, positions, batches, seconds), description, threads used, kind)."""
+    from oracle import ref_selfplay_bench as rb
+    cores, procs, nn_threads = cpu_layout()
+    play, model = ref_conf(sims, filters, blocks, k)
+    if not rb.available():
+        return None, "oracle/_ref not built", 0, "port"
+    run = rb.ReferenceSelfPlay(config_type, procs, 1 if free_nn else nn_threads, play=play, model=model, free_nn=free_nn)
+    try:
+        run.wait_started(timeout=600.0, min_sims=max(1, procs))
+        for _ in range(warm_windows):
+            run.window(window_s)
+        wins = [run.window(window_s) for _ in range(n_windows)]
+    finally:
+        run.close()
+    used = procs + (0 if free_nn else nn_threads)
+    return wins, rb.describe(play, model, procs, nn_threads, free_nn), used, "reference"
+
+
+def port_sample(filters, blocks, sims, k, budget_s):
+    """Fallback when oracle/_ref is absent (a checkout that never saw /root/reference): the oracle port, one process per core."""
     from oracle import cpu_baseline
-    rate, n, dt, _ = cpu_baseline.run(filters, blocks, sims, k, budget_s, procs)
-    return rate, n, dt
+    cores = os.cpu_count() or 1
+    rate, n, dt, _ = cpu_baseline.run(filters, blocks, sims, k, budget_s, cores)
+    return rate, n, dt, cores
+
+
+def cpu_baseline_block(filters, blocks, sims, k, seconds):
+    wins, desc, used, kind = reference_windows(sims, filters, blocks, k, 1, seconds)
+    if wins is None:
+        rate, n, dt, cores = port_sample(filters, blocks, sims, k, seconds)
+        return {"value": rate, "unit": "sims/s", "cores": cores, "kind": "port",
+                "sample": f"oracle/_ref missing -> oracle port (agent/player.py + static_env.py restated), {cores} single-threaded "
+                          f"processes, {n} simulations in a {dt:.1f} s window"}
+    s, p, b, dt = wins[0]
+    return {"value": s / dt, "unit": "sims/s", "cores": used, "kind": kind, "positions_per_s": p / dt, "mean_batch": p / max(1, b),
+            "sample": f"{desc}; one {dt:.0f} s window after start-up ({s} simulations)"}
 
 
 def run_reference_arm(args):
@@ -115,34 +170,241 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     games, sims, filters, blocks = WORKLOADS[args.workload]
-    cores = int(os.environ.get("CZ_BENCH_CPU_PROCS", os.cpu_count() or 1))
-    budget = float(os.environ.get("CZ_BENCH_CPU_SECONDS", max(5.0, min(40.0, 120.0 / max(1, args.steps + args.warmup)))))
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, n, dt = cpu_reference_sample(filters, blocks, sims, args.leaves, budget, cores)
-        if i >= args.warmup:
-            vals.append((v, n, dt))
-    tot_n = sum(x[1] for x in vals)
-    tot_t = sum(x[2] for x in vals)
-    value = sum(x[0] for x in vals) / len(vals)
-    sample = (f"{cores} single-threaded worker processes, each 1 game of self-play from INIT_STATE, search_threads={args.leaves}, "
-              f"{filters}x{blocks} fp32 torch-CPU network, {budget:.0f} s window per step ({tot_n} simulations over {len(vals)} windows)")
+    K = args.leaves
+    cores, procs, nn_threads = cpu_layout()
+    # total timed span >= 60 s split into `steps` windows; the whole run stays within a few minutes
+    window = float(os.environ.get("CZ_BENCH_CPU_WINDOW", max(3.0, 60.0 / max(1, args.steps))))
+    wins, desc, used, kind = reference_windows(sims, filters, blocks, K, args.steps, window, warm_windows=args.warmup)
+    extra = {}
+    if wins is None:
+        vals = [port_sample(filters, blocks, sims, K, window) for _ in range(max(1, min(args.steps, 4)))]
+        tot_n, tot_t = sum(v[1] for v in vals), sum(v[2] for v in vals)
+        value, used, kind = sum(v[0] for v in vals) / len(vals), vals[0][3], "port"
+        desc = "oracle/_ref missing -> oracle port (agent/player.py + static_env.py restated), one single-threaded process per core"
+        per_window = [v[0] for v in vals]
+    else:
+        tot_n, tot_t = sum(w[0] for w in wins), sum(w[3] for w in wins)
+        value = tot_n / tot_t
+        per_window = [w[0] / w[3] for w in wins]
+        extra["nn_positions_per_sec"] = sum(w[1] for w in wins) / tot_t
+        extra["mean_batch"] = sum(w[1] for w in wins) / max(1, sum(w[2] for w in wins))
+        if not args.no_secondary:
+            # BASELINE.json configs[0]: `run.py self --type mini --new` as shipped (1 process, 10 threads, 100 sims, 256x7)
+            os.environ["CZ_BENCH_CPU_PROCS"] = "1"
+            w1, d1, u1, _ = reference_windows(100, 256, 7, 10, 1, 30.0, config_type="mini")
+            os.environ.pop("CZ_BENCH_CPU_PROCS")
+            extra["c1_mini"] = {"value": w1[0][0] / w1[0][3], "unit": "sims/s", "cores": u1, "positions_per_s": w1[0][1] / w1[0][3],
+                                "mean_batch": w1[0][1] / max(1, w1[0][2]), "sample": d1 + f"; one {w1[0][3]:.0f} s window"}
+            # tree-code ceiling: the same plumbing with a constant-output network
+            w2, d2, u2, _ = reference_windows(sims, filters, blocks, K, 1, 20.0, free_nn=True)
+            extra["free_nn_ceiling"] = {"value": w2[0][0] / w2[0][3], "unit": "sims/s", "cores": u2, "sample": d2 + f"; one {w2[0][3]:.0f} s window"}
+    sample = f"{desc}; {len(per_window)} windows of {window:.1f} s after {args.warmup} warm-up windows ({tot_n} simulations in {tot_t:.0f} s)"
     line = {
         "impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, INIT_STATE)",
-        "config": {"workload": f"{args.workload}: {games} games/GPU, {sims} sims/move, {filters}x{blocks} resnet",
-                   "leaves_per_round": args.leaves},
-        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(per_window)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init Keras-equivalent weights, games from INIT_STATE)",
+        "config": bench_config(args.workload, games, sims, filters, blocks, K),
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": used, "kind": kind, "sample": sample,
+                         "host_cores": cores, "max_processes": procs, "nn_threads": nn_threads,
+                         "window_rates": [round(v, 2) for v in per_window]},
         "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    line.update(extra)
     print(json.dumps(line))
     return 0
 
 
+def bench_config(workload, games, sims, filters, blocks, K):
+    """The `config` object BOTH arms print (identical text, so the driver's same-config check can compare them)."""
+    return {"workload": workload_text(workload, games, sims, filters, blocks), "games_per_gpu": games, "sims_per_move": sims,
+            "leaves_per_round": K, "net": f"{filters}x{blocks}"}
+
+
 # ------------------------------------------------------------------------------------------------ our arm
+def make_worker(workload, games, sims, filters, blocks, K, rank, seed, skip_stream, nodes, data_dir, lib):
+    """The drop-in SelfPlayWorker (cczero_b200/self_play.py) on this rank's GPU: it owns the engine the bench times."""
+    from types import SimpleNamespace
+    from cczero_b200.model import CChessModel
+    from cczero_b200.self_play import SelfPlayWorker
+    play = SimpleNamespace(max_processes=1, simulation_num_per_move=sims, search_threads=K, virtual_loss=3, c_puct=1.5, noise_eps=0.15,
+                           dirichlet_alpha=0.2, tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40,
+                           max_game_length=100)
+    mc = SimpleNamespace(cnn_filter_num=filters, res_layer_num=blocks, value_fc_size=256, cnn_first_filter_size=5, cnn_filter_size=3,
+                         input_depth=14)
+    cfg = SimpleNamespace(play=play, model=mc, play_data=SimpleNamespace(nb_game_in_file=1),
+                          resource=SimpleNamespace(play_data_dir=data_dir, play_data_filename_tmpl="play_%s.json"))
+    model = CChessModel(cfg)
+    model.build(seed=0)                      # random-init, Keras-equivalent (agent/model.py:32-66 defaults)
+    w = SelfPlayWorker(cfg, pid=rank, model=model, concurrent_games=games, lib=lib, seed=seed, rank=rank,
+                       engine_kwargs=dict(max_nodes_per_game=nodes or max(4096, 24 * sims), arena=workload == "c5",
+                                          nn_fp32_skip={"auto": None, "fp32": True, "fp16": False}[skip_stream]))
+    if workload == "c5":                     # the arena's second network (next generation): another random init
+        model2 = CChessModel(cfg)
+        model2.build(seed=1)
+        w.engine.set_weights(model2.torch_weights(), net=1)
+        w.engine.reset()
+    return w
+
+
+def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=True, sample_clocks=True):
+    """Device-resident timing (+ optional end-to-end timing) of one workload; returns a dict (rank 0) or None."""
+    import torch
+    from cczero_b200 import records as rec
+    from cczero_b200.lib import get_lib
+
+    lib = get_lib()
+    games, sims, filters, blocks = WORKLOADS[workload]
+    if args.games and workload == args.workload:
+        games = args.games
+    if args.sims and workload == args.workload:
+        sims = args.sims
+    K = args.leaves
+    data_dir = tempfile.mkdtemp(prefix=f"cz_bench_{workload}_")
+    worker = make_worker(workload, games, sims, filters, blocks, K, rank, args.seed, args.skip_stream, args.nodes, data_dir, lib)
+    eng = worker.engine
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gather_ev = []
+
+    def step_device():
+        g, s = eng.selfplay(target_games=0, max_moves=1)
+        n_rec = 0
+        if world > 1:          # the ONE collective of the path: finished-game rings -> rank 0, inside the timed region
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            recs, total = rec.gather_records(eng, dist, world)
+            b.record()
+            gather_ev.append((a, b))
+            n_rec = total
+            if recs:
+                for r, rc in recs:
+                    if not (rc["flags"] & 4):
+                        worker.games_stored += 1
+                        worker.save_play_data(worker.games_stored, rec.record_to_play_data(rc))
+        return s, g, n_rec
+
+    for _ in range(warmup):
+        step_device()
+    gather_ev.clear()
+    # ---- device-resident timing
+    eng.nn_profile(True)
+    st0, c0 = eng.search_stats(), eng.counters()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0 and sample_clocks:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sims_total, games_done, gathered = 0, 0, 0
+    for _ in range(steps):
+        s, g, nr = step_device()
+        sims_total += s
+        games_done += g
+        gathered += nr
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+    conv_ms, conv_launches, conv_flops = eng.nn_profile(False)
+    launches = eng.launch_count() - launches0
+    st1, c1 = eng.search_stats(), eng.counters()
+    gather_ms = sum(a.elapsed_time(b) for a, b in gather_ev)
+    # ---- end-to-end timing through the drop-in worker with host buffers (SelfPlayWorker.host_step)
+    ms_e2e, e2e_sims, h2d, d2h, files = 0.0, 0, 0, 0, 0
+    if want_e2e:
+        stage = rec.RootStage(eng)
+        eng.download_roots(stage)                         # the host-held positions of the first e2e step
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stored0 = worker.games_stored
+        e2.record()
+        rec_bytes = 0
+        for _ in range(steps):
+            s, recs = worker.host_step(stage)
+            e2e_sims += s
+            rec_bytes += sum(16 + 2 * r["n_plies"] for r in recs)
+        e3.record()
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
+        h2d = stage.h2d_bytes
+        d2h = stage.d2h_bytes + 4 * games + rec_bytes // max(1, steps)
+        files = worker.games_stored - stored0
+
+    t = torch.tensor([ms, ms_e2e, conv_ms, gather_ms], device="cuda", dtype=torch.float64)
+    c = torch.tensor([sims_total, e2e_sims, launches, conv_launches, games_done, conv_flops], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    ms, ms_e2e, conv_ms, gather_ms = [float(x) for x in t.tolist()]
+    sims_total, e2e_sims, launches, conv_launches, games_done, conv_flops = [float(x) for x in c.tolist()]
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = (conv_flops / world) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0   # conv_ms: max over ranks, flops: sum
+        d_sims = max(1, st1["sims"] - st0["sims"])
+        depth = (st1["path_edges"] - st0["path_edges"]) / d_sims
+        legal = st1["edges_stored"] / max(1, st1["nodes_stored"])
+        expand = (st1["nodes_created"] - st0["nodes_created"]) / d_sims
+        live = games // 2 if workload == "c5" else games
+        act_mb = games * K * 90 * filters * 2 * 3 / 1e6
+        out = {
+            "value": sims_total / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+            "config": dict(bench_config(workload, games, sims, filters, blocks, K), skip_stream=args.skip_stream,
+                           parallelism=f"dp{world} (games sharded, no data-path collective; finished-game rings all_gathered every step)",
+                           l2=(f"activations {act_mb:.0f} MB per round + tree pools stream through HBM (> 126 MB L2, no flush needed)"
+                               if act_mb > 2 * 126 else
+                               f"activations {act_mb:.0f} MB per round fit the 126 MB L2 and are NOT flushed between steps (secondary "
+                               f"workload; the headline workload c3 streams 1.1 GB per round)"),
+                           games_finished=int(games_done), records_gathered=int(gathered), gather_ms_per_step=gather_ms / steps),
+            "nn_positions_per_sec": (conv_flops / (2.0 * 90 * 9 * filters * filters * 2 * blocks)) / (ms * 1e-3),
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC.get((workload, games, K)),
+                         "kernel": f"igemm::k_igemm2<{filters}> (3x3 residual conv, tcgen05 cta_group::2)",
+                         "launches": int(conv_launches), "avg_launch_ms": conv_ms / max(1.0, conv_launches / world),
+                         "peak_source": peak_src, "share_of_step": conv_ms / ms,
+                         "whole_net_frac_of_step": (conv_flops / (2.0 * 90 * 9 * filters * filters * 2 * blocks)) * net_flops(filters, blocks)
+                                                   / world / (ms * 1e-3) / 1e12 / peak},
+            "search_stats": {
+                "mean_path_edges": depth, "mean_legal_moves": legal, "no_network_rate": (st1["no_network"] - st0["no_network"]) / d_sims,
+                "expansions_per_sim": expand,
+                "waves_per_move": float(c1[2] - c0[2]) / steps,
+                "mean_reused_sims_per_move": sims - (st1["sims"] - st0["sims"]) / (steps * live),
+                "compactions": int(c1[5] - c0[5]), "table_resets": int(c1[4] - c0[4]), "records_dropped": int(c1[3] - c0[3]),
+                "error_flags": int(c1[6]),
+                "tree_bytes_per_sim": depth * (32 + 14 * legal) + depth * 24 + depth * 90
+                                      + expand * ((32 + 22 * legal) + 90 + 2 * legal + 96 + policy_bytes_per_leaf(legal)),
+                "note": "algorithmic HBM bytes of the integer kernels per simulation (SURVEY.md section 8d): select reads + virtual-loss/"
+                        "backup RMW + board replay per path edge; per expansion node+edge write, movegen, leaf record, and what k_apply "
+                        "reads of the network output; compactions / table_resets / records_dropped counted over rank 0's timed region"},
+            "clocks": clocks,
+        }
+        if want_e2e:
+            out["e2e"] = {"value": e2e_sims / (ms_e2e * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                          "ms_per_step": ms_e2e / steps, "play_data_files_written": int(files),
+                          "path": "SelfPlayWorker.host_step: pinned root upload -> cz_search -> visit counts down -> cz_play_move -> "
+                                  "records drained + play-data JSON written -> new roots down"}
+    worker.close()
+    del worker, eng
+    torch.cuda.empty_cache()
+    return out
+
+
+FUSED_POLICY = False     # flipped when the integrated search gathers legal logits itself (no [B][2086] f32 policy row)
+
+
+def policy_bytes_per_leaf(legal):
+    """What k_apply reads of the network output per expanded leaf: the 2086-entry f32 policy row k_softmax wrote, or — fused
+    path — the legal logits (4 bytes each) plus the 9 per-tile softmax statistics (72 bytes)."""
+    return (4 * legal + 72) if FUSED_POLICY else 4 * 2086
+
+
 def run_ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -155,173 +417,32 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from cczero_b200.engine import Engine
-    from cczero_b200.lib import get_lib
-    from cczero_b200 import records as rec
-    from cczero_b200.model import CChessModel
-    from types import SimpleNamespace
-
-    lib = get_lib()
-    games, sims, filters, blocks = WORKLOADS[args.workload]
-    if args.games:
-        games = args.games
-    if args.sims:
-        sims = args.sims
-    K = args.leaves
-    eng = Engine(lib, f"cuda:{local}", n_games=games, sims_per_move=sims, leaves_per_round=K, noise_mode=1,
-                 nn_filters=filters, nn_blocks=blocks, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
-                 tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, max_game_length=100,
-                 max_nodes_per_game=args.nodes or max(4096, 24 * sims), seed=args.seed, rank=rank,
-                 nn_fp32_skip={"auto": None, "fp32": True, "fp16": False}[args.skip_stream], arena=args.workload == "c5")
-    model = CChessModel(SimpleNamespace(model=SimpleNamespace(cnn_filter_num=filters, res_layer_num=blocks, value_fc_size=256,
-                                                              cnn_first_filter_size=5, cnn_filter_size=3, input_depth=14)))
-    model.build(seed=0)                      # random-init, Keras-equivalent (agent/model.py:32-66 defaults)
-    eng.set_weights(model.torch_weights())
-    if args.workload == "c5":                # the arena's second network (next generation): another random init
-        model.build(seed=1)
-        eng.set_weights(model.torch_weights(), net=1)
-    eng.reset()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_device():
-        g, s = eng.selfplay(target_games=0, max_moves=1)
-        return s, g
-
-    # pinned host staging for the end-to-end arm
-    init_boards = rec.init_boards_pinned(games)
-    root_host = rec.RootStage(eng)
-
-    def step_e2e():
-        """Through the host-facing API: root positions come from pinned host memory, the search runs, the move is
-        played and the per-game result (root visit counts + chosen move + finished records) is read back."""
-        boards = eng.download_roots(root_host)            # D2H (previous result feeds the next request)
-        eng.upload_roots(boards)                           # H2D of this step's inputs
-        eng.search(None)
-        stats = eng.download_root_stats(root_host)         # D2H visit counts of every root
-        s = int(eng.sims_run().sum())
-        f = eng.play_move()
-        recs = eng.drain_records()
-        return s, f, stats, recs
-
-    for _ in range(args.warmup):
-        step_device()
-    # ---- device-resident timing
-    eng.nn_profile(True)
-    st0 = eng.search_stats()
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    barrier()
+    main = measure(args, args.workload, args.steps, args.warmup, world, rank, local, dist)
+    secondary = {}
+    if world == 1 and not args.no_secondary and args.workload == "c3":
+        # BASELINE.json configs[1] and configs[4], short, each with its own roofline (driver-visible)
+        for name, st, wu in (("c2", 12, 4), ("c5", 2, 3)):
+            try:
+                m = measure(args, name, st, wu, world, rank, local, dist, want_e2e=False, sample_clocks=False)
+                secondary[name] = {k: m[k] for k in ("value", "ms_per_step", "steps", "warmup", "config", "nn_positions_per_sec", "roofline",
+                                                     "search_stats", "gpu_launches")}
+                secondary[name]["unit"] = "sims/s"
+            except Exception as e:        # a secondary workload must never take the headline down with it
+                secondary[name] = {"error": repr(e)}
     if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    sims_total, games_done = 0, 0
-    for _ in range(args.steps):
-        s, g = step_device()
-        sims_total += s
-        games_done += g
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    conv_ms, conv_launches, conv_flops = eng.nn_profile(False)
-    launches = eng.launch_count() - launches0
-    positions = int(eng.counters()[1])
-    st1 = eng.search_stats()
-    # ---- NCCL gather of finished play records (the only inter-GPU traffic of the path), timed with the step region
-    gathered = 0
-    if world > 1:
-        gathered = rec.gather_records(eng, dist, world)
-    # ---- end-to-end timing through the host API
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    e2e_sims = 0
-    h2d = d2h = 0
-    for _ in range(args.steps):
-        s, f, stats, recs = step_e2e()
-        e2e_sims += s
-        h2d = root_host.h2d_bytes
-        d2h = root_host.d2h_bytes
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-
-    t = torch.tensor([ms, ms_e2e, conv_ms], device="cuda", dtype=torch.float64)
-    c = torch.tensor([sims_total, e2e_sims, launches, conv_launches, games_done], device="cuda", dtype=torch.float64)
-    fl = torch.tensor([conv_flops], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
-    ms, ms_e2e, conv_ms = [float(x) for x in t.tolist()]
-    sims_total, e2e_sims, launches, conv_launches, games_done = [float(x) for x in c.tolist()]
-    conv_flops = float(fl.item())
-
-    act_mb = games * K * 90 * filters * 2 * 3 / 1e6            # three fp16 activation buffers touched by every residual block
-    tree_mb = games * (args.nodes or max(4096, 24 * sims)) * (32 + 48 * 22) / 1e6
-    l2_note = (f"working set larger than the 126 MB L2: activations {act_mb:.0f} MB per round + tree pools {tree_mb / 1e3:.1f} GB "
-               f"(no flush needed)" if act_mb > 2 * 126 else
-               f"activations {act_mb:.0f} MB per round fit the 126 MB L2 and are NOT flushed between steps (secondary workload; the "
-               f"headline workload c3 streams 1.1 GB per round)")
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        # per-rank achieved rate of the dominant kernel (conv_ms is the max over ranks, flops the sum)
-        achieved = (conv_flops / world) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        value = sims_total / (ms * 1e-3)
-        cores = os.cpu_count() or 1
+        games, sims, filters, blocks = WORKLOADS[args.workload]
         cpu = None
         if world == 1 and not args.no_cpu:
-            v, n, dt = cpu_reference_sample(filters, blocks, sims, K, args.cpu_seconds, cores)
-            cpu = {"value": v, "unit": "sims/s", "cores": cores, "kind": "port",
-                   "sample": f"oracle port (agent/player.py + static_env.py restated, fp32 torch-CPU {filters}x{blocks} net): {cores} "
-                             f"single-threaded worker processes x 1 self-play game from INIT_STATE, search_threads={K}, "
-                             f"{n} simulations in a {dt:.1f} s window"}
-        line = {
-            "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16", "data": "synthetic (random-init Keras-equivalent weights, games from INIT_STATE)",
-            "config": {"workload": f"{args.workload} = BASELINE.json configs[{dict(c2=1, c3=2, c5=4).get(args.workload, '-')}]: {games} "
-                                   f"concurrent {'player slots (arena)' if args.workload == 'c5' else 'games'}/GPU, {sims} sims/move, "
-                                   f"{filters}x{blocks} resnet", "games_per_gpu": games, "sims_per_move": sims,
-                       "leaves_per_round": K, "skip_stream": args.skip_stream, "parallelism": f"dp{world} (games sharded, no data-path collective)",
-                       "l2": l2_note, "nn_positions": positions,
-                       "games_finished": games_done, "records_gathered": gathered},
-            "nn_positions_per_sec": None,
-            "e2e": {"value": e2e_sims / (ms_e2e * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC.get((args.workload, games, K)),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full "
-                                           "(profiles/r01c_igemm2_final_ncu_raw.csv, ~4096-board launches of the two-range pipeline): conv1 "
-                                           "339 MB, conv2 with the fp32 skip stream 1090 MB, mean 715 MB = the algorithmic bytes (fp16 in/out "
-                                           "189 MB each, fp32 skip in/out 377 MB each)",
-                         "kernel": "igemm::k_igemm2<C> (3x3 residual conv, tcgen05 cta_group::2)",
-                         "launches": int(conv_launches), "avg_launch_ms": conv_ms / max(1.0, conv_launches / world),
-                         "peak_source": peak_src, "share_of_step": conv_ms / ms},
-            "cpu_baseline": cpu,
-            "clocks": clocks,
-        }
-        # the byte model of the tree kernels (SURVEY.md §8d) evaluated on what rank 0's timed region actually did
-        d_sims = max(1, st1["sims"] - st0["sims"])
-        depth = (st1["path_edges"] - st0["path_edges"]) / d_sims
-        legal = st1["edges_stored"] / max(1, st1["nodes_stored"])
-        expand = (st1["nodes_created"] - st0["nodes_created"]) / d_sims
-        line["search_stats"] = {
-            "mean_path_edges": depth, "mean_legal_moves": legal, "no_network_rate": (st1["no_network"] - st0["no_network"]) / d_sims,
-            "expansions_per_sim": expand,
-            "tree_bytes_per_sim": depth * (32 + 14 * legal) + depth * 24 + depth * 90 + expand * ((32 + 22 * legal) + 90 + 2 * legal
-                                                                                                + 96 + 4 * 2086),
-            "note": "algorithmic HBM bytes of the integer kernels per simulation: select reads + virtual-loss/backup RMW + board "
-                    "replay per path edge; per expansion node+edge write, movegen, leaf record, policy row read by k_apply"}
-        line["nn_positions_per_sec"] = (conv_flops / (2.0 * 90 * 9 * filters * filters * 2 * blocks)) / (ms * 1e-3)
+            cpu = cpu_baseline_block(filters, blocks, sims, args.leaves, args.cpu_seconds)
+        line = {"metric": "mcts_sims_per_sec", "value": main["value"], "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic (random-init Keras-equivalent weights, games from INIT_STATE)",
+                "config": main["config"], "nn_positions_per_sec": main["nn_positions_per_sec"], "e2e": main["e2e"],
+                "gpu_launches": main["gpu_launches"], "roofline": main["roofline"], "cpu_baseline": cpu, "clocks": main["clocks"],
+                "search_stats": main["search_stats"]}
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -341,6 +462,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short c2 / c5 runs (and the c1 / free-NN legs of the CPU arm)")
     ap.add_argument("--skip-stream", default="auto", choices=["auto", "fp32", "fp16"],
                     help="precision of the residual skip stream (auto = fp32 beyond 10 blocks: keeps the 1e-3 parity bound)")
     args = ap.parse_args()

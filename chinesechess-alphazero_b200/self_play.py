@@ -74,7 +74,7 @@ def start(config, games_per_process=128, max_games=None, flush_plies=8, lib=None
 
 class SelfPlayWorker:
     def __init__(self, config, pipes=None, pid=None, use_history=False, model=None, concurrent_games=None, lib=None,
-                 device=None, seed=0, rank=0, external_evaluator=False):
+                 device=None, seed=0, rank=0, external_evaluator=False, engine_kwargs=None):
         self.config = config
         self.cur_pipes = pipes          # unused: evaluation happens inside the engine
         self.id = pid
@@ -92,10 +92,11 @@ class SelfPlayWorker:
             virtual_loss=pc.virtual_loss, noise_mode=1, c_puct=pc.c_puct, noise_eps=pc.noise_eps,
             dirichlet_alpha=pc.dirichlet_alpha, tau_decay_rate=pc.tau_decay_rate, resign_threshold=pc.resign_threshold,
             enable_resign_rate=pc.enable_resign_rate, min_resign_turn=pc.min_resign_turn, max_game_length=pc.max_game_length,
-            max_nodes_per_game=max(4096, 24 * pc.simulation_num_per_move),
-            nn_filters=0 if external_evaluator else mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size,
-            seed=seed, rank=rank,
-            use_history=use_history)    # the game loop never passes `hist` (self_play.py:124): path history only
+            **dict(dict(max_nodes_per_game=max(4096, 24 * pc.simulation_num_per_move),
+                        nn_filters=0 if external_evaluator else mc.cnn_filter_num, nn_blocks=mc.res_layer_num,
+                        nn_value_fc=mc.value_fc_size, seed=seed, rank=rank,
+                        use_history=use_history),   # the game loop never passes `hist` (self_play.py:124): path history only
+                   **(engine_kwargs or {})))
         if not external_evaluator:      # external evaluator: the leaves go to a caller-supplied function (CPU test tier)
             self.engine.set_weights(self.model.torch_weights())
         self.engine.reset()
@@ -172,6 +173,27 @@ class SelfPlayWorker:
                 self.games_stored += 1
                 self.save_play_data(self.games_stored, record_to_play_data(rec))
         return out
+
+    def host_step(self, stage):
+        """One ply of every game with the HOST holding the positions, the way a loop around `CChessPlayer.action(state, ..)`
+        drives the reference (worker/self_play.py:122-147): this ply's root positions go up from pinned host memory, the
+        search runs, every root's visit counts (calc_policy's input, the training target) come back, the moves are played,
+        finished games are drained and stored as play-data files (self_play.py:202-227), and the new positions are read back
+        for the next ply.  `stage` is a records.RootStage (pinned buffers).  Returns (simulations run, finished records)."""
+        eng = self.engine
+        eng.upload_roots(stage.boards)                     # H2D: the inputs of this step
+        eng.search(None)
+        eng.download_root_stats(stage)                     # D2H: N(s, a) of every root + simulations run
+        sims = int(stage.sims.numpy()[eng.active_flags() != 0].sum())
+        recs = []
+        if eng.play_move():
+            recs = eng.drain_records()                     # D2H: finished games
+            for rec in recs:
+                if not (rec["flags"] & 4):
+                    self.games_stored += 1
+                    self.save_play_data(self.games_stored, record_to_play_data(rec))
+        eng.download_roots(stage)                          # D2H: the positions the host holds for the next ply
+        return sims, recs
 
     # ---- self_play.py:214-227
     def save_play_data(self, idx, data):

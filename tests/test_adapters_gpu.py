@@ -187,7 +187,7 @@ def test_evaluator_arena_two_networks(cuda_lib, tmp_path):
     cfg.play.c_puct = 1
     cfg.eval = SimpleNamespace(game_num=2)
     bt, ng = CChessModel(cfg).build(seed=1), CChessModel(cfg).build(seed=2)
-    w = EvaluateWorker(cfg, bt, ng, n_games=6, concurrent_games=4, seed=3)
+    w = EvaluateWorker(cfg, bt, ng, n_games=6, concurrent_games=4, seed=3, playouts=None)
     total, rw, rd, rf, bw, bd, bf = w.start()
     assert rw + rd + rf + bw + bd + bf == 6
     assert 0 <= total <= 6 and abs(total - (rw + bw + 0.5 * (rd + bd))) < 1e-9
@@ -195,8 +195,52 @@ def test_evaluator_arena_two_networks(cuda_lib, tmp_path):
     w.close()
     # identical networks on both sides and no randomness: the same game is played from both colours
     cfg.play.noise_eps = 0
-    w = EvaluateWorker(cfg, bt, bt, n_games=4, concurrent_games=4, seed=3)
+    w = EvaluateWorker(cfg, bt, bt, n_games=4, concurrent_games=4, seed=3, playouts=None)
     w.engine.selfplay(target_games=4, max_moves=0)
     recs = sorted(w.engine.drain_records(), key=lambda r: r["game_index"])
     assert recs[0]["moves"] == recs[1]["moves"] and recs[0]["value_red"] == recs[1]["value_red"]
     w.close()
+
+
+def test_c3_shaped_builtin_search_equals_wave_apply(cuda_lib):
+    """BASELINE configs[2] shape (1024 games x K = 8, 14 planes, 256x20 network, fp32 skip stream): the integrated
+    `cz_search` — two-range pipelined AND single-range — gives bit for bit the statistics of the same search driven from the
+    host through cz_search_wave / cz_leaf_boards / cz_nn_forward_boards / cz_search_apply."""
+    from cczero_b200.engine import Engine
+    from cczero_b200.model import CChessModel
+    from cczero_b200.records import RootStage
+    cfg = _config("/tmp", filters=256, blocks=20)
+    weights = CChessModel(cfg).build(seed=4).torch_weights()
+
+    def run(mode):
+        os.environ.pop("CZ_NO_PIPELINE", None)
+        if mode == "single":
+            os.environ["CZ_NO_PIPELINE"] = "1"
+        try:
+            eng = Engine(cuda_lib, "cuda", n_games=1024, sims_per_move=40, leaves_per_round=8, noise_mode=1, nn_filters=256,
+                         nn_blocks=20, seed=11, max_nodes_per_game=1024)
+        finally:
+            os.environ.pop("CZ_NO_PIPELINE", None)
+        eng.set_weights(weights)
+        eng.reset()
+        st = RootStage(eng)
+        out = []
+        for _ in range(2):                                   # second move: tree reuse + a different position per game
+            if mode == "host":
+                eng.search_begin(None)
+                eng.run_waves(None)
+            else:
+                eng.search(None)
+            n, mv, cnt = eng.download_root_stats(st)
+            roots = [eng.root(g) for g in (0, 1, 511, 512, 777, 1023)]
+            out.append((n.clone(), mv.clone(), cnt.clone(), [(r["n"], r["w"], r["p"], r["sum_n"]) for r in roots]))
+            eng.play_move()
+        assert int(eng.counters()[6]) == 0
+        eng.close()
+        return out
+    host, pipe, single = run("host"), run("pipelined"), run("single")
+    for a in (pipe, single):
+        for (n0, m0, c0, r0), (n1, m1, c1, r1) in zip(host, a):
+            assert torch.equal(n0, n1) and torch.equal(m0, m1) and torch.equal(c0, c1)
+            assert r0 == r1                                  # N, W (f64), P (f32), sum_n of sampled roots, exactly
+    assert int(host[1][0].sum()) > int(host[0][0].sum()) * 0.9

@@ -72,3 +72,19 @@ def test_cuda_env_golden(cuda_env, golden_env):
 @pytest.mark.gpu
 def test_cuda_env_single_api(cuda_env):
     env_checks.check_single_api(cuda_env)
+
+
+def test_emul_env_playout_sweep(emul_env):
+    """The bulk sweep of tests/env_sweep.py on the emulator build (small: the emulator runs lanes one after another)."""
+    from tests.env_sweep import check_sweep
+    st = check_sweep(emul_env, 4000, seed=7, procs=4)
+    assert st["terminal"] > 20 and st["wcc"] > 100 and st["bc"] > 100
+
+
+@pytest.mark.gpu
+def test_cuda_env_playout_sweep_1e5(cuda_env):
+    """>= 1e5 random-playout positions, every rules kernel bit for bit against the oracle."""
+    from tests.env_sweep import check_sweep
+    st = check_sweep(cuda_env, 120000, seed=2024)
+    print("rules sweep:", st)
+    assert st["positions"] == 120000 and st["terminal"] > 1000 and st["checks"] > 500 and st["wcc"] > 5000 and st["bc"] > 5000
