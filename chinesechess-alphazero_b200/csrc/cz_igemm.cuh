@@ -48,7 +48,17 @@ struct Args {
   float* out32;            // optional fp32 copy of the output (the skip stream of the next block) or null
   void* out;
   uint32_t a_bytes;  // TMA bytes per A box
+  // Batch size read on the DEVICE (fixed-shape launches: the host never learns how many leaves a wave produced).  When
+  // n_dev != null, rows = *n_dev * rows_per_unit and m_tiles follows; `rows` / `m_tiles` above are then only upper bounds.
+  const int* n_dev;
+  int rows_per_unit; // 90 pixels per board (dense conv), 1 (GEMM rows = positions)
+  // GEMM mode (out_f32): per output row and N tile the pair {max_j x_j, sum_j exp(x_j - max)} over the tile's valid
+  // columns — the softmax is finished by whoever reads the logits (k_softmax / k_legal_priors), never a second full pass
+  float2* row_stats; // [rows][n_tiles] or null
 };
+
+// rows / m-tiles of this launch (device-side batch size)
+__device__ __forceinline__ int args_rows(const Args& a) { return a.n_dev ? __ldg(a.n_dev) * a.rows_per_unit : a.rows; }
 
 template <int N_TILE>
 struct Cfg {
@@ -93,14 +103,16 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_kb = a.n_taps * a.k_chunks;
-  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int rows = args_rows(a);
+  const int m_tiles = a.n_dev ? (rows + a.box_r * a.box_w - 1) / (a.box_r * a.box_w) : a.m_tiles;   // n_dev: GEMM / dense modes only
+  const int total_tiles = m_tiles * a.n_tiles;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
+        const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
         for (int tap = 0; tap < a.n_taps; ++tap) {
           const int dy = a.n_taps == 9 ? tap / 3 - 1 : 0;
           const int dx = a.n_taps == 9 ? tap % 3 - 1 : 0;
@@ -147,7 +159,7 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     const int m = q * 32 + lane;            // accumulator row == pixel inside the tile
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int m_tile = tile % a.m_tiles, n_tile = tile / a.m_tiles;
+      const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       umma::mbar_wait(&tfull[acc], aph);
       umma::tc_fence_after();
@@ -155,14 +167,26 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
       bool valid, zero = false;
       if (a.conv) {
         const int srow = m_tile * a.box_r + m / 9;          // strip row
-        valid = m < a.box_r * 9 && srow < a.rows;
+        valid = m < a.box_r * 9 && srow < rows;
         zero = (srow % 11) == 10;                           // separator row stays zero
         grow = (long long)m_tile * a.box_r * 9 + m;
       } else {
         grow = (long long)m_tile * kTileM + m;
-        valid = grow < a.rows;
+        valid = grow < rows;
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE;
+      float row_max = -INFINITY, row_sum = 0.f;
+      if (a.row_stats) {                                    // pass 1 over the accumulator: the row maximum of this N tile
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t v[32];
+          umma::tmem_ld_32x32(t_row + c0, v);
+          const int n0 = n_tile * N_TILE + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < a.n_valid) row_max = fmaxf(row_max, __uint_as_float(v[j]) + (a.bias ? __ldg(a.bias + n0 + j) : 0.f));
+        }
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t v[32];
@@ -178,6 +202,11 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           }
           if (a.out_f32) {
             float* o = reinterpret_cast<float*>(a.out) + grow * a.ldo + n0;
+            if (a.row_stats) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < a.n_valid) row_sum += expf(f[j] - row_max);
+            }
             if (n0 + 32 <= a.n_valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) o[j] = a.relu ? fmaxf(f[j], 0.f) : f[j];
@@ -217,6 +246,7 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           }
         }
       }
+      if (a.row_stats && valid) a.row_stats[grow * a.n_tiles + n_tile] = make_float2(row_max, row_sum);
       umma::tc_fence_before();
       umma::mbar_arrive(&tempty[acc]);
     }
@@ -292,7 +322,9 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_kb = a.n_taps * a.k_chunks;
-  const int pairs = (a.m_tiles + 1) / 2;
+  const int rows = args_rows(a);
+  const int m_tiles = a.n_dev ? (rows + kTileM - 1) / kTileM : a.m_tiles;
+  const int pairs = (m_tiles + 1) / 2;
   const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
 
   if (warp == 0) {
@@ -367,7 +399,7 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     auto prefetch_skip = [&](int pr) {
       if (warp != 4 || pr >= pairs || !(a.residual32 || a.residual)) return;
       const long long row0 = (long long)(2 * pr + (int)rank) * kTileM;
-      const long long nrow = a.rows - row0 < kTileM ? a.rows - row0 : kTileM;
+      const long long nrow = rows - row0 < kTileM ? rows - row0 : kTileM;
       if (nrow <= 0) return;
       const size_t esz = a.residual32 ? 4 : 2;
       const char* base = (a.residual32 ? reinterpret_cast<const char*>(a.residual32) : reinterpret_cast<const char*>(a.residual)) +
@@ -390,12 +422,12 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         if (r32) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            nf[k] = (rbase + r4 + 4 * k < a.rows) ? __ldg(reinterpret_cast<const float4*>(r32 + (size_t)(r4 + 4 * k) * a.ldo + ch * 32 + c4))
+            nf[k] = (rbase + r4 + 4 * k < rows) ? __ldg(reinterpret_cast<const float4*>(r32 + (size_t)(r4 + 4 * k) * a.ldo + ch * 32 + c4))
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         } else if (r16) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            nh[k] = (rbase + r8 + 8 * k < a.rows) ? __ldg(reinterpret_cast<const uint4*>(r16 + (size_t)(r8 + 8 * k) * a.ldo + ch * 32 + c8))
+            nh[k] = (rbase + r8 + 8 * k < rows) ? __ldg(reinterpret_cast<const uint4*>(r16 + (size_t)(r8 + 8 * k) * a.ldo + ch * 32 + c8))
                                                   : make_uint4(0u, 0u, 0u, 0u);
         }
       };
@@ -442,7 +474,7 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           float* o32 = a.out32 + rbase * a.ldo + c0;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            if (rbase + r4 + 4 * k < a.rows)
+            if (rbase + r4 + 4 * k < rows)
               *reinterpret_cast<float4*>(o32 + (size_t)(r4 + 4 * k) * a.ldo + c4) = *reinterpret_cast<const float4*>(S + (r4 + 4 * k) * kStageRow + c4);
         }
         {
@@ -455,7 +487,7 @@ k_igemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             __half2* oh = reinterpret_cast<__half2*>(&ov);
             oh[0] = __floats2half2_rn(x0.x, x0.y); oh[1] = __floats2half2_rn(x0.z, x0.w);
             oh[2] = __floats2half2_rn(x1.x, x1.y); oh[3] = __floats2half2_rn(x1.z, x1.w);
-            if (rbase + r8 + 8 * k < a.rows) *reinterpret_cast<uint4*>(o16 + (size_t)(r8 + 8 * k) * a.ldo + c8) = ov;
+            if (rbase + r8 + 8 * k < rows) *reinterpret_cast<uint4*>(o16 + (size_t)(r8 + 8 * k) * a.ldo + c8) = ov;
           }
         }
         __syncwarp();

@@ -222,7 +222,8 @@ __device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 
 // select planes 14-27; board_stride = bytes between records.
 __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
                              const float* __restrict__ shift, __half* __restrict__ out, float* __restrict__ out32, int c_out,
-                             int board_pixels, int in_planes, int board_stride) {
+                             int board_pixels, int in_planes, int board_stride, const int* __restrict__ n_dev) {
+  if ((int)blockIdx.x >= __ldg(n_dev)) return;              // fixed-shape launch: the batch size lives on the device
   __shared__ int8_t pl[2][90];
   __shared__ uint16_t rows[90][52];
   __shared__ uint8_t cnt[90];
@@ -297,8 +298,8 @@ __global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __
 // A block handles kHeadPos positions so the 180 x H value weights are read once per group.
 // Phase 1: warp per pixel, lane owns 8 channels whose 6 x 8 folded weights sit in registers.
 constexpr int kHeadPos = 4;
-__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, const float* __restrict__ act32, int c_in, int n_pos,
-                                                int board_pixels,
+__global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, const float* __restrict__ act32, int c_in,
+                                                const int* __restrict__ n_dev, int board_pixels,
                                                 const float* __restrict__ w6,      // [6][c_in], BN scale folded
                                                 const float* __restrict__ shift6,  // [6]
                                                 const float* __restrict__ wv1,     // [180][H]
@@ -310,6 +311,8 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
   __shared__ float red[kHeadPos][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * kHeadPos;
+  const int n_pos = __ldg(n_dev);
+  if (b0 >= n_pos) return;
   const int npos = n_pos - b0 < kHeadPos ? n_pos - b0 : kHeadPos;
   const int cbase = lane * 8;
   const bool lane_on = cbase < c_in;
@@ -389,41 +392,48 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
   }
 }
 
-// softmax over the 2086 labels; logits [B][ldl] f32 -> policy [B][2086] f32. grid = batch, block = 256.
-__global__ void __launch_bounds__(256) k_softmax(const float* __restrict__ logits, int ldl, float* __restrict__ policy) {
-  __shared__ float red[8];
-  __shared__ float bc;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* l = logits + (size_t)b * ldl;
+// Softmax over the 2086 labels, finished from the per-N-tile statistics the policy GEMM epilogue wrote:
+//   stats[row][t] = {m_t = max_j x_j, s_t = sum_j exp(x_j - m_t)} over the valid columns of tile t
+//   m = max_t m_t,  S = sum_t s_t * exp(m_t - m),  p_j = exp(x_j - m) * (1 / S)
+// `policy_prob` is the ONE definition of a policy probability in this library: k_softmax (the [B][2086] vector the
+// reference-facing API returns) and k_legal_priors (only the legal moves of a search leaf) both evaluate it, so the
+// integrated search sees bit for bit the numbers an external caller of cz_nn_forward would feed back.
+struct RowStat { float mx, inv; };
+__device__ __forceinline__ RowStat combine_stats(const float2* __restrict__ st, int n_tiles) {
   float mx = -INFINITY;
-  for (int i = tid; i < kLabels; i += 256) mx = fmaxf(mx, l[i]);
-  for (int m = 16; m; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  if (tid == 0) { float v = red[0]; for (int i = 1; i < 8; ++i) v = fmaxf(v, red[i]); bc = v; }
-  __syncthreads();
-  mx = bc;
-  float e[(kLabels + 255) / 256];
+  for (int t = 0; t < n_tiles; ++t) mx = fmaxf(mx, __ldg(&st[t].x));
   float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < (kLabels + 255) / 256; ++j) {
-    const int i = tid + j * 256;
-    e[j] = i < kLabels ? expf(l[i] - mx) : 0.f;
-    s += e[j];
-  }
-  for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-  __syncthreads();
-  if (lane == 0) red[warp] = s;
-  __syncthreads();
-  if (tid == 0) { float v = 0.f; for (int i = 0; i < 8; ++i) v += red[i]; bc = 1.f / v; }
-  __syncthreads();
-  const float inv = bc;
-#pragma unroll
-  for (int j = 0; j < (kLabels + 255) / 256; ++j) {
-    const int i = tid + j * 256;
-    if (i < kLabels) policy[(size_t)b * kLabels + i] = e[j] * inv;
+  for (int t = 0; t < n_tiles; ++t) { const float2 v = __ldg(st + t); s = __fmaf_rn(v.y, expf(v.x - mx), s); }
+  RowStat r; r.mx = mx; r.inv = __frcp_rn(s);
+  return r;
+}
+__device__ __forceinline__ float policy_prob(float logit, const RowStat& r) { return __fmul_rn(expf(logit - r.mx), r.inv); }
+
+// logits [B][ldl] f32 -> policy [B][2086] f32. grid = batch, block = 256.
+__global__ void __launch_bounds__(256) k_softmax(const float* __restrict__ logits, int ldl, const float2* __restrict__ stats, int n_tiles,
+                                                  float* __restrict__ policy) {
+  const int b = blockIdx.x;
+  const RowStat rs = combine_stats(stats + (size_t)b * n_tiles, n_tiles);
+  const float* l = logits + (size_t)b * ldl;
+  for (int i = threadIdx.x; i < kLabels; i += 256) policy[(size_t)b * kLabels + i] = policy_prob(l[i], rs);
+}
+
+// Integrated search: softmax probabilities of the LEGAL moves of every leaf only (player.py:272-284 reads nothing else of the
+// policy vector).  labels [n][CZ_MAX_MOVES] int16 (-1 = the move has no label), counts [n]; out [n][CZ_MAX_MOVES] f32.  Warp per leaf.
+__global__ void __launch_bounds__(128) k_legal_priors(const float* __restrict__ logits, int ldl, const float2* __restrict__ stats, int n_tiles,
+                                                       const int16_t* __restrict__ labels, const int32_t* __restrict__ counts,
+                                                       const int* __restrict__ n_dev, float* __restrict__ out) {
+  const int leaf = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (leaf >= __ldg(n_dev)) return;
+  const RowStat rs = combine_stats(stats + (size_t)leaf * n_tiles, n_tiles);
+  const float* l = logits + (size_t)leaf * ldl;
+  const int L = counts[leaf];
+  for (int i = lane; i < L; i += 32) {
+    const int lab = labels[(size_t)leaf * CZ_MAX_MOVES + i];
+    out[(size_t)leaf * CZ_MAX_MOVES + i] = lab >= 0 ? policy_prob(l[lab], rs) : 0.f;
   }
 }
+__global__ void k_set_int(int* p, int v) { *p = v; }
 
 // ---- weight preparation (Keras layout f32 -> folded operands)
 __global__ void k_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float* scale,
@@ -506,6 +516,10 @@ struct NnRuntime {
   __half *x, *t, *y, *pol_feat;
   float *x32, *y32;                      // fp32 skip stream (dense layout only)
   float* logits;
+  float2* stats;                         // [max_batch][kPolN / 256] softmax statistics of the policy GEMM's N tiles
+  int* n_scalar;                         // device copy of a host-known batch size (reference-facing forward)
+  bool capturing;                        // inside cudaStreamBeginCapture: no event records / synchronisation
+  size_t prof_open;                      // event pair opened by nn_prof_begin
   uint8_t* boards_tmp;
   int in_planes;                         // 14, or 28 with use_history (board + history board per position)
   // weights
@@ -567,6 +581,8 @@ static void layout(NnRuntime* r, Carver& cv) {
   r->y32 = (float*)cv.take(act * 2);
   r->pol_feat = (__half*)cv.take(((size_t)r->max_batch + 128) * kPolK * sizeof(__half));
   r->logits = (float*)cv.take((size_t)r->max_batch * kPolN * sizeof(float));
+  r->stats = (float2*)cv.take((size_t)r->max_batch * (kPolN / 256) * sizeof(float2));
+  r->n_scalar = (int*)cv.take(64);
   r->boards_tmp = (uint8_t*)cv.take((size_t)r->max_batch * 2 * CZ_BOARD_STRIDE);
   for (int net = 0; net < r->n_nets; ++net) {
   r->w_first = (__half*)cv.take((size_t)25 * 28 * c * sizeof(__half));
@@ -614,7 +630,7 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   // reference's trained 192x10 net), 1 = always, 2 = never
   r->fp32_skip = fp32_skip_mode == 1 || (fp32_skip_mode == 0 && blocks >= 10);
   { const char* e = getenv("CZ_FP32_SKIP"); if (e && e[0] == '1') r->fp32_skip = true; if (e && e[0] == '0') r->fp32_skip = false; }
-  r->profile = false; r->ev_used = 0; r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0;
+  r->profile = false; r->ev_used = 0; r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0; r->capturing = false;
   Carver cv{(uint8_t*)workspace, 0, bytes};
   layout(r, cv);
   const int c = filters;
@@ -771,27 +787,28 @@ int nn_set_weights(NnRuntime* r, int net, const cz_tensor_desc* descs, int n) {
 }
 
 // ---- forward -----------------------------------------------------------------------------------
-static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* policy, float* value) {
+// One pass over at most `n_max` positions; the ACTUAL batch size is the device integer *n_dev (every launch has a fixed
+// shape sized for n_max, kernels read *n_dev and leave the rest untouched), so a search never has to tell the host how
+// many leaves a wave produced.  Leaves logits [n][kPolN] + per-tile softmax statistics in r->logits / r->stats.
+// The three parts are separate so that the search can capture them into three CUDA graphs and bracket the tower with events.
+static int fw_first(NnRuntime* r, const uint8_t* boards, int n, const int* n_dev) {
+  const int c = r->filters;
+  const bool s32 = r->board_pixels == 90 && r->fp32_skip;
+  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, r->stream>>>(boards, r->w_first, r->shift_first, r->x, s32 ? r->x32 : nullptr, c, r->board_pixels,
+                                                            r->in_planes, (r->in_planes / 14) * CZ_BOARD_STRIDE, n_dev);
+  r->launches++;
+  CZ_CUDA(cudaGetLastError());
+  return 0;
+}
+static int fw_tower(NnRuntime* r, int n, const int* n_dev) {
   const int c = r->filters;
   cudaStream_t st = r->stream;
   const bool dense = r->board_pixels == 90;
   const bool s32 = dense && r->fp32_skip;
   float *x32 = s32 ? r->x32 : nullptr, *y32 = s32 ? r->y32 : nullptr;
-  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, st>>>(boards, r->w_first, r->shift_first, r->x, x32, c, r->board_pixels, r->in_planes,
-                                                     (r->in_planes / 14) * CZ_BOARD_STRIDE);
   CUtensorMap *ix = &r->imap_x, *iy = &r->imap_y;
-  r->launches++;
   __half *x = r->x, *y = r->y;
   CUtensorMap *mx = &r->map_x, *my = &r->map_y;
-  size_t pe = (size_t)-1;
-  if (r->profile) {
-    if (r->ev_used + 2 > 4096) { cudaStreamSynchronize(st); prof_collect(r); }
-    while (r->ev.size() < r->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); r->ev.push_back(e); }
-    pe = r->ev_used; r->ev_used += 2;
-    if (r->ev_flops.size() < r->ev_used / 2) r->ev_flops.resize(r->ev_used / 2);
-    r->ev_flops[pe / 2] = 2.0 * 90.0 * 9.0 * c * c * (double)n * 2.0 * r->blocks;
-    cudaEventRecord(r->ev[pe], st);
-  }
   for (int i = 0; i < r->blocks; ++i) {
     const size_t wsz = (size_t)c;
     igemm::Args a1 = conv_args(n, c, r->shift_conv + (size_t)(2 * i) * wsz, nullptr, r->t, 1);
@@ -799,12 +816,14 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     if (dense) {
       igemm::Args d1 = conv_args_dense(n, c, a1.bias, nullptr, r->t, 1);
       igemm::Args d2 = conv_args_dense(n, c, a2.bias, x, y, 1);
+      d1.n_dev = n_dev; d1.rows_per_unit = 90; d2.n_dev = n_dev; d2.rows_per_unit = 90;
       d2.residual32 = x32; d2.out32 = y32;
       { float* t32 = x32; x32 = y32; y32 = t32; }
       if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
       if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
       CUtensorMap* ti = ix; ix = iy; iy = ti;
     } else {
+      // strip layout (CZ_CONV_STRIP=1 / CZ_IGEMM_1CTA=1 A-B baselines): host-known batch only
       if (launch_igemm(c, *mx, r->map_w[2 * i], a1, st)) return CZ_ERR_CUDA;
       if (launch_igemm(c, r->map_t, r->map_w[2 * i + 1], a2, st)) return CZ_ERR_CUDA;
     }
@@ -812,12 +831,59 @@ static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* poli
     __half* tx = x; x = y; y = tx;
     CUtensorMap* tm = mx; mx = my; my = tm;
   }
-  if (pe != (size_t)-1) cudaEventRecord(r->ev[pe + 1], st);
-  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, st>>>(x, x32, c, n, r->board_pixels, r->w6, r->shift6, r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
+  return 0;
+}
+static int fw_heads(NnRuntime* r, int n, const int* n_dev, float* value) {
+  const int c = r->filters;
+  const bool s32 = r->board_pixels == 90 && r->fp32_skip;
+  const bool odd = (r->blocks & 1) != 0;                   // the tower ping-pongs x <-> y once per block
+  const __half* x = odd ? r->y : r->x;
+  const float* x32 = s32 ? (odd ? r->y32 : r->x32) : nullptr;
+  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, r->stream>>>(x, x32, c, n_dev, r->board_pixels, r->w6, r->shift6, r->wv1, r->bv1, r->wv2,
+                                                                r->bv2, r->value_fc, r->pol_feat, value);
   igemm::Args ap = dense_args(n, kLabels, kPolN, kPolK, 256, r->b_pol, r->logits, kPolN);
-  if (launch_igemm(256, r->map_pf, r->map_wpol, ap, st)) return CZ_ERR_CUDA;
-  k_softmax<<<n, 256, 0, st>>>(r->logits, kPolN, policy);
-  r->launches += 3;
+  ap.n_dev = n_dev; ap.rows_per_unit = 1; ap.row_stats = r->stats;
+  if (launch_igemm(256, r->map_pf, r->map_wpol, ap, r->stream)) return CZ_ERR_CUDA;
+  r->launches += 2;
+  CZ_CUDA(cudaGetLastError());
+  return 0;
+}
+// events around the tower of one forward (bench.py roofline); flops = algorithmic flops of the bracketed launches, or < 0 when
+// only the device knows the batch size (the reader then takes the positions from the search's device counter)
+void nn_prof_begin(NnRuntime* r, double flops) {
+  r->prof_open = (size_t)-1;
+  if (!r->profile) return;
+  if (r->ev_used + 2 > 4096) { cudaStreamSynchronize(r->stream); prof_collect(r); }
+  while (r->ev.size() < r->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); r->ev.push_back(e); }
+  r->prof_open = r->ev_used; r->ev_used += 2;
+  if (r->ev_flops.size() < r->ev_used / 2) r->ev_flops.resize(r->ev_used / 2);
+  r->ev_flops[r->prof_open / 2] = flops > 0 ? flops : 0.0;
+  cudaEventRecord(r->ev[r->prof_open], r->stream);
+}
+void nn_prof_end(NnRuntime* r) {
+  if (r->prof_open != (size_t)-1) cudaEventRecord(r->ev[r->prof_open + 1], r->stream);
+  r->prof_open = (size_t)-1;
+}
+static int forward_tower(NnRuntime* r, const uint8_t* boards, int n_max, const int* n_dev, float* value) {
+  int rc = fw_first(r, boards, n_max, n_dev);
+  if (rc) return rc;
+  nn_prof_begin(r, 2.0 * 90.0 * 9.0 * r->filters * r->filters * (double)n_max * 2.0 * r->blocks);
+  rc = fw_tower(r, n_max, n_dev);
+  nn_prof_end(r);
+  if (rc) return rc;
+  return fw_heads(r, n_max, n_dev, value);
+}
+
+// host-known batch: the reference-facing predict_on_batch (api.py:62-64) -> the full softmax vector
+static int forward_chunk(NnRuntime* r, const uint8_t* boards, int n, float* policy, float* value) {
+  k_set_int<<<1, 1, 0, r->stream>>>(r->n_scalar, n);
+  if (r->board_pixels != 90) {                      // strip-layout baselines launch exact shapes
+    // (the device-side batch size is still honoured by the first conv, the heads and the policy GEMM)
+  }
+  const int rc = forward_tower(r, boards, n, r->n_scalar, value);
+  if (rc) return rc;
+  k_softmax<<<n, 256, 0, r->stream>>>(r->logits, kPolN, r->stats, kPolN / 256, policy);
+  r->launches += 2;
   CZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -847,6 +913,31 @@ int nn_forward_planes(NnRuntime* r, int net, const float* planes, int batch, flo
   }
   return 0;
 }
+
+// The search's evaluation step: up to n_max leaves (actual count *n_dev), boards + legal-move labels in, value [n] and the
+// softmax probabilities of the legal moves [n][CZ_MAX_MOVES] out.  Fixed launch shapes: safe to capture into a CUDA graph.
+int nn_forward_leaves(NnRuntime* r, int net, int part, const uint8_t* boards, int n_max, const int* n_dev, const int16_t* labels,
+                      const int32_t* label_counts, float* legal_p, float* value) {
+  if (!r || net < 0 || net >= r->n_nets) return cz_fail(CZ_ERR_STATE, "no such network");
+  if (n_max > r->max_batch) return cz_fail(CZ_ERR_ARG, "nn_forward_leaves: %d leaves > max batch %d", n_max, r->max_batch);
+  if (r->board_pixels != 90) return cz_fail(CZ_ERR_UNSUPPORTED, "nn_forward_leaves needs the dense (im2col) layout");
+  select_net(r, net);
+  if (!r->ready) return cz_fail(CZ_ERR_STATE, "network weights not set (cz_nn_set_weights)");
+  int rc = 0;
+  if (part & 1) rc = fw_first(r, boards, n_max, n_dev);
+  if (!rc && (part & 2)) rc = fw_tower(r, n_max, n_dev);
+  if (!rc && (part & 4)) rc = fw_heads(r, n_max, n_dev, value);
+  if (rc) return rc;
+  if (part & 4) k_legal_priors<<<(n_max + 3) / 4, 128, 0, r->stream>>>(r->logits, kPolN, r->stats, kPolN / 256, labels, label_counts, n_dev, legal_p);
+  if (part & 4) r->launches++;
+  CZ_CUDA(cudaGetLastError());
+  return 0;
+}
+void nn_set_capturing(NnRuntime* r, bool on) { if (r) r->capturing = on; }
+bool nn_profiling(const NnRuntime* r) { return r && r->profile; }
+void nn_set_stream(NnRuntime* r, void* stream) { if (r) r->stream = (cudaStream_t)stream; }
+int nn_launches_per_forward(const NnRuntime* r) { return r ? 1 + 2 * r->blocks + 3 : 0; }
+double nn_tower_flops_per_position(const NnRuntime* r) { return r ? 2.0 * 90.0 * 9.0 * r->filters * r->filters * 2.0 * r->blocks : 0.0; }
 
 }  // namespace cznn
 

@@ -98,6 +98,9 @@ struct EngineDev {
   int32_t* leaf_off;             // [G]
   int32_t* totals;               // [4]: total leaves, any active, -, -
   uint8_t* leaf_dense;           // [G*K][lb_stride] leaves of all games, dense
+  int16_t* leaf_labels;          // [G*K][MAX_MOVES] dense: action label of every legal move of the leaf (-1 = none)
+  int32_t* leaf_nlab;            // [G*K] dense: legal moves of the leaf
+  int32_t* loop_iter;            // [1] iterations of the device-driven search loop finished (k_loop_flag)
   unsigned long long* counters;  // [8]
   unsigned long long* stat;      // [G][4] since cz_create: simulations backed up, sum of their path lengths, simulations
                                  //        that ended without the network (terminal / repetition / error), nodes created
@@ -499,7 +502,10 @@ CZ_D void game_wave(const EngineDev& E, int g, TreeSmem* sm) {
 }
 
 // ------------------------------------------------------------------ apply: attach evaluations, back up, resume
-CZ_D void game_apply(const EngineDev& E, int g, const float* policy, const float* value, TreeSmem* sm) {
+// policy: [n][2086] softmax vectors (external evaluators: the reference's wire format), or — legal_p != null — the same
+// probabilities already gathered at the leaf's legal-move labels, [n][MAX_MOVES] (integrated search: the 2086-vector is
+// never materialised).  Everything after the gather is identical.
+CZ_D void game_apply(const EngineDev& E, int g, const float* policy, const float* legal_p, const float* value, TreeSmem* sm) {
   const int nl = E.n_leaf[g];
   if (nl == 0) return;
   const int off = E.leaf_off[g];
@@ -510,12 +516,17 @@ CZ_D void game_apply(const EngineDev& E, int g, const float* policy, const float
     const size_t ni = (size_t)g * E.ncap + node;
     const int L = (int)(E.node_meta[ni] & 0xff);
     const size_t eo = (size_t)g * E.ecap + E.node_edge_off[ni];
-    const float* prow = policy + (size_t)(off + j) * N_LABELS;
     // priors of the legal moves, renormalised (player.py:272-284): float32, sequential sum
-    for (int i = czs::lane(); i < L; i += 32) {
-      const move_t m = E.edge_move[eo + i];
-      const int lab = E.label_lut[mv_from(m) * 90 + mv_to(m)];
-      sm->pr[i] = lab >= 0 ? prow[lab] : 0.f;
+    if (legal_p) {
+      const float* lrow = legal_p + (size_t)(off + j) * MAX_MOVES;
+      for (int i = czs::lane(); i < L; i += 32) sm->pr[i] = lrow[i];
+    } else {
+      const float* prow = policy + (size_t)(off + j) * N_LABELS;
+      for (int i = czs::lane(); i < L; i += 32) {
+        const move_t m = E.edge_move[eo + i];
+        const int lab = E.label_lut[mv_from(m) * 90 + mv_to(m)];
+        sm->pr[i] = lab >= 0 ? prow[lab] : 0.f;
+      }
     }
     czs::syncwarp();
     float all_p = 0.f;

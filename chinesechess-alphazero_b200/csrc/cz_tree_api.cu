@@ -45,10 +45,10 @@ CZ_KERNEL(k_wave)(EngineDev E, int g0, int g1) {
   if (g >= g1) return;
   game_wave(E, g, tree_smem());
 }
-CZ_KERNEL(k_apply)(EngineDev E, int g0, int g1, const float* policy, const float* value) {
+CZ_KERNEL(k_apply)(EngineDev E, int g0, int g1, const float* policy, const float* legal_p, const float* value) {
   const int g = g0 + my_game();
   if (g >= g1) return;
-  game_apply(E, g, policy, value, tree_smem());
+  game_apply(E, g, policy, legal_p, value, tree_smem());
 }
 // single warp: exclusive scan of the per-game leaf counts, totals[0] = leaves, totals[1] = any game busy
 CZ_KERNEL(k_scan)(EngineDev E, int gb, int ge, int slot) {
@@ -65,9 +65,18 @@ CZ_KERNEL(k_scan)(EngineDev E, int gb, int ge, int slot) {
     base += tot;
   }
   busy = czs::any(busy != 0) ? 1 : 0;
-  if (czs::lane() == 0) { E.totals[4 * slot] = base; E.totals[4 * slot + 1] = busy; }
+  if (czs::lane() == 0) {
+    E.totals[4 * slot] = base; E.totals[4 * slot + 1] = busy;
+#if defined(CZ_EMUL)
+    E.counters[1] += (unsigned long long)base; E.counters[2] += 1;        // positions sent to the evaluator, wave iterations
+#else
+    atomicAdd(E.counters + 1, (unsigned long long)base); atomicAdd(E.counters + 2, 1ULL);
+#endif
+  }
 }
-CZ_KERNEL(k_gather)(EngineDev E, int g0, int g1, uint8_t* dense) {
+// dense leaf list of a range: boards, and (labels != null) the action labels of each leaf's legal moves in edge order, which
+// is all the evaluation step has to know to hand back exactly the priors the search will read
+CZ_KERNEL(k_gather)(EngineDev E, int g0, int g1, uint8_t* dense, int16_t* labels, int32_t* nlab) {
   const int g = g0 + my_game();
   if (g >= g1) return;
   const int n = E.n_leaf[g], off = E.leaf_off[g];
@@ -75,7 +84,38 @@ CZ_KERNEL(k_gather)(EngineDev E, int g0, int g1, uint8_t* dense) {
     const uint8_t* s = E.leaf_board + ((size_t)g * E.K + j) * E.lb_stride;
     uint8_t* d = dense + (size_t)(off + j) * E.lb_stride;
     if (czs::lane() < E.lb_stride / 16) reinterpret_cast<uint4*>(d)[czs::lane()] = reinterpret_cast<const uint4*>(s)[czs::lane()];
+    if (labels) {
+      const int node = E.sim_leaf_node[(size_t)g * E.K + E.leaf_sim[(size_t)g * E.K + j]];
+      const size_t ni = (size_t)g * E.ncap + node;
+      const int L = (int)(E.node_meta[ni] & 0xff);
+      const size_t eo = (size_t)g * E.ecap + E.node_edge_off[ni];
+      for (int i = czs::lane(); i < L; i += 32) {
+        const move_t m = E.edge_move[eo + i];
+        labels[(size_t)(off + j) * MAX_MOVES + i] = E.label_lut[mv_from(m) * 90 + mv_to(m)];
+      }
+      if (czs::lane() == 0) nlab[off + j] = L;
+    }
   }
+}
+// Device-driven search loop: after every iteration tell the polling host thread (mapped pinned memory) how many iterations
+// are complete and whether any range still has work.  flags[1] (busy) is written before flags[0] (count).
+CZ_KERNEL(k_loop_flag)(EngineDev E, int n_slots, volatile int32_t* flags) {
+  if (czs::lane() != 0) return;
+  int busy = 0;
+  for (int s = 0; s < n_slots; ++s) busy |= (E.totals[4 * s] > 0) | (E.totals[4 * s + 1] != 0);
+  const int it = E.loop_iter[0] + 1;
+  E.loop_iter[0] = it;
+  unsigned long long n_eval = 0;                         // positions the device-driven loop evaluated (cz_nn_profile's flops)
+  for (int s = 0; s < n_slots; ++s) n_eval += (unsigned long long)E.totals[4 * s];
+  E.counters[0] += n_eval;
+  flags[1] = busy;
+#if !defined(CZ_EMUL)
+  __threadfence_system();
+#endif
+  flags[0] = it;
+}
+CZ_KERNEL(k_loop_reset)(EngineDev E) {
+  if (czs::lane() == 0) { E.loop_iter[0] = 0; for (int i = 0; i < 8; ++i) E.totals[i] = 0; }
 }
 CZ_KERNEL(k_planes_dense)(const uint8_t* boards, int n, float* planes, int lb_stride) {
   const int i = my_game();
@@ -242,19 +282,29 @@ struct cz_engine {
   unsigned long long* stat_out;
   cz_root_info* root_info_dev;
   float* policy_buf; float* value_buf;                      // evaluator outputs for the built-in network
+  float* legal_p;                                           // [G*K][MAX_MOVES] priors of the legal moves (integrated search)
   uint8_t* board_stage;                                     // [G][96] staging for reset / set_root
   int32_t* stat_n; uint16_t* stat_mv; int32_t* stat_cnt;    // staging for cz_get_root_stats
   int32_t* sims_stage;                                      // [G] staging for cz_set_game_sims
   int last_leaves;
+  unsigned long long prof_pos0;                             // device counter [0] at the last cz_nn_profile read
+  bool own_stream;                                          // e->stream was created by cz_create (caller passed the default stream)
   int ring_count;                                           // finished-game records in the device ring (as of the last cz_play_move)
   uint64_t launches;
-  uint64_t total_sims, total_positions, total_waves;
+  uint64_t total_sims;
 #if !defined(CZ_EMUL)
   cznn::NnRuntime* nn;
   size_t nn_bytes;
   cudaStream_t tree_stream;                                 // second stream for the pipelined search (NULL = off)
   cudaEvent_t ev_ready[2], ev_done[2];
   int32_t* h_totals;                                        // pinned [8]
+  // device-driven search loop: one iteration = three captured graphs per game range (tree work + first conv | residual
+  // tower | heads + legal priors), launched back to back; the host only polls h_flags (mapped pinned memory)
+  cudaGraphExec_t g_pre[2], g_tower[2], g_post[2];
+  int n_ranges;                                             // 1, or 2 in arena mode (one network per range)
+  bool graphs_built, graph_loop;
+  volatile int32_t* h_flags;                                // mapped pinned [4]: iterations finished, busy
+  int32_t* d_flags;                                         // device view of h_flags
 #endif
 };
 
@@ -291,6 +341,8 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.park_sim = cv.take<int32_t>(G * K); d.park_node = cv.take<int32_t>(G * K); d.n_park = cv.take<int32_t>(G);
   d.leaf_off = cv.take<int32_t>(G); d.totals = cv.take<int32_t>(8);
   d.leaf_dense = cv.take<uint8_t>(G * K * d.lb_stride);
+  d.leaf_labels = cv.take<int16_t>(G * K * MAX_MOVES); d.leaf_nlab = cv.take<int32_t>(G * K);
+  d.loop_iter = cv.take<int32_t>(4);
   d.counters = cv.take<unsigned long long>(8);
   d.stat = cv.take<unsigned long long>(G * 4);
   d.gc_map = cv.take<int32_t>(G * N);
@@ -307,8 +359,9 @@ size_t carve(cz_engine* e, uint8_t* base) {
   if (c.nn_filters > 0) {
     e->policy_buf = cv.take<float>(G * K * (size_t)CZ_N_LABELS);
     e->value_buf = cv.take<float>(G * K);
+    e->legal_p = cv.take<float>(G * K * (size_t)MAX_MOVES);
   } else {
-    e->policy_buf = nullptr; e->value_buf = nullptr;
+    e->policy_buf = nullptr; e->value_buf = nullptr; e->legal_p = nullptr;
   }
   return cv.off + 1024;
 }
@@ -384,8 +437,9 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
   if (!e) return cz_fail(CZ_ERR_STATE, "cz_create: out of host memory");
   e->cfg = *cfg;
   e->stream = (cz_stream_t)stream;
+  e->own_stream = false; e->prof_pos0 = 0;
   e->ws = (uint8_t*)workspace; e->ws_bytes = workspace_bytes;
-  e->launches = 0; e->last_leaves = 0; e->ring_count = 0; e->total_sims = e->total_positions = e->total_waves = 0;
+  e->launches = 0; e->last_leaves = 0; e->ring_count = 0; e->total_sims = 0;
   EngineDev& d = e->d;
   memset(&d, 0, sizeof(d));
   d.n_games = cfg->n_games; d.sims = cfg->sims_per_move; d.K = cfg->leaves_per_round; d.vl = cfg->virtual_loss;
@@ -397,7 +451,17 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
   const size_t used = carve(e, e->ws);
 #if !defined(CZ_EMUL)
   e->nn = nullptr; e->nn_bytes = 0; e->tree_stream = nullptr; e->h_totals = nullptr;
+  e->graphs_built = false; e->h_flags = nullptr; e->d_flags = nullptr; e->n_ranges = cfg->arena ? 2 : 1;
+  for (int i = 0; i < 2; ++i) { e->g_pre[i] = e->g_tower[i] = e->g_post[i] = nullptr; }
+  { const char* m = getenv("CZ_SEARCH_LOOP"); e->graph_loop = !(m && m[0] == 'h'); }     // CZ_SEARCH_LOOP=host: the round-1 host-driven loops
   if (cudaSetDevice(cfg->device) != cudaSuccess) { delete e; return cz_fail(CZ_ERR_CUDA, "cz_create: cudaSetDevice(%d) failed", cfg->device); }
+  if (!e->stream) {
+    // The legacy default stream cannot be captured into a graph.  A BLOCKING stream of our own keeps the caller's ordering:
+    // work the caller issues on the default stream waits for everything queued here and vice versa (implicit synchronisation
+    // between the legacy default stream and blocking streams).
+    if (cudaStreamCreate(&e->stream) != cudaSuccess) { delete e; return cz_fail(CZ_ERR_CUDA, "cz_create: cudaStreamCreate failed"); }
+    e->own_stream = true;
+  }
   if (cfg->nn_filters > 0) {
     const char* off = getenv("CZ_NO_PIPELINE");
     if (!(off && off[0] == '1')) {
@@ -408,6 +472,12 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
       }
     }
     if (cudaMallocHost((void**)&e->h_totals, 8 * sizeof(int32_t)) != cudaSuccess) { delete e; return cz_fail(CZ_ERR_CUDA, "cz_create: cudaMallocHost failed"); }
+    void* hf = nullptr;
+    if (cudaHostAlloc(&hf, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer((void**)&e->d_flags, hf, 0) != cudaSuccess) {
+      delete e; return cz_fail(CZ_ERR_CUDA, "cz_create: mapped host memory for the loop flags failed");
+    }
+    e->h_flags = (volatile int32_t*)hf;
+    memset(hf, 0, 64);
   }
 #endif
   // tables + initial state
@@ -445,6 +515,13 @@ void cz_destroy(cz_engine* e) {
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(e->ev_ready[i]); cudaEventDestroy(e->ev_done[i]); }
   }
   if (e->h_totals) cudaFreeHost(e->h_totals);
+  if (e->h_flags) cudaFreeHost((void*)e->h_flags);
+  if (e->own_stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+  for (int i = 0; i < 2; ++i) {
+    if (e->g_pre[i]) cudaGraphExecDestroy(e->g_pre[i]);
+    if (e->g_tower[i]) cudaGraphExecDestroy(e->g_tower[i]);
+    if (e->g_post[i]) cudaGraphExecDestroy(e->g_post[i]);
+  }
 #endif
   delete e;
 }
@@ -549,13 +626,12 @@ int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active) {
   const int G = e->cfg.n_games;
   RANGE_LAUNCH(e, e->stream, 0, G, k_wave, e->d, 0, G);
   CZ_LAUNCH(k_scan, 1, 1, 0, e->stream, e->d, 0, G, 0);
-  RANGE_LAUNCH(e, e->stream, 0, G, k_gather, e->d, 0, G, e->d.leaf_dense);
+  RANGE_LAUNCH(e, e->stream, 0, G, k_gather, e->d, 0, G, e->d.leaf_dense, e->d.leaf_labels, e->d.leaf_nlab);
   if (launch_ok(e, "cz_search_wave", 3)) return CZ_ERR_CUDA;
   int32_t t[4];
   czrt_copy(t, e->d.totals, sizeof(t), e->stream);
   if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_search_wave: device failure");
   e->last_leaves = t[0];
-  e->total_waves++;
   if (n_leaves) *n_leaves = t[0];
   if (any_active) *any_active = t[1] || t[0] > 0;
   return 0;
@@ -580,10 +656,27 @@ int cz_search_apply(cz_engine* e, const float* policy_dev, const float* value_de
   if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_apply: null engine");
   if (e->last_leaves == 0) return 0;
   if (!policy_dev || !value_dev) return cz_fail(CZ_ERR_ARG, "cz_search_apply: null evaluation");
-  RANGE_LAUNCH(e, e->stream, 0, e->cfg.n_games, k_apply, e->d, 0, e->cfg.n_games, policy_dev, value_dev);
-  e->total_positions += (uint64_t)e->last_leaves;
+  RANGE_LAUNCH(e, e->stream, 0, e->cfg.n_games, k_apply, e->d, 0, e->cfg.n_games, policy_dev, (const float*)nullptr, value_dev);
   e->last_leaves = 0;
   return launch_ok(e, "cz_search_apply");
+}
+
+int cz_leaf_labels(cz_engine* e, int16_t* labels_dev, int32_t* counts_dev) {
+  if (!e || !labels_dev || !counts_dev) return cz_fail(CZ_ERR_ARG, "cz_leaf_labels: bad argument");
+  if (e->last_leaves == 0) return 0;
+  if (czrt_copy(labels_dev, e->d.leaf_labels, (size_t)e->last_leaves * MAX_MOVES * sizeof(int16_t), e->stream) ||
+      czrt_copy(counts_dev, e->d.leaf_nlab, (size_t)e->last_leaves * sizeof(int32_t), e->stream))
+    return cz_fail(CZ_ERR_CUDA, "cz_leaf_labels: copy failed");
+  return 0;
+}
+
+int cz_search_apply_legal(cz_engine* e, const float* legal_p_dev, const float* value_dev) {
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_apply_legal: null engine");
+  if (e->last_leaves == 0) return 0;
+  if (!legal_p_dev || !value_dev) return cz_fail(CZ_ERR_ARG, "cz_search_apply_legal: null evaluation");
+  RANGE_LAUNCH(e, e->stream, 0, e->cfg.n_games, k_apply, e->d, 0, e->cfg.n_games, (const float*)nullptr, legal_p_dev, value_dev);
+  e->last_leaves = 0;
+  return launch_ok(e, "cz_search_apply_legal");
 }
 
 #if !defined(CZ_EMUL)
@@ -612,18 +705,16 @@ int search_pipelined(cz_engine* e) {
     if (!busy[h] && n_in_flight[h] == 0) continue;
     if (n_in_flight[h] > 0) {                                 // evaluation of this half is (being) computed on N
       cudaStreamWaitEvent(T, done[h], 0);
-      RANGE_LAUNCH(e, T, gb[h], ge[h], k_apply, e->d, gb[h], ge[h], (const float*)pol[h], (const float*)val[h]);
-      e->total_positions += (uint64_t)n_in_flight[h];
+      RANGE_LAUNCH(e, T, gb[h], ge[h], k_apply, e->d, gb[h], ge[h], (const float*)pol[h], (const float*)nullptr, (const float*)val[h]);
       e->launches += 1;
       n_in_flight[h] = 0;
     }
     RANGE_LAUNCH(e, T, gb[h], ge[h], k_wave, e->d, gb[h], ge[h]);
     CZ_LAUNCH(k_scan, 1, 1, 0, T, e->d, gb[h], ge[h], h);
-    RANGE_LAUNCH(e, T, gb[h], ge[h], k_gather, e->d, gb[h], ge[h], dense[h]);
+    RANGE_LAUNCH(e, T, gb[h], ge[h], k_gather, e->d, gb[h], ge[h], dense[h], (int16_t*)nullptr, (int32_t*)nullptr);
     cudaMemcpyAsync(e->h_totals + 4 * h, e->d.totals + 4 * h, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, T);
     cudaEventRecord(ready[h], T);
     e->launches += 3;
-    e->total_waves++;
     if (cudaStreamSynchronize(T) != cudaSuccess) return cz_fail(CZ_ERR_CUDA, "cz_search: device failure in the tree stream");
     const int n = e->h_totals[4 * h];
     busy[h] = e->h_totals[4 * h + 1] != 0 || n > 0;
@@ -645,6 +736,120 @@ int search_pipelined(cz_engine* e) {
 }  // namespace
 #endif
 
+#if !defined(CZ_EMUL)
+namespace {
+// ---- device-driven search loop ------------------------------------------------------------------------------------------
+// Range h = games [gb, ge) evaluated by network h (arena: player h's trees; otherwise one range = all games).  One iteration
+// of a range:   apply(previous evaluation) -> wave -> scan -> gather(+labels) -> first conv | tower | heads, policy GEMM,
+// legal priors.  Every launch has a fixed shape; the number of leaves is the device integer totals[4h] that k_scan writes and
+// every network kernel reads, so nothing has to come back to the host between waves.  The three parts are captured once as
+// CUDA graphs; the tower graph is separate only so that cz_nn_profile can bracket it with events.
+struct Range { int gb, ge; uint8_t* dense; int16_t* labels; int32_t* nlab; float* legal_p; float* value; };
+Range range_of(cz_engine* e, int h) {
+  const int G = e->cfg.n_games, K = e->cfg.leaves_per_round;
+  const int mid = e->n_ranges == 2 ? (G + 1) / 2 : G;
+  Range r;
+  r.gb = h == 0 ? 0 : mid; r.ge = h == 0 ? mid : G;
+  const size_t off = (size_t)r.gb * K;
+  r.dense = e->d.leaf_dense + off * e->d.lb_stride;
+  r.labels = e->d.leaf_labels + off * MAX_MOVES; r.nlab = e->d.leaf_nlab + off;
+  r.legal_p = e->legal_p + off * MAX_MOVES; r.value = e->value_buf + off;
+  return r;
+}
+// the launches of one part of one range's iteration (part 1: tree work + first conv, 2: tower, 4: heads + priors + loop flag)
+int enqueue_part(cz_engine* e, int h, int part) {
+  const Range r = range_of(e, h);
+  const int n_max = (r.ge - r.gb) * e->cfg.leaves_per_round;
+  const int* n_dev = e->d.totals + 4 * h;
+  if (part == 1) {
+    RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_apply, e->d, r.gb, r.ge, (const float*)nullptr, (const float*)r.legal_p, (const float*)r.value);
+    RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_wave, e->d, r.gb, r.ge);
+    CZ_LAUNCH(k_scan, 1, 1, 0, e->stream, e->d, r.gb, r.ge, h);
+    RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_gather, e->d, r.gb, r.ge, r.dense, r.labels, r.nlab);
+  }
+  const int rc = cznn::nn_forward_leaves(e->nn, e->cfg.arena ? h : 0, part, r.dense, n_max, n_dev, r.labels, r.nlab, r.legal_p, r.value);
+  if (rc) return rc;
+  if (part == 4 && h == e->n_ranges - 1) CZ_LAUNCH(k_loop_flag, 1, 1, 0, e->stream, e->d, e->n_ranges, (volatile int32_t*)e->d_flags);
+  return 0;
+}
+int capture_part(cz_engine* e, int h, int part, cudaGraphExec_t* out) {
+  cznn::nn_set_capturing(e->nn, true);
+  if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cznn::nn_set_capturing(e->nn, false);
+    return cz_fail(CZ_ERR_CUDA, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  const int rc = enqueue_part(e, h, part);
+  cudaGraph_t g = nullptr;
+  cudaError_t err = cudaStreamEndCapture(e->stream, &g);
+  cznn::nn_set_capturing(e->nn, false);
+  if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+  if (err != cudaSuccess || !g) return cz_fail(CZ_ERR_CUDA, "graph capture (range %d part %d) failed: %s", h, part, cudaGetErrorString(err));
+  err = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  if (err != cudaSuccess) return cz_fail(CZ_ERR_CUDA, "graph instantiate (range %d part %d) failed: %s", h, part, cudaGetErrorString(err));
+  return 0;
+}
+int build_graphs(cz_engine* e) {
+  for (int h = 0; h < e->n_ranges; ++h) {
+    int rc;
+    if ((rc = capture_part(e, h, 1, &e->g_pre[h])) || (rc = capture_part(e, h, 2, &e->g_tower[h])) || (rc = capture_part(e, h, 4, &e->g_post[h])))
+      return rc;
+  }
+  e->graphs_built = true;
+  return 0;
+}
+// launches per iteration of one range, for cz_launch_count (graph launches do not pass through launch_ok)
+int launches_per_iteration(cz_engine* e) { return 4 + cznn::nn_launches_per_forward(e->nn); }
+
+int search_graph_loop(cz_engine* e) {
+  CZ_LAUNCH(k_loop_reset, 1, 1, 0, e->stream, e->d);
+  e->h_flags[0] = 0; e->h_flags[1] = 1;
+  const bool prof = cznn::nn_profiling(e->nn);
+  const int kDepth = 4;                                  // iterations the host may run ahead of the last one it saw finish
+  int launched = 0;
+  for (;;) {
+    for (int h = 0; h < e->n_ranges; ++h) {
+      if (!e->graphs_built) {
+        // The engine's very first iteration runs as plain launches: it loads every kernel and sets their attributes (neither
+        // may happen inside a stream capture) and is otherwise the same work; the graphs are captured right after it.
+        int rc;
+        if ((rc = enqueue_part(e, h, 1))) return rc;
+        if (prof) cznn::nn_prof_begin(e->nn, -1.0);
+        rc = enqueue_part(e, h, 2);
+        if (prof) cznn::nn_prof_end(e->nn);
+        if (rc || (rc = enqueue_part(e, h, 4))) return rc;
+      } else {
+        if (cudaGraphLaunch(e->g_pre[h], e->stream) != cudaSuccess) return cz_fail(CZ_ERR_CUDA, "cz_search: graph launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (prof) cznn::nn_prof_begin(e->nn, -1.0);
+        cudaGraphLaunch(e->g_tower[h], e->stream);
+        if (prof) cznn::nn_prof_end(e->nn);
+        cudaGraphLaunch(e->g_post[h], e->stream);
+      }
+    }
+    if (!e->graphs_built) { const int rc = build_graphs(e); if (rc) return rc; }
+    ++launched;
+    e->launches += (uint64_t)e->n_ranges * launches_per_iteration(e) + 1;
+    // wait until fewer than kDepth iterations are outstanding, then look at the newest report
+    int done;
+    unsigned spins = 0;
+    while (launched - (done = e->h_flags[0]) >= kDepth) {
+      if (++spins >= 1000000u) {                         // every ~second of spinning: is the device still working on it?
+        spins = 0;
+        const cudaError_t q = cudaStreamQuery(e->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return cz_fail(CZ_ERR_CUDA, "cz_search: %s", cudaGetErrorString(q));
+        if (q == cudaSuccess && e->h_flags[0] == done) return cz_fail(CZ_ERR_CUDA, "cz_search: the loop flag of iteration %d never arrived", done + 1);
+      }
+    }
+    if (done > 0 && e->h_flags[1] == 0) break;           // an iteration finished with nothing left to do: the rest are no-ops
+  }
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) return cz_fail(CZ_ERR_CUDA, "cz_search: device failure");
+  const char* msg;
+  if (czrt_last_error(&msg)) return cz_fail(CZ_ERR_CUDA, "cz_search: %s", msg);
+  return 0;
+}
+}  // namespace
+#endif
+
 int cz_search(cz_engine* e, const cz_root_opts* opts) {
 #if defined(CZ_EMUL)
   (void)e; (void)opts;
@@ -654,6 +859,9 @@ int cz_search(cz_engine* e, const cz_root_opts* opts) {
   if (!e->nn || !cznn::nn_ready(e->nn)) return cz_fail(CZ_ERR_STATE, "cz_search: network weights not set");
   int rc = cz_search_begin(e, opts);
   if (rc) return rc;
+  if (e->graph_loop) return search_graph_loop(e);
+  // ---- round-1 host-driven loops (CZ_SEARCH_LOOP=host), kept as the A/B baseline: the full softmax vector per leaf, one
+  // stream synchronisation per wave
   // two half-ranges only pay when each half still fills the tensor cores (>= 4096 leaves per round); the arena always
   // needs them (one range per network)
   const char* force = getenv("CZ_FORCE_PIPELINE");                 // test hook: the two-range path at any size
@@ -707,7 +915,7 @@ int cz_get_counters(cz_engine* e, uint64_t* out) {
   CZ_LAUNCH(k_err_reduce, 1, 1, 0, e->stream, e->d);
   czrt_copy(dc, e->d.counters, sizeof(dc), e->stream);
   if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_get_counters: device failure");
-  out[0] = e->total_sims; out[1] = e->total_positions; out[2] = e->total_waves; out[3] = dc[3]; out[4] = dc[4];   // [3] records dropped
+  out[0] = e->total_sims; out[1] = dc[1]; out[2] = dc[2]; out[3] = dc[3]; out[4] = dc[4];   // [1] positions, [2] waves, [3] records dropped
   out[5] = dc[5]; out[6] = dc[6]; out[7] = dc[7];
   return 0;
 }
@@ -767,7 +975,17 @@ int cz_nn_profile(cz_engine* e, int enable, double* ms, uint64_t* launches, doub
 #else
   if (!e || !e->nn) return cz_fail(CZ_ERR_STATE, "cz_nn_profile: engine has no network");
   cznn::nn_profile(e->nn, enable != 0);
-  return cznn::nn_profile_read(e->nn, ms, launches, flops);
+  double fl = 0.0;
+  const int rc = cznn::nn_profile_read(e->nn, ms, launches, &fl);      // synchronises the stream
+  if (rc) return rc;
+  // launches whose batch size only the device knew: positions evaluated by the loop since the last read
+  unsigned long long pos = 0;
+  czrt_copy(&pos, e->d.counters, sizeof(pos), e->stream);
+  if (czrt_sync(e->stream)) return cz_fail(CZ_ERR_CUDA, "cz_nn_profile: device failure");
+  fl += (double)(pos - e->prof_pos0) * cznn::nn_tower_flops_per_position(e->nn);
+  e->prof_pos0 = pos;
+  if (flops) *flops = fl;
+  return 0;
 #endif
 }
 

@@ -160,6 +160,19 @@ class Engine:
         self._apply_keep = (getattr(self, "_apply_keep", []) + [(policy, value)])[-4:]
         self.lib.call("cz_search_apply", self._h, _ptr(policy), _ptr(value))
 
+    def leaf_labels(self, n):
+        """Action labels of the legal moves of the n leaves of the last wave (cz_leaf_labels): (int16 [n,128], int32 [n])."""
+        lab = torch.full((n, MAX_MOVES), -1, dtype=torch.int16, device=self.device)
+        cnt = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        self.lib.call("cz_leaf_labels", self._h, _ptr(lab), _ptr(cnt))
+        return lab, cnt
+
+    def search_apply_legal(self, legal_p, value):
+        """cz_search_apply_legal: legal_p f32 [n,128] = policy[label] of every legal move (see leaf_labels)."""
+        assert legal_p.dtype == torch.float32 and value.dtype == torch.float32 and legal_p.shape[1] == MAX_MOVES
+        self._apply_keep = (getattr(self, "_apply_keep", []) + [(legal_p, value)])[-4:]
+        self.lib.call("cz_search_apply_legal", self._h, _ptr(legal_p), _ptr(value))
+
     def search_external(self, evaluate_planes, opts=None):
         """Whole search with `evaluate_planes(np.float32[n,14,10,9]) -> (policy[n,2086] f32, value[n] f32)`
         standing in for the network (the role CChessModelAPI plays for the reference player)."""

@@ -96,6 +96,8 @@ _SIGS = {
     "cz_leaf_planes": (C.c_int, [_P, _P]),
     "cz_leaf_boards": (C.c_int, [_P, _P]),
     "cz_search_apply": (C.c_int, [_P, _P, _P]),
+    "cz_leaf_labels": (C.c_int, [_P, _P, _P]),
+    "cz_search_apply_legal": (C.c_int, [_P, _P, _P]),
     "cz_search": (C.c_int, [_P, C.POINTER(CzRootOpts)]),
     "cz_get_root": (C.c_int, [_P, C.c_int, C.POINTER(CzRootInfo)]),
     "cz_get_counters": (C.c_int, [_P, _P]),

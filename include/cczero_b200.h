@@ -167,6 +167,15 @@ int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active);
 int cz_leaf_planes(cz_engine* e, float* planes_dev /* [n_leaves][14][10][9]; [n_leaves][28][10][9] with use_history */);
 int cz_leaf_boards(cz_engine* e, uint8_t* boards_dev /* [n_leaves][CZ_BOARD_STRIDE]; [n_leaves][2][CZ_BOARD_STRIDE] with use_history */);
 int cz_search_apply(cz_engine* e, const float* policy_dev /* [n_leaves][2086] */, const float* value_dev /* [n_leaves] */);
+/* The same hand-over without the 2086-vector: select_action_q_and_u (player.py:272-284) reads the policy only at the labels of
+ * the leaf's legal moves, so an evaluator that is given those labels can return just those entries.
+ *   cz_leaf_labels         labels_dev [n_leaves][CZ_MAX_MOVES] int16 = action label of each legal move in move-list order
+ *                          (-1: the move has no label), counts_dev [n_leaves] int32
+ *   cz_search_apply_legal  legal_p_dev [n_leaves][CZ_MAX_MOVES] f32 = policy[label] per legal move; everything downstream
+ *                          (sequential f32 renormalisation, backup) is the code path of cz_search_apply
+ * This is what the integrated search (cz_search) does on the device: the [n][2086] f32 row never exists there. */
+int cz_leaf_labels(cz_engine* e, int16_t* labels_dev, int32_t* counts_dev);
+int cz_search_apply_legal(cz_engine* e, const float* legal_p_dev, const float* value_dev);
 /* n_sims more simulations for every active game inside the search cz_search_begin opened: same root options, the noise
  * table continues where it stopped, sims_run / noise_used keep counting.  Follow with the wave / apply loop.  Lets a host
  * loop run action()'s rounds (player.py:167-184) in slices: `go infinite` / movetime stops, `info depth` lines between. */
@@ -174,7 +183,10 @@ int cz_search_more(cz_engine* e, int32_t n_sims);
 /* Replace the Dirichlet table of the open search (noise_mode 0) by a longer one holding the same draws plus more; the
  * per-game read position is kept.  Host-side only. */
 int cz_set_noise_table(cz_engine* e, const double* noise_dev, int64_t noise_stride);
-/* Whole search with the built-in network as evaluator (needs cz_nn_set_weights). Synchronises. */
+/* Whole search with the built-in network as evaluator (needs cz_nn_set_weights).  Device-driven: every wave / evaluation /
+ * apply iteration is a fixed-shape sequence of launches (captured CUDA graphs) whose batch size is a device integer; the host
+ * thread only polls a flag in mapped memory to learn that no game has work left.  Synchronises once, at the end.
+ * (CZ_SEARCH_LOOP=host in the environment at cz_create selects the round-1 host-driven loop: the A/B baseline.) */
 int cz_search(cz_engine* e, const cz_root_opts* opts);
 
 typedef struct cz_root_info {

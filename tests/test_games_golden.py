@@ -35,6 +35,9 @@ class _HostDraws:
     def store_lottery(self):
         return random.random()
 
+    def playouts(self, lo, hi):
+        return random.randint(lo, hi) * 100                 # evaluator.py:12,153 `from random import randint`
+
     def choose_with_player(self, player, state, turns, no_act, increase_temp):
         player.increase_temp = increase_temp
         policy, _ = player.calc_policy(state, turns, no_act)
@@ -69,24 +72,34 @@ def test_restated_game_loops_replay_the_real_games():
                 assert r["moves"] == want["moves"]
             kinds.add(("resign" if r["flags"] & 1 else "draw" if r["flags"] & 2 else "capture", want["store"]))
         else:
-            r = oarena.play_arena_game(_pc(g), op.fake_evaluate_states, op.fake_evaluate_states, g["idx"], lambda slot: d, 1,
-                                       max_game_length=g["play"]["max_game_length"])
+            real = not g.get("playouts_patched", True)       # the game ran with the reference's own `randint(8, 12) * 100`
+            pc = _pc(g)
+            if real:
+                pc.simulation_num_per_move = -1              # must come from the draw
+            r = oarena.play_arena_game(pc, op.fake_evaluate_states, op.fake_evaluate_states, g["idx"], lambda slot: d, 1,
+                                       max_game_length=g["play"]["max_game_length"], playouts=(8, 12) if real else None)
+            if real:
+                assert r["playouts"] == want["playouts"] == g["sims"] and g["sims"] in (800, 900, 1000, 1100, 1200)
+                kinds.add("real_playouts")
             assert (r["turns"], r["value_red"]) == (want["turns"], want["value_red"])
             assert r["moves"][:len(want["moves"])] == want["moves"] and len(r["moves"]) - len(want["moves"]) in (0, 1)
-    assert {("resign", False), ("resign", True), ("draw", True), ("capture", True)} <= kinds
+    assert {("resign", False), ("resign", True), ("draw", True), ("capture", True), "real_playouts"} <= kinds
 
 
 def check_device_loop_replays_real_games(lib, device):
     from cczero_b200.engine import Engine
 
-    def play(g, arena, want_records):
+    def play(g, arena, want_records, slots=None, game_sims=None):
         p = g["play"]
-        eng = Engine(lib, device, n_games=2 if arena else 1, sims_per_move=g["sims"], leaves_per_round=1, noise_mode=1,
+        eng = Engine(lib, device, n_games=slots or (2 if arena else 1), sims_per_move=g["sims"] if game_sims is None else 7,
+                     leaves_per_round=1, noise_mode=1,
                      noise_eps=0.0, c_puct=p["c_puct"], tau_decay_rate=0.0, max_game_length=p["max_game_length"],
                      resign_threshold=p["resign_threshold"], enable_resign_rate=0.0, min_resign_turn=p["min_resign_turn"], seed=1,
                      max_nodes_per_game=g["sims"] * 2 * p["max_game_length"] + 64, arena=arena,
                      use_history=bool(g.get("use_history")))
         eng.reset()
+        if game_sims is not None:                            # per-game simulation_num_per_move (evaluator.py:153-154)
+            eng.set_game_sims([game_sims] * eng.n_games)
         recs = []
         for _ in range(want_records * (2 * p["max_game_length"] + 4)):
             eng.search_external(eval_planes, None)
@@ -105,13 +118,23 @@ def check_device_loop_replays_real_games(lib, device):
         want = g["result"]
         assert rec["moves"] == want["moves"], (g["seed"], rec["moves"][:6], want["moves"][:6])
         assert rec["value_red"] == want["value_red"] and rec["n_plies"] == want["turns"]
-    ar = sorted((g for g in det if g["kind"] == "arena"), key=lambda g: g["idx"])
+    ar = sorted((g for g in det if g["kind"] == "arena" and g.get("playouts_patched", True)), key=lambda g: g["idx"])
     assert [g["idx"] for g in ar[:2]] == [0, 1] and ar[0]["sims"] == ar[1]["sims"]
     recs = sorted(play(ar[0], True, 2), key=lambda r: r["game_index"])
     for rec, g in zip(recs, ar):
         want = g["result"]
         assert rec["game_index"] == g["idx"] and rec["value_red"] == want["value_red"] and rec["n_plies"] == want["turns"]
         assert rec["moves"][:len(want["moves"])] == want["moves"]
+    # arena games that ran with the reference's own per-game `randint(8, 12) * 100` playouts: the engine default (7) is wrong on
+    # purpose, the per-game value set through cz_set_game_sims must be what every search of the game runs
+    real = [g for g in det if g["kind"] == "arena" and not g.get("playouts_patched", True)]
+    assert len(real) >= 2 and {g["idx"] for g in real} == {0, 1}
+    for g in real:
+        m = g["idx"] + 1                                     # idx 1 is the second of two concurrent games
+        recs = [r for r in play(g, True, m, slots=2 * m, game_sims=g["sims"]) if r["game_index"] == g["idx"]]
+        want = g["result"]
+        assert len(recs) == 1 and recs[0]["value_red"] == want["value_red"] and recs[0]["n_plies"] == want["turns"]
+        assert recs[0]["moves"][:len(want["moves"])] == want["moves"], (g["seed"], recs[0]["moves"], want["moves"])
 
 
 def test_emul_device_loop_replays_real_games(emul_lib):

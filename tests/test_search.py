@@ -121,3 +121,43 @@ def test_cuda_no_act_and_temp(cuda_lib):
 @pytest.mark.gpu
 def test_cuda_terminal_and_repetition(cuda_lib):
     sc.check_terminal_and_repetition(cuda_lib, "cuda")
+
+
+def test_emul_apply_legal_equals_apply_policy(emul_lib):
+    """cz_leaf_labels + cz_search_apply_legal (the hand-over the integrated search uses on the device: only policy[label] of
+    the legal moves) gives bit for bit the tree of cz_search_apply with the full 2086-vectors."""
+    import numpy as np
+    import torch
+    from cczero_b200.engine import Engine
+    from tests.search_checks import eval_planes, midgame_states
+
+    def run(legal):
+        eng = Engine(emul_lib, "cpu", n_games=3, sims_per_move=48, leaves_per_round=5, noise_mode=1, noise_eps=0.25, seed=9,
+                     max_nodes_per_game=512)
+        eng.reset([s for s in midgame_states(3, 2)])
+        eng.search_begin(None)
+        while True:
+            n, busy = eng.search_wave()
+            if n > 0:
+                pol, val = eval_planes(eng.leaf_planes(n).numpy())
+                pol, val = torch.as_tensor(np.ascontiguousarray(pol, dtype=np.float32)), torch.as_tensor(np.ascontiguousarray(val, dtype=np.float32))
+                if legal:
+                    lab, cnt = eng.leaf_labels(n)
+                    lp = torch.zeros((n, 128), dtype=torch.float32)
+                    for i in range(n):
+                        c = int(cnt[i])
+                        idx = lab[i, :c].long()
+                        assert c > 0 and (idx >= 0).all()
+                        lp[i, :c] = pol[i, idx]
+                    eng.search_apply_legal(lp, val)
+                else:
+                    eng.search_apply(pol, val)
+            if not busy:
+                break
+        out = [eng.root(g) for g in range(3)]
+        c = eng.counters()
+        eng.close()
+        return out, int(c[1]), int(c[2])
+    a, pos_a, waves_a = run(False)
+    b, pos_b, waves_b = run(True)
+    assert a == b and pos_a == pos_b > 100 and waves_a == waves_b > 10      # N, W (f64), P (f32): identical; device-side counters
