@@ -881,6 +881,30 @@ int cz_search(cz_engine* e, const cz_root_opts* opts) {
 #endif
 }
 
+int cz_search_run(cz_engine* e) {
+#if defined(CZ_EMUL)
+  (void)e;
+  return cz_fail(CZ_ERR_UNSUPPORTED, "cz_search_run: the CPU emulation build has no network; use the wave/apply API");
+#else
+  if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_run: null engine");
+  if (!e->nn || !cznn::nn_ready(e->nn)) return cz_fail(CZ_ERR_STATE, "cz_search_run: network weights not set");
+  if (e->last_leaves != 0) return cz_fail(CZ_ERR_STATE, "cz_search_run: %d leaves of a host-driven wave were not applied", e->last_leaves);
+  if (e->graph_loop) return search_graph_loop(e);
+  if (e->cfg.arena) return cz_fail(CZ_ERR_UNSUPPORTED, "cz_search_run: the host-driven loop (CZ_SEARCH_LOOP=host) serves arena engines through cz_search only");
+  for (;;) {
+    int32_t n = 0, busy = 0;
+    int rc;
+    if ((rc = cz_search_wave(e, &n, &busy))) return rc;
+    if (n > 0) {
+      if ((rc = cznn::nn_forward_boards(e->nn, 0, e->d.leaf_dense, n, e->policy_buf, e->value_buf))) return rc;
+      if ((rc = cz_search_apply(e, e->policy_buf, e->value_buf))) return rc;
+    }
+    if (!busy) break;
+  }
+  return 0;
+#endif
+}
+
 int cz_get_root(cz_engine* e, int game, cz_root_info* out) {
   if (!e || !out || game < 0 || game >= e->cfg.n_games) return cz_fail(CZ_ERR_ARG, "cz_get_root: bad argument");
   CZ_LAUNCH(k_root_info, 1, 1, sizeof(TreeSmem), e->stream, e->d, game, e->root_info_dev);

@@ -202,9 +202,14 @@ class Engine:
         self._noise_keep = (getattr(self, "_noise_keep", []) + [t])[-2:]     # the previous table may still be read by a queued kernel
         self.lib.call("cz_set_noise_table", self._h, _ptr(t), t.shape[1])
 
-    def run_waves(self, evaluate_planes=None):
+    def run_waves(self, evaluate_planes=None, host_loop=False):
         """The wave / evaluate / apply loop until every queued simulation is done; evaluate_planes as in search_external,
-        None = the built-in network (cz_nn_forward on the leaf planes)."""
+        None = the built-in network: the engine's own device-driven loop (cz_search_run), or — host_loop=True — this Python
+        loop around cz_nn_forward_boards (full softmax vectors; the parity tests compare the two)."""
+        if evaluate_planes is None and self.lib.is_cuda and self.cfg.nn_filters > 0 and not host_loop:
+            c0 = int(self.counters()[1])
+            self.lib.call("cz_search_run", self._h)          # device-driven loop, no per-wave host round trip
+            return int(self.counters()[1]) - c0
         n_pos = 0
         while True:
             n, busy = self.search_wave()

@@ -99,6 +99,7 @@ _SIGS = {
     "cz_leaf_labels": (C.c_int, [_P, _P, _P]),
     "cz_search_apply_legal": (C.c_int, [_P, _P, _P]),
     "cz_search": (C.c_int, [_P, C.POINTER(CzRootOpts)]),
+    "cz_search_run": (C.c_int, [_P]),
     "cz_get_root": (C.c_int, [_P, C.c_int, C.POINTER(CzRootInfo)]),
     "cz_get_counters": (C.c_int, [_P, _P]),
     "cz_get_search_stats": (C.c_int, [_P, _P]),

@@ -188,6 +188,9 @@ int cz_set_noise_table(cz_engine* e, const double* noise_dev, int64_t noise_stri
  * thread only polls a flag in mapped memory to learn that no game has work left.  Synchronises once, at the end.
  * (CZ_SEARCH_LOOP=host in the environment at cz_create selects the round-1 host-driven loop: the A/B baseline.) */
 int cz_search(cz_engine* e, const cz_root_opts* opts);
+/* The loop of cz_search alone: run the simulations cz_search_begin / cz_search_more queued, built-in network as evaluator.
+ * (A UCI front end slices action()'s rounds with cz_search_more and prints `info depth` lines in between.)  Synchronises. */
+int cz_search_run(cz_engine* e);
 
 typedef struct cz_root_info {
   int32_t n_moves;                 /* legal moves of the root (0 if the root was never expanded) */

@@ -114,9 +114,11 @@ def test_history_network_builtin_search_and_worker(cuda_lib, tmp_path):
     hists = [game_history(12, 3), None, game_history(2, 4)]
     states = [hists[0][-1], osenv.INIT_STATE, hists[2][-1]]
 
-    def run(external, pipelined=False):
+    def run(external, pipelined=False, legacy=False):
+        os.environ["CZ_SEARCH_LOOP"] = "host" if legacy else "graph"        # read by cz_create
         eng = Engine(cuda_lib, "cuda", n_games=3, sims_per_move=64, leaves_per_round=8, noise_mode=1, nn_filters=64, nn_blocks=2,
                      seed=5, use_history=True)
+        os.environ.pop("CZ_SEARCH_LOOP", None)
         eng.set_weights(model.torch_weights())
         os.environ["CZ_FORCE_PIPELINE"] = "1" if pipelined else "0"
         eng.reset(states)
@@ -135,11 +137,12 @@ def test_history_network_builtin_search_and_worker(cuda_lib, tmp_path):
         assert int(eng.counters()[6]) == 0
         eng.close()
         return out, seen
-    a, _ = run(False)
-    b, seen = run(True)
-    c, _ = run(False, pipelined=True)                    # the two-range pipeline carries the 192-byte leaf records too
+    a, _ = run(False)                                     # device-driven loop (graphs, legal priors from logits)
+    b, seen = run(True)                                   # host-driven, full softmax vectors through the reference-facing API
+    c, _ = run(False, pipelined=True, legacy=True)        # round-1 two-range pipeline (carries the 192-byte leaf records too)
+    d, _ = run(False, legacy=True)                        # round-1 sequential loop
     os.environ.pop("CZ_FORCE_PIPELINE", None)
-    assert a == b == c and sum(seen) > 0
+    assert a == b == c == d and sum(seen) > 0
     model.save(cfg.resource.model_best_config_path, cfg.resource.model_best_weight_path)
     w = SelfPlayWorker(cfg, concurrent_games=4, seed=3, use_history=True, model=model)
     recs = w.play_games(2)
@@ -154,13 +157,15 @@ def test_pipelined_search_equals_sequential(cuda_lib):
     cfg = _config("/tmp", filters=64, blocks=2)
     weights = CChessModel(cfg).build(seed=9).torch_weights()
 
-    def run(no_pipeline):
+    def run(no_pipeline, legacy=True):
         os.environ["CZ_NO_PIPELINE"] = "1" if no_pipeline else "0"
+        os.environ["CZ_SEARCH_LOOP"] = "host" if legacy else "graph"
         try:
             eng = Engine(cuda_lib, "cuda", n_games=1024, sims_per_move=24, leaves_per_round=8, noise_mode=1, nn_filters=64,
                          nn_blocks=2, seed=5, max_nodes_per_game=512)
         finally:
             os.environ.pop("CZ_NO_PIPELINE", None)
+            os.environ.pop("CZ_SEARCH_LOOP", None)
         eng.set_weights(weights)
         eng.reset()
         out = []
@@ -174,7 +179,8 @@ def test_pipelined_search_equals_sequential(cuda_lib):
 
     a, sa = run(False)
     b, sb = run(True)
-    assert a == b and sa == sb
+    c, sc = run(True, legacy=False)                       # the device-driven loop (default)
+    assert a == b == c and sa == sb == sc
 
 
 def test_evaluator_arena_two_networks(cuda_lib, tmp_path):
@@ -204,8 +210,10 @@ def test_evaluator_arena_two_networks(cuda_lib, tmp_path):
 
 def test_c3_shaped_builtin_search_equals_wave_apply(cuda_lib):
     """BASELINE configs[2] shape (1024 games x K = 8, 14 planes, 256x20 network, fp32 skip stream): the integrated
-    `cz_search` — two-range pipelined AND single-range — gives bit for bit the statistics of the same search driven from the
-    host through cz_search_wave / cz_leaf_boards / cz_nn_forward_boards / cz_search_apply."""
+    `cz_search` — the device-driven loop (captured graphs, legal priors taken from the logits on the device) and the round-1
+    host-driven loops, two-range pipelined and single-range — gives bit for bit the statistics of the same search driven from
+    the host through cz_search_wave / cz_leaf_boards / cz_nn_forward_boards / cz_search_apply, i.e. through the full
+    [n][2086] softmax vectors of the reference-facing network API."""
     from cczero_b200.engine import Engine
     from cczero_b200.model import CChessModel
     from cczero_b200.records import RootStage
@@ -216,11 +224,13 @@ def test_c3_shaped_builtin_search_equals_wave_apply(cuda_lib):
         os.environ.pop("CZ_NO_PIPELINE", None)
         if mode == "single":
             os.environ["CZ_NO_PIPELINE"] = "1"
+        os.environ["CZ_SEARCH_LOOP"] = "host" if mode in ("single", "pipelined") else "graph"
         try:
             eng = Engine(cuda_lib, "cuda", n_games=1024, sims_per_move=40, leaves_per_round=8, noise_mode=1, nn_filters=256,
                          nn_blocks=20, seed=11, max_nodes_per_game=1024)
         finally:
             os.environ.pop("CZ_NO_PIPELINE", None)
+            os.environ.pop("CZ_SEARCH_LOOP", None)
         eng.set_weights(weights)
         eng.reset()
         st = RootStage(eng)
@@ -228,7 +238,7 @@ def test_c3_shaped_builtin_search_equals_wave_apply(cuda_lib):
         for _ in range(2):                                   # second move: tree reuse + a different position per game
             if mode == "host":
                 eng.search_begin(None)
-                eng.run_waves(None)
+                eng.run_waves(None, host_loop=True)
             else:
                 eng.search(None)
             n, mv, cnt = eng.download_root_stats(st)
@@ -238,8 +248,8 @@ def test_c3_shaped_builtin_search_equals_wave_apply(cuda_lib):
         assert int(eng.counters()[6]) == 0
         eng.close()
         return out
-    host, pipe, single = run("host"), run("pipelined"), run("single")
-    for a in (pipe, single):
+    host, graph, pipe, single = run("host"), run("graph"), run("pipelined"), run("single")
+    for a in (graph, pipe, single):
         for (n0, m0, c0, r0), (n1, m1, c1, r1) in zip(host, a):
             assert torch.equal(n0, n1) and torch.equal(m0, m1) and torch.equal(c0, c1)
             assert r0 == r1                                  # N, W (f64), P (f32), sum_n of sampled roots, exactly
