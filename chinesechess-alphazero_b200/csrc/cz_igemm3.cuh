@@ -1,0 +1,278 @@
+// cz_igemm3.cuh — CTA-pair implicit-GEMM 3x3 convolution (same mainloop as igemm::k_igemm2) with an ALL-TMA epilogue.
+//
+// Why: ncu of k_igemm2 on three shapes (profiles/r02a_*) fits one model: the SM's 128 B/cycle shared-memory data pipe is shared by
+// the TMA operand fills, the UMMA operand reads AND every LSU wavefront of the epilogue.
+//     per M-tile of one CTA:   C=256 conv1  18.4k (operands) + 2.5k (epilogue) + ~2.6k fixed  ~ 21.0k cycles measured
+//                              C=256 conv2  18.4k + 6-8k (fp32 skip in, fp32 + fp16 out)       ~ 24.4k
+//                              C=128 conv1   6.9k + 2-3k                                       ~ 12.1k  (tensor pipe 37 %)
+// The operand traffic is what the MMA needs; the epilogue's share is ours to cut.  k_igemm2 moved every element of the tile
+// through the pipe up to 8 times (coalesced ldg -> sts -> lds row -> sts -> lds -> stg fp32, lds -> stg fp16, with 30 % bank
+// conflicts on top).  Here each element passes at most 4 times and no LSU global access is left:
+//     skip stream  : TMA load  -> swizzled smem tile -> ONE conflict-free lds per thread-row
+//     fp32 output  : written in place over the skip tile -> TMA store
+//     fp16 output  : packed into a swizzled smem tile   -> TMA store
+// Per epilogue warp (8 per CTA: TMEM lane quarter x column half) and 32-column chunk: a 32x32 fp32 tile F (128-byte rows,
+// SWIZZLE_128B) and a 32x32 fp16 tile H (64-byte rows, SWIZZLE_64B), both double-buffered so that the stores of chunk i overlap
+// the math of chunk i+1.  Thread r of the warp owns accumulator row r (tcgen05.ld 32x32b), i.e. one smem row: with the TMA
+// swizzle a warp-wide 16-byte access touches every bank group exactly 4 times = the 4-wavefront minimum for 512 bytes.
+#pragma once
+#include "cz_igemm.cuh"
+
+namespace igemm {
+
+constexpr int kMaxStages3 = 6;
+constexpr int kSmemLimit3 = 232448;                            // opt-in dynamic shared memory per CTA on sm_100
+
+struct Args3 {
+  Args a;
+  int stages;            // smem ring depth (<= kMaxStages3), chosen on the host from what fits beside the epilogue tiles
+  int skip_mode;         // 0 none, 1 fp16 (tmSkip = fp16 map), 2 fp32 (tmSkip = fp32 map)
+  int out32;             // also store the fp32 copy (tmOut32)
+  int fbytes;            // bytes of one F tile: 4096 (fp32 skip and/or fp32 output), 2048 (fp16 skip only), 0 (neither)
+};
+__host__ __device__ constexpr int epi3_warp_bytes(int fbytes) { return 2 * fbytes + 2 * 2048; }    // F[2] + H[2] per epilogue warp
+
+template <int N_TILE>
+struct Cfg3 {
+  static constexpr int kBHalfBytes = (N_TILE / 2) * 128;
+  static constexpr int kStageBytes = kAStageBytes + kBHalfBytes;
+  static constexpr int kTmemCols = Cfg<N_TILE>::kTmemCols;
+  static constexpr int smem_bytes(int stages, int fbytes) { return stages * kStageBytes + kEpiWarps2 * epi3_warp_bytes(fbytes) + 512 + 1024; }
+  static int max_stages(int fbytes) {
+    int s = (kSmemLimit3 - 512 - 1024 - kEpiWarps2 * epi3_warp_bytes(fbytes)) / kStageBytes;
+    return s > kMaxStages3 ? kMaxStages3 : s;
+  }
+  static_assert(N_TILE % 64 == 0 && N_TILE <= 256, "column halves must be multiples of 32");
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* t, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(t)), "r"(umma::smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int N_TILE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut16,
+         const __grid_constant__ CUtensorMap tmSkip, const __grid_constant__ CUtensorMap tmOut32, const Args3 p) {
+  using C = Cfg3<N_TILE>;
+  const Args& a = p.a;
+  const int n_stages = p.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* epi = smem + n_stages * C::kStageBytes;                 // 1024-byte aligned: stage sizes are multiples of 1024
+  const int warp_bytes = epi3_warp_bytes(p.fbytes);                // 4096, 8192 or 12288
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kEpiWarps2 * warp_bytes);
+  uint64_t* full = bars;                       // [kMaxStages3]  (used in the leader only)
+  uint64_t* empty = bars + kMaxStages3;        // [kMaxStages3]  per CTA, signalled by multicast commit
+  uint64_t* tfull = bars + 2 * kMaxStages3;    // [2]
+  uint64_t* tempty = tfull + 2;                // [2]  leader: 512 arrivals (8 epilogue warps of both CTAs)
+  uint64_t* skipbar = tempty + 2;              // [8][2] per epilogue warp: skip tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(skipbar + 2 * kEpiWarps2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = umma::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmA);
+    umma::prefetch_tmap(&tmB);
+    umma::prefetch_tmap(&tmOut16);
+    if (p.skip_mode) umma::prefetch_tmap(&tmSkip);
+    if (p.out32) umma::prefetch_tmap(&tmOut32);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < n_stages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 512); }
+    for (int i = 0; i < 2 * kEpiWarps2; ++i) umma::mbar_init(&skipbar[i], 1);
+    umma::fence_barrier_init();
+    umma::fence_proxy_async();
+  }
+  if (warp == 2) umma::tmem_alloc2<C::kTmemCols>(tmem_slot);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync_all();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_kb = a.n_taps * a.k_chunks;
+  const int rows = args_rows(a);
+  const int m_tiles = a.n_dev ? (rows + kTileM - 1) / kTileM : a.m_tiles;
+  const int pairs = (m_tiles + 1) / 2;
+  const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one per CTA)
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int pair = cluster_id; pair < pairs; pair += n_clusters) {
+        const int m_tile = 2 * pair + (int)rank;
+        const int pix0 = m_tile * kTileM, img0 = pix0 / 90, row0 = (pix0 % 90) / 9, col0 = pix0 % 9;
+        for (int tap = 0; tap < a.n_taps; ++tap) {
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          for (int kc = 0; kc < a.k_chunks; ++kc) {
+            umma::mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sA = smem + s * C::kStageBytes;
+            uint8_t* sB = sA + kAStageBytes;
+            if (leader) umma::mbar_expect_tx(&full[s], 2u * (a.a_bytes + (uint32_t)C::kBHalfBytes));
+            umma::tma2_load_im2col_4d(sA, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1));
+            umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + (int)rank * (N_TILE / 2));
+            if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma::idesc_f16(256, N_TILE);
+      uint32_t s = 0, ph = 0, tcount = 0;
+      for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        umma::mbar_wait(&tempty[acc], aph ^ 1);
+        umma::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          umma::mbar_wait(&full[s], ph);
+          umma::tc_fence_after();
+          const uint32_t sA = umma::smem_u32(smem + s * C::kStageBytes);
+          const uint64_t da = umma::smem_desc_sw128(sA);
+          const uint64_t db = umma::smem_desc_sw128(sA + kAStageBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma::mma2_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma::mma2_commit_multicast(&empty[s]);
+          if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1; }
+        }
+        umma::mma2_commit_multicast(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: TMEM -> registers -> swizzled smem tiles -> TMA
+    const int ew = warp - 4;
+    const int q = warp & 3;                                   // TMEM lane quarter (rows q*32 .. q*32+31 of the CTA's M-tile)
+    const int half = ew >> 2;                                 // column half
+    constexpr int kChunks = N_TILE / 64;                      // 32-column chunks per half
+    const int cbeg = half * (N_TILE / 2);
+    const int fb = p.fbytes;
+    uint8_t* F = epi + ew * warp_bytes;                       // F[2]: fb bytes each, 1024-aligned
+    uint8_t* H = F + 2 * fb;                                  // H[2]: 2048 B each
+    uint64_t* sbar = skipbar + 2 * ew;
+    const uint32_t tempty_remote[2] = {umma::mapa_shared(&tempty[0], 0), umma::mapa_shared(&tempty[1], 0)};
+    const int r7 = lane & 7, r3 = (lane >> 1) & 3;            // swizzle keys of this thread's row: 128B rows / 64B rows
+    uint8_t* const frow0 = F + lane * 128;
+    uint8_t* const hrow0 = H + lane * 64;
+    const bool has_skip = p.skip_mode != 0, skip32 = p.skip_mode == 2;
+    // next tile's skip block -> L2, a whole tile ahead (one warp): the per-chunk TMA loads below then hit L2
+    auto prefetch_skip = [&](int pr) {
+      if (ew != 0 || pr >= pairs || !has_skip) return;
+      const long long row0 = (long long)(2 * pr + (int)rank) * kTileM;
+      const long long nrow = rows - row0 < kTileM ? rows - row0 : kTileM;
+      if (nrow <= 0) return;
+      const size_t esz = skip32 ? 4 : 2;
+      const char* base = (skip32 ? reinterpret_cast<const char*>(a.residual32) : reinterpret_cast<const char*>(a.residual)) + (size_t)row0 * a.ldo * esz;
+      const size_t total = (size_t)nrow * a.ldo * esz;
+      for (size_t off = (size_t)lane * 16384; off < total; off += 32 * 16384)
+        umma::l2_prefetch_bulk(base + off, (uint32_t)(total - off < 16384 ? total - off : 16384));
+    };
+    uint32_t tcount = 0, gchunk = 0;                          // gchunk: chunks processed by this warp (buffer / barrier phase)
+    prefetch_skip(cluster_id);
+    // the very first chunk's skip tile
+    if (has_skip && cluster_id < pairs && lane == 0) {
+      const int row = (2 * cluster_id + (int)rank) * kTileM + q * 32;
+      umma::mbar_expect_tx(&sbar[0], skip32 ? 4096u : 2048u);
+      umma::tma_load_2d(F, &tmSkip, &sbar[0], cbeg, row);
+    }
+    for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
+      const int m_tile = 2 * pair + (int)rank;
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const int rbase = m_tile * kTileM + q * 32;             // first global pixel row of this warp
+      prefetch_skip(pair + n_clusters);
+      umma::mbar_wait(&tfull[acc], aph);
+      umma::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + cbeg;
+#pragma unroll 1
+      for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
+        const uint32_t b = gchunk & 1, bph = (gchunk >> 1) & 1;
+        const int c0 = cbeg + ch * 32;
+        uint8_t* frow = frow0 + b * fb;
+        uint8_t* hrow = hrow0 + b * 2048;
+        uint32_t v[32];
+        umma::tmem_ld_32x32(t_row + ch * 32, v);
+        if (has_skip) umma::mbar_wait(&sbar[b], bph);         // skip tile of this chunk has landed in F[b]
+        const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
+#pragma unroll
+        for (int g = 0; g < 8; g += 2) {
+          float4 x0, x1;
+          {
+            const float4 b0 = __ldg(bp + g), b1 = __ldg(bp + g + 1);
+            x0 = make_float4(__uint_as_float(v[4 * g]) + b0.x, __uint_as_float(v[4 * g + 1]) + b0.y,
+                             __uint_as_float(v[4 * g + 2]) + b0.z, __uint_as_float(v[4 * g + 3]) + b0.w);
+            x1 = make_float4(__uint_as_float(v[4 * g + 4]) + b1.x, __uint_as_float(v[4 * g + 5]) + b1.y,
+                             __uint_as_float(v[4 * g + 6]) + b1.z, __uint_as_float(v[4 * g + 7]) + b1.w);
+          }
+          if (skip32) {
+            const float4 s0 = *reinterpret_cast<const float4*>(frow + ((g ^ r7) << 4));
+            const float4 s1 = *reinterpret_cast<const float4*>(frow + (((g + 1) ^ r7) << 4));
+            x0.x += s0.x; x0.y += s0.y; x0.z += s0.z; x0.w += s0.w;
+            x1.x += s1.x; x1.y += s1.y; x1.z += s1.z; x1.w += s1.w;
+          } else if (has_skip) {                              // fp16 skip tile: 64-byte rows in the first 2 KB of F[b]
+            const uint4 sv = *reinterpret_cast<const uint4*>(F + b * fb + lane * 64 + (((g >> 1) ^ r3) << 4));
+            const __half2* h = reinterpret_cast<const __half2*>(&sv);
+            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+            x0.x += f0.x; x0.y += f0.y; x0.z += f1.x; x0.w += f1.y;
+            x1.x += f2.x; x1.y += f2.y; x1.z += f3.x; x1.w += f3.y;
+          }
+          if (a.relu) {
+            x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
+            x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
+          }
+          if (p.out32) {                                      // in place over the skip tile (or into the free F[b])
+            *reinterpret_cast<float4*>(frow + ((g ^ r7) << 4)) = x0;
+            *reinterpret_cast<float4*>(frow + (((g + 1) ^ r7) << 4)) = x1;
+          }
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
+          oh[0] = __floats2half2_rn(x0.x, x0.y); oh[1] = __floats2half2_rn(x0.z, x0.w);
+          oh[2] = __floats2half2_rn(x1.x, x1.y); oh[3] = __floats2half2_rn(x1.z, x1.w);
+          *reinterpret_cast<uint4*>(hrow + (((g >> 1) ^ r3) << 4)) = ov;
+        }
+        umma::fence_proxy_async();                            // generic-proxy writes above -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          if (p.out32) tma_store_2d(&tmOut32, F + b * fb, c0, rbase);
+          tma_store_2d(&tmOut16, H + b * 2048, c0, rbase);
+          bulk_commit();
+          bulk_wait_read<1>();                                // the stores of the PREVIOUS chunk have read F[b^1], H[b^1]: free
+          if (has_skip) {                                     // skip tile of the next chunk (may belong to the next tile)
+            int nrow = rbase, ncol = c0 + 32;
+            bool more = true;
+            if (ch + 1 == kChunks) { ncol = cbeg; nrow = rbase + 2 * n_clusters * kTileM; more = pair + n_clusters < pairs; }
+            if (more) {
+              umma::mbar_expect_tx(&sbar[b ^ 1], skip32 ? 4096u : 2048u);
+              umma::tma_load_2d(F + (b ^ 1) * fb, &tmSkip, &sbar[b ^ 1], ncol, nrow);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      umma::tc_fence_before();
+      umma::mbar_arrive_cluster(tempty_remote[acc]);
+    }
+    if (lane == 0) bulk_wait_all<0>();                        // every store of this warp has been written before the CTA exits
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync_all();
+  if (warp == 2) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc2<C::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace igemm

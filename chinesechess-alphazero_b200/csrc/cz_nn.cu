@@ -21,6 +21,7 @@
 
 #include "cz_err.h"
 #include "cz_igemm.cuh"
+#include "cz_igemm3.cuh"
 #include "cz_nn.cuh"
 
 namespace cznn {
@@ -108,6 +109,22 @@ static int make_map_2d(CUtensorMap* m, const void* base, int k, long long rows, 
   return 0;
 }
 
+// activation matrix [rows][c] (fp16 or fp32), box {32 columns, 32 rows}: the tiles the conv epilogue loads (skip stream) and
+// stores (outputs) with TMA.  32 fp32 = 128-byte rows -> SWIZZLE_128B, 32 fp16 = 64-byte rows -> SWIZZLE_64B.
+static int make_map_tile32(CUtensorMap* m, const void* base, int c, long long rows, bool f32) {
+  if (load_encode()) return CZ_ERR_CUDA;
+  const cuuint64_t es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)c * es};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t est[2] = {1, 1};
+  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
+                        box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cz_fail(CZ_ERR_CUDA, "cuTensorMapEncodeTiled(tile32) failed: %d", (int)r);
+  return 0;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -159,6 +176,45 @@ static int launch_igemm2(int n_tile, const CUtensorMap& tmA, const CUtensorMap& 
     case 256: return launch_igemm2_t<256>(tmA, tmB_half, a, st);
   }
   return cz_fail(CZ_ERR_UNSUPPORTED, "igemm2: unsupported N tile %d", n_tile);
+}
+// k_igemm3: same mainloop, all-TMA epilogue (cz_igemm3.cuh).  CZ_EPI=2 selects the round-1 epilogue (k_igemm2) for A/B runs.
+static bool use_tma_epilogue() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CZ_EPI"); v = (e && e[0] == '2') ? 0 : 1; }
+  return v == 1;
+}
+template <int N_TILE>
+static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
+                           const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st) {
+  using C = igemm::Cfg3<N_TILE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CZ_CUDA(cudaFuncSetAttribute(igemm::k_igemm3<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, igemm::kSmemLimit3));
+    attr_set = true;
+  }
+  igemm::Args3 p;
+  p.a = a;
+  p.skip_mode = skip_mode; p.out32 = out32 ? 1 : 0;
+  p.fbytes = (skip_mode == 2 || out32) ? 4096 : (skip_mode == 1 ? 2048 : 0);
+  p.stages = C::max_stages(p.fbytes);
+  { static int cap = -1; if (cap < 0) { const char* e = getenv("CZ_STAGES"); cap = e ? atoi(e) : 0; } if (cap > 1 && cap < p.stages) p.stages = cap; }
+  if (p.stages < 2) return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: no room for the operand ring");
+  const int pairs = ((a.n_dev ? (a.rows + igemm::kTileM - 1) / igemm::kTileM : a.m_tiles) + 1) / 2;
+  if (pairs <= 0) return 0;
+  const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
+  igemm::k_igemm3<N_TILE><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
+  CZ_CUDA(cudaGetLastError());
+  return 0;
+}
+static int launch_igemm3(int n_tile, const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
+                         const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st) {
+  switch (n_tile) {
+    case 64: return launch_igemm3_t<64>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 128: return launch_igemm3_t<128>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 192: return launch_igemm3_t<192>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 256: return launch_igemm3_t<256>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+  }
+  return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: unsupported N tile %d", n_tile);
 }
 static bool use_im2col() {
   static int v = -1;
@@ -216,8 +272,8 @@ __device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 
 // 5x5 "same" input convolution + BN + ReLU from packed boards (model.py:34-41, static_env.py:137-156 fused).
 // The 14 input planes are one-hot, so an output pixel is the sum of <= 25 weight rows w[tap][plane(piece on the
 // tapped square)][:].  Phase 1: 90 threads list the occupied taps of their pixel (row index = tap*14 + plane);
-// phase 2: every thread owns two adjacent output channels and walks the lists (half2 loads, fp32 accumulate).
-// grid = batch, block = max(96, C/2) threads.  w: HWIO [5][5][in_planes][C] fp16 (BN scale folded).
+// phase 2: every thread owns two adjacent output channels of a subset of the pixels and walks their lists (half2 loads, fp32
+// accumulate).  grid = batch, block = (C/2) * n_groups >= 96 threads (conv_first_threads).  w: HWIO [5][5][in_planes][C] fp16 (BN scale folded).
 // in_planes = 28 (use_history, static_env.py:158-194): every board record is followed by the history board whose pieces
 // select planes 14-27; board_stride = bytes between records.
 __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
@@ -253,13 +309,15 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
     cnt[t] = (uint8_t)n;
   }
   __syncthreads();
-  const int c = 2 * t;
-  if (c >= c_out) return;
+  // phase 2: thread = (channel pair, pixel group): blockDim.x = (c_out / 2) * n_groups, group g takes pixels g, g + n_groups, ...
+  const int pairs = c_out / 2;
+  const int c = 2 * (t % pairs), grp = t / pairs, n_groups = blockDim.x / pairs;
+  if (grp >= n_groups) return;
   const float2 sh = *reinterpret_cast<const float2*>(shift + c);
   __half* o = out + (size_t)b * board_pixels * c_out;
   const __half2* w2 = reinterpret_cast<const __half2*>(w + c);
   const int stride2 = c_out / 2;
-  for (int pix = 0; pix < 90; ++pix) {
+  for (int pix = grp; pix < 90; pix += n_groups) {
     float a0 = sh.x, a1 = sh.y;
     const int n = cnt[pix];
     for (int k = 0; k < n; ++k) {
@@ -270,7 +328,7 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
     *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = __floats2half2_rn(a0, a1);
     if (out32) *reinterpret_cast<float2*>(out32 + ((size_t)b * board_pixels + pix) * c_out + c) = make_float2(a0, a1);
   }
-  for (int col = 90; col < board_pixels; ++col)
+  for (int col = 90 + grp; col < board_pixels; col += n_groups)
     *reinterpret_cast<__half2*>(o + (size_t)col * c_out + c) = __floats2half2_rn(0.f, 0.f);          // separator row (strip layout)
 }
 
@@ -296,7 +354,9 @@ __global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __
 // Heads (model.py:47-63): 1x1 conv to 4 policy + 2 value channels, BN, ReLU; policy features to the GEMM
 // operand [B][384] (index c*90 + pix, Keras Flatten of channels_first); value: Dense(H)+ReLU, Dense(1)+tanh.
 // A block handles kHeadPos positions so the 180 x H value weights are read once per group.
-// Phase 1: warp per pixel, lane owns 8 channels whose 6 x 8 folded weights sit in registers.
+// Phase 1: one thread per (position, pixel): it streams that pixel's C activations (16-byte loads along its own row; the rows
+// of a warp's 32 pixels are adjacent in memory) against the 6 x C folded weights held in shared memory (broadcast reads) —
+// no cross-lane reduction.  (The round-1 version reduced six sums with 30 shuffles per pixel: 110 us per 2048 positions.)
 constexpr int kHeadPos = 4;
 __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, const float* __restrict__ act32, int c_in,
                                                 const int* __restrict__ n_dev, int board_pixels,
@@ -309,48 +369,38 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
                                                 int hidden, __half* __restrict__ pol_feat, float* __restrict__ value) {
   __shared__ float feat[kHeadPos][6][90];
   __shared__ float red[kHeadPos][8];
+  __shared__ __align__(16) float wsm[256 / 8][6][8];        // [channel group of 8][output][channel in group]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * kHeadPos;
   const int n_pos = __ldg(n_dev);
   if (b0 >= n_pos) return;
   const int npos = n_pos - b0 < kHeadPos ? n_pos - b0 : kHeadPos;
-  const int cbase = lane * 8;
-  const bool lane_on = cbase < c_in;
-  float wr[6][8];
-#pragma unroll
-  for (int o = 0; o < 6; ++o)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wr[o][j] = lane_on ? __ldg(w6 + (size_t)o * c_in + cbase + j) : 0.f;
-  float sh6[6];
-#pragma unroll
-  for (int o = 0; o < 6; ++o) sh6[o] = shift6[o];
-  for (int item = warp; item < npos * 90; item += 8) {
+  for (int i = tid; i < 6 * c_in; i += 256) { const int o = i / c_in, c = i % c_in; wsm[c >> 3][o][c & 7] = __ldg(w6 + i); }
+  __syncthreads();
+  for (int item = tid; item < npos * 90; item += 256) {
     const int p = item / 90, pix = item % 90;
-    const __half* a = act + ((size_t)(b0 + p) * board_pixels + pix) * c_in;
-    float s[6] = {0, 0, 0, 0, 0, 0};
-    if (lane_on) {
+    const size_t row = ((size_t)(b0 + p) * board_pixels + pix) * c_in;
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int g = 0; g < c_in / 8; ++g) {
       float x[8];
       if (act32) {
-        const float4* a4 = reinterpret_cast<const float4*>(act32 + ((size_t)(b0 + p) * board_pixels + pix) * c_in + cbase);
+        const float4* a4 = reinterpret_cast<const float4*>(act32 + row + g * 8);
         const float4 u = __ldg(a4), w4 = __ldg(a4 + 1);
         x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w4.x; x[5] = w4.y; x[6] = w4.z; x[7] = w4.w;
       } else {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + cbase));
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(act + row + g * 8));
         const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
       }
 #pragma unroll
-      for (int o = 0; o < 6; ++o)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s[o] += x[j] * wr[o][j];
+      for (int o = 0; o < 6; ++o) {
+        const float4 wa = *reinterpret_cast<const float4*>(&wsm[g][o][0]), wb = *reinterpret_cast<const float4*>(&wsm[g][o][4]);
+        s[o] += x[0] * wa.x + x[1] * wa.y + x[2] * wa.z + x[3] * wa.w + x[4] * wb.x + x[5] * wb.y + x[6] * wb.z + x[7] * wb.w;
+      }
     }
 #pragma unroll
-    for (int o = 0; o < 6; ++o) {
-      float v = s[o];
-      for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-      if (lane == 0) feat[p][o][pix] = fmaxf(v + sh6[o], 0.f);
-    }
+    for (int o = 0; o < 6; ++o) feat[p][o][pix] = fmaxf(s[o] + __ldg(shift6 + o), 0.f);
   }
   __syncthreads();
   for (int i = tid; i < npos * kPolK1; i += 256) {
@@ -535,6 +585,8 @@ struct NnRuntime {
   bool fp32_skip;                        // keep the residual (skip) stream in fp32: halves the value error of deep nets, ~+30 % time
   int board_pixels;                      // 99 = strip layout (separator row per board), 90 = dense + im2col TMA
   CUtensorMap imap_x, imap_t, imap_y;    // im2col maps of the three activation buffers (dense layout)
+  CUtensorMap omap_x, omap_t, omap_y;    // 32x32 fp16 tile maps of the same buffers (conv epilogue: TMA stores / fp16 skip loads)
+  CUtensorMap fmap_x32, fmap_y32;        // 32x32 fp32 tile maps of the fp32 skip stream
   // optional CUDA-event timing of the residual-tower launches (bench.py roofline)
   bool profile;
   std::vector<cudaEvent_t> ev;        // pairs, recycled
@@ -641,6 +693,11 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
     rc |= make_map_im2col(&r->imap_x, r->x, c, max_batch);
     rc |= make_map_im2col(&r->imap_t, r->t, c, max_batch);
     rc |= make_map_im2col(&r->imap_y, r->y, c, max_batch);
+    rc |= make_map_tile32(&r->omap_x, r->x, c, (long long)max_batch * 90, false);
+    rc |= make_map_tile32(&r->omap_t, r->t, c, (long long)max_batch * 90, false);
+    rc |= make_map_tile32(&r->omap_y, r->y, c, (long long)max_batch * 90, false);
+    rc |= make_map_tile32(&r->fmap_x32, r->x32, c, (long long)max_batch * 90, true);
+    rc |= make_map_tile32(&r->fmap_y32, r->y32, c, (long long)max_batch * 90, true);
   }
   rc |= make_map_3d(&r->map_x, r->x, c, 9, rows, 9, 14);
   rc |= make_map_3d(&r->map_t, r->t, c, 9, rows, 9, 14);
@@ -791,10 +848,17 @@ int nn_set_weights(NnRuntime* r, int net, const cz_tensor_desc* descs, int n) {
 // shape sized for n_max, kernels read *n_dev and leave the rest untouched), so a search never has to tell the host how
 // many leaves a wave produced.  Leaves logits [n][kPolN] + per-tile softmax statistics in r->logits / r->stats.
 // The three parts are separate so that the search can capture them into three CUDA graphs and bracket the tower with events.
+static int conv_first_threads(int c) {                    // (c/2) channel pairs x as many pixel groups as fit 256 threads
+  const int pairs = c / 2;
+  int g = 256 / pairs;
+  if (g < 1) g = 1;
+  while (pairs * g < 96) ++g;                             // phase 1 needs 90 threads
+  return pairs * g;
+}
 static int fw_first(NnRuntime* r, const uint8_t* boards, int n, const int* n_dev) {
   const int c = r->filters;
   const bool s32 = r->board_pixels == 90 && r->fp32_skip;
-  k_conv_first<<<n, c / 2 < 96 ? 96 : c / 2, 0, r->stream>>>(boards, r->w_first, r->shift_first, r->x, s32 ? r->x32 : nullptr, c, r->board_pixels,
+  k_conv_first<<<n, conv_first_threads(c), 0, r->stream>>>(boards, r->w_first, r->shift_first, r->x, s32 ? r->x32 : nullptr, c, r->board_pixels,
                                                             r->in_planes, (r->in_planes / 14) * CZ_BOARD_STRIDE, n_dev);
   r->launches++;
   CZ_CUDA(cudaGetLastError());
@@ -807,8 +871,11 @@ static int fw_tower(NnRuntime* r, int n, const int* n_dev) {
   const bool s32 = dense && r->fp32_skip;
   float *x32 = s32 ? r->x32 : nullptr, *y32 = s32 ? r->y32 : nullptr;
   CUtensorMap *ix = &r->imap_x, *iy = &r->imap_y;
+  CUtensorMap *ox = &r->omap_x, *oy = &r->omap_y;           // fp16 tile maps of x / y
+  CUtensorMap *fx = &r->fmap_x32, *fy = &r->fmap_y32;       // fp32 tile maps of x32 / y32
   __half *x = r->x, *y = r->y;
   CUtensorMap *mx = &r->map_x, *my = &r->map_y;
+  const bool epi3 = dense && use_tma_epilogue();
   for (int i = 0; i < r->blocks; ++i) {
     const size_t wsz = (size_t)c;
     igemm::Args a1 = conv_args(n, c, r->shift_conv + (size_t)(2 * i) * wsz, nullptr, r->t, 1);
@@ -819,9 +886,17 @@ static int fw_tower(NnRuntime* r, int n, const int* n_dev) {
       d1.n_dev = n_dev; d1.rows_per_unit = 90; d2.n_dev = n_dev; d2.rows_per_unit = 90;
       d2.residual32 = x32; d2.out32 = y32;
       { float* t32 = x32; x32 = y32; y32 = t32; }
-      if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
-      if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
+      if (epi3) {
+        // conv1: x -> t (no skip);  conv2: t (+ skip x or x32) -> y (+ y32)
+        if (launch_igemm3(c, *ix, r->map_w_half[2 * i], r->omap_t, r->omap_t, r->omap_t, d1, 0, false, st)) return CZ_ERR_CUDA;
+        if (launch_igemm3(c, r->imap_t, r->map_w_half[2 * i + 1], *oy, s32 ? *fx : *ox, *fy, d2, s32 ? 2 : 1, s32, st)) return CZ_ERR_CUDA;
+      } else {
+        if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
+        if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
+      }
       CUtensorMap* ti = ix; ix = iy; iy = ti;
+      ti = ox; ox = oy; oy = ti;
+      ti = fx; fx = fy; fy = ti;
     } else {
       // strip layout (CZ_CONV_STRIP=1 / CZ_IGEMM_1CTA=1 A-B baselines): host-known batch only
       if (launch_igemm(c, *mx, r->map_w[2 * i], a1, st)) return CZ_ERR_CUDA;
@@ -968,6 +1043,12 @@ int cz_igemm_conv3x3_dense(const void* act_in, const void* w, const float* bias,
   if (make_map_im2col(&ma, act_in, c, n_boards)) return CZ_ERR_CUDA;
   if (make_map_2d(&mb, w, c, 9LL * c, c / 2)) return CZ_ERR_CUDA;
   igemm::Args a = conv_args_dense(n_boards, c, bias, (const __half*)residual, (__half*)act_out, relu);
+  if (use_tma_epilogue()) {
+    CUtensorMap mo, ms;
+    if (make_map_tile32(&mo, act_out, c, (long long)n_boards * 90, false)) return CZ_ERR_CUDA;
+    if (make_map_tile32(&ms, residual ? residual : act_out, c, (long long)n_boards * 90, false)) return CZ_ERR_CUDA;
+    return launch_igemm3(c, ma, mb, mo, ms, mo, a, residual ? 1 : 0, false, (cudaStream_t)stream);
+  }
   return launch_igemm2(c, ma, mb, a, (cudaStream_t)stream);
 }
 

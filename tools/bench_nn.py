@@ -43,7 +43,17 @@ def main():
         useful = 2.0 * nb * 90 * 9 * c * c
         issued = 2.0 * ((nb * 11 + 13) // 14) * 128 * 9 * c * c
         print(f"conv3x3 C={c} boards={nb}: {ms:.3f} ms  useful {useful / ms / 1e9:.1f} TFLOP/s  issued {issued / ms / 1e9:.1f} TFLOP/s")
-    for (f, bl, batch) in ((128, 7, 2048), (256, 20, 8192), (256, 20, 1024)):
+    # the product kernel: CTA-pair conv on dense activations (im2col TMA), without / with the fp16 skip stream
+    for c, nb in ((256, 8192), (256, 4096), (128, 2048), (128, 8192), (192, 4096)):
+        x = torch.randn(nb, 10, 9, c, device="cuda").half()
+        w = (torch.randn(9, c, c, device="cuda") * 0.02).half()
+        b = torch.zeros(c, device="cuda")
+        y = torch.empty_like(x)
+        for res, tag in ((None, "no skip"), (x, "fp16 skip")):
+            ms = time_it(lambda: lib.call("cz_igemm_conv3x3_dense", p(x), p(w), p(b), p(res), p(y), nb, c, 1, st))
+            fl = 2.0 * nb * 90 * 9 * c * c
+            print(f"conv3x3 dense C={c} boards={nb} {tag}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s")
+    for (f, bl, batch) in ((128, 7, 2048), (256, 20, 8192), (256, 20, 1024), (256, 20, 4096)):
         eng = Engine(lib, "cuda", n_games=batch, sims_per_move=8, leaves_per_round=1, nn_filters=f, nn_blocks=bl)
         w = om.init_weights(f, bl, 256, seed=0)
         eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
