@@ -290,8 +290,7 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
     for _ in range(warmup):
         step_device()
     gather_ev.clear()
-    # ---- device-resident timing
-    eng.nn_profile(True)
+    # ---- device-resident timing: the production path (cz_selfplay -> one WHILE-graph launch per search, no host in the loop)
     st0, c0 = eng.search_stats(), eng.counters()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local)
@@ -309,11 +308,24 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
-    conv_ms, conv_launches, conv_flops = eng.nn_profile(False)
     launches = eng.launch_count() - launches0
     st1, c1 = eng.search_stats(), eng.counters()
     gather_ms = sum(a.elapsed_time(b) for a, b in gather_ev)
+    # ---- roofline region: the same steps with CUDA events bracketing every residual-tower launch group.  Events cannot live
+    # inside the WHILE graph, so while cz_nn_profile is on the engine runs the same iteration as three sub-graphs (tree + first
+    # conv | tower | heads) launched from the host with the event records in between: same kernels, same shapes, same stream.
+    prof_steps = max(1, min(steps, 4))
+    eng.nn_profile(True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(prof_steps):
+        step_device()
+    p1.record()
+    barrier()
+    ms_prof = p0.elapsed_time(p1)
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+    conv_ms, conv_launches, conv_flops = eng.nn_profile(False)
     # ---- end-to-end timing through the drop-in worker with host buffers (SelfPlayWorker.host_step)
     ms_e2e, e2e_sims, h2d, d2h, files = 0.0, 0, 0, 0, 0
     if want_e2e:
@@ -335,12 +347,12 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
         d2h = stage.d2h_bytes + 4 * games + rec_bytes // max(1, steps)
         files = worker.games_stored - stored0
 
-    t = torch.tensor([ms, ms_e2e, conv_ms, gather_ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, conv_ms, gather_ms, ms_prof], device="cuda", dtype=torch.float64)
     c = torch.tensor([sims_total, e2e_sims, launches, conv_launches, games_done, conv_flops], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    ms, ms_e2e, conv_ms, gather_ms = [float(x) for x in t.tolist()]
+    ms, ms_e2e, conv_ms, gather_ms, ms_prof = [float(x) for x in t.tolist()]
     sims_total, e2e_sims, launches, conv_launches, games_done, conv_flops = [float(x) for x in c.tolist()]
     out = None
     if rank == 0:
@@ -361,15 +373,17 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
                                f"activations {act_mb:.0f} MB per round fit the 126 MB L2 and are NOT flushed between steps (secondary "
                                f"workload; the headline workload c3 streams 1.1 GB per round)"),
                            games_finished=int(games_done), records_gathered=int(gathered), gather_ms_per_step=gather_ms / steps),
-            "nn_positions_per_sec": (conv_flops / (2.0 * 90 * 9 * filters * filters * 2 * blocks)) / (ms * 1e-3),
+            "nn_positions_per_sec": (st1["nodes_created"] - st0["nodes_created"]) * world / (ms * 1e-3),
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC.get((workload, games, K)),
                          "kernel": f"igemm::k_igemm2<{filters}> (3x3 residual conv, tcgen05 cta_group::2)",
                          "launches": int(conv_launches), "avg_launch_ms": conv_ms / max(1.0, conv_launches / world),
-                         "peak_source": peak_src, "share_of_step": conv_ms / ms,
-                         "whole_net_frac_of_step": (conv_flops / (2.0 * 90 * 9 * filters * filters * 2 * blocks)) * net_flops(filters, blocks)
-                                                   / world / (ms * 1e-3) / 1e12 / peak},
+                         "peak_source": peak_src, "share_of_step": conv_ms / ms_prof,
+                         "measured_over": f"{prof_steps} further steps right after the {steps} timed ones, CUDA events around every tower "
+                                          f"launch group on the engine's stream ({ms_prof / prof_steps:.1f} ms per step in this region)",
+                         "whole_net_frac_of_step": (st1["nodes_created"] - st0["nodes_created"]) * net_flops(filters, blocks)
+                                                   / (ms * 1e-3) / 1e12 / peak},
             "search_stats": {
                 "mean_path_edges": depth, "mean_legal_moves": legal, "no_network_rate": (st1["no_network"] - st0["no_network"]) / d_sims,
                 "expansions_per_sim": expand,
@@ -395,7 +409,7 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
     return out
 
 
-FUSED_POLICY = False     # flipped when the integrated search gathers legal logits itself (no [B][2086] f32 policy row)
+FUSED_POLICY = True      # flipped when the integrated search gathers legal logits itself (no [B][2086] f32 policy row)
 
 
 def policy_bytes_per_leaf(legal):

@@ -20,6 +20,7 @@ enum { NODE_WAITING = 1u << 8 };
 enum { GAME_ERR_PATH = 1, GAME_ERR_POOL = 2, GAME_ERR_NOISE = 4, GAME_ERR_NOMOVE = 8 };
 
 struct RecordHdr { int32_t n_plies, value_red, game_index, flags; };
+struct NoiseRef { const double* table; long long stride; };
 
 // per-game state of the on-device game loop (cz_selfplay.cuh)
 struct SelfplayDev {
@@ -66,7 +67,9 @@ struct EngineDev {
   uint16_t* no_act;              // [G][16]
   int32_t* n_no_act;             // [G]
   int32_t* increase_temp;        // [G]
-  const double* noise_table; long long noise_stride;
+  // Root-noise table of the open search (noise_mode 0).  EngineDev travels BY VALUE into kernel launches that may be frozen
+  // inside a captured CUDA graph, so everything that changes per search lives behind a device pointer:
+  NoiseRef* noise_ref;           // [1] {table, stride}, rewritten by cz_search_begin / cz_set_noise_table
   // ---- tree pools (per game segments)
   int32_t* n_nodes;              // [G]
   int32_t* n_edges;              // [G]
@@ -241,6 +244,7 @@ CZ_D int select_edge(const EngineDev& E, int g, int node, bool is_root) {
   const int nna = is_root ? E.n_no_act[g] : 0;
   const uint16_t* na = E.no_act + (size_t)g * CZ_MAX_NO_ACT;
   const int cursor = E.noise_used[g];
+  const NoiseRef nref = (is_root && E.noise_mode == 0) ? *E.noise_ref : NoiseRef{nullptr, 0};
   double best_s = -99999999.0; int best_i = -1;
   int first_big = 0x7fffffff;
   int seen = 0;                                   // non-skipped edges before this chunk
@@ -261,8 +265,8 @@ CZ_D int select_edge(const EngineDev& E, int g, int node, bool is_root) {
       if (is_root) {
         double nz;
         if (E.noise_mode == 0) {
-          nz = (E.noise_table && (long long)cursor + rank < E.noise_stride)
-                   ? E.noise_table[(size_t)g * E.noise_stride + cursor + rank] : 0.0;
+          nz = (nref.table && (long long)cursor + rank < nref.stride)
+                   ? nref.table[(size_t)g * nref.stride + cursor + rank] : 0.0;
         } else {
           nz = dirichlet_first(E, g, (uint32_t)(cursor + rank), L);
         }
@@ -291,7 +295,7 @@ CZ_D int select_edge(const EngineDev& E, int g, int node, bool is_root) {
     seen += czs::popc(live);
   }
   if (is_root) {
-    if (E.noise_mode == 0 && E.noise_table && (long long)cursor + seen > E.noise_stride && czs::lane() == 0)
+    if (E.noise_mode == 0 && nref.table && (long long)cursor + seen > nref.stride && czs::lane() == 0)
       E.game_err[g] |= GAME_ERR_NOISE;
     if (czs::lane() == 0) E.noise_used[g] = cursor + seen;
     czs::syncwarp();

@@ -99,7 +99,7 @@ CZ_KERNEL(k_gather)(EngineDev E, int g0, int g1, uint8_t* dense, int16_t* labels
 }
 // Device-driven search loop: after every iteration tell the polling host thread (mapped pinned memory) how many iterations
 // are complete and whether any range still has work.  flags[1] (busy) is written before flags[0] (count).
-CZ_KERNEL(k_loop_flag)(EngineDev E, int n_slots, volatile int32_t* flags) {
+CZ_KERNEL(k_loop_flag)(EngineDev E, int n_slots, volatile int32_t* flags, unsigned long long cond_handle, int set_cond) {
   if (czs::lane() != 0) return;
   int busy = 0;
   for (int s = 0; s < n_slots; ++s) busy |= (E.totals[4 * s] > 0) | (E.totals[4 * s + 1] != 0);
@@ -113,6 +113,12 @@ CZ_KERNEL(k_loop_flag)(EngineDev E, int n_slots, volatile int32_t* flags) {
   __threadfence_system();
 #endif
   flags[0] = it;
+#if !defined(CZ_EMUL)
+  // WHILE-node form of the loop (the whole search is ONE graph launch): the body runs again while any range has work
+  if (set_cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, busy ? 1u : 0u);
+#else
+  (void)cond_handle; (void)set_cond;
+#endif
 }
 CZ_KERNEL(k_loop_reset)(EngineDev E) {
   if (czs::lane() == 0) { E.loop_iter[0] = 0; for (int i = 0; i < 8; ++i) E.totals[i] = 0; }
@@ -231,6 +237,9 @@ CZ_KERNEL(k_compact)(EngineDev E) {
     clear_tree(E, g);
   }
 }
+CZ_KERNEL(k_set_noise)(EngineDev E, NoiseRef r) {
+  if (czs::lane() == 0) *E.noise_ref = r;
+}
 CZ_KERNEL(k_set_opts)(EngineDev E, const uint16_t* no_act, const uint8_t* inc, const uint8_t* act, const uint8_t* hist,
                       const uint8_t* hist_given) {
   const int g = my_game();
@@ -301,6 +310,10 @@ struct cz_engine {
   // device-driven search loop: one iteration = three captured graphs per game range (tree work + first conv | residual
   // tower | heads + legal priors), launched back to back; the host only polls h_flags (mapped pinned memory)
   cudaGraphExec_t g_pre[2], g_tower[2], g_post[2];
+  cudaGraphExec_t g_while;                                  // the whole loop as one graph: WHILE conditional node around the iteration
+  unsigned long long while_handle;
+  int capture_cond;                                         // 1 while capturing the body of g_while (k_loop_flag sets the condition)
+  int loop_mode;                                            // 0 host-driven (round 1), 1 sub-graphs + flag polling, 2 WHILE graph
   int n_ranges;                                             // 1, or 2 in arena mode (one network per range)
   bool graphs_built, graph_loop;
   volatile int32_t* h_flags;                                // mapped pinned [4]: iterations finished, busy
@@ -343,6 +356,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.leaf_dense = cv.take<uint8_t>(G * K * d.lb_stride);
   d.leaf_labels = cv.take<int16_t>(G * K * MAX_MOVES); d.leaf_nlab = cv.take<int32_t>(G * K);
   d.loop_iter = cv.take<int32_t>(4);
+  d.noise_ref = cv.take<NoiseRef>(1);
   d.counters = cv.take<unsigned long long>(8);
   d.stat = cv.take<unsigned long long>(G * 4);
   d.gc_map = cv.take<int32_t>(G * N);
@@ -453,7 +467,10 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
   e->nn = nullptr; e->nn_bytes = 0; e->tree_stream = nullptr; e->h_totals = nullptr;
   e->graphs_built = false; e->h_flags = nullptr; e->d_flags = nullptr; e->n_ranges = cfg->arena ? 2 : 1;
   for (int i = 0; i < 2; ++i) { e->g_pre[i] = e->g_tower[i] = e->g_post[i] = nullptr; }
-  { const char* m = getenv("CZ_SEARCH_LOOP"); e->graph_loop = !(m && m[0] == 'h'); }     // CZ_SEARCH_LOOP=host: the round-1 host-driven loops
+  // CZ_SEARCH_LOOP = while (default: one graph launch per search, loop on the device) | graph (three sub-graphs per iteration,
+  // the host polls a mapped flag; also what runs while cz_nn_profile brackets the tower) | host (round-1 host-driven loops)
+  { const char* m = getenv("CZ_SEARCH_LOOP"); e->loop_mode = (m && m[0] == 'h') ? 0 : (m && m[0] == 'g') ? 1 : 2; e->graph_loop = e->loop_mode != 0; }
+  e->g_while = nullptr; e->while_handle = 0; e->capture_cond = 0;
   if (cudaSetDevice(cfg->device) != cudaSuccess) { delete e; return cz_fail(CZ_ERR_CUDA, "cz_create: cudaSetDevice(%d) failed", cfg->device); }
   if (!e->stream) {
     // The legacy default stream cannot be captured into a graph.  A BLOCKING stream of our own keeps the caller's ordering:
@@ -522,6 +539,7 @@ void cz_destroy(cz_engine* e) {
     if (e->g_tower[i]) cudaGraphExecDestroy(e->g_tower[i]);
     if (e->g_post[i]) cudaGraphExecDestroy(e->g_post[i]);
   }
+  if (e->g_while) cudaGraphExecDestroy(e->g_while);
 #endif
   delete e;
 }
@@ -585,7 +603,7 @@ int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {
   const uint16_t* na = nullptr; const uint8_t* inc = nullptr; const uint8_t* act = nullptr;
   const uint8_t* hist = nullptr; const uint8_t* hist_given = nullptr;
   int sims_override = 0, raw_tasks = 0;
-  e->d.noise_table = nullptr; e->d.noise_stride = 0;
+  NoiseRef nref{nullptr, 0};
   if (opts && opts->struct_bytes != (int)sizeof(cz_root_opts))
     return cz_fail(CZ_ERR_ARG, "cz_root_opts: struct_bytes mismatch (%d vs %d)", opts->struct_bytes, (int)sizeof(cz_root_opts));
   if (opts) {
@@ -597,20 +615,22 @@ int cz_search_begin(cz_engine* e, const cz_root_opts* opts) {
       czrt_copy(e->opt_hist, opts->root_hist_host, G * BOARD_STRIDE, e->stream); hist = e->opt_hist;
       czrt_copy(e->opt_hist_given, opts->root_hist_given_host, G, e->stream); hist_given = e->opt_hist_given;
     }
-    e->d.noise_table = opts->noise_dev; e->d.noise_stride = opts->noise_stride;
+    nref.table = opts->noise_dev; nref.stride = opts->noise_stride;
     sims_override = opts->sims_override;
     raw_tasks = opts->raw_tasks;
   }
+  CZ_LAUNCH(k_set_noise, 1, 1, 0, e->stream, e->d, nref);
   if (opts) GAME_LAUNCH(e, k_set_opts, e->d, na, inc, act, hist, hist_given);   // NULL keeps the options the game loop maintains
   GAME_LAUNCH(e, k_begin, e->d, sims_override, raw_tasks);
   e->last_leaves = 0;
-  return launch_ok(e, "cz_search_begin", 2);
+  return launch_ok(e, "cz_search_begin", 3);
 }
 
 int cz_set_noise_table(cz_engine* e, const double* noise_dev, int64_t noise_stride) {
   if (!e) return cz_fail(CZ_ERR_ARG, "cz_set_noise_table: null engine");
-  e->d.noise_table = noise_dev; e->d.noise_stride = noise_stride;
-  return 0;
+  NoiseRef nref{noise_dev, noise_stride};
+  CZ_LAUNCH(k_set_noise, 1, 1, 0, e->stream, e->d, nref);
+  return launch_ok(e, "cz_set_noise_table");
 }
 
 int cz_search_more(cz_engine* e, int32_t n_sims) {
@@ -769,8 +789,49 @@ int enqueue_part(cz_engine* e, int h, int part) {
   }
   const int rc = cznn::nn_forward_leaves(e->nn, e->cfg.arena ? h : 0, part, r.dense, n_max, n_dev, r.labels, r.nlab, r.legal_p, r.value);
   if (rc) return rc;
-  if (part == 4 && h == e->n_ranges - 1) CZ_LAUNCH(k_loop_flag, 1, 1, 0, e->stream, e->d, e->n_ranges, (volatile int32_t*)e->d_flags);
+  if (part == 4 && h == e->n_ranges - 1)
+    CZ_LAUNCH(k_loop_flag, 1, 1, 0, e->stream, e->d, e->n_ranges, (volatile int32_t*)e->d_flags, e->while_handle, e->capture_cond);
   return 0;
+}
+// The whole loop as ONE graph: a WHILE conditional node whose body is one iteration of every range; k_loop_flag ends each
+// iteration by setting the condition to "some range still has work".  No host involvement until the final synchronise.
+int build_while_graph(cz_engine* e) {
+  cudaGraph_t g = nullptr;
+  if (cudaGraphCreate(&g, 0) != cudaSuccess) return cz_fail(CZ_ERR_CUDA, "cudaGraphCreate failed");
+  cudaGraphConditionalHandle handle;
+  if (cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) {
+    cudaGraphDestroy(g);
+    return cz_fail(CZ_ERR_CUDA, "cudaGraphConditionalHandleCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  if (cudaGraphAddNode(&node, g, nullptr, 0, &np) != cudaSuccess) {
+    cudaGraphDestroy(g);
+    return cz_fail(CZ_ERR_CUDA, "cudaGraphAddNode(conditional) failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  e->while_handle = (unsigned long long)handle;
+  e->capture_cond = 1;
+  cznn::nn_set_capturing(e->nn, true);
+  int rc = 0;
+  if (cudaStreamBeginCaptureToGraph(e->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    rc = cz_fail(CZ_ERR_CUDA, "cudaStreamBeginCaptureToGraph failed: %s", cudaGetErrorString(cudaGetLastError()));
+  } else {
+    for (int h = 0; h < e->n_ranges && !rc; ++h)
+      for (int part = 1; part <= 4 && !rc; part <<= 1) rc = enqueue_part(e, h, part);
+    cudaGraph_t out = nullptr;
+    const cudaError_t err = cudaStreamEndCapture(e->stream, &out);
+    if (!rc && err != cudaSuccess) rc = cz_fail(CZ_ERR_CUDA, "capture of the loop body failed: %s", cudaGetErrorString(err));
+  }
+  cznn::nn_set_capturing(e->nn, false);
+  e->capture_cond = 0;
+  if (!rc && cudaGraphInstantiate(&e->g_while, g, 0) != cudaSuccess)
+    rc = cz_fail(CZ_ERR_CUDA, "instantiate of the WHILE graph failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaGraphDestroy(g);
+  return rc;
 }
 int capture_part(cz_engine* e, int h, int part, cudaGraphExec_t* out) {
   cznn::nn_set_capturing(e->nn, true);
@@ -805,7 +866,17 @@ int search_graph_loop(cz_engine* e) {
   CZ_LAUNCH(k_loop_reset, 1, 1, 0, e->stream, e->d);
   e->h_flags[0] = 0; e->h_flags[1] = 1;
   const bool prof = cznn::nn_profiling(e->nn);
-  const int kDepth = 4;                                  // iterations the host may run ahead of the last one it saw finish
+  if (e->graphs_built && e->g_while && !prof) {
+    // the whole loop is one graph launch (WHILE conditional node): the device iterates until no range has work left
+    if (cudaGraphLaunch(e->g_while, e->stream) != cudaSuccess)
+      return cz_fail(CZ_ERR_CUDA, "cz_search: WHILE graph launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return cz_fail(CZ_ERR_CUDA, "cz_search: device failure in the loop graph");
+    e->launches += (uint64_t)e->h_flags[0] * ((uint64_t)e->n_ranges * launches_per_iteration(e) + 1);
+    const char* m;
+    if (czrt_last_error(&m)) return cz_fail(CZ_ERR_CUDA, "cz_search: %s", m);
+    return 0;
+  }
+  const int kDepth = e->cfg.n_games * e->cfg.leaves_per_round >= 1024 ? 4 : 2;   // iterations the host may run ahead of the last one it saw finish
   int launched = 0;
   for (;;) {
     for (int h = 0; h < e->n_ranges; ++h) {
@@ -826,9 +897,14 @@ int search_graph_loop(cz_engine* e) {
         cudaGraphLaunch(e->g_post[h], e->stream);
       }
     }
-    if (!e->graphs_built) { const int rc = build_graphs(e); if (rc) return rc; }
+    if (!e->graphs_built) {
+      int rc = build_graphs(e);
+      if (!rc && e->loop_mode == 2) rc = build_while_graph(e);
+      if (rc) return rc;
+    }
     ++launched;
     e->launches += (uint64_t)e->n_ranges * launches_per_iteration(e) + 1;
+
     // wait until fewer than kDepth iterations are outstanding, then look at the newest report
     int done;
     unsigned spins = 0;

@@ -181,7 +181,7 @@ int cz_search_apply_legal(cz_engine* e, const float* legal_p_dev, const float* v
  * loop run action()'s rounds (player.py:167-184) in slices: `go infinite` / movetime stops, `info depth` lines between. */
 int cz_search_more(cz_engine* e, int32_t n_sims);
 /* Replace the Dirichlet table of the open search (noise_mode 0) by a longer one holding the same draws plus more; the
- * per-game read position is kept.  Host-side only. */
+ * per-game read position is kept.  Stream-ordered. */
 int cz_set_noise_table(cz_engine* e, const double* noise_dev, int64_t noise_stride);
 /* Whole search with the built-in network as evaluator (needs cz_nn_set_weights).  Device-driven: every wave / evaluation /
  * apply iteration is a fixed-shape sequence of launches (captured CUDA graphs) whose batch size is a device integer; the host
