@@ -11,39 +11,59 @@
 //     skip stream  : TMA load  -> swizzled smem tile -> ONE conflict-free lds per thread-row
 //     fp32 output  : written in place over the skip tile -> TMA store
 //     fp16 output  : packed into a swizzled smem tile   -> TMA store
-// Per epilogue warp (8 per CTA: TMEM lane quarter x column half) and 32-column chunk: a 32x32 fp32 tile F (128-byte rows,
-// SWIZZLE_128B) and a 32x32 fp16 tile H (64-byte rows, SWIZZLE_64B), both double-buffered so that the stores of chunk i overlap
-// the math of chunk i+1.  Thread r of the warp owns accumulator row r (tcgen05.ld 32x32b), i.e. one smem row: with the TMA
-// swizzle a warp-wide 16-byte access touches every bank group exactly 4 times = the 4-wavefront minimum for 512 bytes.
+// Per epilogue warp (8 per CTA: TMEM lane quarter x column half) and 16-column chunk: a ring of 32x16 fp32 tiles F (64-byte
+// rows, SWIZZLE_64B) and two 32x16 fp16 tiles H (32-byte rows, SWIZZLE_32B): the stores of chunk i overlap the math of chunk
+// i+1 and the skip tiles are requested nf-2 chunks ahead.  The tiles are small on purpose: the operand ring needs every
+// kilobyte (a C=128 k-block is consumed in 256 cycles, so hiding a ~2k-cycle TMA fill takes 8 stages; ncu on the first
+// 32-column version showed the MMA starving with 6).  Thread r of the warp owns accumulator row r (tcgen05.ld 32x32b), i.e. one
+// smem row: with the TMA swizzle a warp-wide 16-byte access touches every bank group exactly 4 times = the 4-wavefront
+// minimum for 512 bytes.
 #pragma once
 #include "cz_igemm.cuh"
 
 namespace igemm {
 
-constexpr int kMaxStages3 = 6;
+constexpr int kMaxStages3 = 9;
 constexpr int kSmemLimit3 = 232448;                            // opt-in dynamic shared memory per CTA on sm_100
+constexpr int kChunkCols3 = 16;                                // columns per epilogue chunk
+constexpr int kHBytes3 = 32 * kChunkCols3 * 2;                 // fp16 output tile of one chunk: 32 rows x 32 B (SWIZZLE_32B)
+constexpr int kNH3 = 2;                                        // H ring
+constexpr int kMaxNF3 = 4;                                     // F ring (skip tiles in flight / fp32 output tiles being stored)
 
 struct Args3 {
   Args a;
   int stages;            // smem ring depth (<= kMaxStages3), chosen on the host from what fits beside the epilogue tiles
   int skip_mode;         // 0 none, 1 fp16 (tmSkip = fp16 map), 2 fp32 (tmSkip = fp32 map)
   int out32;             // also store the fp32 copy (tmOut32)
-  int fbytes;            // bytes of one F tile: 4096 (fp32 skip and/or fp32 output), 2048 (fp16 skip only), 0 (neither)
+  int fbytes;            // bytes of one F tile: 2048 (fp32 skip and/or fp32 output), 1024 (fp16 skip only), 0 (neither)
+  int nf;                // F tiles per epilogue warp (3 .. kMaxNF3): skip loads run nf - 2 chunks ahead
 };
-__host__ __device__ constexpr int epi3_warp_bytes(int fbytes) { return 2 * fbytes + 2 * 2048; }    // F[2] + H[2] per epilogue warp
+__host__ __device__ constexpr int epi3_warp_bytes(int fbytes, int nf) { return nf * fbytes + kNH3 * kHBytes3; }
 
 template <int N_TILE>
 struct Cfg3 {
   static constexpr int kBHalfBytes = (N_TILE / 2) * 128;
   static constexpr int kStageBytes = kAStageBytes + kBHalfBytes;
   static constexpr int kTmemCols = Cfg<N_TILE>::kTmemCols;
-  static constexpr int smem_bytes(int stages, int fbytes) { return stages * kStageBytes + kEpiWarps2 * epi3_warp_bytes(fbytes) + 512 + 1024; }
-  static int max_stages(int fbytes) {
-    int s = (kSmemLimit3 - 512 - 1024 - kEpiWarps2 * epi3_warp_bytes(fbytes)) / kStageBytes;
+  static constexpr int smem_bytes(int stages, int fbytes, int nf) { return stages * kStageBytes + kEpiWarps2 * epi3_warp_bytes(fbytes, nf) + 512 + 1024; }
+  static int max_stages(int fbytes, int nf) {
+    int s = (kSmemLimit3 - 512 - 1024 - kEpiWarps2 * epi3_warp_bytes(fbytes, nf)) / kStageBytes;
     return s > kMaxStages3 ? kMaxStages3 : s;
   }
   static_assert(N_TILE % 64 == 0 && N_TILE <= 256, "column halves must be multiples of 32");
 };
+
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* t, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -65,14 +85,14 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* epi = smem + n_stages * C::kStageBytes;                 // 1024-byte aligned: stage sizes are multiples of 1024
-  const int warp_bytes = epi3_warp_bytes(p.fbytes);                // 4096, 8192 or 12288
+  const int warp_bytes = epi3_warp_bytes(p.fbytes, p.nf);          // multiple of 1024
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kEpiWarps2 * warp_bytes);
   uint64_t* full = bars;                       // [kMaxStages3]  (used in the leader only)
   uint64_t* empty = bars + kMaxStages3;        // [kMaxStages3]  per CTA, signalled by multicast commit
   uint64_t* tfull = bars + 2 * kMaxStages3;    // [2]
   uint64_t* tempty = tfull + 2;                // [2]  leader: 512 arrivals (8 epilogue warps of both CTAs)
-  uint64_t* skipbar = tempty + 2;              // [8][2] per epilogue warp: skip tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(skipbar + 2 * kEpiWarps2);
+  uint64_t* skipbar = tempty + 2;              // [8][kMaxNF3] per epilogue warp: skip tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(skipbar + kMaxNF3 * kEpiWarps2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = umma::cluster_ctarank();
@@ -88,7 +108,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < n_stages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 512); }
-    for (int i = 0; i < 2 * kEpiWarps2; ++i) umma::mbar_init(&skipbar[i], 1);
+    for (int i = 0; i < kMaxNF3 * kEpiWarps2; ++i) umma::mbar_init(&skipbar[i], 1);
     umma::fence_barrier_init();
     umma::fence_proxy_async();
   }
@@ -153,20 +173,24 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> swizzled smem tiles -> TMA
+    // Chunk = 16 columns.  Per warp: F ring of nf tiles (fp32 32x16 = 64-byte rows, SWIZZLE_64B; or fp16 skip 32-byte rows,
+    // SWIZZLE_32B) and an H ring of 2 fp16 tiles (32-byte rows, SWIZZLE_32B).  The skip tile of chunk i + nf - 2 is requested at
+    // the top of chunk i — its F slot was last read by the store of chunk i - 2, which bulk_wait_read<1> has seen finish —
+    // so a TMA round trip is hidden behind nf - 2 chunks of work instead of being paid once per chunk.
     const int ew = warp - 4;
     const int q = warp & 3;                                   // TMEM lane quarter (rows q*32 .. q*32+31 of the CTA's M-tile)
     const int half = ew >> 2;                                 // column half
-    constexpr int kChunks = N_TILE / 64;                      // 32-column chunks per half
+    constexpr int kChunks = (N_TILE / 2) / kChunkCols3;       // chunks per half
     const int cbeg = half * (N_TILE / 2);
-    const int fb = p.fbytes;
-    uint8_t* F = epi + ew * warp_bytes;                       // F[2]: fb bytes each, 1024-aligned
-    uint8_t* H = F + 2 * fb;                                  // H[2]: 2048 B each
-    uint64_t* sbar = skipbar + 2 * ew;
+    const int fb = p.fbytes, nf = p.nf;
+    uint8_t* F = epi + ew * warp_bytes;                       // F[nf]: fb bytes each
+    uint8_t* H = F + nf * fb;                                 // H[2]: 1024 B each
+    uint64_t* sbar = skipbar + kMaxNF3 * ew;
     const uint32_t tempty_remote[2] = {umma::mapa_shared(&tempty[0], 0), umma::mapa_shared(&tempty[1], 0)};
-    const int r7 = lane & 7, r3 = (lane >> 1) & 3;            // swizzle keys of this thread's row: 128B rows / 64B rows
-    uint8_t* const frow0 = F + lane * 128;
-    uint8_t* const hrow0 = H + lane * 64;
+    const int r3 = (lane >> 1) & 3;                           // SWIZZLE_64B key of this thread's 64-byte row
+    const int r1 = (lane >> 2) & 1;                           // SWIZZLE_32B key of this thread's 32-byte row
     const bool has_skip = p.skip_mode != 0, skip32 = p.skip_mode == 2;
+    const uint32_t skip_bytes = skip32 ? 2048u : 1024u;
     // next tile's skip block -> L2, a whole tile ahead (one warp): the per-chunk TMA loads below then hit L2
     auto prefetch_skip = [&](int pr) {
       if (ew != 0 || pr >= pairs || !has_skip) return;
@@ -179,14 +203,22 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       for (size_t off = (size_t)lane * 16384; off < total; off += 32 * 16384)
         umma::l2_prefetch_bulk(base + off, (uint32_t)(total - off < 16384 ? total - off : 16384));
     };
-    uint32_t tcount = 0, gchunk = 0;                          // gchunk: chunks processed by this warp (buffer / barrier phase)
+    // global chunk counter of this warp: chunk index g -> (tile = g / kChunks, chunk in tile = g % kChunks); F slot g % nf
+    int my_tiles = 0;
+    for (int pr = cluster_id; pr < pairs; pr += n_clusters) ++my_tiles;
+    const uint32_t total_chunks = (uint32_t)my_tiles * kChunks;
+    auto request_skip = [&](uint32_t g) {                     // lane 0 only
+      if (!has_skip || g >= total_chunks) return;
+      const int t = (int)(g / kChunks), ch = (int)(g % kChunks);
+      const int row = (2 * (cluster_id + t * n_clusters) + (int)rank) * kTileM + q * 32;
+      const uint32_t slot = g % (uint32_t)nf;
+      umma::mbar_expect_tx(&sbar[slot], skip_bytes);
+      umma::tma_load_2d(F + slot * fb, &tmSkip, &sbar[slot], cbeg + ch * kChunkCols3, row);
+    };
+    uint32_t tcount = 0, g = 0;
     prefetch_skip(cluster_id);
-    // the very first chunk's skip tile
-    if (has_skip && cluster_id < pairs && lane == 0) {
-      const int row = (2 * cluster_id + (int)rank) * kTileM + q * 32;
-      umma::mbar_expect_tx(&sbar[0], skip32 ? 4096u : 2048u);
-      umma::tma_load_2d(F, &tmSkip, &sbar[0], cbeg, row);
-    }
+    if (lane == 0)
+      for (int k = 0; k < nf - 2; ++k) request_skip((uint32_t)k);   // prime the ring: chunks 0 .. nf-3
     for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
       const int m_tile = 2 * pair + (int)rank;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
@@ -196,32 +228,39 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       umma::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + cbeg;
 #pragma unroll 1
-      for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
-        const uint32_t b = gchunk & 1, bph = (gchunk >> 1) & 1;
-        const int c0 = cbeg + ch * 32;
-        uint8_t* frow = frow0 + b * fb;
-        uint8_t* hrow = hrow0 + b * 2048;
-        uint32_t v[32];
-        umma::tmem_ld_32x32(t_row + ch * 32, v);
-        if (has_skip) umma::mbar_wait(&sbar[b], bph);         // skip tile of this chunk has landed in F[b]
+      for (int ch = 0; ch < kChunks; ++ch, ++g) {
+        const uint32_t slot = g % (uint32_t)nf, sph = (g / (uint32_t)nf) & 1, hb = g & 1;
+        const int c0 = cbeg + ch * kChunkCols3;
+        if (lane == 0) {
+          // At most the store group of chunk g-1 may still be reading its tiles; chunk g-2 and older are done, so H[g & 1]
+          // and the F slot of chunk g-2 — which is the slot of chunk g + nf - 2 — are free.
+          bulk_wait_read<1>();
+          request_skip(g + (uint32_t)nf - 2);
+        }
+        uint32_t v[16];
+        tmem_ld_32x16(t_row + ch * kChunkCols3, v);
+        __syncwarp();                                         // H[hb] is free for everybody (lane 0 waited above)
+        if (has_skip) umma::mbar_wait(&sbar[slot], sph);      // skip tile of this chunk has landed in F[slot]
+        uint8_t* frow = F + slot * fb + lane * 64;
+        uint8_t* hrow = H + hb * kHBytes3 + lane * 32;
         const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
 #pragma unroll
-        for (int g = 0; g < 8; g += 2) {
+        for (int gq = 0; gq < 4; gq += 2) {
           float4 x0, x1;
           {
-            const float4 b0 = __ldg(bp + g), b1 = __ldg(bp + g + 1);
-            x0 = make_float4(__uint_as_float(v[4 * g]) + b0.x, __uint_as_float(v[4 * g + 1]) + b0.y,
-                             __uint_as_float(v[4 * g + 2]) + b0.z, __uint_as_float(v[4 * g + 3]) + b0.w);
-            x1 = make_float4(__uint_as_float(v[4 * g + 4]) + b1.x, __uint_as_float(v[4 * g + 5]) + b1.y,
-                             __uint_as_float(v[4 * g + 6]) + b1.z, __uint_as_float(v[4 * g + 7]) + b1.w);
+            const float4 b0 = __ldg(bp + gq), b1 = __ldg(bp + gq + 1);
+            x0 = make_float4(__uint_as_float(v[4 * gq]) + b0.x, __uint_as_float(v[4 * gq + 1]) + b0.y,
+                             __uint_as_float(v[4 * gq + 2]) + b0.z, __uint_as_float(v[4 * gq + 3]) + b0.w);
+            x1 = make_float4(__uint_as_float(v[4 * gq + 4]) + b1.x, __uint_as_float(v[4 * gq + 5]) + b1.y,
+                             __uint_as_float(v[4 * gq + 6]) + b1.z, __uint_as_float(v[4 * gq + 7]) + b1.w);
           }
           if (skip32) {
-            const float4 s0 = *reinterpret_cast<const float4*>(frow + ((g ^ r7) << 4));
-            const float4 s1 = *reinterpret_cast<const float4*>(frow + (((g + 1) ^ r7) << 4));
+            const float4 s0 = *reinterpret_cast<const float4*>(frow + ((gq ^ r3) << 4));
+            const float4 s1 = *reinterpret_cast<const float4*>(frow + (((gq + 1) ^ r3) << 4));
             x0.x += s0.x; x0.y += s0.y; x0.z += s0.z; x0.w += s0.w;
             x1.x += s1.x; x1.y += s1.y; x1.z += s1.z; x1.w += s1.w;
-          } else if (has_skip) {                              // fp16 skip tile: 64-byte rows in the first 2 KB of F[b]
-            const uint4 sv = *reinterpret_cast<const uint4*>(F + b * fb + lane * 64 + (((g >> 1) ^ r3) << 4));
+          } else if (has_skip) {                              // fp16 skip tile: 32-byte rows at the start of F[slot]
+            const uint4 sv = *reinterpret_cast<const uint4*>(F + slot * fb + lane * 32 + (((gq >> 1) ^ r1) << 4));
             const __half2* h = reinterpret_cast<const __half2*>(&sv);
             const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
             x0.x += f0.x; x0.y += f0.y; x0.z += f1.x; x0.w += f1.y;
@@ -231,34 +270,23 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
             x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
           }
-          if (p.out32) {                                      // in place over the skip tile (or into the free F[b])
-            *reinterpret_cast<float4*>(frow + ((g ^ r7) << 4)) = x0;
-            *reinterpret_cast<float4*>(frow + (((g + 1) ^ r7) << 4)) = x1;
+          if (p.out32) {                                      // in place over the skip tile
+            *reinterpret_cast<float4*>(frow + ((gq ^ r3) << 4)) = x0;
+            *reinterpret_cast<float4*>(frow + (((gq + 1) ^ r3) << 4)) = x1;
           }
           uint4 ov;
           __half2* oh = reinterpret_cast<__half2*>(&ov);
           oh[0] = __floats2half2_rn(x0.x, x0.y); oh[1] = __floats2half2_rn(x0.z, x0.w);
           oh[2] = __floats2half2_rn(x1.x, x1.y); oh[3] = __floats2half2_rn(x1.z, x1.w);
-          *reinterpret_cast<uint4*>(hrow + (((g >> 1) ^ r3) << 4)) = ov;
+          *reinterpret_cast<uint4*>(hrow + (((gq >> 1) ^ r1) << 4)) = ov;
         }
         umma::fence_proxy_async();                            // generic-proxy writes above -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-          if (p.out32) tma_store_2d(&tmOut32, F + b * fb, c0, rbase);
-          tma_store_2d(&tmOut16, H + b * 2048, c0, rbase);
+          if (p.out32) tma_store_2d(&tmOut32, F + slot * fb, c0, rbase);
+          tma_store_2d(&tmOut16, H + hb * kHBytes3, c0, rbase);
           bulk_commit();
-          bulk_wait_read<1>();                                // the stores of the PREVIOUS chunk have read F[b^1], H[b^1]: free
-          if (has_skip) {                                     // skip tile of the next chunk (may belong to the next tile)
-            int nrow = rbase, ncol = c0 + 32;
-            bool more = true;
-            if (ch + 1 == kChunks) { ncol = cbeg; nrow = rbase + 2 * n_clusters * kTileM; more = pair + n_clusters < pairs; }
-            if (more) {
-              umma::mbar_expect_tx(&sbar[b ^ 1], skip32 ? 4096u : 2048u);
-              umma::tma_load_2d(F + (b ^ 1) * fb, &tmSkip, &sbar[b ^ 1], ncol, nrow);
-            }
-          }
         }
-        __syncwarp();
       }
       umma::tc_fence_before();
       umma::mbar_arrive_cluster(tempty_remote[acc]);

@@ -109,17 +109,17 @@ static int make_map_2d(CUtensorMap* m, const void* base, int k, long long rows, 
   return 0;
 }
 
-// activation matrix [rows][c] (fp16 or fp32), box {32 columns, 32 rows}: the tiles the conv epilogue loads (skip stream) and
-// stores (outputs) with TMA.  32 fp32 = 128-byte rows -> SWIZZLE_128B, 32 fp16 = 64-byte rows -> SWIZZLE_64B.
+// activation matrix [rows][c] (fp16 or fp32), box {16 columns, 32 rows}: the tiles the conv epilogue loads (skip stream) and
+// stores (outputs) with TMA.  16 fp32 = 64-byte rows -> SWIZZLE_64B, 16 fp16 = 32-byte rows -> SWIZZLE_32B.
 static int make_map_tile32(CUtensorMap* m, const void* base, int c, long long rows, bool f32) {
   if (load_encode()) return CZ_ERR_CUDA;
   const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)c * es};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {igemm::kChunkCols3, 32};
   cuuint32_t est[2] = {1, 1};
   CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
-                        box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cz_fail(CZ_ERR_CUDA, "cuTensorMapEncodeTiled(tile32) failed: %d", (int)r);
   return 0;
@@ -177,11 +177,20 @@ static int launch_igemm2(int n_tile, const CUtensorMap& tmA, const CUtensorMap& 
   }
   return cz_fail(CZ_ERR_UNSUPPORTED, "igemm2: unsupported N tile %d", n_tile);
 }
-// k_igemm3: same mainloop, all-TMA epilogue (cz_igemm3.cuh).  CZ_EPI=2 selects the round-1 epilogue (k_igemm2) for A/B runs.
-static bool use_tma_epilogue() {
+// k_igemm3: same mainloop, all-TMA epilogue (cz_igemm3.cuh).  Measured (profiles/r02c_*): +15 % (C=128, no skip) to +41 % (C=128,
+// fp16 skip) and +35 % (C=192) over k_igemm2, equal at C=256 without the fp32 skip stream (tensor pipe 90 %); with the fp32
+// stream (4-deep operand ring beside 96 KB of epilogue tiles, TMA round trips serialised per chunk) it is ~4 % slower in the
+// power-capped 256x20 forward, so that one launch shape keeps k_igemm2.  CZ_EPI=2 / 3 force the old / new epilogue everywhere.
+static int epilogue_choice() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("CZ_EPI"); v = (e && e[0] == '2') ? 0 : 1; }
-  return v == 1;
+  if (v < 0) { const char* e = getenv("CZ_EPI"); v = (e && e[0] == '2') ? 2 : (e && e[0] == '3') ? 3 : 0; }
+  return v;
+}
+static bool use_tma_epilogue() { return epilogue_choice() != 2; }
+static bool use_tma_epilogue_for(int c, bool fp32_stream) {
+  if (epilogue_choice() == 2) return false;
+  if (epilogue_choice() == 3) return true;
+  return !(c == 256 && fp32_stream);
 }
 template <int N_TILE>
 static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
@@ -195,14 +204,15 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   igemm::Args3 p;
   p.a = a;
   p.skip_mode = skip_mode; p.out32 = out32 ? 1 : 0;
-  p.fbytes = (skip_mode == 2 || out32) ? 4096 : (skip_mode == 1 ? 2048 : 0);
-  p.stages = C::max_stages(p.fbytes);
+  p.fbytes = (skip_mode == 2 || out32) ? 2048 : (skip_mode == 1 ? 1024 : 0);
+  { static int nf = -1; if (nf < 0) { const char* e = getenv("CZ_NF"); nf = e ? atoi(e) : 4; if (nf < 3) nf = 3; if (nf > igemm::kMaxNF3) nf = igemm::kMaxNF3; } p.nf = nf; }
+  p.stages = C::max_stages(p.fbytes, p.nf);
   { static int cap = -1; if (cap < 0) { const char* e = getenv("CZ_STAGES"); cap = e ? atoi(e) : 0; } if (cap > 1 && cap < p.stages) p.stages = cap; }
   if (p.stages < 2) return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: no room for the operand ring");
   const int pairs = ((a.n_dev ? (a.rows + igemm::kTileM - 1) / igemm::kTileM : a.m_tiles) + 1) / 2;
   if (pairs <= 0) return 0;
   const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
-  igemm::k_igemm3<N_TILE><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
+  igemm::k_igemm3<N_TILE><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
   CZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -886,14 +896,13 @@ static int fw_tower(NnRuntime* r, int n, const int* n_dev) {
       d1.n_dev = n_dev; d1.rows_per_unit = 90; d2.n_dev = n_dev; d2.rows_per_unit = 90;
       d2.residual32 = x32; d2.out32 = y32;
       { float* t32 = x32; x32 = y32; y32 = t32; }
-      if (epi3) {
-        // conv1: x -> t (no skip);  conv2: t (+ skip x or x32) -> y (+ y32)
+      // conv1: x -> t (no skip);  conv2: t (+ skip x or x32) -> y (+ y32)
+      if (epi3 && use_tma_epilogue_for(c, false)) {
         if (launch_igemm3(c, *ix, r->map_w_half[2 * i], r->omap_t, r->omap_t, r->omap_t, d1, 0, false, st)) return CZ_ERR_CUDA;
+      } else if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
+      if (epi3 && use_tma_epilogue_for(c, s32)) {
         if (launch_igemm3(c, r->imap_t, r->map_w_half[2 * i + 1], *oy, s32 ? *fx : *ox, *fy, d2, s32 ? 2 : 1, s32, st)) return CZ_ERR_CUDA;
-      } else {
-        if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
-        if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
-      }
+      } else if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
       CUtensorMap* ti = ix; ix = iy; iy = ti;
       ti = ox; ox = oy; oy = ti;
       ti = fx; fx = fy; fy = ti;
