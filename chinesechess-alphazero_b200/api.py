@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from .engine import Engine
+from .model import engine_net_kwargs
 from .lib import get_lib
 
 logger = getLogger(__name__)
@@ -43,7 +44,7 @@ class CChessModelAPI:
             mc = self.config.model
             self.engine = Engine(self.lib, self.device, n_games=self.max_batch, sims_per_move=1, leaves_per_round=1,
                                  max_nodes_per_game=16, max_edges_per_game=256, max_path=8,
-                                 nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size,
+                                 **engine_net_kwargs(mc),
                                  use_history=bool(getattr(self.agent_model, "use_history", False)))
             self.engine.set_weights(self.agent_model.torch_weights())
 

@@ -33,8 +33,10 @@ namespace cznn {
   } while (0)
 
 constexpr int kLabels = CZ_N_LABELS;
-constexpr int kPolK1 = 384;     // 360 policy features padded to 6 k-blocks
-constexpr int kPolK = 3 * kPolK1;  // the policy Dense runs as a split-precision GEMM on the tensor cores:
+// Head widths are a property of the weight file: agent/model.py:47-61 builds 4 policy / 2 value channels, the older configs shipped
+// under data/model/ (model_128f.json, model_256f.json: 2 / 4; model_128_l1_config.json: 32 / 4) are served too.
+//   pol_k1 = policy features (policy channels x 90) padded to whole 64-column k-blocks, pol_k = 3 * pol_k1:
+//            the policy Dense runs as a split-precision GEMM on the tensor cores:
                                    //   x = x_hi + x_lo, w = w_hi + w_lo (fp16 each); logits = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo
                                    // laid out along K as A' = [x_hi | x_lo | x_hi], W' = [w_hi | w_hi | w_lo] -> one GEMM, ~fp32 accuracy
                                    // (fp16 operands alone cost 1.1e-3 of policy probability on the reference's trained 192x10 net)
@@ -368,58 +370,69 @@ __global__ void k_planes_to_boards(const float* __restrict__ planes, uint8_t* __
 // of a warp's 32 pixels are adjacent in memory) against the 6 x C folded weights held in shared memory (broadcast reads) —
 // no cross-lane reduction.  (The round-1 version reduced six sums with 30 shuffles per pixel: 110 us per 2048 positions.)
 constexpr int kHeadPos = 4;
+constexpr int kMaxHeadOut = 36;                                   // 32 policy + 4 value channels
+static size_t heads_smem_bytes(int c_in, int n_out) { return ((size_t)kHeadPos * n_out * 90 + (size_t)(c_in / 8) * n_out * 8 + kHeadPos * 8) * sizeof(float); }
 __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, const float* __restrict__ act32, int c_in,
-                                                const int* __restrict__ n_dev, int board_pixels,
-                                                const float* __restrict__ w6,      // [6][c_in], BN scale folded
-                                                const float* __restrict__ shift6,  // [6]
-                                                const float* __restrict__ wv1,     // [180][H]
+                                                const int* __restrict__ n_dev, int board_pixels, int pol_c, int val_c, int pol_k1,
+                                                const float* __restrict__ wh,      // [pol_c + val_c][c_in], BN scale folded
+                                                const float* __restrict__ shifth,  // [pol_c + val_c]
+                                                const float* __restrict__ wv1,     // [val_c * 90][H]
                                                 const float* __restrict__ bv1,     // [H]
                                                 const float* __restrict__ wv2,     // [H]
                                                 const float* __restrict__ bv2,     // [1]
                                                 int hidden, __half* __restrict__ pol_feat, float* __restrict__ value) {
-  __shared__ float feat[kHeadPos][6][90];
-  __shared__ float red[kHeadPos][8];
-  __shared__ __align__(16) float wsm[256 / 8][6][8];        // [channel group of 8][output][channel in group]
+  extern __shared__ __align__(16) float hsm[];
+  const int n_out = pol_c + val_c;
+  float* feat = hsm;                                         // [kHeadPos][n_out][90]
+  float* wsm = feat + kHeadPos * n_out * 90;                 // [c_in / 8][n_out][8]
+  float* red = wsm + (c_in / 8) * n_out * 8;                 // [kHeadPos][8]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * kHeadPos;
   const int n_pos = __ldg(n_dev);
   if (b0 >= n_pos) return;
   const int npos = n_pos - b0 < kHeadPos ? n_pos - b0 : kHeadPos;
-  for (int i = tid; i < 6 * c_in; i += 256) { const int o = i / c_in, c = i % c_in; wsm[c >> 3][o][c & 7] = __ldg(w6 + i); }
+  for (int i = tid; i < n_out * c_in; i += 256) { const int o = i / c_in, c = i % c_in; wsm[((c >> 3) * n_out + o) * 8 + (c & 7)] = __ldg(wh + i); }
   __syncthreads();
   for (int item = tid; item < npos * 90; item += 256) {
     const int p = item / 90, pix = item % 90;
     const size_t row = ((size_t)(b0 + p) * board_pixels + pix) * c_in;
-    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int g = 0; g < c_in / 8; ++g) {
-      float x[8];
-      if (act32) {
-        const float4* a4 = reinterpret_cast<const float4*>(act32 + row + g * 8);
-        const float4 u = __ldg(a4), w4 = __ldg(a4 + 1);
-        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w4.x; x[5] = w4.y; x[6] = w4.z; x[7] = w4.w;
-      } else {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(act + row + g * 8));
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
+    for (int o0 = 0; o0 < n_out; o0 += 6) {                  // six outputs per pass over the pixel's row (the row stays in L1)
+      float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int g = 0; g < c_in / 8; ++g) {
+        float x[8];
+        if (act32) {
+          const float4* a4 = reinterpret_cast<const float4*>(act32 + row + g * 8);
+          const float4 u = __ldg(a4), w4 = __ldg(a4 + 1);
+          x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w4.x; x[5] = w4.y; x[6] = w4.z; x[7] = w4.w;
+        } else {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(act + row + g * 8));
+          const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+          for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+        }
+#pragma unroll
+        for (int o = 0; o < 6; ++o) {
+          if (o0 + o < n_out) {
+            const float* wp = wsm + (g * n_out + o0 + o) * 8;
+            const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 4);
+            s[o] += x[0] * wa.x + x[1] * wa.y + x[2] * wa.z + x[3] * wa.w + x[4] * wb.x + x[5] * wb.y + x[6] * wb.z + x[7] * wb.w;
+          }
+        }
       }
 #pragma unroll
-      for (int o = 0; o < 6; ++o) {
-        const float4 wa = *reinterpret_cast<const float4*>(&wsm[g][o][0]), wb = *reinterpret_cast<const float4*>(&wsm[g][o][4]);
-        s[o] += x[0] * wa.x + x[1] * wa.y + x[2] * wa.z + x[3] * wa.w + x[4] * wb.x + x[5] * wb.y + x[6] * wb.z + x[7] * wb.w;
-      }
+      for (int o = 0; o < 6; ++o)
+        if (o0 + o < n_out) feat[(p * n_out + o0 + o) * 90 + pix] = fmaxf(s[o] + __ldg(shifth + o0 + o), 0.f);
     }
-#pragma unroll
-    for (int o = 0; o < 6; ++o) feat[p][o][pix] = fmaxf(s[o] + __ldg(shift6 + o), 0.f);
   }
   __syncthreads();
-  for (int i = tid; i < npos * kPolK1; i += 256) {
-    const int p = i / kPolK1, k = i % kPolK1;
-    const float f = k < 360 ? feat[p][k / 90][k % 90] : 0.f;
+  const int pol_in = pol_c * 90, pol_k = 3 * pol_k1;
+  for (int i = tid; i < npos * pol_k1; i += 256) {
+    const int p = i / pol_k1, k = i % pol_k1;
+    const float f = k < pol_in ? feat[(p * n_out + k / 90) * 90 + k % 90] : 0.f;      // Keras Flatten of channels_first: c*90 + pix
     const __half hi = __float2half_rn(f);
     const __half lo = __float2half_rn(f - __half2float(hi));
-    __half* row = pol_feat + (size_t)(b0 + p) * kPolK;
-    row[k] = hi; row[kPolK1 + k] = lo; row[2 * kPolK1 + k] = hi;
+    __half* row = pol_feat + (size_t)(b0 + p) * pol_k;
+    row[k] = hi; row[pol_k1 + k] = lo; row[2 * pol_k1 + k] = hi;
   }
   float h[kHeadPos];
 #pragma unroll
@@ -429,10 +442,10 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
     const float bb = bv1[tid];
 #pragma unroll
     for (int p = 0; p < kHeadPos; ++p) acc[p] = bb;
-    for (int i = 0; i < 180; ++i) {
+    for (int i = 0; i < val_c * 90; ++i) {
       const float wv = __ldg(wv1 + (size_t)i * hidden + tid);
 #pragma unroll
-      for (int p = 0; p < kHeadPos; ++p) acc[p] += feat[p][4 + i / 90][i % 90] * wv;
+      for (int p = 0; p < kHeadPos; ++p) acc[p] += feat[(p * n_out + pol_c + i / 90) * 90 + i % 90] * wv;
     }
     const float w2 = wv2[tid];
 #pragma unroll
@@ -442,12 +455,12 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
   for (int p = 0; p < kHeadPos; ++p) {
     float v = h[p];
     for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    if (lane == 0) red[p][warp] = v;
+    if (lane == 0) red[p * 8 + warp] = v;
   }
   __syncthreads();
   if (tid < npos) {
     float sum = bv2[0];
-    for (int i = 0; i < 8; ++i) sum += red[tid][i];
+    for (int i = 0; i < 8; ++i) sum += red[tid * 8 + i];
     value[b0 + tid] = tanhf(sum);
   }
 }
@@ -527,16 +540,16 @@ __global__ void k_prep_1x1(const float* w, const float* scale, float* out, int c
     out[(size_t)co * ci_n + ci] = w[(size_t)ci * co_n + co] * scale[co];
   }
 }
-// Dense (in,out) [360][2086] -> [kPolN][kPolK] fp16 (zero padded), K-major, split as [w_hi | w_hi | w_lo]
-__global__ void k_prep_policy(const float* w, __half* out) {
+// Dense (in,out) [pol_in][2086] -> [kPolN][3 * pol_k1] fp16 (zero padded), K-major, split as [w_hi | w_hi | w_lo]
+__global__ void k_prep_policy(const float* w, __half* out, int pol_in, int pol_k1) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < (long long)kPolN * kPolK1) {
-    const int k = (int)(i % kPolK1), n = (int)(i / kPolK1);
-    const float f = (k < 360 && n < kLabels) ? w[(size_t)k * kLabels + n] : 0.f;
+  if (i < (long long)kPolN * pol_k1) {
+    const int k = (int)(i % pol_k1), n = (int)(i / pol_k1);
+    const float f = (k < pol_in && n < kLabels) ? w[(size_t)k * kLabels + n] : 0.f;
     const __half hi = __float2half_rn(f);
     const __half lo = __float2half_rn(f - __half2float(hi));
-    __half* row = out + (size_t)n * kPolK;
-    row[k] = hi; row[kPolK1 + k] = hi; row[2 * kPolK1 + k] = lo;
+    __half* row = out + (size_t)n * 3 * pol_k1;
+    row[k] = hi; row[pol_k1 + k] = hi; row[2 * pol_k1 + k] = lo;
   }
 }
 __global__ void k_copy_pad(const float* src, float* dst, int n_src, int n_dst) {
@@ -559,7 +572,7 @@ struct Carver {
 struct NetWeights {
   __half* w_first; float* shift_first;
   __half* w_conv;  float* shift_conv;
-  float *w6, *shift6, *wv1, *bv1, *wv2, *bv2;
+  float *wh, *shifth, *wv1, *bv1, *wv2, *bv2;
   __half* w_pol; float* b_pol;
   CUtensorMap map_wpol;
   std::vector<CUtensorMap> map_w, map_w_half;
@@ -568,6 +581,7 @@ struct NetWeights {
 
 struct NnRuntime {
   int filters, blocks, value_fc, max_batch;
+  int pol_c, val_c, pol_k1;               // head widths (policy / value conv channels) and the padded policy feature count
   NetWeights nets[2]; int n_nets, cur;     // the weight fields below alias nets[cur] (select_net / store_net)
   cudaStream_t stream;
   bool ready;
@@ -578,6 +592,7 @@ struct NnRuntime {
   float* logits;
   float2* stats;                         // [max_batch][kPolN / 256] softmax statistics of the policy GEMM's N tiles
   int* n_scalar;                         // device copy of a host-known batch size (reference-facing forward)
+  bool heads_attr;                       // k_heads was granted > 48 KB of dynamic shared memory (wide legacy heads)
   bool capturing;                        // inside cudaStreamBeginCapture: no event records / synchronisation
   size_t prof_open;                      // event pair opened by nn_prof_begin
   uint8_t* boards_tmp;
@@ -585,7 +600,7 @@ struct NnRuntime {
   // weights
   __half* w_first; float* shift_first;
   __half* w_conv;  float* shift_conv;      // [2*blocks][9*C*C], [2*blocks][C]
-  float *w6, *shift6, *wv1, *bv1, *wv2, *bv2;
+  float *wh, *shifth, *wv1, *bv1, *wv2, *bv2;
   __half* w_pol; float* b_pol;
   float* scratch;                            // 2*C floats for BN folding
   // tensor maps
@@ -608,7 +623,7 @@ struct NnRuntime {
 static void store_net(NnRuntime* r, int k) {
   NetWeights& n = r->nets[k];
   n.w_first = r->w_first; n.shift_first = r->shift_first; n.w_conv = r->w_conv; n.shift_conv = r->shift_conv;
-  n.w6 = r->w6; n.shift6 = r->shift6; n.wv1 = r->wv1; n.bv1 = r->bv1; n.wv2 = r->wv2; n.bv2 = r->bv2;
+  n.wh = r->wh; n.shifth = r->shifth; n.wv1 = r->wv1; n.bv1 = r->bv1; n.wv2 = r->wv2; n.bv2 = r->bv2;
   n.w_pol = r->w_pol; n.b_pol = r->b_pol; n.map_wpol = r->map_wpol; n.map_w = r->map_w; n.map_w_half = r->map_w_half;
   n.ready = r->ready;
 }
@@ -617,7 +632,7 @@ static void select_net(NnRuntime* r, int k) {
   store_net(r, r->cur);
   const NetWeights& n = r->nets[k];
   r->w_first = n.w_first; r->shift_first = n.shift_first; r->w_conv = n.w_conv; r->shift_conv = n.shift_conv;
-  r->w6 = n.w6; r->shift6 = n.shift6; r->wv1 = n.wv1; r->bv1 = n.bv1; r->wv2 = n.wv2; r->bv2 = n.bv2;
+  r->wh = n.wh; r->shifth = n.shifth; r->wv1 = n.wv1; r->bv1 = n.bv1; r->wv2 = n.wv2; r->bv2 = n.bv2;
   r->w_pol = n.w_pol; r->b_pol = n.b_pol; r->map_wpol = n.map_wpol; r->map_w = n.map_w; r->map_w_half = n.map_w_half;
   r->ready = n.ready;
   r->cur = k;
@@ -641,7 +656,7 @@ static void layout(NnRuntime* r, Carver& cv) {
   r->y = (__half*)cv.take(act);
   r->x32 = (float*)cv.take(act * 2);
   r->y32 = (float*)cv.take(act * 2);
-  r->pol_feat = (__half*)cv.take(((size_t)r->max_batch + 128) * kPolK * sizeof(__half));
+  r->pol_feat = (__half*)cv.take(((size_t)r->max_batch + 128) * 3 * r->pol_k1 * sizeof(__half));
   r->logits = (float*)cv.take((size_t)r->max_batch * kPolN * sizeof(float));
   r->stats = (float2*)cv.take((size_t)r->max_batch * (kPolN / 256) * sizeof(float2));
   r->n_scalar = (int*)cv.take(64);
@@ -651,13 +666,13 @@ static void layout(NnRuntime* r, Carver& cv) {
   r->shift_first = (float*)cv.take(c * sizeof(float));
   r->w_conv = (__half*)cv.take((size_t)2 * r->blocks * 9 * c * c * sizeof(__half));
   r->shift_conv = (float*)cv.take((size_t)2 * r->blocks * c * sizeof(float));
-  r->w6 = (float*)cv.take((size_t)6 * c * sizeof(float));
-  r->shift6 = (float*)cv.take(8 * sizeof(float));
-  r->wv1 = (float*)cv.take((size_t)180 * r->value_fc * sizeof(float));
+  r->wh = (float*)cv.take((size_t)(r->pol_c + r->val_c) * c * sizeof(float));
+  r->shifth = (float*)cv.take((size_t)(r->pol_c + r->val_c + 4) * sizeof(float));
+  r->wv1 = (float*)cv.take((size_t)r->val_c * 90 * r->value_fc * sizeof(float));
   r->bv1 = (float*)cv.take(r->value_fc * sizeof(float));
   r->wv2 = (float*)cv.take(r->value_fc * sizeof(float));
   r->bv2 = (float*)cv.take(4 * sizeof(float));
-  r->w_pol = (__half*)cv.take((size_t)kPolN * kPolK * sizeof(__half));
+  r->w_pol = (__half*)cv.take((size_t)kPolN * 3 * r->pol_k1 * sizeof(__half));
   r->b_pol = (float*)cv.take(kPolN * sizeof(float));
   r->ready = false;
   r->cur = net;
@@ -665,25 +680,35 @@ static void layout(NnRuntime* r, Carver& cv) {
   }
   if (r->n_nets > 1) { r->cur = r->n_nets - 1; select_net(r, 0); }
   r->cur = 0;
-  r->scratch = (float*)cv.take((size_t)2 * 256 * sizeof(float));
+  r->scratch = (float*)cv.take((size_t)(2 * 256 + 2 * kMaxHeadOut) * sizeof(float));
 }
 
-size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch, int n_nets) {
+static void set_heads(NnRuntime* r, int pol_c, int val_c) {
+  r->pol_c = pol_c > 0 ? pol_c : 4; r->val_c = val_c > 0 ? val_c : 2;     // agent/model.py:47-61 defaults
+  r->pol_k1 = (r->pol_c * 90 + 63) / 64 * 64;
+}
+size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch, int n_nets, int pol_c, int val_c) {
   NnRuntime tmp;
   tmp.filters = filters; tmp.blocks = blocks; tmp.value_fc = value_fc; tmp.max_batch = max_batch; tmp.n_nets = n_nets; tmp.cur = 0;
+  set_heads(&tmp, pol_c, val_c);
   Carver cv{nullptr, 0, 0};
   layout(&tmp, cv);
   return cv.off + 4096;
 }
 
 NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_batch, void* workspace, size_t bytes,
-                     void* stream, int fp32_skip_mode, int n_nets, int in_planes) {
+                     void* stream, int fp32_skip_mode, int n_nets, int in_planes, int pol_c, int val_c) {
   (void)device;
   if (filters % 64 != 0 || filters < 64 || filters > 256) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: filters must be 64..256 step 64"); return nullptr; }
   if (value_fc > 256 || value_fc < 1) { cz_fail(CZ_ERR_UNSUPPORTED, "nn: value_fc_size must be <= 256"); return nullptr; }
   if (n_nets < 1 || n_nets > 2) { cz_fail(CZ_ERR_ARG, "nn: 1 or 2 networks"); return nullptr; }
-  if (bytes < nn_workspace_bytes(filters, blocks, value_fc, max_batch, n_nets)) { cz_fail(CZ_ERR_ARG, "nn: workspace too small"); return nullptr; }
+  if (pol_c < 0 || val_c < 0 || pol_c > 32 || val_c > 4 || (pol_c > 0 ? pol_c : 4) + (val_c > 0 ? val_c : 2) > kMaxHeadOut) {
+    cz_fail(CZ_ERR_UNSUPPORTED, "nn: head widths up to 32 policy / 4 value channels"); return nullptr;
+  }
+  if (bytes < nn_workspace_bytes(filters, blocks, value_fc, max_batch, n_nets, pol_c, val_c)) { cz_fail(CZ_ERR_ARG, "nn: workspace too small"); return nullptr; }
   NnRuntime* r = new NnRuntime();
+  set_heads(r, pol_c, val_c);
+  r->heads_attr = false;
   r->filters = filters; r->blocks = blocks; r->value_fc = value_fc; r->max_batch = max_batch; r->n_nets = n_nets; r->cur = 0;
   r->stream = (cudaStream_t)stream; r->ready = false; r->launches = 0;
   r->in_planes = in_planes == 28 ? 28 : 14;
@@ -712,10 +737,10 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   rc |= make_map_3d(&r->map_x, r->x, c, 9, rows, 9, 14);
   rc |= make_map_3d(&r->map_t, r->t, c, 9, rows, 9, 14);
   rc |= make_map_3d(&r->map_y, r->y, c, 9, rows, 9, 14);
-  rc |= make_map_3d(&r->map_pf, r->pol_feat, kPolK, 1, (long long)max_batch + 128, 1, 128);
+  rc |= make_map_3d(&r->map_pf, r->pol_feat, 3 * r->pol_k1, 1, (long long)max_batch + 128, 1, 128);
   for (int net = n_nets - 1; net >= 0; --net) {
     select_net(r, net);
-    rc |= make_map_2d(&r->map_wpol, r->w_pol, kPolK, kPolN, 256);
+    rc |= make_map_2d(&r->map_wpol, r->w_pol, 3 * r->pol_k1, kPolN, 256);
     r->map_w.resize(2 * blocks);
     r->map_w_half.resize(2 * blocks);
     for (int i = 0; i < 2 * blocks; ++i) {
@@ -729,7 +754,7 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   cudaMemsetAsync(r->x, 0, (size_t)max_batch * 11 * 9 * c * 2, r->stream);
   cudaMemsetAsync(r->t, 0, (size_t)max_batch * 11 * 9 * c * 2, r->stream);
   cudaMemsetAsync(r->y, 0, (size_t)max_batch * 11 * 9 * c * 2, r->stream);
-  cudaMemsetAsync(r->pol_feat, 0, ((size_t)max_batch + 128) * kPolK * 2, r->stream);
+  cudaMemsetAsync(r->pol_feat, 0, ((size_t)max_batch + 128) * 3 * r->pol_k1 * 2, r->stream);
   return r;
 }
 
@@ -821,27 +846,29 @@ int nn_set_weights(NnRuntime* r, int net, const cz_tensor_desc* descs, int n) {
     }
   }
   {
-    NEED(kp, "policy_conv", "kernel", 4LL * c);
-    if (fold_bn(r, ws, "policy_batchnorm", 4, scale, r->shift6)) return CZ_ERR_ARG;
-    k_prep_1x1<<<(4 * c + 255) / 256, 256, 0, st>>>((const float*)kp->dev, scale, r->w6, c, 4);
-    NEED(kv, "value_conv", "kernel", 2LL * c);
-    if (fold_bn(r, ws, "value_batchnorm", 2, scale + 8, r->shift6 + 4)) return CZ_ERR_ARG;
-    k_prep_1x1<<<(2 * c + 255) / 256, 256, 0, st>>>((const float*)kv->dev, scale + 8, r->w6 + (size_t)4 * c, c, 2);
+    const int pc = r->pol_c, vc = r->val_c;
+    NEED(kp, "policy_conv", "kernel", (long long)pc * c);
+    if (fold_bn(r, ws, "policy_batchnorm", pc, scale, r->shifth)) return CZ_ERR_ARG;
+    k_prep_1x1<<<(pc * c + 255) / 256, 256, 0, st>>>((const float*)kp->dev, scale, r->wh, c, pc);
+    NEED(kv, "value_conv", "kernel", (long long)vc * c);
+    float* scale_v = r->scratch + 2 * 256 + kMaxHeadOut;     // k_bn_fold of the policy head above may still be reading `scale`
+    if (fold_bn(r, ws, "value_batchnorm", vc, scale_v, r->shifth + pc)) return CZ_ERR_ARG;
+    k_prep_1x1<<<(vc * c + 255) / 256, 256, 0, st>>>((const float*)kv->dev, scale_v, r->wh + (size_t)pc * c, c, vc);
   }
   {
-    NEED(k, "policy_out", "kernel", 360LL * kLabels);
+    NEED(k, "policy_out", "kernel", (long long)r->pol_c * 90 * kLabels);
     NEED(b, "policy_out", "bias", kLabels);
-    const long long nn = (long long)kPolN * kPolK1;
-    k_prep_policy<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>((const float*)k->dev, r->w_pol);
+    const long long nn = (long long)kPolN * r->pol_k1;
+    k_prep_policy<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>((const float*)k->dev, r->w_pol, r->pol_c * 90, r->pol_k1);
     k_copy_pad<<<(kPolN + 255) / 256, 256, 0, st>>>((const float*)b->dev, r->b_pol, kLabels, kPolN);
   }
   {
     const int h = r->value_fc;
-    NEED(k1, "value_dense", "kernel", 180LL * h);
+    NEED(k1, "value_dense", "kernel", (long long)r->val_c * 90 * h);
     NEED(b1, "value_dense", "bias", h);
     NEED(k2, "value_out", "kernel", h);
     NEED(b2, "value_out", "bias", 1);
-    CZ_CUDA(cudaMemcpyAsync(r->wv1, k1->dev, (size_t)180 * h * 4, cudaMemcpyDeviceToDevice, st));
+    CZ_CUDA(cudaMemcpyAsync(r->wv1, k1->dev, (size_t)r->val_c * 90 * h * 4, cudaMemcpyDeviceToDevice, st));
     CZ_CUDA(cudaMemcpyAsync(r->bv1, b1->dev, (size_t)h * 4, cudaMemcpyDeviceToDevice, st));
     CZ_CUDA(cudaMemcpyAsync(r->wv2, k2->dev, (size_t)h * 4, cudaMemcpyDeviceToDevice, st));
     CZ_CUDA(cudaMemcpyAsync(r->bv2, b2->dev, 4, cudaMemcpyDeviceToDevice, st));
@@ -923,9 +950,14 @@ static int fw_heads(NnRuntime* r, int n, const int* n_dev, float* value) {
   const bool odd = (r->blocks & 1) != 0;                   // the tower ping-pongs x <-> y once per block
   const __half* x = odd ? r->y : r->x;
   const float* x32 = s32 ? (odd ? r->y32 : r->x32) : nullptr;
-  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, 0, r->stream>>>(x, x32, c, n_dev, r->board_pixels, r->w6, r->shift6, r->wv1, r->bv1, r->wv2,
-                                                                r->bv2, r->value_fc, r->pol_feat, value);
-  igemm::Args ap = dense_args(n, kLabels, kPolN, kPolK, 256, r->b_pol, r->logits, kPolN);
+  const size_t hsm = heads_smem_bytes(c, r->pol_c + r->val_c);
+  if (hsm > 48 * 1024 && !r->heads_attr) {
+    CZ_CUDA(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+    r->heads_attr = true;
+  }
+  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, hsm, r->stream>>>(x, x32, c, n_dev, r->board_pixels, r->pol_c, r->val_c, r->pol_k1, r->wh, r->shifth,
+                                                                  r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
+  igemm::Args ap = dense_args(n, kLabels, kPolN, 3 * r->pol_k1, 256, r->b_pol, r->logits, kPolN);
   ap.n_dev = n_dev; ap.rows_per_unit = 1; ap.row_stats = r->stats;
   if (launch_igemm(256, r->map_pf, r->map_wpol, ap, r->stream)) return CZ_ERR_CUDA;
   r->launches += 2;

@@ -9,10 +9,11 @@ namespace cznn {
 struct NnRuntime;
 
 // bytes of device workspace the runtime needs for batches up to max_batch positions
-size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch, int n_nets);
+// pol_c / val_c: channels of the policy / value 1x1 convolutions (0 = agent/model.py's 4 / 2)
+size_t nn_workspace_bytes(int filters, int blocks, int value_fc, int max_batch, int n_nets, int pol_c, int val_c);
 // returns nullptr and sets cz_last_error on failure
 NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_batch, void* workspace, size_t bytes,
-                     void* stream, int fp32_skip_mode, int n_nets, int in_planes /* 14 or 28 */);
+                     void* stream, int fp32_skip_mode, int n_nets, int in_planes /* 14 or 28 */, int pol_c, int val_c);
 void nn_destroy(NnRuntime*);
 int nn_set_weights(NnRuntime*, int net, const cz_tensor_desc* descs, int n);
 bool nn_ready(const NnRuntime*);

@@ -436,7 +436,8 @@ int cz_workspace_bytes(const cz_config* cfg, uint64_t* bytes) {
   size_t n = carve(&tmp, nullptr);
 #if !defined(CZ_EMUL)
   if (cfg->nn_filters > 0)
-    n += cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, cfg->n_games * cfg->leaves_per_round, cfg->arena ? 2 : 1) + 4096;
+    n += cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, cfg->n_games * cfg->leaves_per_round, cfg->arena ? 2 : 1,
+                                  cfg->nn_policy_channels, cfg->nn_value_channels) + 4096;
 #endif
   *bytes = n;
   return 0;
@@ -510,9 +511,11 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
 #if !defined(CZ_EMUL)
   if (cfg->nn_filters > 0) {
     const int maxb = cfg->n_games * cfg->leaves_per_round;
-    e->nn_bytes = cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, cfg->arena ? 2 : 1);
+    e->nn_bytes = cznn::nn_workspace_bytes(cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, cfg->arena ? 2 : 1,
+                                           cfg->nn_policy_channels, cfg->nn_value_channels);
     uint8_t* nnws = e->ws + ((used + 4095) & ~(size_t)4095);
-    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream, cfg->nn_fp32_skip, cfg->arena ? 2 : 1, cfg->use_history ? 28 : 14);
+    e->nn = cznn::nn_create(cfg->device, cfg->nn_filters, cfg->nn_blocks, cfg->nn_value_fc, maxb, nnws, e->nn_bytes, (void*)e->stream, cfg->nn_fp32_skip, cfg->arena ? 2 : 1, cfg->use_history ? 28 : 14,
+                           cfg->nn_policy_channels, cfg->nn_value_channels);
     if (!e->nn) { delete e; return CZ_ERR_CUDA; }
   }
 #else

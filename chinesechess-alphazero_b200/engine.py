@@ -22,7 +22,7 @@ class Engine:
                  max_nodes_per_game=None, max_edges_per_game=None, max_path=128, noise_mode=1, max_game_length=100,
                  nn_filters=0, nn_blocks=0, nn_value_fc=256, c_puct=1.5, noise_eps=0.15, dirichlet_alpha=0.2,
                  tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40, seed=0, rank=0, nn_fp32_skip=None, arena=False,
-                 use_history=False, game_quota=0, playouts=None):
+                 use_history=False, game_quota=0, playouts=None, nn_policy_channels=0, nn_value_channels=0):
         self.lib = lib or get_lib()
         if device is None:
             device = 'cuda' if self.lib.is_cuda else 'cpu'
@@ -49,6 +49,8 @@ class Engine:
         cfg.use_history = 1 if use_history else 0
         cfg.game_quota = int(game_quota or 0)        # > 0: play exactly the games with running index < game_quota, then retire
         cfg.playouts_lo, cfg.playouts_hi = (playouts or (0, 0))   # arena: per-game randint(lo, hi) * 100 simulations per move
+        # head widths of the weight file (0 = agent/model.py's 4 policy / 2 value channels; legacy configs: 2 or 32 / 4)
+        cfg.nn_policy_channels, cfg.nn_value_channels = int(nn_policy_channels or 0), int(nn_value_channels or 0)
         self.use_history = bool(use_history)
         self.in_planes = 28 if use_history else 14
         self.cfg = cfg

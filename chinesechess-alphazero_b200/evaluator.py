@@ -9,6 +9,7 @@ per player), network 0 = best model, network 1 = next generation, evaluator draw
 from logging import getLogger
 
 from .engine import Engine
+from .model import engine_net_kwargs
 from .lib import get_lib
 
 logger = getLogger(__name__)
@@ -50,7 +51,7 @@ class EvaluateWorker:
             leaves_per_round=pc.search_threads, virtual_loss=getattr(pc, "virtual_loss", 3), noise_mode=1, c_puct=pc.c_puct,
             noise_eps=pc.noise_eps, dirichlet_alpha=getattr(pc, "dirichlet_alpha", 0.2), tau_decay_rate=pc.tau_decay_rate,
             enable_resign_rate=0.0, max_game_length=pc.max_game_length, max_nodes_per_game=max(4096, 16 * sims_max),
-            nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size, seed=seed, arena=True,
+            seed=seed, arena=True, **engine_net_kwargs(mc),
             game_quota=self.n_games, playouts=playouts)   # exactly the games 0 .. n_games-1, each played to its end
         self.engine.set_weights(model_bt.torch_weights(), net=0)
         self.engine.set_weights(model_ng.torch_weights(), net=1)

@@ -31,7 +31,8 @@ class CzConfig(C.Structure):
         ("tau_decay_rate", C.c_double), ("resign_threshold", C.c_double), ("enable_resign_rate", C.c_double),
         ("min_resign_turn", C.c_int32), ("max_game_length", C.c_int32),
         ("seed", C.c_uint64), ("rank", C.c_int32), ("arena", C.c_int32), ("nn_fp32_skip", C.c_int32), ("use_history", C.c_int32),
-        ("game_quota", C.c_int32), ("playouts_lo", C.c_int32), ("playouts_hi", C.c_int32), ("reserved0", C.c_int32),
+        ("game_quota", C.c_int32), ("playouts_lo", C.c_int32), ("playouts_hi", C.c_int32),
+        ("nn_policy_channels", C.c_int32), ("nn_value_channels", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -33,6 +33,19 @@ def layer_names(filters, blocks, first=5, k=3):
     return conv, bn, ["policy_out", "value_dense", "value_out"]
 
 
+def head_channels(mc):
+    """(policy, value) 1x1-convolution filters of a model config: agent/model.py:47-61 builds 4 / 2; the older configs under
+    the reference's data/model/ have 2 / 4 (model_128f.json, model_256f.json) and 32 / 4 (model_128_l1_config.json)."""
+    return int(getattr(mc, "policy_channels", 0) or 4), int(getattr(mc, "value_channels", 0) or 2)
+
+
+def engine_net_kwargs(mc):
+    """The network geometry arguments of `Engine(...)` for a model config."""
+    pol_c, val_c = head_channels(mc)
+    return dict(nn_filters=mc.cnn_filter_num, nn_blocks=mc.res_layer_num, nn_value_fc=mc.value_fc_size,
+                nn_policy_channels=pol_c, nn_value_channels=val_c)
+
+
 class CChessModel:
     def __init__(self, config):
         self.config = config
@@ -79,12 +92,13 @@ class CChessModel:
             for j in (1, 2):
                 conv(f"res{i}_conv{j}-{k}-{f}", k, f, f)
                 bn(f"res{i}_batchnorm{j}", f)
-        conv("policy_conv-1-2", 1, f, 4)
-        bn("policy_batchnorm", 4)
-        dense("policy_out", 360, N_LABELS)
-        conv("value_conv-1-4", 1, f, 2)
-        bn("value_batchnorm", 2)
-        dense("value_dense", 180, vfc)
+        pol_c, val_c = head_channels(mc)               # agent/model.py:47-61: 4 / 2 (the layer NAMES say "-1-2" / "-1-4")
+        conv("policy_conv-1-2", 1, f, pol_c)
+        bn("policy_batchnorm", pol_c)
+        dense("policy_out", pol_c * 90, N_LABELS)
+        conv("value_conv-1-4", 1, f, val_c)
+        bn("value_batchnorm", val_c)
+        dense("value_dense", val_c * 90, vfc)
         dense("value_out", vfc, 1)
         self.weights = w
         self.model = self
@@ -120,6 +134,7 @@ class CChessModel:
         mc.value_fc_size = cfg.get("value_fc_size", 256)
         with np.load(weight_path) as z:
             self.weights = {k.replace("__", "/"): z[k].astype(np.float32) for k in z.files}
+        self._infer_geometry()
         self.digest = self.fetch_digest(weight_path)
         self.model = self
         return True
@@ -134,6 +149,8 @@ class CChessModel:
         mc.cnn_filter_num = int(k.shape[3])
         mc.res_layer_num = max(int(n[3:n.index("_")]) for n in self.weights if n.startswith("res"))
         mc.value_fc_size = int(self.weights["value_dense/bias"].shape[0])
+        mc.policy_channels = int(next(v for n, v in self.weights.items() if n.startswith("policy_conv") and n.endswith("/kernel")).shape[3])
+        mc.value_channels = int(next(v for n, v in self.weights.items() if n.startswith("value_conv") and n.endswith("/kernel")).shape[3])
 
     @property
     def use_history(self):

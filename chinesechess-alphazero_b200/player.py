@@ -27,6 +27,7 @@ import torch
 from .engine import Engine
 from .env import StaticEnv, flip_move, to_uci_move
 from .lib import get_lib
+from .model import engine_net_kwargs
 
 
 class EdgeView:
@@ -93,8 +94,7 @@ class CChessPlayer:
             resign_threshold=getattr(pc, "resign_threshold", -1.0), min_resign_turn=getattr(pc, "min_resign_turn", 0),
             max_game_length=getattr(pc, "max_game_length", 100),
             max_nodes_per_game=max(4096, 8 * pc.simulation_num_per_move, (infinite_capacity + 64) if uci else 0),
-            nn_filters=mc.cnn_filter_num if (use_nn and mc) else 0, nn_blocks=mc.res_layer_num if (use_nn and mc) else 0,
-            nn_value_fc=mc.value_fc_size if (use_nn and mc) else 256, use_history=use_history)
+            use_history=use_history, **(engine_net_kwargs(mc) if (use_nn and mc) else {}))
         if use_nn:
             if weights is None:
                 raise ValueError("CChessPlayer without pipes needs `weights` (Keras-named tensors) for the built-in network")

@@ -13,7 +13,7 @@ from time import time
 
 from .engine import Engine
 from .lib import get_lib
-from .model import CChessModel
+from .model import CChessModel, engine_net_kwargs
 from .records import record_to_play_data, write_play_data
 from .env import INIT_STATE, StaticEnv
 
@@ -93,8 +93,7 @@ class SelfPlayWorker:
             dirichlet_alpha=pc.dirichlet_alpha, tau_decay_rate=pc.tau_decay_rate, resign_threshold=pc.resign_threshold,
             enable_resign_rate=pc.enable_resign_rate, min_resign_turn=pc.min_resign_turn, max_game_length=pc.max_game_length,
             **dict(dict(max_nodes_per_game=max(4096, 24 * pc.simulation_num_per_move),
-                        nn_filters=0 if external_evaluator else mc.cnn_filter_num, nn_blocks=mc.res_layer_num,
-                        nn_value_fc=mc.value_fc_size, seed=seed, rank=rank,
+                        seed=seed, rank=rank, **({} if external_evaluator else engine_net_kwargs(mc)),
                         use_history=use_history),   # the game loop never passes `hist` (self_play.py:124): path history only
                    **(engine_kwargs or {})))
         if not external_evaluator:      # external evaluator: the leaves go to a caller-supplied function (CPU test tier)

@@ -112,6 +112,9 @@ typedef struct cz_config {
                                 * game index would reach the quota retires instead of restarting.  0 = restart for ever */
   int32_t playouts_lo;         /* arena, > 0: every game draws its own simulations per move = randint(playouts_lo, playouts_hi) * 100 */
   int32_t playouts_hi;         /*   when it starts (evaluator.py:153-154: randint(8, 12) * 100), from the Philox stream of the game */
+  int32_t nn_policy_channels;  /* filters of the policy 1x1 convolution: 0 = 4 (agent/model.py:47); the older shipped configs use 2
+                                * (data/model/model_128f.json, model_256f.json) and 32 (model_128_l1_config.json) */
+  int32_t nn_value_channels;   /* filters of the value 1x1 convolution: 0 = 2 (agent/model.py:56); the older configs use 4 */
   int32_t reserved0;
 } cz_config;
 

@@ -122,3 +122,37 @@ def test_deep_net_fp16_skip_stream_bound(cuda_lib, cuda_env):
     assert np.abs(pol.cpu().numpy() - ref_p).max() < 1e-3
     assert np.abs(val.cpu().numpy() - ref_v).max() < 3e-3
     eng.close()
+
+
+@pytest.mark.parametrize("filters,blocks,pol_c,val_c,in_planes", [
+    (128, 7, 2, 4, 14),       # data/model/model_128f.json
+    (256, 7, 2, 4, 14),       # data/model/model_256f.json
+    (128, 7, 32, 4, 28),      # data/model/model_128_l1_config.json (28-plane history input)
+])
+def test_legacy_head_widths(cuda_lib, cuda_env, filters, blocks, pol_c, val_c, in_planes):
+    """The older configs shipped under the reference's data/model/ have other head widths than agent/model.py:47-61 builds
+    (policy 2 or 32 channels, value 4): the engine serves them, within 1e-3 of the fp32 restatement (which
+    tests/test_oracle_vs_reference.py pins to those very JSON files through oracle/keras_graph.py)."""
+    from cczero_b200.engine import Engine
+    w = om.init_weights(filters, blocks, 256, seed=pol_c + val_c, trained_like=True, spread=0.3, in_planes=in_planes,
+                        policy_filters=pol_c, value_filters=val_c)
+    assert w["policy_out/kernel"].shape == (90 * pol_c, 2086) and w["value_dense/kernel"].shape == (90 * val_c, 256)
+    states = [osenv.INIT_STATE] + midgame_states(24, 5, lo=1, hi=100)
+    hist = in_planes == 28
+    planes = np.stack([osenv.state_history_to_planes(s, [s]) if hist else osenv.state_to_planes(s) for s in states])
+    ref_p, ref_v = om.forward(w, planes, blocks)
+    eng = Engine(cuda_lib, "cuda", n_games=32, sims_per_move=8, leaves_per_round=1, nn_filters=filters, nn_blocks=blocks,
+                 nn_value_fc=256, use_history=hist, nn_policy_channels=pol_c, nn_value_channels=val_c)
+    eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    pol, val = eng.nn_forward_planes(torch.as_tensor(planes).cuda())
+    pol, val = pol.cpu().numpy(), val.cpu().numpy()
+    assert np.abs(pol.sum(1) - 1).max() < 1e-4
+    assert np.abs(pol - ref_p).max() < 1e-3, np.abs(pol - ref_p).max()
+    assert np.abs(val - ref_v).max() < 1e-3, np.abs(val - ref_v).max()
+    # wrong widths are refused loudly, not silently mis-read
+    from cczero_b200.lib import CzError
+    eng2 = Engine(cuda_lib, "cuda", n_games=8, sims_per_move=8, leaves_per_round=1, nn_filters=filters, nn_blocks=blocks, use_history=hist)
+    with pytest.raises(CzError, match="mis-sized"):
+        eng2.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    eng.close()
+    eng2.close()
