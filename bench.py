@@ -190,9 +190,16 @@ def run_reference_arm(args):
         extra["mean_batch"] = sum(w[1] for w in wins) / max(1, sum(w[2] for w in wins))
         if not args.no_secondary:
             # BASELINE.json configs[0]: `run.py self --type mini --new` as shipped (1 process, 10 threads, 100 sims, 256x7)
-            os.environ["CZ_BENCH_CPU_PROCS"] = "1"
+            # one player process whose batches are <= 10 positions: more than one intra-op thread only oversubscribes (BASELINE.md
+            # section 4: 70.9 sims/s with OMP_NUM_THREADS=1 vs 9.2 with 8 threads on the survey box)
+            saved = {k: os.environ.get(k) for k in ("CZ_BENCH_CPU_PROCS", "CZ_BENCH_CPU_NN_THREADS")}
+            os.environ["CZ_BENCH_CPU_PROCS"], os.environ["CZ_BENCH_CPU_NN_THREADS"] = "1", "1"
             w1, d1, u1, _ = reference_windows(100, 256, 7, 10, 1, 30.0, config_type="mini")
-            os.environ.pop("CZ_BENCH_CPU_PROCS")
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
             extra["c1_mini"] = {"value": w1[0][0] / w1[0][3], "unit": "sims/s", "cores": u1, "positions_per_s": w1[0][1] / w1[0][3],
                                 "mean_batch": w1[0][1] / max(1, w1[0][2]), "sample": d1 + f"; one {w1[0][3]:.0f} s window"}
             # tree-code ceiling: the same plumbing with a constant-output network
