@@ -228,14 +228,14 @@ def bench_config(workload, games, sims, filters, blocks, K):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def make_worker(workload, games, sims, filters, blocks, K, rank, seed, skip_stream, nodes, data_dir, lib):
+def make_worker(workload, games, sims, filters, blocks, K, rank, seed, skip_stream, nodes, data_dir, lib, max_game_length=100):
     """The drop-in SelfPlayWorker (cczero_b200/self_play.py) on this rank's GPU: it owns the engine the bench times."""
     from types import SimpleNamespace
     from cczero_b200.model import CChessModel
     from cczero_b200.self_play import SelfPlayWorker
     play = SimpleNamespace(max_processes=1, simulation_num_per_move=sims, search_threads=K, virtual_loss=3, c_puct=1.5, noise_eps=0.15,
                            dirichlet_alpha=0.2, tau_decay_rate=0.9, resign_threshold=-0.98, enable_resign_rate=0.5, min_resign_turn=40,
-                           max_game_length=100)
+                           max_game_length=max_game_length)
     mc = SimpleNamespace(cnn_filter_num=filters, res_layer_num=blocks, value_fc_size=256, cnn_first_filter_size=5, cnn_filter_size=3,
                          input_depth=14)
     cfg = SimpleNamespace(play=play, model=mc, play_data=SimpleNamespace(nb_game_in_file=1),
@@ -267,7 +267,8 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
         sims = args.sims
     K = args.leaves
     data_dir = tempfile.mkdtemp(prefix=f"cz_bench_{workload}_")
-    worker = make_worker(workload, games, sims, filters, blocks, K, rank, args.seed, args.skip_stream, args.nodes, data_dir, lib)
+    worker = make_worker(workload, games, sims, filters, blocks, K, rank, args.seed, args.skip_stream, args.nodes, data_dir, lib,
+                         args.max_game_length)
     eng = worker.engine
 
     def barrier():
@@ -482,6 +483,8 @@ def main():
     ap.add_argument("--nodes", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--max-game-length", type=int, default=100, help="play_config.max_game_length (configs/normal.py: 100); smaller "
+                    "values make games finish inside a short run so that the record gather / file writes carry data")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short c2 / c5 runs (and the c1 / free-NN legs of the CPU arm)")
     ap.add_argument("--skip-stream", default="auto", choices=["auto", "fp32", "fp16"],
