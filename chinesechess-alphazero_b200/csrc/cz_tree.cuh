@@ -182,28 +182,37 @@ CZ_D double dirichlet_first(const EngineDev& E, int game, uint32_t index, int n)
 }
 
 // ------------------------------------------------------------------ transposition table
+// Linear probing, 32 slots per step: lane i looks at slot s + i (one round trip of hash + key loads for the whole probe
+// sequence instead of one dependent round trip per slot).  The key, if stored, sits before the first empty slot.
 CZ_D int tt_lookup(const EngineDev& E, int g, uint64_t k0, uint64_t k1) {
-  int res = -1;
-  if (czs::lane() == 0) {
-    const uint32_t mask = (uint32_t)E.hcap - 1;
-    const uint32_t* h = E.hash + (size_t)g * E.hcap;
-    uint32_t s = (uint32_t)k0 & mask;
-    for (int probe = 0; probe < E.hcap; ++probe, s = (s + 1) & mask) {
-      const uint32_t v = h[s];
-      if (v == 0) break;
+  const uint32_t mask = (uint32_t)E.hcap - 1;
+  const uint32_t* h = E.hash + (size_t)g * E.hcap;
+  const uint32_t s0 = (uint32_t)k0 & mask;
+  for (int base = 0; base < E.hcap; base += 32) {
+    const uint32_t v = h[(s0 + (uint32_t)(base + czs::lane())) & mask];
+    bool match = false;
+    if (v != 0) {
       const size_t ni = (size_t)g * E.ncap + (v - 1);
-      if (E.node_key0[ni] == k0 && E.node_key1[ni] == k1) { res = (int)(v - 1); break; }
+      match = E.node_key0[ni] == k0 && E.node_key1[ni] == k1;
     }
+    const unsigned m_empty = czs::ballot(v == 0), m_match = czs::ballot(match);
+    const unsigned before = m_empty ? ((1u << (czs::ffs(m_empty) - 1)) - 1u) : 0xffffffffu;   // lanes ahead of the first empty slot
+    if (m_match & before) return (int)czs::shfl(v, czs::ffs(m_match & before) - 1) - 1;
+    if (m_empty) return -1;
   }
-  return czs::shfl(res, 0);
+  return -1;
 }
 CZ_D void tt_insert(const EngineDev& E, int g, uint64_t k0, int node) {
-  if (czs::lane() == 0) {
-    const uint32_t mask = (uint32_t)E.hcap - 1;
-    uint32_t* h = E.hash + (size_t)g * E.hcap;
-    uint32_t s = (uint32_t)k0 & mask;
-    while (h[s] != 0) s = (s + 1) & mask;
-    h[s] = (uint32_t)node + 1;
+  const uint32_t mask = (uint32_t)E.hcap - 1;
+  uint32_t* h = E.hash + (size_t)g * E.hcap;
+  const uint32_t s0 = (uint32_t)k0 & mask;
+  for (int base = 0; base < E.hcap; base += 32) {
+    const uint32_t slot = (s0 + (uint32_t)(base + czs::lane())) & mask;
+    const unsigned m_empty = czs::ballot(h[slot] == 0);
+    if (m_empty) {
+      if (czs::lane() == czs::ffs(m_empty) - 1) h[slot] = (uint32_t)node + 1;      // the first empty slot of the probe sequence
+      break;
+    }
   }
   czs::syncwarp();
 }
@@ -304,19 +313,24 @@ CZ_D int select_edge(const EngineDev& E, int g, int node, bool is_root) {
 }
 
 // ------------------------------------------------------------------ backup (update_tree, player.py:355-366)
+// One lane per path level: the edges of a path are distinct (a repeated node ends the simulation before it is selected from
+// again), so the read-modify-writes are independent and cost one memory round trip instead of one per level.  The value
+// alternates in sign from the leaf upwards (v = -v before every level, :357-359); negation is exact, so every edge receives
+// bit for bit what the sequential loop would add.
 CZ_D void backup(const EngineDev& E, int g, int sim, double v) {
-  if (czs::lane() == 0) {
-    const size_t so = ((size_t)g * E.K + sim) * E.max_path;
-    const int depth = E.sim_depth[(size_t)g * E.K + sim];
-    const double vl = (double)E.vl;
-    E.stat[(size_t)g * 4 + 0] += 1; E.stat[(size_t)g * 4 + 1] += (unsigned long long)depth;
-    for (int l = depth - 1; l >= 0; --l) {
-      v = -v;
+  const size_t so = ((size_t)g * E.K + sim) * E.max_path;
+  const int depth = E.sim_depth[(size_t)g * E.K + sim];
+  const double vl = (double)E.vl;
+  for (int base = 0; base < depth; base += 32) {
+    const int l = base + czs::lane();
+    if (l < depth) {
+      const double vs = ((depth - l) & 1) ? -v : v;
       const size_t e = (size_t)g * E.ecap + E.sim_edge[so + l];
       E.edge_n[e] += 1 - E.vl;
-      E.edge_w[e] = E.edge_w[e] + (v + vl);
+      E.edge_w[e] = E.edge_w[e] + (vs + vl);
     }
   }
+  if (czs::lane() == 0) { E.stat[(size_t)g * 4 + 0] += 1; E.stat[(size_t)g * 4 + 1] += (unsigned long long)depth; }
   czs::syncwarp();
 }
 
