@@ -136,6 +136,7 @@ def reference_windows(sims, filters, blocks, k, n_windows, window_s, warm_window
     run = rb.ReferenceSelfPlay(config_type, procs, 1 if free_nn else nn_threads, play=play, model=model, free_nn=free_nn)
     try:
         run.wait_started(timeout=600.0, min_sims=max(1, procs))
+        run.window(float(os.environ.get("CZ_BENCH_CPU_SETTLE", 8.0)))      # every process past its first batches before anything counts
         for _ in range(warm_windows):
             run.window(window_s)
         wins = [run.window(window_s) for _ in range(n_windows)]

@@ -37,6 +37,7 @@ struct Args3 {
   int out32;             // also store the fp32 copy (tmOut32)
   int fbytes;            // bytes of one F tile: 2048 (fp32 skip and/or fp32 output), 1024 (fp16 skip only), 0 (neither)
   int nf;                // F tiles per epilogue warp (3 .. kMaxNF3): skip loads run nf - 2 chunks ahead
+  int split_producer;    // 1: warp 0 issues the A (im2col) loads, warp 3 the B (weight) loads — two TMA issue streams per CTA
 };
 __host__ __device__ constexpr int epi3_warp_bytes(int fbytes, int nf) { return nf * fbytes + kNH3 * kHBytes3; }
 
@@ -125,9 +126,12 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   const int pairs = (m_tiles + 1) / 2;
   const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (one per CTA)
+  if (warp == 0 || (warp == 3 && p.split_producer)) {
+    // ------------------------------------------------------------ TMA producer(s): one thread per CTA issues both operand
+    // loads of a stage, or — split_producer — warp 0 the A tiles and warp 3 the B tiles (each waits for the stage to be free
+    // on its own; the transaction count covers both)
     if (lane == 0) {
+      const bool do_a = warp == 0, do_b = warp == 3 || !p.split_producer;
       uint32_t s = 0, ph = 0;
       for (int pair = cluster_id; pair < pairs; pair += n_clusters) {
         const int m_tile = 2 * pair + (int)rank;
@@ -138,9 +142,9 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             umma::mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sA = smem + s * C::kStageBytes;
             uint8_t* sB = sA + kAStageBytes;
-            if (leader) umma::mbar_expect_tx(&full[s], 2u * (a.a_bytes + (uint32_t)C::kBHalfBytes));
-            umma::tma2_load_im2col_4d(sA, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1));
-            umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + (int)rank * (N_TILE / 2));
+            if (leader && do_a) umma::mbar_expect_tx(&full[s], 2u * (a.a_bytes + (uint32_t)C::kBHalfBytes));
+            if (do_a) umma::tma2_load_im2col_4d(sA, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1));
+            if (do_b) umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + (int)rank * (N_TILE / 2));
             if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1; }
           }
         }

@@ -50,6 +50,15 @@ CZ_KERNEL(k_apply)(EngineDev E, int g0, int g1, const float* policy, const float
   if (g >= g1) return;
   game_apply(E, g, policy, legal_p, value, tree_smem());
 }
+// device-driven loop: the same warp applies the evaluation of the previous wave and walks the next one (the game's state stays hot)
+CZ_KERNEL(k_apply_wave)(EngineDev E, int g0, int g1, const float* legal_p, const float* value) {
+  const int g = g0 + my_game();
+  if (g >= g1) return;
+  TreeSmem* sm = tree_smem();
+  game_apply(E, g, nullptr, legal_p, value, sm);
+  czs::syncwarp();
+  game_wave(E, g, sm);
+}
 // single warp: exclusive scan of the per-game leaf counts, totals[0] = leaves, totals[1] = any game busy
 CZ_KERNEL(k_scan)(EngineDev E, int gb, int ge, int slot) {
   int base = 0, busy = 0;
@@ -76,6 +85,38 @@ CZ_KERNEL(k_scan)(EngineDev E, int gb, int ge, int slot) {
 }
 // dense leaf list of a range: boards, and (labels != null) the action labels of each leaf's legal moves in edge order, which
 // is all the evaluation step has to know to hand back exactly the priors the search will read
+#if !defined(CZ_EMUL)
+// The same scan with one thread per game (1024 threads, chunked): the single-warp version walks 32 dependent chunks at
+// 1024 games (52 us in the c3 launch list); this one is a couple of microseconds.  Same outputs, same counters.
+__global__ void __launch_bounds__(1024) k_scan_block(EngineDev E, int gb, int ge, int slot) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s, busy_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { carry_s = 0; busy_s = 0; }
+  __syncthreads();
+  for (int g0 = gb; g0 < ge; g0 += 1024) {
+    const int g = g0 + tid;
+    const int n = g < ge ? E.n_leaf[g] : 0;
+    int x = n;
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) warp_tot[warp] = x;
+    if (g < ge && E.active[g] && (E.round_pending[g] > 0 || E.tasks_left[g] > 0)) busy_s = 1;     // benign race: all writers store 1
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+    const int carry = carry_s;
+    if (g < ge) E.leaf_off[g] = carry + wbase + x - n;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wbase + x;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int base = carry_s;
+    E.totals[4 * slot] = base; E.totals[4 * slot + 1] = busy_s;
+    atomicAdd(E.counters + 1, (unsigned long long)base); atomicAdd(E.counters + 2, 1ULL);
+  }
+}
+#endif
 CZ_KERNEL(k_gather)(EngineDev E, int g0, int g1, uint8_t* dense, int16_t* labels, int32_t* nlab) {
   const int g = g0 + my_game();
   if (g >= g1) return;
@@ -785,9 +826,8 @@ int enqueue_part(cz_engine* e, int h, int part) {
   const int n_max = (r.ge - r.gb) * e->cfg.leaves_per_round;
   const int* n_dev = e->d.totals + 4 * h;
   if (part == 1) {
-    RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_apply, e->d, r.gb, r.ge, (const float*)nullptr, (const float*)r.legal_p, (const float*)r.value);
-    RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_wave, e->d, r.gb, r.ge);
-    CZ_LAUNCH(k_scan, 1, 1, 0, e->stream, e->d, r.gb, r.ge, h);
+    RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_apply_wave, e->d, r.gb, r.ge, (const float*)r.legal_p, (const float*)r.value);
+    k_scan_block<<<1, 1024, 0, e->stream>>>(e->d, r.gb, r.ge, h);
     RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_gather, e->d, r.gb, r.ge, r.dense, r.labels, r.nlab);
   }
   const int rc = cznn::nn_forward_leaves(e->nn, e->cfg.arena ? h : 0, part, r.dense, n_max, n_dev, r.labels, r.nlab, r.legal_p, r.value);
@@ -863,7 +903,7 @@ int build_graphs(cz_engine* e) {
   return 0;
 }
 // launches per iteration of one range, for cz_launch_count (graph launches do not pass through launch_ok)
-int launches_per_iteration(cz_engine* e) { return 4 + cznn::nn_launches_per_forward(e->nn); }
+int launches_per_iteration(cz_engine* e) { return 3 + cznn::nn_launches_per_forward(e->nn); }
 
 int search_graph_loop(cz_engine* e) {
   CZ_LAUNCH(k_loop_reset, 1, 1, 0, e->stream, e->d);

@@ -29,6 +29,8 @@ class Engine:
         self.device = torch.device(device)
         if self.lib.is_cuda and self.device.type != 'cuda':
             raise ValueError("the CUDA library needs a CUDA device")
+        if self.device.type == 'cuda' and self.device.index is None:      # "cuda" = the process's current device (one rank per GPU)
+            self.device = torch.device('cuda', torch.cuda.current_device())
         if max_nodes_per_game is None:
             max_nodes_per_game = max(64, 4 * sims_per_move + 64)
         if max_edges_per_game is None:

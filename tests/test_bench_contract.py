@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
-    env = dict(os.environ, CZ_BENCH_CPU_PROCS="2", CZ_BENCH_CPU_NN_THREADS="2", CZ_BENCH_CPU_WINDOW="3")
+    env = dict(os.environ, CZ_BENCH_CPU_PROCS="2", CZ_BENCH_CPU_NN_THREADS="2", CZ_BENCH_CPU_WINDOW="3", CZ_BENCH_CPU_SETTLE="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "2",
                           "--warmup", "0", "--no-secondary"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
