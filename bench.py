@@ -211,7 +211,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(per_window)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init Keras-equivalent weights, games from INIT_STATE)",
-        "config": bench_config(args.workload, games, sims, filters, blocks, K),
+        "config": bench_config(args.workload, games, sims, filters, blocks, K, args.gpus, args.skip_stream),
         "cpu_baseline": {"value": value, "unit": "sims/s", "cores": used, "kind": kind, "sample": sample,
                          "host_cores": cores, "max_processes": procs, "nn_threads": nn_threads,
                          "window_rates": [round(v, 2) for v in per_window]},
@@ -222,10 +222,17 @@ def run_reference_arm(args):
     return 0
 
 
-def bench_config(workload, games, sims, filters, blocks, K):
-    """The `config` object BOTH arms print (identical text, so the driver's same-config check can compare them)."""
+def bench_config(workload, games, sims, filters, blocks, K, world=1, skip_stream="auto"):
+    """The `config` object BOTH arms print — identical, key for key, so that the driver's same-config check can compare them
+    (what differs between runs — games finished, records gathered, gather time — is in `run_info`)."""
+    act_mb = games * K * 90 * filters * 2 * 3 / 1e6
     return {"workload": workload_text(workload, games, sims, filters, blocks), "games_per_gpu": games, "sims_per_move": sims,
-            "leaves_per_round": K, "net": f"{filters}x{blocks}"}
+            "leaves_per_round": K, "net": f"{filters}x{blocks}", "skip_stream": skip_stream,
+            "parallelism": f"dp{world} (games sharded, no data-path collective; finished-game rings all_gathered every step)",
+            "l2": (f"GPU arm: activations {act_mb:.0f} MB per round + tree pools stream through HBM (> 126 MB L2, no flush needed)"
+                   if act_mb > 2 * 126 else
+                   f"GPU arm: activations {act_mb:.0f} MB per round fit the 126 MB L2 and are NOT flushed between steps (secondary "
+                   f"workload; the headline workload c3 streams 1.1 GB per round)")}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -372,16 +379,11 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
         legal = st1["edges_stored"] / max(1, st1["nodes_stored"])
         expand = (st1["nodes_created"] - st0["nodes_created"]) / d_sims
         live = games // 2 if workload == "c5" else games
-        act_mb = games * K * 90 * filters * 2 * 3 / 1e6
         out = {
             "value": sims_total / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
-            "config": dict(bench_config(workload, games, sims, filters, blocks, K), skip_stream=args.skip_stream,
-                           parallelism=f"dp{world} (games sharded, no data-path collective; finished-game rings all_gathered every step)",
-                           l2=(f"activations {act_mb:.0f} MB per round + tree pools stream through HBM (> 126 MB L2, no flush needed)"
-                               if act_mb > 2 * 126 else
-                               f"activations {act_mb:.0f} MB per round fit the 126 MB L2 and are NOT flushed between steps (secondary "
-                               f"workload; the headline workload c3 streams 1.1 GB per round)"),
-                           games_finished=int(games_done), records_gathered=int(gathered), gather_ms_per_step=gather_ms / steps),
+            "config": bench_config(workload, games, sims, filters, blocks, K, world, args.skip_stream),
+            "run_info": {"games_finished": int(games_done), "records_gathered": int(gathered), "gather_ms_per_step": gather_ms / steps,
+                         "search_loop": os.environ.get("CZ_SEARCH_LOOP", "while (one graph launch per search)")},
             "nn_positions_per_sec": (st1["nodes_created"] - st0["nodes_created"]) * world / (ms * 1e-3),
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -447,8 +449,8 @@ def run_ours(args):
         for name, st, wu in (("c2", 12, 4), ("c5", 2, 3)):
             try:
                 m = measure(args, name, st, wu, world, rank, local, dist, want_e2e=False, sample_clocks=False)
-                secondary[name] = {k: m[k] for k in ("value", "ms_per_step", "steps", "warmup", "config", "nn_positions_per_sec", "roofline",
-                                                     "search_stats", "gpu_launches")}
+                secondary[name] = {k: m[k] for k in ("value", "ms_per_step", "steps", "warmup", "config", "run_info", "nn_positions_per_sec",
+                                                     "roofline", "search_stats", "gpu_launches")}
                 secondary[name]["unit"] = "sims/s"
             except Exception as e:        # a secondary workload must never take the headline down with it
                 secondary[name] = {"error": repr(e)}
@@ -460,7 +462,7 @@ def run_ours(args):
         line = {"metric": "mcts_sims_per_sec", "value": main["value"], "unit": "sims/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic (random-init Keras-equivalent weights, games from INIT_STATE)",
-                "config": main["config"], "nn_positions_per_sec": main["nn_positions_per_sec"], "e2e": main["e2e"],
+                "config": main["config"], "run_info": main["run_info"], "nn_positions_per_sec": main["nn_positions_per_sec"], "e2e": main["e2e"],
                 "gpu_launches": main["gpu_launches"], "roofline": main["roofline"], "cpu_baseline": cpu, "clocks": main["clocks"],
                 "search_stats": main["search_stats"]}
         if secondary:
