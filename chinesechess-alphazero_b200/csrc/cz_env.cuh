@@ -119,32 +119,153 @@ struct EmitSink {
   CZ_DM void operator()(int to) { if (pos < MAX_MOVES) list[pos] = mv_make(from, to); ++pos; }
 };
 
-// Ordered pseudo-legal move list of the side to move (static_env.py:256-321).
-// The reference scans squares y-major then x (== ascending sq) and emits each piece's moves in turn.  Here the own
-// pieces are compacted in that order (three ballots over the 90 squares) and piece k goes to lane k % 32, so one pass
-// of count / scan / emit serves up to 32 pieces (a legal position has at most 16) instead of one pass per 32 SQUARES
-// with mostly idle lanes.  Returns the count (<= MAX_MOVES).
-CZ_D int movegen(const uint8_t* b, move_t* list) {
-  unsigned own[3];
+// ------------------------------------------------------------------ occupancy bitboards (movegen)
+// The board as bit sets built with six ballots: occ / own over sq = y*9 + x (ranks are 9 consecutive bits) and the same two
+// sets transposed, over sqT = x*10 + y (files are 10 consecutive bits).  A sliding piece then finds its blockers with two
+// mask operations per direction instead of a dependent shared-memory load per square, and every piece describes its moves
+// ONCE (PieceMoves); counting and emitting read the description (gen_piece above walked the board twice per piece).
+struct BoardBits { unsigned occ[3], own[3], occT[3], ownT[3]; };
+CZ_D unsigned bits96(const unsigned* w, int pos, int n) {       // n <= 16 bits starting at bit `pos` of a 96-bit set
+  const int i = pos >> 5, sh = pos & 31;
+  const unsigned lo = i == 0 ? w[0] : (i == 1 ? w[1] : w[2]);
+  const unsigned hi = i == 0 ? w[1] : (i == 1 ? w[2] : 0u);
+  const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32);
+  return (unsigned)(v >> sh) & ((1u << n) - 1u);
+}
+CZ_D bool bit96(const unsigned* w, int pos) { return bits96(w, pos, 1) != 0u; }
+CZ_D void board_bits(const uint8_t* b, BoardBits* bb) {
   for (int j = 0; j < 3; ++j) {
     const int sq = j * 32 + czs::lane();
-    own[j] = czs::ballot(sq < NSQ && pc_own(b[sq]));
+    const uint8_t c = sq < NSQ ? b[sq] : (uint8_t)0;
+    bb->occ[j] = czs::ballot(c != 0);
+    bb->own[j] = czs::ballot(pc_own(c));
+    const uint8_t t = sq < NSQ ? b[(sq % 10) * 9 + sq / 10] : (uint8_t)0;      // sqT = x*10 + y  ->  square y*9 + x
+    bb->occT[j] = czs::ballot(t != 0);
+    bb->ownT[j] = czs::ballot(pc_own(t));
   }
-  const int n0 = czs::popc(own[0]), n1 = czs::popc(own[1]), n2 = czs::popc(own[2]);
+}
+
+// The pseudo-legal moves of one own piece, described once: sliders by their blocker coordinates and capture squares, step
+// pieces by a validity mask over their direction table (+ the king's flying-general square).
+struct PieceMoves {
+  int kind;                 // 0 none, 1 slider (rook / cannon), 2 step piece
+  int x, y;
+  int l, r, d, u;           // slider: nearest occupied column left / right (-1 / 9), row below / above (-1 / 10)
+  int cap[4];               // slider: capture square to the left, right, below, above, or -1
+  uint64_t dirs; int nd;    // step piece: direction table (gen_piece's packing) ...
+  unsigned valid;           // ... and which entries are playable
+  int fly;                  // king: flying-general capture square or -1
+  int count;
+};
+CZ_D int lowest_above(unsigned mask, int i, int none) { const unsigned m = mask >> (i + 1); return m ? i + czs::ffs(m) : none; }
+CZ_D int highest_below(unsigned mask, int i) { return czs::fls(mask & ((1u << i) - 1u)) - 1; }      // -1 if none
+
+CZ_D void piece_moves(const uint8_t* b, const BoardBits& bb, int sq, uint8_t c, PieceMoves* pm) {
+  pm->kind = 0; pm->count = 0; pm->fly = -1;
+  if (sq < 0) return;
+  const int x = sq % 9, y = sq / 9;
+  pm->x = x; pm->y = y;
+  if (c == PC_R || c == PC_C) {
+    const unsigned R = bits96(bb.occ, y * 9, 9), F = bits96(bb.occT, x * 10, 10);
+    const unsigned Ro = bits96(bb.own, y * 9, 9), Fo = bits96(bb.ownT, x * 10, 10);
+    const int l = highest_below(R, x), r = lowest_above(R, x, 9), d = highest_below(F, y), u = lowest_above(F, y, 10);
+    pm->kind = 1; pm->l = l; pm->r = r; pm->d = d; pm->u = u;
+    int tl = l, tr = r, td = d, tu = u;                                       // rook: the blocker itself
+    if (c == PC_C) {                                                          // cannon: the next piece behind the screen
+      tl = l > -1 ? highest_below(R, l) : -1;
+      tr = r < 9 ? lowest_above(R, r, 9) : 9;
+      td = d > -1 ? highest_below(F, d) : -1;
+      tu = u < 10 ? lowest_above(F, u, 10) : 10;
+    }
+    pm->cap[0] = (tl > -1 && !((Ro >> tl) & 1u)) ? y * 9 + tl : -1;
+    pm->cap[1] = (tr < 9 && !((Ro >> tr) & 1u)) ? y * 9 + tr : -1;
+    pm->cap[2] = (td > -1 && !((Fo >> td) & 1u)) ? td * 9 + x : -1;
+    pm->cap[3] = (tu < 10 && !((Fo >> tu) & 1u)) ? tu * 9 + x : -1;
+    pm->count = (x - l - 1) + (r - x - 1) + (y - d - 1) + (u - y - 1) + (pm->cap[0] >= 0) + (pm->cap[1] >= 0) + (pm->cap[2] >= 0) + (pm->cap[3] >= 0);
+    return;
+  }
+  int nd;
+  uint64_t dirs;
+#define CZ_DIR(dx, dy) ((uint64_t)(((dx) + 2) | (((dy) + 2) << 3)))
+  switch (c) {
+    case PC_K: nd = 4; dirs = CZ_DIR(0, -1) | CZ_DIR(1, 0) << 6 | CZ_DIR(0, 1) << 12 | CZ_DIR(-1, 0) << 18; break;
+    case PC_A: nd = 4; dirs = CZ_DIR(-1, -1) | CZ_DIR(1, -1) << 6 | CZ_DIR(-1, 1) << 12 | CZ_DIR(1, 1) << 18; break;
+    case PC_E: nd = 4; dirs = CZ_DIR(-2, -2) | CZ_DIR(2, -2) << 6 | CZ_DIR(2, 2) << 12 | CZ_DIR(-2, 2) << 18; break;
+    case PC_N: nd = 8; dirs = CZ_DIR(-1, -2) | CZ_DIR(1, -2) << 6 | CZ_DIR(2, -1) << 12 | CZ_DIR(2, 1) << 18 |
+                             CZ_DIR(1, 2) << 24 | CZ_DIR(-1, 2) << 30 | CZ_DIR(-2, 1) << 36 | CZ_DIR(-2, -1) << 42; break;
+    case PC_P: nd = 3; dirs = CZ_DIR(0, 1) | CZ_DIR(-1, 0) << 6 | CZ_DIR(1, 0) << 12; break;
+    default: return;
+  }
+#undef CZ_DIR
+  pm->kind = 2; pm->dirs = dirs; pm->nd = nd;
+  if (c == PC_K) {                                            // static_env.py:283-286: the first piece up the file is their king
+    const unsigned F = bits96(bb.occT, x * 10, 10);
+    const int u = lowest_above(F, y, 10);
+    if (u < 10 && b[u * 9 + x] == (PC_K | PC_OPP)) pm->fly = u * 9 + x;
+  }
+  unsigned valid = 0;
+  for (int i = 0; i < nd; ++i) {
+    const int dd = (int)((dirs >> (6 * i)) & 63);
+    const int dx = (dd & 7) - 2, dy = (dd >> 3) - 2;
+    const int x_ = x + dx, y_ = y + dy;
+    if (x_ < 0 || x_ > 8 || y_ < 0 || y_ > 9) continue;
+    if (bit96(bb.own, y_ * 9 + x_)) continue;                // can_move
+    if (c == PC_P) {
+      if (y < 5 && x_ != x) continue;                        // no sideways step before the river
+    } else if (c == PC_N || c == PC_E) {
+      if (bit96(bb.occ, (y + dy / 2) * 9 + (x + dx / 2))) continue;   // leg / eye blocked
+      if (c == PC_E && y_ > 4) continue;
+    } else {
+      if (x_ < 3 || x_ > 5) continue;
+      if (y_ > 2) continue;
+    }
+    valid |= 1u << i;
+  }
+  pm->valid = valid;
+  pm->count = czs::popc(valid) * (pm->fly >= 0 ? 2 : 1);
+}
+// writes the described moves, in the reference order, to list[pos ...]; entries past MAX_MOVES are dropped
+CZ_D void piece_emit(const PieceMoves& pm, int from, move_t* list, int pos) {
+  EmitSink out{list, pos, from};
+  if (pm.kind == 1) {
+    const int x = pm.x, y = pm.y;
+    for (int x_ = pm.l + 1; x_ < x; ++x_) out(y * 9 + x_);
+    for (int x_ = x + 1; x_ < pm.r; ++x_) out(y * 9 + x_);
+    for (int y_ = pm.d + 1; y_ < y; ++y_) out(y_ * 9 + x);
+    for (int y_ = y + 1; y_ < pm.u; ++y_) out(y_ * 9 + x);
+    for (int k = 0; k < 4; ++k) if (pm.cap[k] >= 0) out(pm.cap[k]);
+  } else if (pm.kind == 2) {
+    for (int i = 0; i < pm.nd; ++i) {
+      if (!((pm.valid >> i) & 1u)) continue;
+      const int dd = (int)((pm.dirs >> (6 * i)) & 63);
+      out((pm.y + (dd >> 3) - 2) * 9 + pm.x + (dd & 7) - 2);
+      if (pm.fly >= 0) out(pm.fly);
+    }
+  }
+}
+
+// Ordered pseudo-legal move list of the side to move (static_env.py:256-321).
+// The reference scans squares y-major then x (== ascending sq) and emits each piece's moves in turn.  Here the own
+// pieces are compacted in that order (the `own` ballots), piece k goes to lane k % 32, describes its moves once from the
+// bitboards, and one warp scan of the counts places every piece's block in the list.  Returns the count (<= MAX_MOVES).
+CZ_D int movegen(const uint8_t* b, move_t* list) {
+  BoardBits bb;
+  board_bits(b, &bb);
+  const int n0 = czs::popc(bb.own[0]), n1 = czs::popc(bb.own[1]), n2 = czs::popc(bb.own[2]);
   const int pieces = n0 + n1 + n2;
   int base = 0;
   for (int first = 0; first < pieces; first += 32) {
     const int k = first + czs::lane();                       // this lane's piece, in scan order
     int sq = -1;
-    if (k < n0) sq = czs::nth_set_bit(own[0], k);
-    else if (k < n0 + n1) sq = 32 + czs::nth_set_bit(own[1], k - n0);
-    else if (k < pieces) sq = 64 + czs::nth_set_bit(own[2], k - n0 - n1);
+    if (k < n0) sq = czs::nth_set_bit(bb.own[0], k);
+    else if (k < n0 + n1) sq = 32 + czs::nth_set_bit(bb.own[1], k - n0);
+    else if (k < pieces) sq = 64 + czs::nth_set_bit(bb.own[2], k - n0 - n1);
     const uint8_t c = sq >= 0 ? b[sq] : (uint8_t)0;
-    int cnt = 0;
-    if (sq >= 0) { CountSink cs{0}; gen_piece(b, sq, c, cs); cnt = cs.n; }
+    PieceMoves pm;
+    piece_moves(b, bb, sq, c, &pm);
     int tot;
-    const int off = czs::warp_excl_scan(cnt, &tot);
-    if (cnt) { EmitSink es{list, base + off, sq}; gen_piece(b, sq, c, es); }
+    const int off = czs::warp_excl_scan(pm.count, &tot);
+    if (pm.count) piece_emit(pm, sq, list, base + off);
     base += tot;
   }
   czs::syncwarp();
