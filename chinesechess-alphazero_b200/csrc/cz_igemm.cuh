@@ -205,7 +205,7 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             if (a.row_stats) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (n0 + j < a.n_valid) row_sum += expf(f[j] - row_max);
+                if (n0 + j < a.n_valid) row_sum += __expf(f[j] - row_max);   // SFU exp: 256 per thread sit on this tile's critical path
             }
             if (n0 + 32 <= a.n_valid) {
 #pragma unroll
