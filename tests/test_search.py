@@ -161,3 +161,56 @@ def test_emul_apply_legal_equals_apply_policy(emul_lib):
     a, pos_a, waves_a = run(False)
     b, pos_b, waves_b = run(True)
     assert a == b and pos_a == pos_b > 100 and waves_a == waves_b > 10      # N, W (f64), P (f32): identical; device-side counters
+
+
+def check_k10_statistics_vs_real_threaded_player(lib, device):
+    """K = 10 against the REAL reference player (a racy thread pool, only statistically comparable): root visit distributions
+    recorded from 16 independent real searches per position (tests/golden/mcts_k10_threaded.json.gz, oracle/gen_golden_k10.py).
+    The engine's distributions over 16 games with independent Philox noise streams must be as close to the real ones as the real
+    ones are to each other (total-variation distance), and the seed-averaged distributions must agree."""
+    import gzip
+    import json
+    import os
+    import numpy as np
+    from cczero_b200.engine import Engine
+    from tests.search_checks import eval_planes
+    with gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mcts_k10_threaded.json.gz"), "rt") as f:
+        gold = json.load(f)
+    rows = gold["rows"]
+    per = len(rows[0]["visits"])
+    eng = Engine(lib, device, n_games=per * len(rows), sims_per_move=gold["sims"], leaves_per_round=gold["search_threads"], noise_mode=1,
+                 c_puct=gold["c_puct"], noise_eps=gold["noise_eps"], dirichlet_alpha=gold["dirichlet_alpha"], seed=77, max_nodes_per_game=1024)
+    eng.reset([r["state"] for r in rows for _ in range(per)])
+    eng.search_external(eval_planes, None)
+
+    def tv(a, b):
+        return 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+    for k, r in enumerate(rows):
+        real = [np.asarray(v, float) for v in r["visits"]]
+        mine = []
+        for j in range(per):
+            root = eng.root(k * per + j)
+            assert root["moves"] == r["moves"]
+            mine.append(np.asarray(root["n"], float))
+        assert all(x.sum() == gold["sims"] - 1 for x in real + mine)
+        spread_real = np.mean([tv(real[i], real[j]) for i in range(per) for j in range(i)])
+        cross = np.mean([tv(a, b) for a in real for b in mine])
+        print(f"K=10 vs real threaded player, position {k}: real-real TV {spread_real:.3f}, real-engine TV {cross:.3f}, "
+              f"averaged distributions {tv(sum(real), sum(mine)):.3f}")
+        assert cross <= 1.5 * spread_real + 0.02, (k, cross, spread_real)
+        # Seed-averaged distributions: 0.02-0.03 at quiet positions; at the sharp middlegame position the canonical schedule
+        # (network replies delivered when the queue is dry: every simulation of a round sees its predecessors' virtual losses)
+        # spreads a little more than the real thread pool, whose replies arrive mid-round: 23 % vs 26 % of the visits on the top
+        # move, TV 0.08.  Both are legal interleavings of the same code; the bound is the real player's own spread.
+        assert tv(sum(real), sum(mine)) < spread_real + 0.01, k
+    assert int(eng.counters()[6]) == 0
+    eng.close()
+
+
+def test_emul_k10_statistics_vs_real_threaded_player(emul_lib):
+    check_k10_statistics_vs_real_threaded_player(emul_lib, "cpu")
+
+
+@pytest.mark.gpu
+def test_cuda_k10_statistics_vs_real_threaded_player(cuda_lib):
+    check_k10_statistics_vs_real_threaded_player(cuda_lib, "cuda")
