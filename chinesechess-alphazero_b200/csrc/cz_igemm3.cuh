@@ -41,11 +41,18 @@ struct Args3 {
 };
 __host__ __device__ constexpr int epi3_warp_bytes(int fbytes, int nf) { return nf * fbytes + kNH3 * kHBytes3; }
 
-template <int N_TILE>
+// MT = M-tiles per CTA that share one weight stage (cta_group::2: the pair computes 2*MT tiles per pass).  MT = 2 needs
+// 2 (double buffer) x 2 x N_TILE TMEM columns <= 512, i.e. N_TILE <= 128 — exactly the shapes whose weight tile is too narrow
+// to amortise its fill: per k-block the pipe then moves 2 x 16 KB of pixels + 8 KB of weights for TWICE the MMA work
+// (40 KB per 128x128x64 instead of 48 KB), the weight TMA count halves, and one stage feeds 512 instead of 256 cycles of MMA,
+// so the ring covers a TMA round trip with 5 stages where the single-tile form starved with 8.
+template <int N_TILE, int MT = 1>
 struct Cfg3 {
   static constexpr int kBHalfBytes = (N_TILE / 2) * 128;
-  static constexpr int kStageBytes = kAStageBytes + kBHalfBytes;
-  static constexpr int kTmemCols = Cfg<N_TILE>::kTmemCols;
+  static constexpr int kStageBytes = MT * kAStageBytes + kBHalfBytes;
+  static constexpr int kTmemCols = (2 * MT * N_TILE <= 32) ? 32 : (2 * MT * N_TILE <= 64) ? 64 : (2 * MT * N_TILE <= 128) ? 128
+                                   : (2 * MT * N_TILE <= 256) ? 256 : 512;
+  static_assert(2 * MT * N_TILE <= 512, "accumulators (double-buffered) must fit TMEM");
   static constexpr int smem_bytes(int stages, int fbytes, int nf) { return stages * kStageBytes + kEpiWarps2 * epi3_warp_bytes(fbytes, nf) + 512 + 1024; }
   static int max_stages(int fbytes, int nf) {
     int s = (kSmemLimit3 - 512 - 1024 - kEpiWarps2 * epi3_warp_bytes(fbytes, nf)) / kStageBytes;
@@ -76,11 +83,11 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int N_TILE>
+template <int N_TILE, int MT = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut16,
          const __grid_constant__ CUtensorMap tmSkip, const __grid_constant__ CUtensorMap tmOut32, const Args3 p) {
-  using C = Cfg3<N_TILE>;
+  using C = Cfg3<N_TILE, MT>;
   const Args& a = p.a;
   const int n_stages = p.stages;
   extern __shared__ uint8_t smem_raw[];
@@ -123,7 +130,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   const int n_kb = a.n_taps * a.k_chunks;
   const int rows = args_rows(a);
   const int m_tiles = a.n_dev ? (rows + kTileM - 1) / kTileM : a.m_tiles;
-  const int pairs = (m_tiles + 1) / 2;
+  const int pairs = (m_tiles + 2 * MT - 1) / (2 * MT);     // one pass of a CTA pair = 2 * MT consecutive M-tiles
   const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
 
   if (warp == 0 || (warp == 3 && p.split_producer)) {
@@ -134,16 +141,21 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const bool do_a = warp == 0, do_b = warp == 3 || !p.split_producer;
       uint32_t s = 0, ph = 0;
       for (int pair = cluster_id; pair < pairs; pair += n_clusters) {
-        const int m_tile = 2 * pair + (int)rank;
-        const int pix0 = m_tile * kTileM, img0 = pix0 / 90, row0 = (pix0 % 90) / 9, col0 = pix0 % 9;
+        const int m_tile = MT * (2 * pair + (int)rank);     // this CTA's first tile of the pass
         for (int tap = 0; tap < a.n_taps; ++tap) {
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
           for (int kc = 0; kc < a.k_chunks; ++kc) {
             umma::mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sA = smem + s * C::kStageBytes;
-            uint8_t* sB = sA + kAStageBytes;
-            if (leader && do_a) umma::mbar_expect_tx(&full[s], 2u * (a.a_bytes + (uint32_t)C::kBHalfBytes));
-            if (do_a) umma::tma2_load_im2col_4d(sA, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1));
+            uint8_t* sB = sA + MT * kAStageBytes;
+            if (leader && do_a) umma::mbar_expect_tx(&full[s], 2u * ((uint32_t)MT * a.a_bytes + (uint32_t)C::kBHalfBytes));
+            if (do_a) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const int pix0 = (m_tile + mt) * kTileM, img0 = pix0 / 90, row0 = (pix0 % 90) / 9, col0 = pix0 % 9;
+                umma::tma2_load_im2col_4d(sA + mt * kAStageBytes, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1));
+              }
+            }
             if (do_b) umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + (int)rank * (N_TILE / 2));
             if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1; }
           }
@@ -159,16 +171,19 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         umma::mbar_wait(&tempty[acc], aph ^ 1);
         umma::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        const uint32_t d_tmem = tmem_base + acc * (MT * N_TILE);
         for (int kb = 0; kb < n_kb; ++kb) {
           umma::mbar_wait(&full[s], ph);
           umma::tc_fence_after();
           const uint32_t sA = umma::smem_u32(smem + s * C::kStageBytes);
-          const uint64_t da = umma::smem_desc_sw128(sA);
-          const uint64_t db = umma::smem_desc_sw128(sA + kAStageBytes);
+          const uint64_t db = umma::smem_desc_sw128(sA + MT * kAStageBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma::mma2_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int mt = 0; mt < MT; ++mt) {                 // the same weight stage against MT pixel tiles / accumulators
+            const uint64_t da = umma::smem_desc_sw128(sA + mt * kAStageBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma::mma2_f16_ss(d_tmem + mt * N_TILE, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
           umma::mma2_commit_multicast(&empty[s]);
           if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1; }
         }
@@ -198,8 +213,8 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     // next tile's skip block -> L2, a whole tile ahead (one warp): the per-chunk TMA loads below then hit L2
     auto prefetch_skip = [&](int pr) {
       if (ew != 0 || pr >= pairs || !has_skip) return;
-      const long long row0 = (long long)(2 * pr + (int)rank) * kTileM;
-      const long long nrow = rows - row0 < kTileM ? rows - row0 : kTileM;
+      const long long row0 = (long long)MT * (2 * pr + (int)rank) * kTileM;
+      const long long nrow = rows - row0 < MT * kTileM ? rows - row0 : MT * kTileM;
       if (nrow <= 0) return;
       const size_t esz = skip32 ? 4 : 2;
       const char* base = (skip32 ? reinterpret_cast<const char*>(a.residual32) : reinterpret_cast<const char*>(a.residual)) + (size_t)row0 * a.ldo * esz;
@@ -210,11 +225,11 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     // global chunk counter of this warp: chunk index g -> (tile = g / kChunks, chunk in tile = g % kChunks); F slot g % nf
     int my_tiles = 0;
     for (int pr = cluster_id; pr < pairs; pr += n_clusters) ++my_tiles;
-    const uint32_t total_chunks = (uint32_t)my_tiles * kChunks;
+    const uint32_t total_chunks = (uint32_t)my_tiles * (MT * kChunks);
     auto request_skip = [&](uint32_t g) {                     // lane 0 only
       if (!has_skip || g >= total_chunks) return;
-      const int t = (int)(g / kChunks), ch = (int)(g % kChunks);
-      const int row = (2 * (cluster_id + t * n_clusters) + (int)rank) * kTileM + q * 32;
+      const int t = (int)(g / (MT * kChunks)), rem = (int)(g % (MT * kChunks)), mt = rem / kChunks, ch = rem % kChunks;
+      const int row = (MT * (2 * (cluster_id + t * n_clusters) + (int)rank) + mt) * kTileM + q * 32;
       const uint32_t slot = g % (uint32_t)nf;
       umma::mbar_expect_tx(&sbar[slot], skip_bytes);
       umma::tma_load_2d(F + slot * fb, &tmSkip, &sbar[slot], cbeg + ch * kChunkCols3, row);
@@ -224,13 +239,15 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (lane == 0)
       for (int k = 0; k < nf - 2; ++k) request_skip((uint32_t)k);   // prime the ring: chunks 0 .. nf-3
     for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
-      const int m_tile = 2 * pair + (int)rank;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      const int rbase = m_tile * kTileM + q * 32;             // first global pixel row of this warp
       prefetch_skip(pair + n_clusters);
       umma::mbar_wait(&tfull[acc], aph);
       umma::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + cbeg;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int m_tile = MT * (2 * pair + (int)rank) + mt;
+      const int rbase = m_tile * kTileM + q * 32;             // first global pixel row of this warp
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * N_TILE + cbeg;
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch, ++g) {
         const uint32_t slot = g % (uint32_t)nf, sph = (g / (uint32_t)nf) & 1, hb = g & 1;
@@ -291,6 +308,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           tma_store_2d(&tmOut16, H + hb * kHBytes3, c0, rbase);
           bulk_commit();
         }
+      }
       }
       umma::tc_fence_before();
       umma::mbar_arrive_cluster(tempty_remote[acc]);

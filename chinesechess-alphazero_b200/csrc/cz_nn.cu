@@ -194,13 +194,13 @@ static bool use_tma_epilogue_for(int c, bool fp32_stream) {
   if (epilogue_choice() == 3) return true;
   return !(c == 256 && fp32_stream);
 }
-template <int N_TILE>
+template <int N_TILE, int MT>
 static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
                            const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st) {
-  using C = igemm::Cfg3<N_TILE>;
+  using C = igemm::Cfg3<N_TILE, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    CZ_CUDA(cudaFuncSetAttribute(igemm::k_igemm3<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, igemm::kSmemLimit3));
+    CZ_CUDA(cudaFuncSetAttribute(igemm::k_igemm3<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, igemm::kSmemLimit3));
     attr_set = true;
   }
   igemm::Args3 p;
@@ -212,20 +212,25 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   p.stages = C::max_stages(p.fbytes, p.nf);
   { static int cap = -1; if (cap < 0) { const char* e = getenv("CZ_STAGES"); cap = e ? atoi(e) : 0; } if (cap > 1 && cap < p.stages) p.stages = cap; }
   if (p.stages < 2) return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: no room for the operand ring");
-  const int pairs = ((a.n_dev ? (a.rows + igemm::kTileM - 1) / igemm::kTileM : a.m_tiles) + 1) / 2;
+  const int pairs = ((a.n_dev ? (a.rows + igemm::kTileM - 1) / igemm::kTileM : a.m_tiles) + 2 * MT - 1) / (2 * MT);
   if (pairs <= 0) return 0;
   const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
-  igemm::k_igemm3<N_TILE><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
+  igemm::k_igemm3<N_TILE, MT><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
   CZ_CUDA(cudaGetLastError());
   return 0;
 }
 static int launch_igemm3(int n_tile, const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
                          const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st) {
+  // two M-tiles per CTA against each weight stage wherever the accumulators fit TMEM (C <= 128); CZ_MT=1 forces the single-tile form
+  static int mt2 = -1;
+  if (mt2 < 0) { const char* e = getenv("CZ_MT"); mt2 = (e && e[0] == '1') ? 0 : 1; }
   switch (n_tile) {
-    case 64: return launch_igemm3_t<64>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
-    case 128: return launch_igemm3_t<128>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
-    case 192: return launch_igemm3_t<192>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
-    case 256: return launch_igemm3_t<256>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 64: return mt2 ? launch_igemm3_t<64, 2>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st)
+                        : launch_igemm3_t<64, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 128: return mt2 ? launch_igemm3_t<128, 2>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st)
+                         : launch_igemm3_t<128, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 192: return launch_igemm3_t<192, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 256: return launch_igemm3_t<256, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
   }
   return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: unsupported N tile %d", n_tile);
 }

@@ -13,8 +13,14 @@ VARIANTS = {
     "auto (igemm3; igemm2 for C=256 fp32 skip)": {},
     "igemm3 everywhere, nf=3": {"CZ_EPI": "3", "CZ_NF": "3"},
     "igemm3 everywhere, nf=4": {"CZ_EPI": "3", "CZ_NF": "4"},
+    "auto, one M-tile per CTA at C<=128": {"CZ_MT": "1"},
 }
 SHAPES = [(256, 20, 8192, 3.0), (128, 7, 2048, 1.5), (192, 10, 4096, 1.5)]
+if os.environ.get("AB_ONLY"):                      # e.g. AB_ONLY="auto,one M-tile" AB_SHAPES=small
+    keep = [k.strip() for k in os.environ["AB_ONLY"].split(",")]
+    VARIANTS = {k: v for k, v in VARIANTS.items() if any(k.startswith(p) for p in keep)}
+if os.environ.get("AB_SHAPES") == "small":
+    SHAPES = [(128, 7, 2048, 1.5), (128, 7, 8192, 1.5), (64, 4, 2048, 1.0)]
 
 CHILD = r'''
 import sys, time, json, torch
