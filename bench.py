@@ -33,8 +33,12 @@ WORKLOADS = {
 }
 CONFIG_INDEX = dict(c2=1, c3=2, c5=4)
 
-# DRAM bytes per launch of the dominant kernel measured once with ncu --set full (None where no capture exists); see profiles/
-NCU_TRAFFIC = {("c3", 1024, 8): 7.15e8}
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel from `ncu --set full` (None where no
+# capture exists).  c3, 8192-board launches (profiles/r02i_conv_256_ncu_raw_subset.csv): conv1 (k_igemm3, fp16 in / out)
+# 0.332 + 0.290 GB, conv2 (k_igemm2, + fp32 skip in / fp32 copy out) 1.399 + 0.943 GB; mean of the two = one launch of the
+# tower on average.  Algorithmic bytes: 0.754 GB and 2.264 GB (conv1 reads part of its input from L2: 126 MB of the 377 MB
+# the previous launch wrote).  c2, 2048-board launches (r02i_conv_128_*): 0.057 / 0.118 GB (activations are L2-resident).
+NCU_TRAFFIC = {("c3", 1024, 8): 1.482e9, ("c2", 256, 8): 0.0875e9}
 
 
 def net_flops(filters, blocks):

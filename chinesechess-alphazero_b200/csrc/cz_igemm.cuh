@@ -197,8 +197,9 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (a.bias) {
+            const float4* bp4 = reinterpret_cast<const float4*>(a.bias + n0);     // bias arrays are padded to the N tile
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __ldg(a.bias + n0 + j);
+            for (int j = 0; j < 32; j += 4) { const float4 b4 = __ldg(bp4 + j / 4); f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w; }
           }
           if (a.out_f32) {
             float* o = reinterpret_cast<float*>(a.out) + grow * a.ldo + n0;
@@ -207,7 +208,14 @@ k_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
               for (int j = 0; j < 32; ++j)
                 if (n0 + j < a.n_valid) row_sum += __expf(f[j] - row_max);   // SFU exp: 256 per thread sit on this tile's critical path
             }
-            if (n0 + 32 <= a.n_valid) {
+            if (n0 + 32 <= a.n_valid && (a.ldo & 3) == 0) {   // 16-byte stores: the row pitch and n0 are multiples of 4 floats
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 x = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                if (a.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                *reinterpret_cast<float4*>(o + j) = x;
+              }
+            } else if (n0 + 32 <= a.n_valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) o[j] = a.relu ? fmaxf(f[j], 0.f) : f[j];
             } else {

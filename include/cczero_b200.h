@@ -318,7 +318,8 @@ int cz_igemm_conv3x3_dense(const void* act_in_dev, const void* w_dev, const floa
 /* `count` draws of the on-device root-noise sampler (noise_mode 1): the first component of
  * Dirichlet(alpha * 1_n_moves), i.e. what np.random.dirichlet(alpha*ones(n))[0] (player.py:304) is distributed as. */
 int cz_noise_sample(cz_engine* e, int game, int n_moves, int count, double* out_dev);
-/* out[m][n] = sum_k a[m][k] * w[n][k] + bias[n]; a fp16 [m][k], w fp16 [n_pad][k], out f32 [m][ldo]. */
+/* out[m][n] = sum_k a[m][k] * w[n][k] + bias[n]; a fp16 [m][k], w fp16 [n_pad][k], bias f32 [n_pad] (padded like w),
+ * out f32 [m][ldo], 16-byte aligned with ldo a multiple of 4. */
 int cz_igemm_dense(const void* a_dev, const void* w_dev, const float* bias_dev, float* out_dev, int m, int n_valid,
                    int n_pad, int k, int n_tile, int ldo, void* stream);
 
