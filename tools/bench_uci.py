@@ -1,7 +1,8 @@
 """Single-game latency path: one `CChessPlayer(uci=True)` on the built-in network answering `go depth 8` (= 800 simulations,
 uci.py:293-327 -> player.py:160-161), the way the reference's UCI front end drives its player.  Prints the wall time of the
 search, simulations/s and the `nps` figure computed with the REFERENCE'S formula, nps = int(depth * 100 / duration) * 1000
-(agent/player.py:446-447), for the device-driven loop and — CZ_SEARCH_LOOP=host — the round-1 host-driven loop.
+(agent/player.py:446-447), for the device-driven loop in both forms (CZ_SEARCH_LOOP=while, the default: one graph launch per
+slice of the search; =graph: three sub-graphs per iteration and a polled flag) and the round-1 host-driven loop (=host).
 
     python tools/bench_uci.py [filters blocks] [depth] [search_threads]
 Weights: the reference's trained 192x10 network (tests/golden/model_best_192x10.npz) by default."""
@@ -61,7 +62,7 @@ def main():
         weights = {key: torch.as_tensor(v) for key, v in om.init_weights(filters, blocks, 256, seed=0).items()}
         src = "random-init weights"
     res = {"net": f"{filters}x{blocks}", "weights": src, "go": f"depth {depth} ({depth * 100} simulations), search_threads {k}"}
-    for loop in ("graph", "host"):
+    for loop in ("while", "graph", "host"):      # one WHILE-graph launch per slice (default) | three sub-graphs per iteration | round-1 host loop
         runs, info = run(loop, filters, blocks, depth, k, weights)
         res[loop] = {"best": min(runs[1:], key=lambda r: r["seconds"]), "runs": runs, "last_info_line": info}
     print(json.dumps(res))
