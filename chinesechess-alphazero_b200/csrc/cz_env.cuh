@@ -248,7 +248,7 @@ CZ_D void piece_emit(const PieceMoves& pm, int from, move_t* list, int pos) {
 // The reference scans squares y-major then x (== ascending sq) and emits each piece's moves in turn.  Here the own
 // pieces are compacted in that order (the `own` ballots), piece k goes to lane k % 32, describes its moves once from the
 // bitboards, and one warp scan of the counts places every piece's block in the list.  Returns the count (<= MAX_MOVES).
-CZ_D int movegen(const uint8_t* b, move_t* list) {
+CZ_DN int movegen(const uint8_t* b, move_t* list) {
   BoardBits bb;
   board_bits(b, &bb);
   const int n0 = czs::popc(bb.own[0]), n1 = czs::popc(bb.own[1]), n2 = czs::popc(bb.own[2]);
@@ -415,7 +415,7 @@ struct EnvScratch {             // per-warp scratch in shared memory
 };
 
 // be_catched (static_env.py:456-469): is the piece standing on mv_from(m) attacked right now.
-CZ_D bool be_catched(const uint8_t* b, move_t m, EnvScratch* sc) {
+CZ_DN bool be_catched(const uint8_t* b, move_t m, EnvScratch* sc) {
   flip_only(b, sc->b2);
   const int n = movegen(sc->b2, sc->l2);
   return first_move_to(sc->l2, n, 89 - mv_from(m)) >= 0;
@@ -423,7 +423,7 @@ CZ_D bool be_catched(const uint8_t* b, move_t m, EnvScratch* sc) {
 
 // get_catch_list (static_env.py:423-454): set of (piece, from, target, to) the mover threatens
 // to capture for free.  Keys are written to `set` (deduplicated); returns the set size.
-CZ_D int catch_list(const uint8_t* b, const move_t* moves, int n, uint32_t* set, EnvScratch* sc) {
+CZ_DN int catch_list(const uint8_t* b, const move_t* moves, int n, uint32_t* set, EnvScratch* sc) {
   int cnt = 0;
   for (int i = 0; i < n; ++i) {
     const move_t m = moves[i];
@@ -449,7 +449,7 @@ CZ_D int catch_list(const uint8_t* b, const move_t* moves, int n, uint32_t* set,
 
 // will_check_or_catch (static_env.py:390-421): does playing `m` give check or create a new
 // unanswerable capture threat.
-CZ_D bool will_check_or_catch(const uint8_t* b, move_t m, EnvScratch* sc) {
+CZ_DN bool will_check_or_catch(const uint8_t* b, move_t m, EnvScratch* sc) {
   step_flip(b, m, sc->b0);                                   // state after the move (their view)
   const int their_k = find_piece_last(sc->b0, PC_K);
   flip_only(sc->b0, sc->b1);                                 // black_state: mover to move again

@@ -17,6 +17,7 @@
 #include <math.h>
 #include <string.h>
 #define CZ_D static inline
+#define CZ_DN static
 #define CZ_DM inline
 #define CZ_HD static inline
 #define CZ_KERNEL(name) void name
@@ -69,6 +70,9 @@ template <class T> CZ_D T ldg(const T* p) { return *p; }
 // ---------------------------------------------------------------- device (nvcc)
 #include <cuda_runtime.h>
 #define CZ_D __device__ __forceinline__
+// Big, multiply-called rules functions are real calls on the device: inlined at every site the search kernel grew to 33 k SASS
+// instructions (527 KB), far beyond the instruction cache (ncu: 12 % of its issue slots waited for instruction fetch).
+#define CZ_DN static __device__ __noinline__
 #define CZ_DM __device__ __forceinline__
 #define CZ_HD __host__ __device__ __forceinline__
 #define CZ_KERNEL(name) __global__ void name
