@@ -226,6 +226,17 @@ def run_reference_arm(args):
     return 0
 
 
+def conv_kernel_names(filters):
+    """The residual-conv kernels cz_nn.cu's launch selection runs at this width (use_tma_epilogue_for): all-TMA-epilogue pair kernel,
+    two M-tiles per CTA at C <= 128; the fp32-skip conv2 of the 256-wide tower keeps the round-1 pair kernel."""
+    if filters <= 128:
+        return f"igemm::k_igemm3<{filters}, 2> (3x3 residual conv, tcgen05 cta_group::2, two M-tiles per CTA)"
+    if filters >= 256:
+        return (f"igemm::k_igemm3<{filters}, 1> (conv1) + igemm::k_igemm2<{filters}> (conv2, fp32 skip stream): 3x3 residual conv, "
+                "tcgen05 cta_group::2")
+    return f"igemm::k_igemm3<{filters}, 1> (3x3 residual conv, tcgen05 cta_group::2)"
+
+
 def bench_config(workload, games, sims, filters, blocks, K, world=1, skip_stream="auto"):
     """The `config` object BOTH arms print — identical, key for key, so that the driver's same-config check can compare them
     (what differs between runs — games finished, records gathered, gather time — is in `run_info`)."""
@@ -392,7 +403,7 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC.get((workload, games, K)),
-                         "kernel": f"igemm::k_igemm2<{filters}> (3x3 residual conv, tcgen05 cta_group::2)",
+                         "kernel": conv_kernel_names(filters),
                          "launches": int(conv_launches), "avg_launch_ms": conv_ms / max(1.0, conv_launches / world),
                          "peak_source": peak_src, "share_of_step": conv_ms / ms_prof,
                          "measured_over": f"{prof_steps} further steps right after the {steps} timed ones, CUDA events around every tower "
