@@ -62,7 +62,7 @@ def main():
         weights = {key: torch.as_tensor(v) for key, v in om.init_weights(filters, blocks, 256, seed=0).items()}
         src = "random-init weights"
     res = {"net": f"{filters}x{blocks}", "weights": src, "go": f"depth {depth} ({depth * 100} simulations), search_threads {k}"}
-    for loop in ("while", "graph", "host"):      # one WHILE-graph launch per slice (default) | three sub-graphs per iteration | round-1 host loop
+    for loop in os.environ.get("UCI_LOOPS", "while,graph,host").split(","):      # one WHILE-graph launch per slice (default) | three sub-graphs per iteration | round-1 host loop
         runs, info = run(loop, filters, blocks, depth, k, weights)
         res[loop] = {"best": min(runs[1:], key=lambda r: r["seconds"]), "runs": runs, "last_info_line": info}
     print(json.dumps(res))
