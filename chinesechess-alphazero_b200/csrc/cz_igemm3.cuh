@@ -38,6 +38,10 @@ struct Args3 {
   int fbytes;            // bytes of one F tile: 2048 (fp32 skip and/or fp32 output), 1024 (fp16 skip only), 0 (neither)
   int nf;                // F tiles per epilogue warp (3 .. kMaxNF3): skip loads run nf - 2 chunks ahead
   int split_producer;    // 1: warp 0 issues the A (im2col) loads, warp 3 the B (weight) loads — two TMA issue streams per CTA
+  int n_split;           // N tiles of N_TILE columns (1 = the tile is the whole width).  Small batches (a single game's leaves)
+                         // run as pairs x n_split work items so that a launch of a few M-tiles still spreads over many SMs and
+                         // each CTA's exposed epilogue is N_TILE / 16 chunks instead of C / 16; the K order per output is unchanged,
+                         // so the numbers are bit for bit those of the full-width tile
 };
 __host__ __device__ constexpr int epi3_warp_bytes(int fbytes, int nf) { return nf * fbytes + kNH3 * kHBytes3; }
 
@@ -131,6 +135,8 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   const int rows = args_rows(a);
   const int m_tiles = a.n_dev ? (rows + kTileM - 1) / kTileM : a.m_tiles;
   const int pairs = (m_tiles + 2 * MT - 1) / (2 * MT);     // one pass of a CTA pair = 2 * MT consecutive M-tiles
+  const int ns = p.n_split > 1 ? p.n_split : 1;            // work item = (pair, N tile): item / ns, item % ns
+  const int items = pairs * ns;
   const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
 
   if (warp == 0 || (warp == 3 && p.split_producer)) {
@@ -140,7 +146,8 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (lane == 0) {
       const bool do_a = warp == 0, do_b = warp == 3 || !p.split_producer;
       uint32_t s = 0, ph = 0;
-      for (int pair = cluster_id; pair < pairs; pair += n_clusters) {
+      for (int item = cluster_id; item < items; item += n_clusters) {
+        const int pair = item / ns, n0 = (item % ns) * N_TILE;
         const int m_tile = MT * (2 * pair + (int)rank);     // this CTA's first tile of the pass
         for (int tap = 0; tap < a.n_taps; ++tap) {
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -156,7 +163,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                 umma::tma2_load_im2col_4d(sA + mt * kAStageBytes, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1));
               }
             }
-            if (do_b) umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + (int)rank * (N_TILE / 2));
+            if (do_b) umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + n0 + (int)rank * (N_TILE / 2));
             if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1; }
           }
         }
@@ -167,7 +174,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (leader && lane == 0) {
       constexpr uint32_t idesc = umma::idesc_f16(256, N_TILE);
       uint32_t s = 0, ph = 0, tcount = 0;
-      for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
+      for (int item = cluster_id; item < items; item += n_clusters, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         umma::mbar_wait(&tempty[acc], aph ^ 1);
         umma::tc_fence_after();
@@ -211,8 +218,9 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const bool has_skip = p.skip_mode != 0, skip32 = p.skip_mode == 2;
     const uint32_t skip_bytes = skip32 ? 2048u : 1024u;
     // next tile's skip block -> L2, a whole tile ahead (one warp): the per-chunk TMA loads below then hit L2
-    auto prefetch_skip = [&](int pr) {
-      if (ew != 0 || pr >= pairs || !has_skip) return;
+    auto prefetch_skip = [&](int item) {
+      if (ew != 0 || item >= items || !has_skip || ns > 1) return;   // (split launches are a few tiles: nothing to run ahead of)
+      const int pr = item;
       const long long row0 = (long long)MT * (2 * pr + (int)rank) * kTileM;
       const long long nrow = rows - row0 < MT * kTileM ? rows - row0 : MT * kTileM;
       if (nrow <= 0) return;
@@ -224,23 +232,25 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     };
     // global chunk counter of this warp: chunk index g -> (tile = g / kChunks, chunk in tile = g % kChunks); F slot g % nf
     int my_tiles = 0;
-    for (int pr = cluster_id; pr < pairs; pr += n_clusters) ++my_tiles;
+    for (int it = cluster_id; it < items; it += n_clusters) ++my_tiles;
     const uint32_t total_chunks = (uint32_t)my_tiles * (MT * kChunks);
     auto request_skip = [&](uint32_t g) {                     // lane 0 only
       if (!has_skip || g >= total_chunks) return;
       const int t = (int)(g / (MT * kChunks)), rem = (int)(g % (MT * kChunks)), mt = rem / kChunks, ch = rem % kChunks;
-      const int row = (MT * (2 * (cluster_id + t * n_clusters) + (int)rank) + mt) * kTileM + q * 32;
+      const int item = cluster_id + t * n_clusters;
+      const int row = (MT * (2 * (item / ns) + (int)rank) + mt) * kTileM + q * 32;
       const uint32_t slot = g % (uint32_t)nf;
       umma::mbar_expect_tx(&sbar[slot], skip_bytes);
-      umma::tma_load_2d(F + slot * fb, &tmSkip, &sbar[slot], cbeg + ch * kChunkCols3, row);
+      umma::tma_load_2d(F + slot * fb, &tmSkip, &sbar[slot], (item % ns) * N_TILE + cbeg + ch * kChunkCols3, row);
     };
     uint32_t tcount = 0, g = 0;
     prefetch_skip(cluster_id);
     if (lane == 0)
       for (int k = 0; k < nf - 2; ++k) request_skip((uint32_t)k);   // prime the ring: chunks 0 .. nf-3
-    for (int pair = cluster_id; pair < pairs; pair += n_clusters, ++tcount) {
+    for (int item = cluster_id; item < items; item += n_clusters, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      prefetch_skip(pair + n_clusters);
+      const int pair = item / ns, n0 = (item % ns) * N_TILE;
+      prefetch_skip(item + n_clusters);
       umma::mbar_wait(&tfull[acc], aph);
       umma::tc_fence_after();
 #pragma unroll 1
@@ -251,7 +261,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch, ++g) {
         const uint32_t slot = g % (uint32_t)nf, sph = (g / (uint32_t)nf) & 1, hb = g & 1;
-        const int c0 = cbeg + ch * kChunkCols3;
+        const int c0 = n0 + cbeg + ch * kChunkCols3;
         if (lane == 0) {
           // At most the store group of chunk g-1 may still be reading its tiles; chunk g-2 and older are done, so H[g & 1]
           // and the F slot of chunk g-2 — which is the slot of chunk g + nf - 2 — are free.

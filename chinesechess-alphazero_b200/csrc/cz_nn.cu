@@ -196,7 +196,7 @@ static bool use_tma_epilogue_for(int c, bool fp32_stream) {
 }
 template <int N_TILE, int MT>
 static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
-                           const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st) {
+                           const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st, int n_split = 1) {
   using C = igemm::Cfg3<N_TILE, MT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -205,7 +205,7 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   }
   igemm::Args3 p;
   p.a = a;
-  p.skip_mode = skip_mode; p.out32 = out32 ? 1 : 0;
+  p.skip_mode = skip_mode; p.out32 = out32 ? 1 : 0; p.n_split = n_split;
   p.fbytes = (skip_mode == 2 || out32) ? 2048 : (skip_mode == 1 ? 1024 : 0);
   { static int nf = -1; if (nf < 0) { const char* e = getenv("CZ_NF"); nf = e ? atoi(e) : 3; if (nf < 3) nf = 3; if (nf > igemm::kMaxNF3) nf = igemm::kMaxNF3; } p.nf = nf; }
   { static int sp = -1; if (sp < 0) { const char* e = getenv("CZ_SPLIT_PROD"); sp = (e && e[0] == '1') ? 1 : 0; } p.split_producer = sp; }
@@ -214,7 +214,8 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   if (p.stages < 2) return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: no room for the operand ring");
   const int pairs = ((a.n_dev ? (a.rows + igemm::kTileM - 1) / igemm::kTileM : a.m_tiles) + 2 * MT - 1) / (2 * MT);
   if (pairs <= 0) return 0;
-  const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
+  const int items = pairs * (n_split > 1 ? n_split : 1);
+  const int clusters = items < num_sms() / 2 ? items : num_sms() / 2;
   igemm::k_igemm3<N_TILE, MT><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
   CZ_CUDA(cudaGetLastError());
   return 0;
@@ -233,6 +234,19 @@ static int launch_igemm3(int n_tile, const CUtensorMap& tmA, const CUtensorMap& 
     case 256: return launch_igemm3_t<256, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
   }
   return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: unsupported N tile %d", n_tile);
+}
+// Small batches (one game's leaves: the UCI / play_games latency path): 64-column tiles, pairs x C/64 work items, as long as
+// every item gets its own CTA pair in one wave.  tmB_32 = the weight map with 32-row boxes.  CZ_NSPLIT=0 turns it off.
+static bool use_n_split(int n_boards, int c) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("CZ_NSPLIT"); on = (e && e[0] == '0') ? 0 : 1; }
+  if (!on || c <= 64) return false;
+  const int pairs = ((n_boards * 90 + igemm::kTileM - 1) / igemm::kTileM + 1) / 2;
+  return pairs * (c / 64) <= num_sms() / 2;
+}
+static int launch_igemm3_split(int c, const CUtensorMap& tmA, const CUtensorMap& tmB_32, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
+                               const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st) {
+  return launch_igemm3_t<64, 1>(tmA, tmB_32, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, c / 64);
 }
 static bool use_im2col() {
   static int v = -1;
@@ -309,8 +323,11 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
       pl[h][t] = (int8_t)plane_of(boards[(size_t)b * board_stride + h * CZ_BOARD_STRIDE + (9 - r) * 9 + col]);
   }
   __syncthreads();
-  if (t < 90) {
-    const int r = t / 9, col = t % 9;
+  // gridDim.y slices of the 90 pixels (small batches: one CTA per position would leave the GPU to a handful of CTAs that each
+  // walk 90 x <= 50 dependent-latency loads)
+  const int per = (90 + (int)gridDim.y - 1) / (int)gridDim.y, p0 = (int)blockIdx.y * per, p1 = p0 + per < 90 ? p0 + per : 90;
+  if (t < p1 - p0) {
+    const int r = (p0 + t) / 9, col = (p0 + t) % 9;
     int n = 0;
     for (int kh = 0; kh < 5; ++kh) {
       const int rr = r + kh - 2;
@@ -335,17 +352,18 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
   __half* o = out + (size_t)b * board_pixels * c_out;
   const __half2* w2 = reinterpret_cast<const __half2*>(w + c);
   const int stride2 = c_out / 2;
-  for (int pix = grp; pix < 90; pix += n_groups) {
+  for (int pix = p0 + grp; pix < p1; pix += n_groups) {
     float a0 = sh.x, a1 = sh.y;
-    const int n = cnt[pix];
+    const int n = cnt[pix - p0];
     for (int k = 0; k < n; ++k) {
-      const float2 v = __half22float2(__ldg(w2 + (size_t)rows[pix][k] * stride2));
+      const float2 v = __half22float2(__ldg(w2 + (size_t)rows[pix - p0][k] * stride2));
       a0 += v.x; a1 += v.y;
     }
     a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
     *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = __floats2half2_rn(a0, a1);
     if (out32) *reinterpret_cast<float2*>(out32 + ((size_t)b * board_pixels + pix) * c_out + c) = make_float2(a0, a1);
   }
+  if (blockIdx.y == 0)
   for (int col = 90 + grp; col < board_pixels; col += n_groups)
     *reinterpret_cast<__half2*>(o + (size_t)col * c_out + c) = __floats2half2_rn(0.f, 0.f);          // separator row (strip layout)
 }
@@ -386,17 +404,18 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
                                                 const float* __restrict__ bv1,     // [H]
                                                 const float* __restrict__ wv2,     // [H]
                                                 const float* __restrict__ bv2,     // [1]
-                                                int hidden, __half* __restrict__ pol_feat, float* __restrict__ value) {
+                                                int hidden, __half* __restrict__ pol_feat, float* __restrict__ value,
+                                                int hp) {          // positions per block: kHeadPos, or 1 for small batches
   extern __shared__ __align__(16) float hsm[];
   const int n_out = pol_c + val_c;
   float* feat = hsm;                                         // [kHeadPos][n_out][90]
   float* wsm = feat + kHeadPos * n_out * 90;                 // [c_in / 8][n_out][8]
   float* red = wsm + (c_in / 8) * n_out * 8;                 // [kHeadPos][8]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0 = blockIdx.x * kHeadPos;
+  const int b0 = blockIdx.x * hp;
   const int n_pos = __ldg(n_dev);
   if (b0 >= n_pos) return;
-  const int npos = n_pos - b0 < kHeadPos ? n_pos - b0 : kHeadPos;
+  const int npos = n_pos - b0 < hp ? n_pos - b0 : hp;
   for (int i = tid; i < n_out * c_in; i += 256) { const int o = i / c_in, c = i % c_in; wsm[((c >> 3) * n_out + o) * 8 + (c & 7)] = __ldg(wh + i); }
   __syncthreads();
   for (int item = tid; item < npos * 90; item += 256) {
@@ -404,6 +423,7 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
     const size_t row = ((size_t)(b0 + p) * board_pixels + pix) * c_in;
     for (int o0 = 0; o0 < n_out; o0 += 6) {                  // six outputs per pass over the pixel's row (the row stays in L1)
       float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
       for (int g = 0; g < c_in / 8; ++g) {
         float x[8];
         if (act32) {
@@ -448,6 +468,7 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
     const float bb = bv1[tid];
 #pragma unroll
     for (int p = 0; p < kHeadPos; ++p) acc[p] = bb;
+#pragma unroll 10
     for (int i = 0; i < val_c * 90; ++i) {
       const float wv = __ldg(wv1 + (size_t)i * hidden + tid);
 #pragma unroll
@@ -581,7 +602,7 @@ struct NetWeights {
   float *wh, *shifth, *wv1, *bv1, *wv2, *bv2;
   __half* w_pol; float* b_pol;
   CUtensorMap map_wpol;
-  std::vector<CUtensorMap> map_w, map_w_half;
+  std::vector<CUtensorMap> map_w, map_w_half, map_w_32;
   bool ready;
 };
 
@@ -613,6 +634,7 @@ struct NnRuntime {
   CUtensorMap map_x, map_t, map_y, map_pf, map_wpol;
   std::vector<CUtensorMap> map_w;
   std::vector<CUtensorMap> map_w_half;   // box rows = C/2 for the CTA-pair kernel
+  std::vector<CUtensorMap> map_w_32;     // box rows = 32: 64-column tiles of the small-batch launches (use_n_split)
   bool fp32_skip;                        // keep the residual (skip) stream in fp32: halves the value error of deep nets, ~+30 % time
   int board_pixels;                      // 99 = strip layout (separator row per board), 90 = dense + im2col TMA
   CUtensorMap imap_x, imap_t, imap_y;    // im2col maps of the three activation buffers (dense layout)
@@ -630,7 +652,7 @@ static void store_net(NnRuntime* r, int k) {
   NetWeights& n = r->nets[k];
   n.w_first = r->w_first; n.shift_first = r->shift_first; n.w_conv = r->w_conv; n.shift_conv = r->shift_conv;
   n.wh = r->wh; n.shifth = r->shifth; n.wv1 = r->wv1; n.bv1 = r->bv1; n.wv2 = r->wv2; n.bv2 = r->bv2;
-  n.w_pol = r->w_pol; n.b_pol = r->b_pol; n.map_wpol = r->map_wpol; n.map_w = r->map_w; n.map_w_half = r->map_w_half;
+  n.w_pol = r->w_pol; n.b_pol = r->b_pol; n.map_wpol = r->map_wpol; n.map_w = r->map_w; n.map_w_half = r->map_w_half; n.map_w_32 = r->map_w_32;
   n.ready = r->ready;
 }
 static void select_net(NnRuntime* r, int k) {
@@ -639,7 +661,7 @@ static void select_net(NnRuntime* r, int k) {
   const NetWeights& n = r->nets[k];
   r->w_first = n.w_first; r->shift_first = n.shift_first; r->w_conv = n.w_conv; r->shift_conv = n.shift_conv;
   r->wh = n.wh; r->shifth = n.shifth; r->wv1 = n.wv1; r->bv1 = n.bv1; r->wv2 = n.wv2; r->bv2 = n.bv2;
-  r->w_pol = n.w_pol; r->b_pol = n.b_pol; r->map_wpol = n.map_wpol; r->map_w = n.map_w; r->map_w_half = n.map_w_half;
+  r->w_pol = n.w_pol; r->b_pol = n.b_pol; r->map_wpol = n.map_wpol; r->map_w = n.map_w; r->map_w_half = n.map_w_half; r->map_w_32 = n.map_w_32;
   r->ready = n.ready;
   r->cur = k;
 }
@@ -749,9 +771,11 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
     rc |= make_map_2d(&r->map_wpol, r->w_pol, 3 * r->pol_k1, kPolN, 256);
     r->map_w.resize(2 * blocks);
     r->map_w_half.resize(2 * blocks);
+    r->map_w_32.resize(2 * blocks);
     for (int i = 0; i < 2 * blocks; ++i) {
       rc |= make_map_2d(&r->map_w[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c);
       rc |= make_map_2d(&r->map_w_half[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, c / 2);
+      rc |= make_map_2d(&r->map_w_32[i], r->w_conv + (size_t)i * 9 * c * c, c, 9LL * c, 32);
     }
     store_net(r, net);
   }
@@ -901,7 +925,9 @@ static int conv_first_threads(int c) {                    // (c/2) channel pairs
 static int fw_first(NnRuntime* r, const uint8_t* boards, int n, const int* n_dev) {
   const int c = r->filters;
   const bool s32 = r->board_pixels == 90 && r->fp32_skip;
-  k_conv_first<<<n, conv_first_threads(c), 0, r->stream>>>(boards, r->w_first, r->shift_first, r->x, s32 ? r->x32 : nullptr, c, r->board_pixels,
+  int slices = (2 * num_sms() + n - 1) / n;                // >= 2 CTAs per SM in flight; big batches: one CTA per position
+  if (slices > 15) slices = 15;
+  k_conv_first<<<dim3(n, slices), conv_first_threads(c), 0, r->stream>>>(boards, r->w_first, r->shift_first, r->x, s32 ? r->x32 : nullptr, c, r->board_pixels,
                                                             r->in_planes, (r->in_planes / 14) * CZ_BOARD_STRIDE, n_dev);
   r->launches++;
   CZ_CUDA(cudaGetLastError());
@@ -930,12 +956,17 @@ static int fw_tower(NnRuntime* r, int n, const int* n_dev) {
       d2.residual32 = x32; d2.out32 = y32;
       { float* t32 = x32; x32 = y32; y32 = t32; }
       // conv1: x -> t (no skip);  conv2: t (+ skip x or x32) -> y (+ y32)
+      if (epi3 && use_n_split(n, c)) {
+        if (launch_igemm3_split(c, *ix, r->map_w_32[2 * i], r->omap_t, r->omap_t, r->omap_t, d1, 0, false, st)) return CZ_ERR_CUDA;
+        if (launch_igemm3_split(c, r->imap_t, r->map_w_32[2 * i + 1], *oy, s32 ? *fx : *ox, *fy, d2, s32 ? 2 : 1, s32, st)) return CZ_ERR_CUDA;
+      } else {
       if (epi3 && use_tma_epilogue_for(c, false)) {
         if (launch_igemm3(c, *ix, r->map_w_half[2 * i], r->omap_t, r->omap_t, r->omap_t, d1, 0, false, st)) return CZ_ERR_CUDA;
       } else if (launch_igemm2(c, *ix, r->map_w_half[2 * i], d1, st)) return CZ_ERR_CUDA;
       if (epi3 && use_tma_epilogue_for(c, s32)) {
         if (launch_igemm3(c, r->imap_t, r->map_w_half[2 * i + 1], *oy, s32 ? *fx : *ox, *fy, d2, s32 ? 2 : 1, s32, st)) return CZ_ERR_CUDA;
       } else if (launch_igemm2(c, r->imap_t, r->map_w_half[2 * i + 1], d2, st)) return CZ_ERR_CUDA;
+      }
       CUtensorMap* ti = ix; ix = iy; iy = ti;
       ti = ox; ox = oy; oy = ti;
       ti = fx; fx = fy; fy = ti;
@@ -961,8 +992,9 @@ static int fw_heads(NnRuntime* r, int n, const int* n_dev, float* value) {
     CZ_CUDA(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
     r->heads_attr = true;
   }
-  k_heads<<<(n + kHeadPos - 1) / kHeadPos, 256, hsm, r->stream>>>(x, x32, c, n_dev, r->board_pixels, r->pol_c, r->val_c, r->pol_k1, r->wh, r->shifth,
-                                                                  r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value);
+  const int hp = n <= 2 * num_sms() ? 1 : kHeadPos;       // small batches: a block per position (same arithmetic per position)
+  k_heads<<<(n + hp - 1) / hp, 256, hsm, r->stream>>>(x, x32, c, n_dev, r->board_pixels, r->pol_c, r->val_c, r->pol_k1, r->wh, r->shifth,
+                                                      r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value, hp);
   igemm::Args ap = dense_args(n, kLabels, kPolN, 3 * r->pol_k1, 256, r->b_pol, r->logits, kPolN);
   ap.n_dev = n_dev; ap.rows_per_unit = 1; ap.row_stats = r->stats;
   if (launch_igemm(256, r->map_pf, r->map_wpol, ap, r->stream)) return CZ_ERR_CUDA;

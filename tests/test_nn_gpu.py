@@ -76,6 +76,30 @@ def test_forward_chunks_and_batch_of_one(cuda_lib, cuda_env):
     eng.close()
 
 
+@pytest.mark.parametrize("filters,blocks,fp32_skip", [(128, 7, None), (192, 10, None), (256, 20, None), (256, 3, False)])
+def test_small_batch_tiles_equal_full_width_tiles(cuda_lib, cuda_env, filters, blocks, fp32_skip):
+    """A few positions (one game's leaves: UCI / play_games) run the residual convs as 64-column tiles spread over many CTA pairs
+    (cz_nn.cu use_n_split); the same positions inside a batch of 1024 run the full-width tiles.  The K order of every output is the
+    same, so policy and value agree bit for bit, and both keep the 1e-3 bound."""
+    w = om.init_weights(filters, blocks, 256, seed=3, trained_like=True, spread=0.1)
+    states = [osenv.INIT_STATE] + midgame_states(9, 11, lo=1, hi=100)
+    boards = cuda_env.boards_from_states(states)
+    small = _engine(cuda_lib, filters, blocks, 16, fp32_skip)
+    big = _engine(cuda_lib, filters, blocks, 1024, fp32_skip)
+    for e in (small, big):
+        e.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
+    p_s, v_s = small.nn_forward_boards(boards)
+    reps = (1024 + len(states) - 1) // len(states)
+    p_b, v_b = big.nn_forward_boards(boards.repeat(reps, 1)[:1024])
+    torch.cuda.synchronize()
+    n = len(states)
+    assert torch.equal(p_s, p_b[:n]) and torch.equal(v_s, v_b[:n])
+    assert torch.equal(p_b[:n], p_b[n:2 * n])
+    ref_p, ref_v = om.forward(w, np.stack([osenv.state_to_planes(s) for s in states]), blocks)
+    assert np.abs(p_s.cpu().numpy() - ref_p).max() < 1e-3 and np.abs(v_s.cpu().numpy() - ref_v).max() < 1e-3
+    small.close(); big.close()
+
+
 @pytest.mark.parametrize("filters,blocks,trained", [(128, 7, False), (192, 4, True)])
 def test_forward_28_planes_with_history(cuda_lib, cuda_env, filters, blocks, trained):
     """use_history networks (data/model/model_128_l1_config.json: Input (28,10,9)): planes 14-27 = the position two plies
