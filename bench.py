@@ -444,6 +444,33 @@ def policy_bytes_per_leaf(legal):
     return (4 * legal + 72) if FUSED_POLICY else 4 * 2086
 
 
+def uci_latency_block():
+    """Single-game latency path: `go depth 8` (800 simulations, search_threads 10) through the drop-in
+    `CChessPlayer(uci=True)` on the reference's trained 192x10 weights (committed fixture), wall clock around `action()`, with the
+    nps figure the REFERENCE's formula gives (agent/player.py:446-447).  tools/bench_uci.py is the measurement."""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_uci", os.path.join(ROOT, "tools", "bench_uci.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        if not os.path.exists(os.path.join(ROOT, "tests", "golden", "model_best_192x10.npz")):
+            return {"error": "tests/golden/model_best_192x10.npz missing"}
+        weights, src = mod.load_weights(192, 10)
+        keep = os.environ.get("CZ_SEARCH_LOOP")
+        try:
+            runs, info = mod.run(keep or "while", 192, 10, 8, 10, weights)
+        finally:
+            if keep is not None:
+                os.environ["CZ_SEARCH_LOOP"] = keep
+        best = min(runs[1:], key=lambda r: r["seconds"])
+        return {"go": "depth 8 = 800 simulations, search_threads 10, one game", "net": "192x10", "weights": src,
+                "ms": best["seconds"] * 1e3, "sims_per_s": best["sims_per_s"], "waves": best["waves"],
+                "nps_reference_formula": best["nps_reference_formula"], "runs_ms": [r["seconds"] * 1e3 for r in runs],
+                "last_info_line": info}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -469,6 +496,7 @@ def run_ours(args):
                 secondary[name]["unit"] = "sims/s"
             except Exception as e:        # a secondary workload must never take the headline down with it
                 secondary[name] = {"error": repr(e)}
+        secondary["uci"] = uci_latency_block()
     if rank == 0:
         games, sims, filters, blocks = WORKLOADS[args.workload]
         cpu = None

@@ -47,20 +47,21 @@ def run(loop, filters, blocks, depth, k, weights):
     return out, last_info
 
 
+def load_weights(filters, blocks):
+    npz = os.path.join(ROOT, "tests", "golden", "model_best_192x10.npz")
+    if (filters, blocks) == (192, 10) and os.path.exists(npz):
+        with np.load(npz) as z:
+            return {key.replace("__", "/"): torch.as_tensor(z[key]) for key in z.files}, "reference's trained 192x10 weights"
+    from oracle import model as om
+    return {key: torch.as_tensor(v) for key, v in om.init_weights(filters, blocks, 256, seed=0).items()}, "random-init weights"
+
+
 def main():
     filters = int(sys.argv[1]) if len(sys.argv) > 2 else 192
     blocks = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     depth = int(sys.argv[3]) if len(sys.argv) > 3 else 8
     k = int(sys.argv[4]) if len(sys.argv) > 4 else 10      # configs/distribute.py: search_threads = 10
-    npz = os.path.join(ROOT, "tests", "golden", "model_best_192x10.npz")
-    if (filters, blocks) == (192, 10) and os.path.exists(npz):
-        with np.load(npz) as z:
-            weights = {key.replace("__", "/"): torch.as_tensor(z[key]) for key in z.files}
-        src = "reference's trained 192x10 weights"
-    else:
-        from oracle import model as om
-        weights = {key: torch.as_tensor(v) for key, v in om.init_weights(filters, blocks, 256, seed=0).items()}
-        src = "random-init weights"
+    weights, src = load_weights(filters, blocks)
     res = {"net": f"{filters}x{blocks}", "weights": src, "go": f"depth {depth} ({depth * 100} simulations), search_threads {k}"}
     for loop in os.environ.get("UCI_LOOPS", "while,graph,host").split(","):      # one WHILE-graph launch per slice (default) | three sub-graphs per iteration | round-1 host loop
         runs, info = run(loop, filters, blocks, depth, k, weights)
