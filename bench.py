@@ -179,7 +179,10 @@ def run_reference_arm(args):
     cores, procs, nn_threads = cpu_layout()
     # total timed span >= 60 s split into `steps` windows; the whole run stays within a few minutes
     window = float(os.environ.get("CZ_BENCH_CPU_WINDOW", max(3.0, 60.0 / max(1, args.steps))))
+    load0 = os.getloadavg()[0]          # runnable tasks on the box BEFORE this arm starts: the boxes of the pool are shared, and the
+                                        # rates of the same plumbing differed 4x between boxes (56 ... 221 sims/s, profiles/README.md)
     wins, desc, used, kind = reference_windows(sims, filters, blocks, K, args.steps, window, warm_windows=args.warmup)
+    load1 = os.getloadavg()[0]
     extra = {}
     if wins is None:
         vals = [port_sample(filters, blocks, sims, K, window) for _ in range(max(1, min(args.steps, 4)))]
@@ -218,7 +221,8 @@ def run_reference_arm(args):
         "config": bench_config(args.workload, games, sims, filters, blocks, K, args.gpus, args.skip_stream),
         "cpu_baseline": {"value": value, "unit": "sims/s", "cores": used, "kind": kind, "sample": sample,
                          "host_cores": cores, "max_processes": procs, "nn_threads": nn_threads,
-                         "window_rates": [round(v, 2) for v in per_window]},
+                         "window_rates": [round(v, 2) for v in per_window],
+                         "host_loadavg_1min": {"before": round(load0, 1), "at_end_of_windows": round(load1, 1)}},
         "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     line.update(extra)

@@ -125,11 +125,14 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     umma::fence_proxy_async();
   }
   if (warp == 2) umma::tmem_alloc2<C::kTmemCols>(tmem_slot);
+  umma::griddep_launch_dependents();     // (PDL launches only) the next conv may set up its barriers / TMEM while this one runs
   umma::tc_fence_before();
   __syncthreads();
   umma::cluster_sync_all();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  umma::griddep_wait();                  // (PDL launches only) the producer of this conv's input has completed; nothing above
+                                         // touched global memory other than the tensor maps in the parameter space
 
   const int n_kb = a.n_taps * a.k_chunks;
   const int rows = args_rows(a);

@@ -216,7 +216,23 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   if (pairs <= 0) return 0;
   const int items = pairs * (n_split > 1 ? n_split : 1);
   const int clusters = items < num_sms() / 2 ? items : num_sms() / 2;
-  igemm::k_igemm3<N_TILE, MT><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
+  // CZ_PDL=1: programmatic dependent launch — this conv's CTAs may become resident and run their prologue (barriers, TMEM, tensor
+  // map prefetch) while the previous kernel of the stream is still running; griddepcontrol.wait in the kernel orders the data.
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("CZ_PDL"); pdl = (e && e[0] == '1') ? 1 : 0; }
+  if (pdl) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(2 * clusters); lc.blockDim = dim3(igemm::kThreads2);
+    lc.dynamicSmemBytes = C::smem_bytes(p.stages, p.fbytes, p.nf); lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CZ_CUDA(cudaLaunchKernelEx(&lc, igemm::k_igemm3<N_TILE, MT>, tmA, tmB_half, tmOut16, tmSkip, tmOut32, p));
+  } else {
+    igemm::k_igemm3<N_TILE, MT><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
+  }
   CZ_CUDA(cudaGetLastError());
   return 0;
 }
