@@ -85,7 +85,9 @@ typedef struct cz_config {
   int32_t max_nodes_per_game;  /* node pool capacity per game */
   int32_t max_edges_per_game;  /* edge pool capacity per game */
   int32_t max_path;            /* longest root->leaf path stored per simulation */
-  int32_t noise_mode;          /* 0 = host table (parity), 1 = on-device Philox gamma sampler */
+  int32_t noise_mode;          /* 0 = host table (parity), 1 = on-device Philox gamma sampler: stream = (seed, rank, game slot,
+                                * search number on that slot since the last reset), counter = draw index — every root visit of
+                                * every move draws fresh noise like player.py:303-304 */
   int32_t max_plies;           /* 2*max_game_length, capacity of the per-game record */
   int32_t nn_filters;          /* cnn_filter_num (0 = no network, external evaluator only) */
   int32_t nn_blocks;           /* res_layer_num */
@@ -316,7 +318,8 @@ int cz_igemm_conv3x3(const void* act_in_dev, const void* w_dev, const float* bia
 int cz_igemm_conv3x3_dense(const void* act_in_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
                            void* act_out_dev, int n_boards, int c, int relu, void* stream);
 /* `count` draws of the on-device root-noise sampler (noise_mode 1): the first component of
- * Dirichlet(alpha * 1_n_moves), i.e. what np.random.dirichlet(alpha*ones(n))[0] (player.py:304) is distributed as. */
+ * Dirichlet(alpha * 1_n_moves), i.e. what np.random.dirichlet(alpha*ones(n))[0] (player.py:304) is distributed as: draws
+ * 0 .. count-1 of the stream slot `game` is on (it moves to a new stream with every search opened on the slot). */
 int cz_noise_sample(cz_engine* e, int game, int n_moves, int count, double* out_dev);
 /* out[m][n] = sum_k a[m][k] * w[n][k] + bias[n]; a fp16 [m][k], w fp16 [n_pad][k], bias f32 [n_pad] (padded like w),
  * out f32 [m][ldo], 16-byte aligned with ldo a multiple of 4. */
