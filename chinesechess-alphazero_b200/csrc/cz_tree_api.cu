@@ -1137,7 +1137,7 @@ int cz_nn_forward_boards(cz_engine* e, const uint8_t* boards_dev, int32_t batch,
 }
 
 int cz_noise_sample(cz_engine* e, int game, int n_moves, int count, double* out_dev) {
-  if (!e || !out_dev || count < 0 || n_moves < 1) return cz_fail(CZ_ERR_ARG, "cz_noise_sample: bad argument");
+  if (!e || !out_dev || count < 0 || n_moves < 1 || game < 0 || game >= e->cfg.n_games) return cz_fail(CZ_ERR_ARG, "cz_noise_sample: bad argument");
   CZ_LAUNCH(k_noise_sample, 64, 1, 0, e->stream, e->d, game, n_moves, count, out_dev);
   return launch_ok(e, "cz_noise_sample");
 }
