@@ -65,13 +65,6 @@ struct EngineDev {
   int32_t* noise_used;           // [G]
   int32_t* noise_epoch;          // [G] searches opened on this slot since the last reset: part of the Philox counter of the root
                                  //     noise, so that every move of every game draws from its own stream
-  // Root-noise draws of the coming wave, generated ahead by K warps per game (k_noise_fill) instead of by the one warp that walks
-  // the game's simulations.  A pure cache of dirichlet_first(): entry i holds the draw with absolute index noise_pre_base + i for a
-  // root of noise_pre_L legal moves; select_edge falls back to computing the draw wherever the cache does not cover it.
-  float* noise_pre;              // [G][K * MAX_MOVES]
-  int32_t* noise_pre_base;       // [G]
-  int32_t* noise_pre_cnt;        // [G] valid entries (0 = none)
-  int32_t* noise_pre_L;          // [G]
   int32_t* game_err;             // [G]
   uint16_t* no_act;              // [G][16]
   int32_t* n_no_act;             // [G]
@@ -181,8 +174,7 @@ struct Rng {                     // a private stream: key = (seed, rank), counte
   }
 };
 // first component of Dirichlet(alpha * 1_n): Gamma(alpha) / (Gamma(alpha) + Gamma((n-1) alpha))
-// One real function on the device (CZ_DN): the ahead-of-time fill and the in-line fallback must give the same bits.
-CZ_DN double dirichlet_first(const EngineDev& E, int game, uint32_t index, int n) {
+CZ_D double dirichlet_first(const EngineDev& E, int game, uint32_t index, int n) {
   Rng r; r.init(E.seed, E.rank, (uint32_t)game, 1u | ((uint32_t)E.noise_epoch[game] << 8), index);
   const float g1 = r.gamma_f((float)E.alpha);
   if (n <= 1) return 1.0;
@@ -264,9 +256,6 @@ CZ_D int select_edge(const EngineDev& E, int g, int node, bool is_root) {
   const uint16_t* na = E.no_act + (size_t)g * CZ_MAX_NO_ACT;
   const int cursor = E.noise_used[g];
   const NoiseRef nref = (is_root && E.noise_mode == 0) ? *E.noise_ref : NoiseRef{nullptr, 0};
-  const bool pre_ok = is_root && E.noise_mode != 0 && E.noise_pre_L[g] == L;
-  const int pre_base = pre_ok ? E.noise_pre_base[g] : 0, pre_cnt = pre_ok ? E.noise_pre_cnt[g] : 0;
-  const float* pre = E.noise_pre + (size_t)g * E.K * MAX_MOVES;
   double best_s = -99999999.0; int best_i = -1;
   int first_big = 0x7fffffff;
   int seen = 0;                                   // non-skipped edges before this chunk
@@ -292,8 +281,7 @@ CZ_D int select_edge(const EngineDev& E, int g, int node, bool is_root) {
         } else if (E.noise_eps == 0.0) {
           nz = 0.0;                                 // eps * nz adds +0.0 whatever the draw: the cursor advances, nothing is sampled
         } else {
-          const int off = cursor + rank - pre_base;
-          nz = (off >= 0 && off < pre_cnt) ? (double)pre[off] : dirichlet_first(E, g, (uint32_t)(cursor + rank), L);
+          nz = dirichlet_first(E, g, (uint32_t)(cursor + rank), L);
         }
         const double pmix = (double)(omef * p) + E.noise_eps * nz;
         cp_p = E.c_puct * pmix;
@@ -736,7 +724,6 @@ CZ_D void game_begin(const EngineDev& E, int g, int sims_override, bool raw_task
     E.sims_run[g] = 0;
     E.noise_used[g] = 0;
     E.noise_epoch[g] += 1;
-    E.noise_pre_cnt[g] = 0;
     E.n_leaf[g] = 0; E.n_park[g] = 0; E.n_resume[g] = 0;
   }
   czs::syncwarp();

@@ -59,26 +59,6 @@ CZ_KERNEL(k_apply_wave)(EngineDev E, int g0, int g1, const float* legal_p, const
   czs::syncwarp();
   game_wave(E, g, sm);
 }
-// Root noise of the coming wave, K warps per game (noise_mode 1): warp (g, j) draws the values the j-th root visit of the wave
-// may consume — absolute indices noise_used + j*L .. + L-1 — with all lanes busy, instead of the game's single walking warp
-// drawing them one visit at a time on its critical path (ncu: 16 % of the search kernel's instructions).  A wave makes at most K
-// root visits and a visit consumes at most L draws, so K*L entries cover it; select_edge computes anything else itself.
-CZ_KERNEL(k_noise_fill)(EngineDev E, int g0, int g1) {
-  const int w = czs::block_idx() * czs::warps_per_block() + czs::warp_in_block();
-  const int g = g0 + w / E.K, j = w % E.K;
-  if (g >= g1 || E.noise_mode == 0 || E.noise_eps == 0.0) return;
-  const int root = E.root_node[g];
-  const bool want = E.active[g] && root >= 0 && (E.tasks_left[g] > 0 || E.round_pending[g] > 0);
-  if (!want) {
-    if (j == 0 && czs::lane() == 0) E.noise_pre_cnt[g] = 0;
-    return;
-  }
-  const int L = (int)(E.node_meta[(size_t)g * E.ncap + root] & 0xff);
-  const int base = E.noise_used[g];
-  float* out = E.noise_pre + (size_t)g * E.K * MAX_MOVES + (size_t)j * L;
-  for (int i = czs::lane(); i < L; i += 32) out[i] = (float)dirichlet_first(E, g, (uint32_t)(base + j * L + i), L);
-  if (j == 0 && czs::lane() == 0) { E.noise_pre_base[g] = base; E.noise_pre_cnt[g] = E.K * L; E.noise_pre_L[g] = L; }
-}
 // single warp: exclusive scan of the per-game leaf counts, totals[0] = leaves, totals[1] = any game busy
 CZ_KERNEL(k_scan)(EngineDev E, int gb, int ge, int slot) {
   int base = 0, busy = 0;
@@ -206,7 +186,7 @@ CZ_KERNEL(k_reset)(EngineDev E, const uint8_t* boards /* [G][96] or null */, con
   if (czs::lane() == 0) {
     E.n_nodes[g] = 0; E.n_edges[g] = 0; E.root_node[g] = -1;
     E.tasks_left[g] = 0; E.round_pending[g] = 0; E.n_leaf[g] = 0; E.n_park[g] = 0; E.n_resume[g] = 0;
-    E.sims_run[g] = 0; E.noise_used[g] = 0; E.noise_epoch[g] = 0; E.noise_pre_cnt[g] = 0; E.noise_pre_L[g] = 0; E.game_err[g] = 0; E.n_no_act[g] = 0; E.increase_temp[g] = 0; E.active[g] = 1;
+    E.sims_run[g] = 0; E.noise_used[g] = 0; E.noise_epoch[g] = 0; E.game_err[g] = 0; E.n_no_act[g] = 0; E.increase_temp[g] = 0; E.active[g] = 1;
     E.root_has_hist[g] = 0;
   }
   czs::syncwarp();
@@ -360,7 +340,6 @@ struct cz_engine {
   unsigned long long prof_pos0;                             // device counter [0] at the last cz_nn_profile read
   bool own_stream;                                          // e->stream was created by cz_create (caller passed the default stream)
   int ring_count;                                           // finished-game records in the device ring (as of the last cz_play_move)
-  bool noise_ahead;                                         // k_noise_fill before every wave (CZ_NOISE_AHEAD=0 at cz_create turns it off: A/B and the transparency test)
   uint64_t launches;
   uint64_t total_sims;
 #if !defined(CZ_EMUL)
@@ -399,8 +378,7 @@ size_t carve(cz_engine* e, uint8_t* base) {
   d.root_hist = cv.take<uint8_t>(G * BOARD_STRIDE); d.root_has_hist = cv.take<int32_t>(G);
   d.root_node = cv.take<int32_t>(G); d.active = cv.take<int32_t>(G); d.tasks_left = cv.take<int32_t>(G);
   d.round_pending = cv.take<int32_t>(G); d.sims_run = cv.take<int32_t>(G); d.noise_used = cv.take<int32_t>(G);
-  d.noise_epoch = cv.take<int32_t>(G); d.noise_pre_base = cv.take<int32_t>(G); d.noise_pre_cnt = cv.take<int32_t>(G);
-  d.noise_pre_L = cv.take<int32_t>(G); d.noise_pre = cv.take<float>(G * K * MAX_MOVES);
+  d.noise_epoch = cv.take<int32_t>(G);
   d.game_err = cv.take<int32_t>(G); d.no_act = cv.take<uint16_t>(G * CZ_MAX_NO_ACT); d.n_no_act = cv.take<int32_t>(G);
   d.increase_temp = cv.take<int32_t>(G);
   d.n_nodes = cv.take<int32_t>(G); d.n_edges = cv.take<int32_t>(G);
@@ -488,10 +466,6 @@ int launch_ok(cz_engine* e, const char* what, int n = 1) {
   CZ_LAUNCH(kern, ((e)->cfg.n_games + kWarps - 1) / kWarps, kWarps, sizeof(TreeSmem) * kWarps, (e)->stream, __VA_ARGS__)
 #define RANGE_LAUNCH(e, st, g0, g1, kern, ...) \
   CZ_LAUNCH(kern, ((g1) - (g0) + kWarps - 1) / kWarps, kWarps, sizeof(TreeSmem) * kWarps, st, __VA_ARGS__)
-// before every wave of a range: the root noise its walkers will consume (no-op unless noise_mode 1 with eps > 0)
-#define NOISE_LAUNCH(e, st, g0, g1) \
-  do { if ((e)->noise_ahead && (e)->cfg.noise_mode != 0 && (e)->cfg.noise_eps != 0.0) \
-         CZ_LAUNCH(k_noise_fill, (((g1) - (g0)) * (e)->cfg.leaves_per_round + kWarps - 1) / kWarps, kWarps, 0, st, (e)->d, g0, g1); } while (0)
 
 }  // namespace
 
@@ -523,7 +497,6 @@ int cz_create(const cz_config* cfg, void* workspace, uint64_t workspace_bytes, v
   e->own_stream = false; e->prof_pos0 = 0;
   e->ws = (uint8_t*)workspace; e->ws_bytes = workspace_bytes;
   e->launches = 0; e->last_leaves = 0; e->ring_count = 0; e->total_sims = 0;
-  { const char* na = getenv("CZ_NOISE_AHEAD"); e->noise_ahead = !(na && na[0] == '0'); }
   EngineDev& d = e->d;
   memset(&d, 0, sizeof(d));
   d.n_games = cfg->n_games; d.sims = cfg->sims_per_move; d.K = cfg->leaves_per_round; d.vl = cfg->virtual_loss;
@@ -716,7 +689,6 @@ int cz_search_wave(cz_engine* e, int32_t* n_leaves, int32_t* any_active) {
   if (!e) return cz_fail(CZ_ERR_ARG, "cz_search_wave: null engine");
   if (e->last_leaves != 0) return cz_fail(CZ_ERR_STATE, "cz_search_wave: %d leaves of the previous wave were not applied", e->last_leaves);
   const int G = e->cfg.n_games;
-  NOISE_LAUNCH(e, e->stream, 0, G);
   RANGE_LAUNCH(e, e->stream, 0, G, k_wave, e->d, 0, G);
   CZ_LAUNCH(k_scan, 1, 1, 0, e->stream, e->d, 0, G, 0);
   RANGE_LAUNCH(e, e->stream, 0, G, k_gather, e->d, 0, G, e->d.leaf_dense, e->d.leaf_labels, e->d.leaf_nlab);
@@ -802,7 +774,6 @@ int search_pipelined(cz_engine* e) {
       e->launches += 1;
       n_in_flight[h] = 0;
     }
-    NOISE_LAUNCH(e, T, gb[h], ge[h]);
     RANGE_LAUNCH(e, T, gb[h], ge[h], k_wave, e->d, gb[h], ge[h]);
     CZ_LAUNCH(k_scan, 1, 1, 0, T, e->d, gb[h], ge[h], h);
     RANGE_LAUNCH(e, T, gb[h], ge[h], k_gather, e->d, gb[h], ge[h], dense[h], (int16_t*)nullptr, (int32_t*)nullptr);
@@ -856,7 +827,6 @@ int enqueue_part(cz_engine* e, int h, int part) {
   const int n_max = (r.ge - r.gb) * e->cfg.leaves_per_round;
   const int* n_dev = e->d.totals + 4 * h;
   if (part == 1) {
-    NOISE_LAUNCH(e, e->stream, r.gb, r.ge);
     RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_apply_wave, e->d, r.gb, r.ge, (const float*)r.legal_p, (const float*)r.value);
     k_scan_block<<<1, 1024, 0, e->stream>>>(e->d, r.gb, r.ge, h);
     RANGE_LAUNCH(e, e->stream, r.gb, r.ge, k_gather, e->d, r.gb, r.ge, r.dense, r.labels, r.nlab);
