@@ -305,13 +305,13 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
 
     gather_ev = []
 
-    def step_device():
+    def step_device(warm=False):
         g, s = eng.selfplay(target_games=0, max_moves=1)
         n_rec = 0
         if world > 1:          # the ONE collective of the path: finished-game rings -> rank 0, inside the timed region
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            recs, total = rec.gather_records(eng, dist, world)
+            recs, total = rec.gather_records(eng, dist, world, warm=warm)
             b.record()
             gather_ev.append((a, b))
             n_rec = total
@@ -323,7 +323,7 @@ def measure(args, workload, steps, warmup, world, rank, local, dist, want_e2e=Tr
         return s, g, n_rec
 
     for _ in range(warmup):
-        step_device()
+        step_device(warm=True)
     gather_ev.clear()
     # ---- device-resident timing: the production path (cz_selfplay -> one WHILE-graph launch per search, no host in the loop)
     st0, c0 = eng.search_stats(), eng.counters()

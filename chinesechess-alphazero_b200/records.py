@@ -89,13 +89,14 @@ def record_layout(engine):
     return tuple(int(x) for x in a)
 
 
-def gather_records(engine, dist, world, decode_on=0, clear=True):
+def gather_records(engine, dist, world, decode_on=0, clear=True, warm=False):
     """all_gather (NCCL on GPUs, gloo in the CPU tests) of the finished-game record ring of every rank — SURVEY.md §8e:
     the only inter-GPU traffic of the path, the analogue of the reference uploading its play-data files
     (worker/self_play.py:228-241).  The ring lives inside the engine's workspace tensor, so the collective reads it in
     place; every rank must call this at the same point of its loop.  Returns (records, total): on rank `decode_on` the
     decoded records of ALL ranks as [(rank, record dict), ...] (None elsewhere: other ranks only forward), and the
-    number of records gathered.  clear=True empties the local ring afterwards (its content now lives on rank decode_on)."""
+    number of records gathered.  clear=True empties the local ring afterwards (its content now lives on rank decode_on).
+    warm=True: also run the ring collective when no rank has a record yet (first call of a long run, bench warm-up)."""
     import ctypes as C
     ptr, nbytes, ready = C.c_void_p(0), C.c_uint64(0), C.c_int32(0)
     engine.lib.call("cz_record_buffer", engine._h, C.byref(ptr), C.byref(nbytes), C.byref(ready))
@@ -107,6 +108,8 @@ def gather_records(engine, dist, world, decode_on=0, clear=True):
     counts = [int(c.item()) for c in counts]
     total = sum(counts)
     records = None
+    if warm and total == 0:                     # warm-up call: run the ring collective once so that its one-off set-up (NCCL picks
+        dist.all_gather([torch.empty_like(ring) for _ in range(world)], ring)   # channels per message size) is not paid later
     if total > 0:                               # same decision on every rank (they all hold the same counts)
         rings = [torch.empty_like(ring) for _ in range(world)]
         dist.all_gather(rings, ring)
