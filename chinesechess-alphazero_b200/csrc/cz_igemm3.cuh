@@ -30,33 +30,12 @@ constexpr int kHBytes3 = 32 * kChunkCols3 * 2;                 // fp16 output ti
 constexpr int kNH3 = 2;                                        // H ring
 constexpr int kMaxNF3 = 4;                                     // F ring (skip tiles in flight / fp32 output tiles being stored)
 
-// ---- split skip stream ("fp16 + 8"): a residual-stream value v is kept as hi = fp16_rn(v) — the activation tensor the next conv
-// reads anyway — plus one signed byte q that places v inside hi's rounding interval:  v ~ float(hi) + q * ulp(hi) / 256.
-// 2^-19 relative instead of fp16's 2^-11, for 3 bytes instead of the 6 an extra fp32 copy costs (conv2 of a block moves
-// 8 bytes per element instead of 12).  ulp(hi) / 256 = 2^(max(e, 1) - 33) with e = hi's exponent field (subnormals share e = 1).
-__device__ __forceinline__ float split8_unit(uint32_t hbits) {          // ulp(hi) / 256
-  uint32_t e = (hbits >> 10) & 0x1fu; e = e < 1u ? 1u : e;
-  return __uint_as_float((e + 94u) << 23);
-}
-__device__ __forceinline__ float split8_decode(uint32_t hbits, int q) {
-  return fmaf((float)q, split8_unit(hbits), __half2float(__ushort_as_half((unsigned short)hbits)));
-}
-__device__ __forceinline__ uint32_t split8_encode(float v, uint32_t hbits) {   // the byte (two's complement) for v given hi = fp16_rn(v)
-  uint32_t e = (hbits >> 10) & 0x1fu; e = e < 1u ? 1u : e;
-  const float inv = __uint_as_float((160u - e) << 23);                  // 256 / ulp(hi)
-  int q = __float2int_rn((v - __half2float(__ushort_as_half((unsigned short)hbits))) * inv);
-  q = q > 127 ? 127 : (q < -127 ? -127 : q);
-  return (uint32_t)q & 0xffu;
-}
-
 struct Args3 {
   Args a;
   int stages;            // smem ring depth (<= kMaxStages3), chosen on the host from what fits beside the epilogue tiles
-  int skip_mode;         // 0 none, 1 fp16 (tmSkip = fp16 map), 2 fp32 (tmSkip = fp32 map), 3 fp16 + 8 (tmSkip fp16 map, tmSkipLo byte map)
+  int skip_mode;         // 0 none, 1 fp16 (tmSkip = fp16 map), 2 fp32 (tmSkip = fp32 map)
   int out32;             // also store the fp32 copy (tmOut32)
-  int out8;              // also store the byte plane of the fp16 + 8 stream (tmOut32 is then the byte map of the output)
-  int fbytes;            // bytes of one F tile: 2048 (fp32 skip and/or fp32 output; fp16 + 8: skip hi at +0, skip bytes at +1024,
-                         // output bytes at +1536), 1024 (fp16 skip only), 0 (neither)
+  int fbytes;            // bytes of one F tile: 2048 (fp32 skip and/or fp32 output), 1024 (fp16 skip only), 0 (neither)
   int nf;                // F tiles per epilogue warp (3 .. kMaxNF3): skip loads run nf - 2 chunks ahead
   int split_producer;    // 1: warp 0 issues the A (im2col) loads, warp 3 the B (weight) loads — two TMA issue streams per CTA
   int n_split;           // N tiles of N_TILE columns (1 = the tile is the whole width).  Small batches (a single game's leaves)
@@ -111,8 +90,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 template <int N_TILE, int MT = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut16,
-         const __grid_constant__ CUtensorMap tmSkip, const __grid_constant__ CUtensorMap tmOut32, const __grid_constant__ CUtensorMap tmSkipLo,
-         const Args3 p) {
+         const __grid_constant__ CUtensorMap tmSkip, const __grid_constant__ CUtensorMap tmOut32, const Args3 p) {
   using C = Cfg3<N_TILE, MT>;
   const Args& a = p.a;
   const int n_stages = p.stages;
@@ -137,8 +115,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     umma::prefetch_tmap(&tmB);
     umma::prefetch_tmap(&tmOut16);
     if (p.skip_mode) umma::prefetch_tmap(&tmSkip);
-    if (p.out32 || p.out8) umma::prefetch_tmap(&tmOut32);
-    if (p.skip_mode == 3) umma::prefetch_tmap(&tmSkipLo);
+    if (p.out32) umma::prefetch_tmap(&tmOut32);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < n_stages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
@@ -241,8 +218,8 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const uint32_t tempty_remote[2] = {umma::mapa_shared(&tempty[0], 0), umma::mapa_shared(&tempty[1], 0)};
     const int r3 = (lane >> 1) & 3;                           // SWIZZLE_64B key of this thread's 64-byte row
     const int r1 = (lane >> 2) & 1;                           // SWIZZLE_32B key of this thread's 32-byte row
-    const bool has_skip = p.skip_mode != 0, skip32 = p.skip_mode == 2, split8 = p.skip_mode == 3;
-    const uint32_t skip_bytes = skip32 ? 2048u : (split8 ? 1536u : 1024u);
+    const bool has_skip = p.skip_mode != 0, skip32 = p.skip_mode == 2;
+    const uint32_t skip_bytes = skip32 ? 2048u : 1024u;
     // next tile's skip block -> L2, a whole tile ahead (one warp): the per-chunk TMA loads below then hit L2
     auto prefetch_skip = [&](int item) {
       if (ew != 0 || item >= items || !has_skip || ns > 1) return;   // (split launches are a few tiles: nothing to run ahead of)
@@ -268,7 +245,6 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const uint32_t slot = g % (uint32_t)nf;
       umma::mbar_expect_tx(&sbar[slot], skip_bytes);
       umma::tma_load_2d(F + slot * fb, &tmSkip, &sbar[slot], (item % ns) * N_TILE + cbeg + ch * kChunkCols3, row);
-      if (split8) umma::tma_load_2d(F + slot * fb + 1024, &tmSkipLo, &sbar[slot], (item % ns) * N_TILE + cbeg + ch * kChunkCols3, row);
     };
     uint32_t tcount = 0, g = 0;
     prefetch_skip(cluster_id);
@@ -302,8 +278,6 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         uint8_t* frow = F + slot * fb + lane * 64;
         uint8_t* hrow = H + hb * kHBytes3 + lane * 32;
         const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
-        uint4 lo_in = make_uint4(0u, 0u, 0u, 0u), lo_out = make_uint4(0u, 0u, 0u, 0u);
-        if (split8) lo_in = *reinterpret_cast<const uint4*>(F + slot * fb + 1024 + lane * 16);   // 16 bytes = this row's 16 columns
 #pragma unroll
         for (int gq = 0; gq < 4; gq += 2) {
           float4 x0, x1;
@@ -319,18 +293,6 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             const float4 s1 = *reinterpret_cast<const float4*>(frow + (((gq + 1) ^ r3) << 4));
             x0.x += s0.x; x0.y += s0.y; x0.z += s0.z; x0.w += s0.w;
             x1.x += s1.x; x1.y += s1.y; x1.z += s1.z; x1.w += s1.w;
-          } else if (split8) {                                // fp16 tile + byte tile -> the stream's value
-            const uint4 sv = *reinterpret_cast<const uint4*>(F + slot * fb + lane * 32 + (((gq >> 1) ^ r1) << 4));
-            const uint32_t hw[4] = {sv.x, sv.y, sv.z, sv.w};
-            const uint32_t b0 = gq == 0 ? lo_in.x : lo_in.z, b1 = gq == 0 ? lo_in.y : lo_in.w;   // bytes of columns 8*(gq/2) .. +7
-            x0.x += split8_decode(hw[0] & 0xffffu, (int)(int8_t)(b0 & 0xffu));
-            x0.y += split8_decode(hw[0] >> 16, (int)(int8_t)((b0 >> 8) & 0xffu));
-            x0.z += split8_decode(hw[1] & 0xffffu, (int)(int8_t)((b0 >> 16) & 0xffu));
-            x0.w += split8_decode(hw[1] >> 16, (int)(int8_t)(b0 >> 24));
-            x1.x += split8_decode(hw[2] & 0xffffu, (int)(int8_t)(b1 & 0xffu));
-            x1.y += split8_decode(hw[2] >> 16, (int)(int8_t)((b1 >> 8) & 0xffu));
-            x1.z += split8_decode(hw[3] & 0xffffu, (int)(int8_t)((b1 >> 16) & 0xffu));
-            x1.w += split8_decode(hw[3] >> 16, (int)(int8_t)(b1 >> 24));
           } else if (has_skip) {                              // fp16 skip tile: 32-byte rows at the start of F[slot]
             const uint4 sv = *reinterpret_cast<const uint4*>(F + slot * fb + lane * 32 + (((gq >> 1) ^ r1) << 4));
             const __half2* h = reinterpret_cast<const __half2*>(&sv);
@@ -351,20 +313,11 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           oh[0] = __floats2half2_rn(x0.x, x0.y); oh[1] = __floats2half2_rn(x0.z, x0.w);
           oh[2] = __floats2half2_rn(x1.x, x1.y); oh[3] = __floats2half2_rn(x1.z, x1.w);
           *reinterpret_cast<uint4*>(hrow + (((gq >> 1) ^ r1) << 4)) = ov;
-          if (p.out8) {                                       // where inside fp16's rounding interval each value lies
-            const uint32_t w0 = split8_encode(x0.x, ov.x & 0xffffu) | (split8_encode(x0.y, ov.x >> 16) << 8) |
-                                (split8_encode(x0.z, ov.y & 0xffffu) << 16) | (split8_encode(x0.w, ov.y >> 16) << 24);
-            const uint32_t w1 = split8_encode(x1.x, ov.z & 0xffffu) | (split8_encode(x1.y, ov.z >> 16) << 8) |
-                                (split8_encode(x1.z, ov.w & 0xffffu) << 16) | (split8_encode(x1.w, ov.w >> 16) << 24);
-            if (gq == 0) { lo_out.x = w0; lo_out.y = w1; } else { lo_out.z = w0; lo_out.w = w1; }
-          }
         }
-        if (p.out8) *reinterpret_cast<uint4*>(F + slot * fb + 1536 + lane * 16) = lo_out;
         umma::fence_proxy_async();                            // generic-proxy writes above -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
           if (p.out32) tma_store_2d(&tmOut32, F + slot * fb, c0, rbase);
-          if (p.out8) tma_store_2d(&tmOut32, F + slot * fb + 1536, c0, rbase);
           tma_store_2d(&tmOut16, H + hb * kHBytes3, c0, rbase);
           bulk_commit();
         }

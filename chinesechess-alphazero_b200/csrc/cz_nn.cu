@@ -127,19 +127,6 @@ static int make_map_tile32(CUtensorMap* m, const void* base, int c, long long ro
   return 0;
 }
 
-// byte matrix [rows][c], box {16 columns, 32 rows}: the byte plane of the fp16 + 8 skip stream (16-byte rows, no swizzle)
-static int make_map_tile8(CUtensorMap* m, const void* base, int c, long long rows) {
-  if (load_encode()) return CZ_ERR_CUDA;
-  cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)c};
-  cuuint32_t box[2] = {igemm::kChunkCols3, 32};
-  cuuint32_t est[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return cz_fail(CZ_ERR_CUDA, "cuTensorMapEncodeTiled(tile8) failed: %d", (int)r);
-  return 0;
-}
-
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -209,10 +196,7 @@ static bool use_tma_epilogue_for(int c, bool fp32_stream) {
 }
 template <int N_TILE, int MT>
 static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
-                           const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st, int n_split = 1,
-                           const CUtensorMap* tmSkipLo = nullptr) {
-  // skip_mode 3 (fp16 + 8): tmSkip = fp16 map of the skip activations, *tmSkipLo = their byte plane, tmOut32 = byte plane of the output
-  const CUtensorMap& tmLo = tmSkipLo ? *tmSkipLo : tmSkip;
+                           const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st, int n_split = 1) {
   using C = igemm::Cfg3<N_TILE, MT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -221,8 +205,8 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   }
   igemm::Args3 p;
   p.a = a;
-  p.skip_mode = skip_mode; p.out32 = (out32 && skip_mode != 3) ? 1 : 0; p.out8 = skip_mode == 3 ? 1 : 0; p.n_split = n_split;
-  p.fbytes = (skip_mode == 2 || skip_mode == 3 || out32) ? 2048 : (skip_mode == 1 ? 1024 : 0);
+  p.skip_mode = skip_mode; p.out32 = out32 ? 1 : 0; p.n_split = n_split;
+  p.fbytes = (skip_mode == 2 || out32) ? 2048 : (skip_mode == 1 ? 1024 : 0);
   { static int nf = -1; if (nf < 0) { const char* e = getenv("CZ_NF"); nf = e ? atoi(e) : 3; if (nf < 3) nf = 3; if (nf > igemm::kMaxNF3) nf = igemm::kMaxNF3; } p.nf = nf; }
   { static int sp = -1; if (sp < 0) { const char* e = getenv("CZ_SPLIT_PROD"); sp = (e && e[0] == '1') ? 1 : 0; } p.split_producer = sp; }
   p.stages = C::max_stages(p.fbytes, p.nf);
@@ -247,26 +231,25 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    CZ_CUDA(cudaLaunchKernelEx(&lc, igemm::k_igemm3<N_TILE, MT>, tmA, tmB_half, tmOut16, tmSkip, tmOut32, tmLo, p));
+    CZ_CUDA(cudaLaunchKernelEx(&lc, igemm::k_igemm3<N_TILE, MT>, tmA, tmB_half, tmOut16, tmSkip, tmOut32, p));
   } else {
-    igemm::k_igemm3<N_TILE, MT><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, tmLo, p);
+    igemm::k_igemm3<N_TILE, MT><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
   }
   CZ_CUDA(cudaGetLastError());
   return 0;
 }
 static int launch_igemm3(int n_tile, const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
-                         const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st,
-                         const CUtensorMap* lo = nullptr) {
+                         const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st) {
   // two M-tiles per CTA against each weight stage wherever the accumulators fit TMEM (C <= 128); CZ_MT=1 forces the single-tile form
   static int mt2 = -1;
   if (mt2 < 0) { const char* e = getenv("CZ_MT"); mt2 = (e && e[0] == '1') ? 0 : 1; }
   switch (n_tile) {
-    case 64: return mt2 ? launch_igemm3_t<64, 2>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, 1, lo)
-                        : launch_igemm3_t<64, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, 1, lo);
-    case 128: return mt2 ? launch_igemm3_t<128, 2>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, 1, lo)
-                         : launch_igemm3_t<128, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, 1, lo);
-    case 192: return launch_igemm3_t<192, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, 1, lo);
-    case 256: return launch_igemm3_t<256, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, 1, lo);
+    case 64: return mt2 ? launch_igemm3_t<64, 2>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st)
+                        : launch_igemm3_t<64, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 128: return mt2 ? launch_igemm3_t<128, 2>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st)
+                         : launch_igemm3_t<128, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 192: return launch_igemm3_t<192, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 256: return launch_igemm3_t<256, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
   }
   return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: unsupported N tile %d", n_tile);
 }
@@ -280,9 +263,8 @@ static bool use_n_split(int n_boards, int c) {
   return pairs * (c / 64) <= num_sms() / 2;
 }
 static int launch_igemm3_split(int c, const CUtensorMap& tmA, const CUtensorMap& tmB_32, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
-                               const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st,
-                               const CUtensorMap* lo = nullptr) {
-  return launch_igemm3_t<64, 1>(tmA, tmB_32, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, c / 64, lo);
+                               const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st) {
+  return launch_igemm3_t<64, 1>(tmA, tmB_32, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st, c / 64);
 }
 static bool use_im2col() {
   static int v = -1;
@@ -346,8 +328,7 @@ __device__ __forceinline__ int plane_of(uint8_t c) { return c == 0 ? -1 : ((c & 
 // select planes 14-27; board_stride = bytes between records.
 __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* __restrict__ w,
                              const float* __restrict__ shift, __half* __restrict__ out, float* __restrict__ out32, int c_out,
-                             int board_pixels, int in_planes, int board_stride, const int* __restrict__ n_dev,
-                             uint8_t* __restrict__ out8) {      // byte plane of the fp16 + 8 stream (instead of out32)
+                             int board_pixels, int in_planes, int board_stride, const int* __restrict__ n_dev) {
   if ((int)blockIdx.x >= __ldg(n_dev)) return;              // fixed-shape launch: the batch size lives on the device
   __shared__ int8_t pl[2][90];
   __shared__ uint16_t rows[90][52];
@@ -397,14 +378,8 @@ __global__ void k_conv_first(const uint8_t* __restrict__ boards, const __half* _
       a0 += v.x; a1 += v.y;
     }
     a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
-    const __half2 h2 = __floats2half2_rn(a0, a1);
-    *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = h2;
+    *reinterpret_cast<__half2*>(o + (size_t)pix * c_out + c) = __floats2half2_rn(a0, a1);
     if (out32) *reinterpret_cast<float2*>(out32 + ((size_t)b * board_pixels + pix) * c_out + c) = make_float2(a0, a1);
-    if (out8) {
-      const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-      *reinterpret_cast<uint16_t*>(out8 + ((size_t)b * board_pixels + pix) * c_out + c) =
-          (uint16_t)(igemm::split8_encode(a0, hb & 0xffffu) | (igemm::split8_encode(a1, hb >> 16) << 8));
-    }
   }
   if (blockIdx.y == 0)
   for (int col = 90 + grp; col < board_pixels; col += n_groups)
@@ -448,8 +423,7 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
                                                 const float* __restrict__ wv2,     // [H]
                                                 const float* __restrict__ bv2,     // [1]
                                                 int hidden, __half* __restrict__ pol_feat, float* __restrict__ value,
-                                                int hp,            // positions per block: kHeadPos, or 1 for small batches
-                                                const uint8_t* __restrict__ act8) {   // byte plane of the fp16 + 8 stream (with act)
+                                                int hp) {          // positions per block: kHeadPos, or 1 for small batches
   extern __shared__ __align__(16) float hsm[];
   const int n_out = pol_c + val_c;
   float* feat = hsm;                                         // [kHeadPos][n_out][90]
@@ -474,13 +448,6 @@ __global__ void __launch_bounds__(256) k_heads(const __half* __restrict__ act, c
           const float4* a4 = reinterpret_cast<const float4*>(act32 + row + g * 8);
           const float4 u = __ldg(a4), w4 = __ldg(a4 + 1);
           x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w4.x; x[5] = w4.y; x[6] = w4.z; x[7] = w4.w;
-        } else if (act8) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(act + row + g * 8));
-          const uint2 q = __ldg(reinterpret_cast<const uint2*>(act8 + row + g * 8));
-          const uint32_t hw[4] = {v.x, v.y, v.z, v.w}, qb[2] = {q.x, q.y};
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            x[j] = igemm::split8_decode((hw[j >> 1] >> ((j & 1) * 16)) & 0xffffu, (int)(int8_t)((qb[j >> 2] >> ((j & 3) * 8)) & 0xffu));
         } else {
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(act + row + g * 8));
           const __half2* h = reinterpret_cast<const __half2*>(&v);
@@ -691,8 +658,6 @@ struct NnRuntime {
   CUtensorMap imap_x, imap_t, imap_y;    // im2col maps of the three activation buffers (dense layout)
   CUtensorMap omap_x, omap_t, omap_y;    // 32x32 fp16 tile maps of the same buffers (conv epilogue: TMA stores / fp16 skip loads)
   CUtensorMap fmap_x32, fmap_y32;        // 32x32 fp32 tile maps of the fp32 skip stream
-  bool split8;                           // the wide skip stream is fp16 + 8 (cz_igemm3.cuh) instead of fp32: x32 / y32 then hold its byte planes
-  CUtensorMap lmap_x8, lmap_y8;          // 32x16-byte tile maps of those planes
   // optional CUDA-event timing of the residual-tower launches (bench.py roofline)
   bool profile;
   std::vector<cudaEvent_t> ev;        // pairs, recycled
@@ -798,8 +763,6 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   // reference's trained 192x10 net), 1 = always, 2 = never
   r->fp32_skip = fp32_skip_mode == 1 || (fp32_skip_mode == 0 && blocks >= 10);
   { const char* e = getenv("CZ_FP32_SKIP"); if (e && e[0] == '1') r->fp32_skip = true; if (e && e[0] == '0') r->fp32_skip = false; }
-  // the wide stream's format: fp32 copy (12 bytes per element through conv2) or fp16 + 8 (8 bytes).  CZ_SKIP_FORMAT=fp32 / split8
-  { const char* e = getenv("CZ_SKIP_FORMAT"); r->split8 = e && e[0] == 's'; }
   r->profile = false; r->ev_used = 0; r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0; r->capturing = false;
   Carver cv{(uint8_t*)workspace, 0, bytes};
   layout(r, cv);
@@ -816,8 +779,6 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
     rc |= make_map_tile32(&r->omap_y, r->y, c, (long long)max_batch * 90, false);
     rc |= make_map_tile32(&r->fmap_x32, r->x32, c, (long long)max_batch * 90, true);
     rc |= make_map_tile32(&r->fmap_y32, r->y32, c, (long long)max_batch * 90, true);
-    rc |= make_map_tile8(&r->lmap_x8, r->x32, c, (long long)max_batch * 90);
-    rc |= make_map_tile8(&r->lmap_y8, r->y32, c, (long long)max_batch * 90);
   }
   rc |= make_map_3d(&r->map_x, r->x, c, 9, rows, 9, 14);
   rc |= make_map_3d(&r->map_t, r->t, c, 9, rows, 9, 14);
@@ -979,17 +940,13 @@ static int conv_first_threads(int c) {                    // (c/2) channel pairs
   while (pairs * g < 96) ++g;                             // phase 1 needs 90 threads
   return pairs * g;
 }
-// the wide skip stream runs as fp16 + 8 only through the all-TMA epilogue kernel (dense layout)
-static bool wide_is_split8(const NnRuntime* r) { return r->split8 && r->board_pixels == 90 && use_tma_epilogue(); }
 static int fw_first(NnRuntime* r, const uint8_t* boards, int n, const int* n_dev) {
   const int c = r->filters;
   const bool s32 = r->board_pixels == 90 && r->fp32_skip;
   int slices = (2 * num_sms() + n - 1) / n;                // >= 2 CTAs per SM in flight; big batches: one CTA per position
   if (slices > 15) slices = 15;
-  const bool s8 = s32 && wide_is_split8(r);
-  k_conv_first<<<dim3(n, slices), conv_first_threads(c), 0, r->stream>>>(boards, r->w_first, r->shift_first, r->x, (s32 && !s8) ? r->x32 : nullptr, c,
-                                                                         r->board_pixels, r->in_planes, (r->in_planes / 14) * CZ_BOARD_STRIDE, n_dev,
-                                                                         s8 ? reinterpret_cast<uint8_t*>(r->x32) : nullptr);
+  k_conv_first<<<dim3(n, slices), conv_first_threads(c), 0, r->stream>>>(boards, r->w_first, r->shift_first, r->x, s32 ? r->x32 : nullptr, c, r->board_pixels,
+                                                            r->in_planes, (r->in_planes / 14) * CZ_BOARD_STRIDE, n_dev);
   r->launches++;
   CZ_CUDA(cudaGetLastError());
   return 0;
@@ -1003,8 +960,6 @@ static int fw_tower(NnRuntime* r, int n, const int* n_dev) {
   CUtensorMap *ix = &r->imap_x, *iy = &r->imap_y;
   CUtensorMap *ox = &r->omap_x, *oy = &r->omap_y;           // fp16 tile maps of x / y
   CUtensorMap *fx = &r->fmap_x32, *fy = &r->fmap_y32;       // fp32 tile maps of x32 / y32
-  CUtensorMap *lx = &r->lmap_x8, *ly = &r->lmap_y8;         // byte-plane maps of the same buffers (fp16 + 8 stream)
-  const bool s8 = s32 && wide_is_split8(r);
   __half *x = r->x, *y = r->y;
   CUtensorMap *mx = &r->map_x, *my = &r->map_y;
   const bool epi3 = dense && use_tma_epilogue();
@@ -1021,12 +976,7 @@ static int fw_tower(NnRuntime* r, int n, const int* n_dev) {
       // conv1: x -> t (no skip);  conv2: t (+ skip x or x32) -> y (+ y32)
       if (epi3 && use_n_split(n, c)) {
         if (launch_igemm3_split(c, *ix, r->map_w_32[2 * i], r->omap_t, r->omap_t, r->omap_t, d1, 0, false, st)) return CZ_ERR_CUDA;
-        if (s8) {
-          if (launch_igemm3_split(c, r->imap_t, r->map_w_32[2 * i + 1], *oy, *ox, *ly, d2, 3, false, st, lx)) return CZ_ERR_CUDA;
-        } else if (launch_igemm3_split(c, r->imap_t, r->map_w_32[2 * i + 1], *oy, s32 ? *fx : *ox, *fy, d2, s32 ? 2 : 1, s32, st)) return CZ_ERR_CUDA;
-      } else if (s8) {
-        if (launch_igemm3(c, *ix, r->map_w_half[2 * i], r->omap_t, r->omap_t, r->omap_t, d1, 0, false, st)) return CZ_ERR_CUDA;
-        if (launch_igemm3(c, r->imap_t, r->map_w_half[2 * i + 1], *oy, *ox, *ly, d2, 3, false, st, lx)) return CZ_ERR_CUDA;
+        if (launch_igemm3_split(c, r->imap_t, r->map_w_32[2 * i + 1], *oy, s32 ? *fx : *ox, *fy, d2, s32 ? 2 : 1, s32, st)) return CZ_ERR_CUDA;
       } else {
       if (epi3 && use_tma_epilogue_for(c, false)) {
         if (launch_igemm3(c, *ix, r->map_w_half[2 * i], r->omap_t, r->omap_t, r->omap_t, d1, 0, false, st)) return CZ_ERR_CUDA;
@@ -1038,7 +988,6 @@ static int fw_tower(NnRuntime* r, int n, const int* n_dev) {
       CUtensorMap* ti = ix; ix = iy; iy = ti;
       ti = ox; ox = oy; oy = ti;
       ti = fx; fx = fy; fy = ti;
-      ti = lx; lx = ly; ly = ti;
     } else {
       // strip layout (CZ_CONV_STRIP=1 / CZ_IGEMM_1CTA=1 A-B baselines): host-known batch only
       if (launch_igemm(c, *mx, r->map_w[2 * i], a1, st)) return CZ_ERR_CUDA;
@@ -1062,10 +1011,8 @@ static int fw_heads(NnRuntime* r, int n, const int* n_dev, float* value) {
     r->heads_attr = true;
   }
   const int hp = n <= 2 * num_sms() ? 1 : kHeadPos;       // small batches: a block per position (same arithmetic per position)
-  const bool s8 = s32 && wide_is_split8(r);
-  k_heads<<<(n + hp - 1) / hp, 256, hsm, r->stream>>>(x, s8 ? nullptr : x32, c, n_dev, r->board_pixels, r->pol_c, r->val_c, r->pol_k1, r->wh, r->shifth,
-                                                      r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value, hp,
-                                                      s8 ? reinterpret_cast<const uint8_t*>(x32) : nullptr);
+  k_heads<<<(n + hp - 1) / hp, 256, hsm, r->stream>>>(x, x32, c, n_dev, r->board_pixels, r->pol_c, r->val_c, r->pol_k1, r->wh, r->shifth,
+                                                      r->wv1, r->bv1, r->wv2, r->bv2, r->value_fc, r->pol_feat, value, hp);
   igemm::Args ap = dense_args(n, kLabels, kPolN, 3 * r->pol_k1, 256, r->b_pol, r->logits, kPolN);
   ap.n_dev = n_dev; ap.rows_per_unit = 1; ap.row_stats = r->stats;
   if (launch_igemm(256, r->map_pf, r->map_wpol, ap, r->stream)) return CZ_ERR_CUDA;

@@ -100,32 +100,6 @@ def test_small_batch_tiles_equal_full_width_tiles(cuda_lib, cuda_env, filters, b
     small.close(); big.close()
 
 
-@pytest.mark.parametrize("filters,blocks,batch", [(256, 20, 48), (256, 20, 600), (192, 10, 48), (128, 12, 300)])
-def test_wide_skip_stream_formats(cuda_lib, cuda_env, filters, blocks, batch, monkeypatch):
-    """The residual stream of towers of 10+ blocks is kept wider than fp16, either as an fp32 copy or as fp16 + one byte per element
-    (cz_igemm3.cuh: the byte places the value inside fp16's rounding interval, 2^-19 relative).  Both keep the 1e-3 bound and agree
-    with each other far inside it; both launch forms of the conv kernel (64-column tiles for small batches, full width) are covered."""
-    w = om.init_weights(filters, blocks, 256, seed=5, trained_like=True, spread=0.1)
-    states = ([osenv.INIT_STATE] + midgame_states(47, 13, lo=1, hi=110))
-    boards = cuda_env.boards_from_states(states)
-    reps = (batch + len(states) - 1) // len(states)
-    big = boards.repeat(reps, 1)[:batch]
-    ref_p, ref_v = om.forward(w, np.stack([osenv.state_to_planes(s) for s in states]), blocks)
-    out = {}
-    for fmt in ("fp32", "split8"):
-        monkeypatch.setenv("CZ_SKIP_FORMAT", fmt)
-        eng = _engine(cuda_lib, filters, blocks, batch, True)
-        monkeypatch.delenv("CZ_SKIP_FORMAT")
-        eng.set_weights({k: torch.as_tensor(v) for k, v in w.items()})
-        p, v = eng.nn_forward_boards(big)
-        torch.cuda.synchronize()
-        n = min(len(states), batch)
-        out[fmt] = (p[:n].cpu().numpy(), v[:n].cpu().numpy())
-        assert np.abs(out[fmt][0] - ref_p[:n]).max() < 1e-3 and np.abs(out[fmt][1] - ref_v[:n]).max() < 1e-3, fmt
-        eng.close()
-    assert np.abs(out["fp32"][0] - out["split8"][0]).max() < 2e-4 and np.abs(out["fp32"][1] - out["split8"][1]).max() < 2e-4
-
-
 @pytest.mark.parametrize("filters,blocks,trained", [(128, 7, False), (192, 4, True)])
 def test_forward_28_planes_with_history(cuda_lib, cuda_env, filters, blocks, trained):
     """use_history networks (data/model/model_128_l1_config.json: Input (28,10,9)): planes 14-27 = the position two plies

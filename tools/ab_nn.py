@@ -14,8 +14,7 @@ VARIANTS = {
     "igemm3 everywhere, nf=3": {"CZ_EPI": "3", "CZ_NF": "3"},
     "igemm3 everywhere, nf=4": {"CZ_EPI": "3", "CZ_NF": "4"},
     "auto, one M-tile per CTA at C<=128": {"CZ_MT": "1"},
-    "skip fp32 (wide stream = fp32 copy)": {"CZ_SKIP_FORMAT": "fp32"},
-    "skip fp16+8 (wide stream = fp16 + byte plane)": {"CZ_SKIP_FORMAT": "split8"},
+    "skip default (fp32 copy of the residual stream beyond 10 blocks)": {},
     "skip fp16 only (upper bound: breaks 1e-3 at 20 blocks)": {"CZ_FP32_SKIP": "0"},
 }
 SHAPES = [(256, 20, 8192, 3.0), (128, 7, 2048, 1.5), (192, 10, 4096, 1.5)]
