@@ -212,7 +212,8 @@ def run_reference_arm(args):
                                 "mean_batch": w1[0][1] / max(1, w1[0][2]), "sample": d1 + f"; one {w1[0][3]:.0f} s window"}
             # tree-code ceiling: the same plumbing with a constant-output network
             w2, d2, u2, _ = reference_windows(sims, filters, blocks, K, 1, 20.0, free_nn=True)
-            extra["free_nn_ceiling"] = {"value": w2[0][0] / w2[0][3], "unit": "sims/s", "cores": u2, "sample": d2 + f"; one {w2[0][3]:.0f} s window"}
+            extra["free_nn_ceiling"] = {"value": w2[0][0] / w2[0][3], "unit": "sims/s", "cores": u2,
+                                        "sample": d2 + f"; one {w2[0][3]:.0f} s window of a separate run of the plumbing (on a shared box its rate moves with the host load, like the main windows)"}
     sample = f"{desc}; {len(per_window)} windows of {window:.1f} s after {args.warmup} warm-up windows ({tot_n} simulations in {tot_t:.0f} s)"
     line = {
         "impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
