@@ -49,7 +49,7 @@ def _worker(rank, world, port, emul_path, out):
             break
     gathered, total = records.gather_records(eng, dist, world, clear=False)
     mine = eng.drain_records()                       # what this rank's ring held
-    again, total2 = records.gather_records(eng, dist, world)      # rings are empty now: nothing is shipped twice
+    again, total2 = records.gather_records(eng, dist, world, warm=True)   # rings are empty now: nothing is shipped twice (warm: the ring collective still runs once)
     out.put((rank, finished, total, total2, mine, gathered, first_moves))
     eng.close()
     dist.destroy_process_group()
