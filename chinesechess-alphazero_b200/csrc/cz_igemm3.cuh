@@ -38,8 +38,6 @@ struct Args3 {
   int fbytes;            // bytes of one F tile: 2048 (fp32 skip and/or fp32 output), 1024 (fp16 skip only), 0 (neither)
   int nf;                // F tiles per epilogue warp (3 .. kMaxNF3): skip loads run nf - 2 chunks ahead
   int split_producer;    // 1: warp 0 issues the A (im2col) loads, warp 3 the B (weight) loads — two TMA issue streams per CTA
-  int l2_hint;           // 1: the fp32 skip stream (read once, written once per block, 755 MB per 8192 positions at C = 256) moves with
-                         // an L2 evict_first policy so that it does not push out the activation tiles the im2col loads re-read nine times
   int n_split;           // N tiles of N_TILE columns (1 = the tile is the whole width).  Small batches (a single game's leaves)
                          // run as pairs x n_split work items so that a launch of a few M-tiles still spreads over many SMs and
                          // each CTA's exposed epilogue is N_TILE / 16 chunks instead of C / 16; the K order per output is unchanged,
@@ -82,10 +80,6 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* t, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(t)), "r"(umma::smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* t, const void* src, int c0, int c1, uint64_t policy) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
-               ::"l"(reinterpret_cast<uint64_t>(t)), "r"(umma::smem_u32(src)), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -226,8 +220,6 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const int r1 = (lane >> 2) & 1;                           // SWIZZLE_32B key of this thread's 32-byte row
     const bool has_skip = p.skip_mode != 0, skip32 = p.skip_mode == 2;
     const uint32_t skip_bytes = skip32 ? 2048u : 1024u;
-    const bool hint = p.l2_hint != 0 && skip32;
-    const uint64_t pol = hint ? umma::l2_policy_evict_first() : 0ull;
     // next tile's skip block -> L2, a whole tile ahead (one warp): the per-chunk TMA loads below then hit L2
     auto prefetch_skip = [&](int item) {
       if (ew != 0 || item >= items || !has_skip || ns > 1) return;   // (split launches are a few tiles: nothing to run ahead of)
@@ -252,8 +244,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int row = (MT * (2 * (item / ns) + (int)rank) + mt) * kTileM + q * 32;
       const uint32_t slot = g % (uint32_t)nf;
       umma::mbar_expect_tx(&sbar[slot], skip_bytes);
-      if (hint) umma::tma_load_2d_hint(F + slot * fb, &tmSkip, &sbar[slot], (item % ns) * N_TILE + cbeg + ch * kChunkCols3, row, pol);
-      else umma::tma_load_2d(F + slot * fb, &tmSkip, &sbar[slot], (item % ns) * N_TILE + cbeg + ch * kChunkCols3, row);
+      umma::tma_load_2d(F + slot * fb, &tmSkip, &sbar[slot], (item % ns) * N_TILE + cbeg + ch * kChunkCols3, row);
     };
     uint32_t tcount = 0, g = 0;
     prefetch_skip(cluster_id);
@@ -326,7 +317,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         umma::fence_proxy_async();                            // generic-proxy writes above -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-          if (p.out32) { if (hint) tma_store_2d_hint(&tmOut32, F + slot * fb, c0, rbase, pol); else tma_store_2d(&tmOut32, F + slot * fb, c0, rbase); }
+          if (p.out32) tma_store_2d(&tmOut32, F + slot * fb, c0, rbase);
           tma_store_2d(&tmOut16, H + hb * kHBytes3, c0, rbase);
           bulk_commit();
         }

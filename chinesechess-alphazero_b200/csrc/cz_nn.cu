@@ -209,7 +209,6 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   p.fbytes = (skip_mode == 2 || out32) ? 2048 : (skip_mode == 1 ? 1024 : 0);
   { static int nf = -1; if (nf < 0) { const char* e = getenv("CZ_NF"); nf = e ? atoi(e) : 3; if (nf < 3) nf = 3; if (nf > igemm::kMaxNF3) nf = igemm::kMaxNF3; } p.nf = nf; }
   { static int sp = -1; if (sp < 0) { const char* e = getenv("CZ_SPLIT_PROD"); sp = (e && e[0] == '1') ? 1 : 0; } p.split_producer = sp; }
-  { static int lh = -1; if (lh < 0) { const char* e = getenv("CZ_L2HINT"); lh = (e && e[0] == '1') ? 1 : 0; } p.l2_hint = lh; }
   p.stages = C::max_stages(p.fbytes, p.nf);
   { static int cap = -1; if (cap < 0) { const char* e = getenv("CZ_STAGES"); cap = e ? atoi(e) : 0; } if (cap > 1 && cap < p.stages) p.stages = cap; }
   if (p.stages < 2) return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: no room for the operand ring");

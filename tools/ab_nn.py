@@ -15,9 +15,6 @@ VARIANTS = {
     "igemm3 everywhere, nf=4": {"CZ_EPI": "3", "CZ_NF": "4"},
     "auto, one M-tile per CTA at C<=128": {"CZ_MT": "1"},
     "skip default (fp32 copy of the residual stream beyond 10 blocks)": {},
-    "hint off: conv2 on igemm3": {"CZ_EPI": "3"},
-    "hint on: conv2 on igemm3, fp32 stream with L2 evict_first": {"CZ_EPI": "3", "CZ_L2HINT": "1"},
-    "hint on + nf=4": {"CZ_EPI": "3", "CZ_L2HINT": "1", "CZ_NF": "4"},
     "skip fp16 only (upper bound: breaks 1e-3 at 20 blocks)": {"CZ_FP32_SKIP": "0"},
 }
 SHAPES = [(256, 20, 8192, 3.0), (128, 7, 2048, 1.5), (192, 10, 4096, 1.5)]
