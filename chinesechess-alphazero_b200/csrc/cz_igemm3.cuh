@@ -87,8 +87,12 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int N_TILE, int MT = 1>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+// PAIRS = CTA pairs per cluster.  PAIRS = 2 (experiment, CZ_CLUSTER4=1): the two pairs of a 4-CTA cluster walk their tiles in lockstep
+// and share every weight stage — pair 0's CTAs load their halves of the weight tile with TMA multicast into both pairs' shared
+// memory — so a CTA pulls 16 + 8 KB per k-block instead of 16 + 16.  Every CTA's `empty` barrier then waits for BOTH pairs' MMA
+// commits (a stage is refilled only when neither pair reads it any more); everything else stays per pair.
+template <int N_TILE, int MT = 1, int PAIRS = 1>
+__global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(kThreads2, 1)
 k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut16,
          const __grid_constant__ CUtensorMap tmSkip, const __grid_constant__ CUtensorMap tmOut32, const Args3 p) {
   using C = Cfg3<N_TILE, MT>;
@@ -107,7 +111,10 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(skipbar + kMaxNF3 * kEpiWarps2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = umma::cluster_ctarank();
+  const uint32_t crank = umma::cluster_ctarank();          // rank in the cluster
+  const uint32_t rank = crank & 1u;                        // rank in the CTA pair
+  const uint32_t pp = crank >> 1;                          // pair in the cluster
+  const uint32_t lrank = crank & ~1u;                      // cluster rank of this pair's leader
   const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
@@ -118,7 +125,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (p.out32) umma::prefetch_tmap(&tmOut32);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < n_stages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < n_stages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], PAIRS); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 512); }
     for (int i = 0; i < kMaxNF3 * kEpiWarps2; ++i) umma::mbar_init(&skipbar[i], 1);
     umma::fence_barrier_init();
@@ -139,8 +146,10 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   const int m_tiles = a.n_dev ? (rows + kTileM - 1) / kTileM : a.m_tiles;
   const int pairs = (m_tiles + 2 * MT - 1) / (2 * MT);     // one pass of a CTA pair = 2 * MT consecutive M-tiles
   const int ns = p.n_split > 1 ? p.n_split : 1;            // work item = (pair, N tile): item / ns, item % ns
-  const int items = pairs * ns;
-  const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int items = pairs * ns;                            // (PAIRS = 2 runs with ns = 1)
+  const int items_c = (items + PAIRS - 1) / PAIRS;         // per cluster step every pair takes one item; the last may lie past the
+                                                           // end: an all-out-of-bounds tile (zero-filled loads, clipped stores)
+  const int n_clusters = gridDim.x / (2 * PAIRS), cluster_id = blockIdx.x / (2 * PAIRS);
 
   if (warp == 0 || (warp == 3 && p.split_producer)) {
     // ------------------------------------------------------------ TMA producer(s): one thread per CTA issues both operand
@@ -149,7 +158,8 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (lane == 0) {
       const bool do_a = warp == 0, do_b = warp == 3 || !p.split_producer;
       uint32_t s = 0, ph = 0;
-      for (int item = cluster_id; item < items; item += n_clusters) {
+      for (int it = cluster_id; it < items_c; it += n_clusters) {
+        const int item = it * PAIRS + (int)pp;
         const int pair = item / ns, n0 = (item % ns) * N_TILE;
         const int m_tile = MT * (2 * pair + (int)rank);     // this CTA's first tile of the pass
         for (int tap = 0; tap < a.n_taps; ++tap) {
@@ -163,10 +173,15 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 const int pix0 = (m_tile + mt) * kTileM, img0 = pix0 / 90, row0 = (pix0 % 90) / 9, col0 = pix0 % 9;
-                umma::tma2_load_im2col_4d(sA + mt * kAStageBytes, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1));
+                umma::tma2_load_im2col_4d_r(sA + mt * kAStageBytes, &tmA, &full[s], kc * kBlockK, col0 - 1, row0 - 1, img0, (uint16_t)(dx + 1), (uint16_t)(dy + 1), lrank);
               }
             }
-            if (do_b) umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + n0 + (int)rank * (N_TILE / 2));
+            if (do_b) {
+              if (PAIRS == 1) umma::tma2_load_2d(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + n0 + (int)rank * (N_TILE / 2));
+              else if (pp == 0)                             // this half of the weight tile -> the CTAs of this rank in both pairs
+                umma::tma2_load_2d_mc(sB, &tmB, &full[s], kc * kBlockK, tap * a.n_total + n0 + (int)rank * (N_TILE / 2),
+                                      (uint16_t)((1u << rank) | (1u << (rank + 2))));
+            }
             if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1; }
           }
         }
@@ -177,7 +192,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (leader && lane == 0) {
       constexpr uint32_t idesc = umma::idesc_f16(256, N_TILE);
       uint32_t s = 0, ph = 0, tcount = 0;
-      for (int item = cluster_id; item < items; item += n_clusters, ++tcount) {
+      for (int it = cluster_id; it < items_c; it += n_clusters, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         umma::mbar_wait(&tempty[acc], aph ^ 1);
         umma::tc_fence_after();
@@ -194,10 +209,10 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             for (int k = 0; k < kBlockK / 16; ++k)
               umma::mma2_f16_ss(d_tmem + mt * N_TILE, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          umma::mma2_commit_multicast(&empty[s]);
+          umma::mma2_commit_mask(&empty[s], PAIRS == 1 ? (uint16_t)3 : (uint16_t)0xF);
           if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1; }
         }
-        umma::mma2_commit_multicast(&tfull[acc]);
+        umma::mma2_commit_mask(&tfull[acc], (uint16_t)(3u << (2 * pp)));
       }
     }
   } else if (warp >= 4) {
@@ -215,7 +230,7 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     uint8_t* F = epi + ew * warp_bytes;                       // F[nf]: fb bytes each
     uint8_t* H = F + nf * fb;                                 // H[2]: 1024 B each
     uint64_t* sbar = skipbar + kMaxNF3 * ew;
-    const uint32_t tempty_remote[2] = {umma::mapa_shared(&tempty[0], 0), umma::mapa_shared(&tempty[1], 0)};
+    const uint32_t tempty_remote[2] = {umma::mapa_shared(&tempty[0], lrank), umma::mapa_shared(&tempty[1], lrank)};
     const int r3 = (lane >> 1) & 3;                           // SWIZZLE_64B key of this thread's 64-byte row
     const int r1 = (lane >> 2) & 1;                           // SWIZZLE_32B key of this thread's 32-byte row
     const bool has_skip = p.skip_mode != 0, skip32 = p.skip_mode == 2;
@@ -235,25 +250,26 @@ k_igemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     };
     // global chunk counter of this warp: chunk index g -> (tile = g / kChunks, chunk in tile = g % kChunks); F slot g % nf
     int my_tiles = 0;
-    for (int it = cluster_id; it < items; it += n_clusters) ++my_tiles;
+    for (int it = cluster_id; it < items_c; it += n_clusters) ++my_tiles;
     const uint32_t total_chunks = (uint32_t)my_tiles * (MT * kChunks);
     auto request_skip = [&](uint32_t g) {                     // lane 0 only
       if (!has_skip || g >= total_chunks) return;
       const int t = (int)(g / (MT * kChunks)), rem = (int)(g % (MT * kChunks)), mt = rem / kChunks, ch = rem % kChunks;
-      const int item = cluster_id + t * n_clusters;
+      const int item = (cluster_id + t * n_clusters) * PAIRS + (int)pp;
       const int row = (MT * (2 * (item / ns) + (int)rank) + mt) * kTileM + q * 32;
       const uint32_t slot = g % (uint32_t)nf;
       umma::mbar_expect_tx(&sbar[slot], skip_bytes);
       umma::tma_load_2d(F + slot * fb, &tmSkip, &sbar[slot], (item % ns) * N_TILE + cbeg + ch * kChunkCols3, row);
     };
     uint32_t tcount = 0, g = 0;
-    prefetch_skip(cluster_id);
+    prefetch_skip(cluster_id * PAIRS + (int)pp);
     if (lane == 0)
       for (int k = 0; k < nf - 2; ++k) request_skip((uint32_t)k);   // prime the ring: chunks 0 .. nf-3
-    for (int item = cluster_id; item < items; item += n_clusters, ++tcount) {
+    for (int it = cluster_id; it < items_c; it += n_clusters, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const int item = it * PAIRS + (int)pp;
       const int pair = item / ns, n0 = (item % ns) * N_TILE;
-      prefetch_skip(item + n_clusters);
+      prefetch_skip(item + n_clusters * PAIRS);
       umma::mbar_wait(&tfull[acc], aph);
       umma::tc_fence_after();
 #pragma unroll 1

@@ -194,14 +194,27 @@ static bool use_tma_epilogue_for(int c, bool fp32_stream) {
   if (epilogue_choice() == 3) return true;
   return !(c == 256 && fp32_stream);
 }
-template <int N_TILE, int MT>
+static int g_cluster4 = 0;                 // set by nn_create from CZ_CLUSTER4 (launch_igemm3, C = 256)
+template <int N_TILE, int MT, int PAIRS = 1>
 static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmOut16, const CUtensorMap& tmSkip,
                            const CUtensorMap& tmOut32, const igemm::Args& a, int skip_mode, bool out32, cudaStream_t st, int n_split = 1) {
   using C = igemm::Cfg3<N_TILE, MT>;
   static bool attr_set = false;
+  static int max_clusters = 0;
   if (!attr_set) {
-    CZ_CUDA(cudaFuncSetAttribute(igemm::k_igemm3<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, igemm::kSmemLimit3));
+    CZ_CUDA(cudaFuncSetAttribute(igemm::k_igemm3<N_TILE, MT, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, igemm::kSmemLimit3));
     attr_set = true;
+    max_clusters = num_sms() / (2 * PAIRS);
+    if (PAIRS > 1) {                       // 4-CTA clusters must fit inside a GPC: ask how many can be resident at once
+      cudaLaunchConfig_t oc;
+      memset(&oc, 0, sizeof(oc));
+      oc.gridDim = dim3(2 * PAIRS * max_clusters); oc.blockDim = dim3(igemm::kThreads2); oc.dynamicSmemBytes = igemm::kSmemLimit3;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, igemm::k_igemm3<N_TILE, MT, PAIRS>, &oc) == cudaSuccess && nc > 0 && nc < max_clusters) max_clusters = nc;
+      else (void)cudaGetLastError();
+      fprintf(stderr, "[cczero] 4-CTA clusters of k_igemm3<%d, %d>: %d resident at once (%d of %d SMs)\n", N_TILE, MT, max_clusters,
+              4 * max_clusters, num_sms());
+    }
   }
   igemm::Args3 p;
   p.a = a;
@@ -214,8 +227,8 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   if (p.stages < 2) return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: no room for the operand ring");
   const int pairs = ((a.n_dev ? (a.rows + igemm::kTileM - 1) / igemm::kTileM : a.m_tiles) + 2 * MT - 1) / (2 * MT);
   if (pairs <= 0) return 0;
-  const int items = pairs * (n_split > 1 ? n_split : 1);
-  const int clusters = items < num_sms() / 2 ? items : num_sms() / 2;
+  const int items = (pairs * (n_split > 1 ? n_split : 1) + PAIRS - 1) / PAIRS;     // cluster-level steps
+  const int clusters = items < max_clusters ? items : max_clusters;
   // Programmatic dependent launch: this conv's CTAs may become resident and run their prologue (barriers, TMEM, tensor map
   // prefetch) while the previous kernel of the stream is still running; griddepcontrol.wait in the kernel orders the data.
   // Measured on one box, interleaved (profiles/r02o_*): UCI go depth 8 56.7 -> 54.3 ms, c2 1.521 -> 1.540 M sims/s, c3 equal.
@@ -225,15 +238,15 @@ static int launch_igemm3_t(const CUtensorMap& tmA, const CUtensorMap& tmB_half, 
   if (pdl) {
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3(2 * clusters); lc.blockDim = dim3(igemm::kThreads2);
+    lc.gridDim = dim3(2 * PAIRS * clusters); lc.blockDim = dim3(igemm::kThreads2);
     lc.dynamicSmemBytes = C::smem_bytes(p.stages, p.fbytes, p.nf); lc.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    CZ_CUDA(cudaLaunchKernelEx(&lc, igemm::k_igemm3<N_TILE, MT>, tmA, tmB_half, tmOut16, tmSkip, tmOut32, p));
+    CZ_CUDA(cudaLaunchKernelEx(&lc, igemm::k_igemm3<N_TILE, MT, PAIRS>, tmA, tmB_half, tmOut16, tmSkip, tmOut32, p));
   } else {
-    igemm::k_igemm3<N_TILE, MT><<<2 * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
+    igemm::k_igemm3<N_TILE, MT, PAIRS><<<2 * PAIRS * clusters, igemm::kThreads2, C::smem_bytes(p.stages, p.fbytes, p.nf), st>>>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, p);
   }
   CZ_CUDA(cudaGetLastError());
   return 0;
@@ -249,7 +262,13 @@ static int launch_igemm3(int n_tile, const CUtensorMap& tmA, const CUtensorMap& 
     case 128: return mt2 ? launch_igemm3_t<128, 2>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st)
                          : launch_igemm3_t<128, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
     case 192: return launch_igemm3_t<192, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
-    case 256: return launch_igemm3_t<256, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    case 256: {
+      // CZ_CLUSTER4=1 when a network runtime is created (experiment, off by default): two CTA pairs per cluster share every
+      // weight stage by TMA multicast.  Bit-identical results (test_cluster4_weight_multicast); on the pool's B200 it is 1.6 %
+      // SLOWER on the 256x20 forward (profiles/r02y_ab_nn.log) — see DESIGN.md section 3.1.
+      if (g_cluster4) return launch_igemm3_t<256, 1, 2>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+      return launch_igemm3_t<256, 1>(tmA, tmB_half, tmOut16, tmSkip, tmOut32, a, skip_mode, out32, st);
+    }
   }
   return cz_fail(CZ_ERR_UNSUPPORTED, "igemm3: unsupported N tile %d", n_tile);
 }
@@ -763,6 +782,7 @@ NnRuntime* nn_create(int device, int filters, int blocks, int value_fc, int max_
   // reference's trained 192x10 net), 1 = always, 2 = never
   r->fp32_skip = fp32_skip_mode == 1 || (fp32_skip_mode == 0 && blocks >= 10);
   { const char* e = getenv("CZ_FP32_SKIP"); if (e && e[0] == '1') r->fp32_skip = true; if (e && e[0] == '0') r->fp32_skip = false; }
+  { const char* e = getenv("CZ_CLUSTER4"); g_cluster4 = (e && e[0] == '1') ? 1 : 0; }
   r->profile = false; r->ev_used = 0; r->prof_ms = 0; r->prof_flops = 0; r->prof_launches = 0; r->capturing = false;
   Carver cv{(uint8_t*)workspace, 0, bytes};
   layout(r, cv);

@@ -184,6 +184,30 @@ __device__ __forceinline__ void tma2_load_im2col_4d(void* dst, const CUtensorMap
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(t)), "r"(mapa_shared(bar, 0)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
       : "memory");
 }
+// ---- the same loads for a CTA pair that is not the first pair of its cluster (4-CTA clusters: two pairs).  `lr` = cluster rank of
+// this pair's leader: the transaction bytes are signalled on ITS barrier.
+__device__ __forceinline__ void tma2_load_2d_r(void* dst, const CUtensorMap* t, uint64_t* bar, int c0, int c1, uint32_t lr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(t)), "r"(mapa_shared(bar, lr)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d_r(void* dst, const CUtensorMap* t, uint64_t* bar, int c, int w, int h, int n,
+                                                      uint16_t ow, uint16_t oh, uint32_t lr) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(t)), "r"(mapa_shared(bar, lr)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+      : "memory");
+}
+// Multicast form: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each destination's transaction
+// bytes are signalled on the barrier at `bar`'s offset in the LEADER of that destination's pair (shared::cta address with the
+// pair's peer bit cleared: the convention of the 2-SM TMA multicast loads).
+__device__ __forceinline__ void tma2_load_2d_mc(void* dst, const CUtensorMap* t, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(t)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc2(uint32_t* slot_in_smem) {   // one full warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(kCols)
@@ -204,6 +228,10 @@ __device__ __forceinline__ void mma2_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 // Arrive on the barrier at this offset in BOTH CTAs once all prior MMAs of the pair have completed.
+__device__ __forceinline__ void mma2_commit_mask(uint64_t* bar, uint16_t mask) {   // arrive on `bar`'s offset in every CTA of `mask`
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void mma2_commit_multicast(uint64_t* bar) {
   const uint16_t mask = 3;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

@@ -16,6 +16,8 @@ VARIANTS = {
     "auto, one M-tile per CTA at C<=128": {"CZ_MT": "1"},
     "skip default (fp32 copy of the residual stream beyond 10 blocks)": {},
     "conv2 on igemm3": {"CZ_EPI": "3"},
+    "cluster4: two CTA pairs per cluster share the weight stages (conv1)": {"CZ_CLUSTER4": "1"},
+    "cluster4 + conv2 on igemm3": {"CZ_CLUSTER4": "1", "CZ_EPI": "3"},
     "skip fp16 only (upper bound: breaks 1e-3 at 20 blocks)": {"CZ_FP32_SKIP": "0"},
 }
 SHAPES = [(256, 20, 8192, 3.0), (128, 7, 2048, 1.5), (192, 10, 4096, 1.5)]
@@ -23,7 +25,7 @@ if os.environ.get("AB_ONLY"):                      # e.g. AB_ONLY="auto,one M-ti
     keep = [k.strip() for k in os.environ["AB_ONLY"].split(",")]
     VARIANTS = {k: v for k, v in VARIANTS.items() if any(k.startswith(p) for p in keep)}
 if os.environ.get("AB_SHAPES") == "c3":
-    SHAPES = [(256, 20, 8192, 3.0), (128, 7, 2048, 1.5)]
+    SHAPES = [(256, 20, 8192, 3.0)]
 if os.environ.get("AB_SHAPES") == "small":
     SHAPES = [(128, 7, 2048, 1.5), (128, 7, 8192, 1.5), (64, 4, 2048, 1.0)]
 
