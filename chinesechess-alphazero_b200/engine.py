@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from .env import board_to_state, move_to_u16, state_to_board, u16_to_move
+from .env import move_to_u16, state_to_board, u16_to_move
 from .lib import (BOARD_STRIDE, MAX_MOVES, MAX_NO_ACT, N_LABELS, CzConfig, CzPvInfo, CzRecordHdr, CzRootInfo, CzRootOpts,
                   get_lib)
 

@@ -22,7 +22,6 @@ import threading
 from time import time
 
 import numpy as np
-import torch
 
 from .engine import Engine
 from .env import StaticEnv, flip_move, to_uci_move
